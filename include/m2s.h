@@ -1,0 +1,195 @@
+/*
+ * m2s.h -- C ABI of libm2s.so, the sm_100a (B200) implementation of the
+ * rtMRI-video -> mel -> waveform inference path of YamaneKoyo/mri-to-speech.
+ *
+ * The reference is pure Python/PyTorch and has NO plugin / FFI layer (SURVEY.md
+ * section 1): its boundary for this path is the nn.Module API
+ *   models.Generator.forward                      (reference models.py:113-131)
+ *   OTNLikeCNNBiLSTM.forward                      (reference mri2speech_code/mri_acoustic_model.py:116-136)
+ *   the mel glue in scripts/run_mri_video_inference.py:160-163,227-239
+ * This header is the binding a maintainer puts UNDER those modules (ctypes stub in
+ * INTEGRATION.md; our own host-side mirror lives in mri2speech_b200/).  Every
+ * entry point takes plain pointers and sizes -- no torch types.
+ *
+ * Conventions
+ *   - all device pointers are on the current CUDA device, float32 unless noted;
+ *   - no allocation and no synchronisation inside *_forward: the caller owns
+ *     inputs, outputs and the workspace (size from *_workspace_bytes);
+ *   - every call returns M2S_OK (0) or a negative m2s_status; the message of the
+ *     last failure on the calling thread is m2s_last_error_string();
+ *   - calls on distinct streams / distinct handles are thread-safe;
+ *   - anything but an sm_100 device is refused (there is no CPU fallback).
+ */
+#ifndef M2S_H_
+#define M2S_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* m2s_stream_t; /* == cudaStream_t */
+
+typedef enum {
+  M2S_OK = 0,
+  M2S_ERR_BAD_ARG = -1,
+  M2S_ERR_UNSUPPORTED = -2,
+  M2S_ERR_CUDA = -3,
+  M2S_ERR_DEVICE = -4,
+  M2S_ERR_WORKSPACE = -5,
+  M2S_ERR_MISSING_TENSOR = -6
+} m2s_status;
+
+/* arithmetic of the GEMM-shaped layers */
+enum {
+  M2S_PREC_TF32 = 0, /* tcgen05 kind::tf32, fp32 accumulate in TMEM (default build) */
+  M2S_PREC_FP32 = 1  /* CUDA-core fp32 FMA kernels (exact-fp32 build, slow)          */
+};
+
+const char* m2s_version(void);
+const char* m2s_last_error_string(void);
+/* 0 if `device` is an sm_100 part, M2S_ERR_DEVICE otherwise. */
+int m2s_device_check(int device);
+
+/* A named host tensor, exactly one state_dict entry of the reference checkpoints
+ * (keys as listed in SURVEY.md 8a-1/8a-3/8a-5). */
+typedef struct {
+  const char* name;
+  const float* data; /* host, contiguous, row-major */
+  int32_t ndim;
+  int64_t shape[4];
+} m2s_tensor;
+
+/* ------------------------------------------------------------------------- */
+/* Generic multi-tap implicit-GEMM convolution (the engine every GEMM-shaped  */
+/* layer of the path runs on).  Exposed for parity tests of the kernel itself.*/
+/*   D[b, q + d_row_offset, n] = epi( sum_j sum_c A[b, q + shift[j], c] * W[j][n][c] ) */
+/* Rows of A outside [0, a_rows) read as zero.  Activations are channels-last. */
+/* ------------------------------------------------------------------------- */
+enum { M2S_ACT_NONE = 0, M2S_ACT_LRELU = 1, M2S_ACT_SILU = 2 };
+enum { M2S_MASK_NONE = 0, M2S_MASK_LEN = 1, M2S_MASK_PITCH = 2 };
+enum { M2S_IMPL_TCGEN05 = 0, M2S_IMPL_SIMT = 1 };
+#define M2S_MAX_TAPS 16
+
+typedef struct {
+  /* A operand */
+  const float* a;
+  int64_t a_batch_rows; /* rows between consecutive batch items            */
+  int32_t a_rows;       /* valid rows per batch item (zero beyond)         */
+  int32_t a_ld;         /* elements per row (multiple of 4)                */
+  int32_t c_in;         /* channels contracted per tap (multiple of 4)     */
+  int32_t batch;
+  int32_t l_out;        /* rows computed per batch item                    */
+  int32_t taps;
+  int32_t shift[M2S_MAX_TAPS];
+  /* weights: plain host-order device array [taps][n][c_in] */
+  const float* w;
+  int32_t n;
+  /* output */
+  float* d;
+  int64_t d_batch_rows;
+  int32_t d_ld;
+  int32_t d_row_offset;
+  /* fused epilogue: v = acc + bias[n] + inv_lrelu(res) + accum; v *= out_scale; v = act(v); mask; round */
+  const float* bias;     /* [n] or NULL */
+  const float* res;      /* indexed like d (same rows), NULL = none */
+  int32_t res_ld;
+  float res_inv_slope;   /* res >= 0 ? res : res*res_inv_slope  (1 = plain residual) */
+  const float* accum;    /* indexed like d, NULL = none */
+  int32_t accum_ld;
+  float out_scale;
+  int32_t act;
+  float act_slope;
+  int32_t round_tf32;    /* store RNE-rounded-to-TF32 values (operand of a later tcgen05 layer) */
+  int32_t mask_mode;
+  const int32_t* lens;   /* M2S_MASK_LEN: row valid iff (q + d_row_offset) < lens[b]*len_scale */
+  int32_t len_scale;
+  int32_t pitch, i_lo, i_hi, j_lo, j_hi; /* M2S_MASK_PITCH: (i,j)=divmod(row,pitch) inside the box */
+} m2s_conv_args;
+
+int m2s_conv_fwd(const m2s_conv_args* args, int impl, m2s_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* HiFi-GAN Generator (reference models.py:88-131, config_custom.json)        */
+/* ------------------------------------------------------------------------- */
+#define M2S_MAX_UPS 8
+#define M2S_MAX_RBK 8
+typedef struct {
+  int32_t num_mels;                 /* h.num_mels                      */
+  int32_t upsample_initial_channel; /* h.upsample_initial_channel      */
+  int32_t num_upsamples;
+  int32_t upsample_rates[M2S_MAX_UPS];
+  int32_t upsample_kernel_sizes[M2S_MAX_UPS];
+  int32_t num_kernels;
+  int32_t resblock_kernel_sizes[M2S_MAX_RBK];
+  int32_t resblock_dilations[M2S_MAX_RBK][3];
+  int32_t precision;                /* M2S_PREC_*                      */
+} m2s_generator_config;
+
+typedef struct m2s_generator m2s_generator;
+
+/* Tensors: the Generator state_dict (233 entries for config_custom.json), either
+ * weight_g/weight_v pairs or plain .weight (weight-norm removed). */
+int m2s_generator_create(const m2s_generator_config* cfg, const m2s_tensor* tensors, int32_t n_tensors,
+                         m2s_generator** out);
+void m2s_generator_destroy(m2s_generator* g);
+size_t m2s_generator_workspace_bytes(const m2s_generator* g, int32_t batch, int32_t frames);
+/* mel: device (batch, num_mels, frames) -- the layout Generator.forward takes.
+ * lengths: device int32[batch] valid mel frames per utterance, or NULL (all = frames).
+ * audio:  device (batch, 1, frames * prod(upsample_rates)). */
+int m2s_generator_forward(m2s_generator* g, const float* mel, int32_t batch, int32_t frames,
+                          const int32_t* lengths, float* audio, void* workspace, size_t workspace_bytes,
+                          m2s_stream_t stream);
+/* Number of kernels one forward launches (for bench.py's gpu_launches). */
+int m2s_generator_launches(const m2s_generator* g);
+
+/* ------------------------------------------------------------------------- */
+/* Acoustic model: frame-CNN encoder + BiLSTM (sum merge) + mel head           */
+/* (reference mri2speech_code/mri_acoustic_model.py:20-136)                    */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_mels;
+  int32_t rnn_hidden;
+  int32_t height, width; /* frame size, 256 x 256 */
+  int32_t precision;
+} m2s_acoustic_config;
+
+typedef struct m2s_acoustic m2s_acoustic;
+
+int m2s_acoustic_create(const m2s_acoustic_config* cfg, const m2s_tensor* tensors, int32_t n_tensors,
+                        m2s_acoustic** out);
+void m2s_acoustic_destroy(m2s_acoustic* m);
+size_t m2s_acoustic_workspace_bytes(const m2s_acoustic* m, int32_t batch, int32_t frames);
+/* frames: device (batch, frames, height, width) float32 in [0,1];
+ * lengths: device int32[batch] or NULL; lengths_host: the same values on the host
+ * (needed to size the recurrence; NULL iff lengths is NULL);
+ * mel_norm: device (batch, frames, n_mels) normalised mel (rows past lengths[b] are zero). */
+int m2s_acoustic_forward(m2s_acoustic* m, const float* frames_dev, int32_t batch, int32_t frames,
+                         const int32_t* lengths, const int32_t* lengths_host, float* mel_norm,
+                         void* workspace, size_t workspace_bytes, m2s_stream_t stream);
+/* Encoder only: (n_frames, height, width) -> (n_frames, 208) features. */
+int m2s_acoustic_encode(m2s_acoustic* m, const float* frames_dev, int32_t n_frames, float* feats,
+                        void* workspace, size_t workspace_bytes, m2s_stream_t stream);
+/* BiLSTM + head only: feats (batch, frames, 208) -> mel_norm (batch, frames, n_mels). */
+int m2s_acoustic_rnn_head(m2s_acoustic* m, const float* feats, int32_t batch, int32_t frames,
+                          const int32_t* lengths, const int32_t* lengths_host, float* mel_norm,
+                          void* workspace, size_t workspace_bytes, m2s_stream_t stream);
+int m2s_acoustic_launches(const m2s_acoustic* m);
+
+/* ------------------------------------------------------------------------- */
+/* Mel glue (reference scripts/run_mri_video_inference.py:160-163,232-239)     */
+/*   mel_db  = pred*std + mean                       (batch, frames, n_mels)   */
+/*   mel_log = log(clamp(10^(mel_db/10), 1e-5))      (batch, frames, n_mels)   */
+/*   voc_in  = mel_log transposed                    (batch, n_mels, frames)   */
+/* Rows past lengths[b] are written as zero.  Any output may be NULL.          */
+/* ------------------------------------------------------------------------- */
+int m2s_mel_glue(const float* pred_norm, const float* mean, const float* std, int32_t batch,
+                 int32_t frames, int32_t n_mels, const int32_t* lengths, float* mel_db, float* mel_log,
+                 float* voc_in, m2s_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M2S_H_ */

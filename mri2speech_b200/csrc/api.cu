@@ -1,0 +1,86 @@
+// C-ABI plumbing: errors, device check, the generic conv test entry, mel glue.
+#include "m2s_common.cuh"
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace m2s {
+
+static thread_local char g_error[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int fail(int status, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+  return status;
+}
+
+int mel_glue(const float* pred, const float* mean, const float* stdv, int batch, int frames, int n_mels,
+             const int32_t* lens, float* mel_db, float* mel_log, float* voc_in, cudaStream_t stream);
+
+}  // namespace m2s
+
+using namespace m2s;
+
+extern "C" const char* m2s_version(void) { return "m2s 0.1.0 (sm_100a; tcgen05 tf32 conv engine)"; }
+
+extern "C" const char* m2s_last_error_string(void) { return g_error; }
+
+extern "C" int m2s_device_check(int device) {
+  int dev = device;
+  if (dev < 0) M2S_CUDA_OK(cudaGetDevice(&dev));
+  int major = 0, minor = 0;
+  M2S_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  M2S_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (major != 10)
+    return fail(M2S_ERR_DEVICE, "device %d is sm_%d%d; libm2s is built for sm_100a only and has no fallback", dev,
+                major, minor);
+  return M2S_OK;
+}
+
+extern "C" int m2s_debug_set_knob(const char* name, int value) {
+  EngineKnobs& k = engine_knobs();
+  if (!std::strcmp(name, "base_offset_mode")) k.base_offset_mode = value;
+  else if (!std::strcmp(name, "msub")) k.msub = value;
+  else if (!std::strcmp(name, "tmap_tf32")) k.tmap_tf32 = value;
+  else if (!std::strcmp(name, "max_ctas")) k.max_ctas = value;
+  else if (!std::strcmp(name, "a_per_tap")) k.a_per_tap = value;
+  else return fail(M2S_ERR_BAD_ARG, "unknown knob %s", name);
+  return M2S_OK;
+}
+
+// Test entry: weights arrive as a plain device array [taps][n][c_in]; the tcgen05 path packs them on the fly.
+extern "C" int m2s_conv_fwd(const m2s_conv_args* args, int impl, m2s_stream_t stream) {
+  if (!args || !args->a || !args->w || !args->d) return fail(M2S_ERR_BAD_ARG, "null argument");
+  M2S_TRY(m2s_device_check(-1));
+  ConvProblem p = problem_from_args(*args);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (impl == M2S_IMPL_SIMT) return conv_simt(p, args->w, st);
+  if (impl != M2S_IMPL_TCGEN05) return fail(M2S_ERR_BAD_ARG, "unknown impl %d", impl);
+  const size_t nw = static_cast<size_t>(p.taps) * p.n * p.c_in;
+  std::vector<float> hw(nw);
+  M2S_CUDA_OK(cudaMemcpy(hw.data(), args->w, nw * sizeof(float), cudaMemcpyDeviceToHost));
+  PackedWeights w;
+  M2S_TRY(pack_weights(hw.data(), p.taps, p.n, p.c_in, false, &w));
+  int s = conv_tcgen05(p, w, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  free_weights(&w);
+  if (s == M2S_OK && e != cudaSuccess) return fail(M2S_ERR_CUDA, "conv kernel failed: %s", cudaGetErrorString(e));
+  return s;
+}
+
+extern "C" int m2s_mel_glue(const float* pred_norm, const float* mean, const float* std, int32_t batch, int32_t frames,
+                            int32_t n_mels, const int32_t* lengths, float* mel_db, float* mel_log, float* voc_in,
+                            m2s_stream_t stream) {
+  if (!pred_norm || !mean || !std) return fail(M2S_ERR_BAD_ARG, "null argument");
+  return mel_glue(pred_norm, mean, std, batch, frames, n_mels, lengths, mel_db, mel_log, voc_in,
+                  reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,563 @@
+// Multi-tap implicit-GEMM convolution engine for sm_100a: TMA -> SMEM (128B swizzle) -> tcgen05.mma
+// (kind::tf32, accumulators in TMEM) -> fused epilogue -> global.
+//
+// One kernel serves every GEMM-shaped layer of the path (reference call sites):
+//   * HiFi-GAN ResBlock1 causal dilated Conv1d           models.py:35-49 (72 convs)
+//   * conv_pre (anti-causal k7)                          models.py:114-115
+//   * ConvTranspose1d as a 3-tap polyphase GEMM          models.py:118
+//   * LSTM input projection, mel head                    mri_acoustic_model.py:57-71,135
+//   * EfficientNetV2 1x1 convs and stride-1 3x3 convs (as shifted-row taps over a zero-bordered
+//     NHWC image flattened to rows)                      mri_acoustic_model.py:28-46 (timm)
+//
+// D[b, q + d_row_offset, n] = epi( sum_{tap j} sum_c A[b, q + shift[j], c] * W[j][n][c] )
+//
+// Activations are channels-last fp32, so the contraction (channel) dimension is contiguous and a
+// conv tap is a row-shifted view of ONE SMEM tile: the A tile for a 32-channel block is loaded once
+// with its halo (TMA zero-fills rows outside [0, a_rows): causal / anti-causal / image-border
+// padding for free) and each tap issues tcgen05.mma with the A descriptor start address advanced by
+// rel_shift[j] rows.  Weights are pre-packed on the host in the exact swizzled SMEM image and
+// streamed per (channel block, tap) with 1-D bulk copies.
+//
+// Warp roles (192 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0   : TMA producer (one lane)
+//   warp 1   : TMEM allocator + MMA issuer (one lane)
+//   warps 2-5: epilogue (TMEM lane quadrant = warp_idx % 4): tcgen05.ld -> bias / residual /
+//              MRF accumulate / scale / activation / mask / TF32 rounding -> global
+#include "m2s_common.cuh"
+#include <cuda.h>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace m2s {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kKBlock = 32;     // tf32 elements per 128-byte swizzle row
+constexpr int kRowBytes = 128;
+constexpr int kTmemCols = 512;
+constexpr int kMaxStagesA = 4;
+constexpr int kMaxStagesB = 8;
+constexpr uint32_t kSmemBudget = 200 * 1024;  // > 114 KB forces 1 CTA / SM (TMEM is allocated whole)
+
+struct EngineParams {
+  ConvProblem p;
+  const float* wpacked;
+  int n_tile, n_tiles, msub, m_tile;
+  int tiles_per_batch, total_tiles;
+  int cblocks;
+  int a_box_rows, a_nbox, shift_min;
+  int na, nb;
+  uint32_t a_stage_bytes, b_stage_bytes;
+  int nacc, acc_stride;
+  uint32_t idesc;
+  int base_offset_mode;
+  int a_per_tap;
+  int rel_shift[M2S_MAX_TAPS];
+};
+
+// ---- PTX wrappers ------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug must trap, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("m2s conv engine: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// SMEM matrix descriptor, K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, int base_offset_mode) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);        // start address  [0,14)
+  d |= static_cast<uint64_t>(1) << 16;                       // LBO (unused for swizzled K-major) [16,30)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;               // SBO = 1024 B   [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                       // descriptor version (Blackwell) [46,48)
+  if (base_offset_mode) d |= static_cast<uint64_t>((saddr >> 7) & 7) << 49;  // base offset [49,52)
+  d |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B    [61,64)
+  return d;
+}
+
+// ---- the kernel ----------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ EngineParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [A stages][B stages][barriers][tmem ptr]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = a_base + prm.na * prm.a_stage_bytes;
+  const uint32_t bar_base = b_base + prm.nb * prm.b_stage_bytes;
+  // barrier slots (8 B each)
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (kMaxStagesA + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * kMaxStagesA + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * kMaxStagesA + kMaxStagesB + s); };
+  auto acc_full = [&](int s) { return bar_base + 8u * (2 * kMaxStagesA + 2 * kMaxStagesB + s); };
+  auto acc_empty = [&](int s) { return bar_base + 8u * (2 * kMaxStagesA + 2 * kMaxStagesB + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStagesA + 2 * kMaxStagesB + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const ConvProblem& p = prm.p;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < prm.na; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < prm.nb; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    for (int s = 0; s < prm.nacc; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 4); }
+    fence_barrier_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int ksteps_full = kKBlock / 8;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
+        const int nt = tile % prm.n_tiles;
+        const int mt = (tile / prm.n_tiles) % prm.tiles_per_batch;
+        const int b = tile / (prm.n_tiles * prm.tiles_per_batch);
+        const int q0 = mt * prm.m_tile;
+        for (int cb = 0; cb < prm.cblocks; ++cb) {
+          if (!prm.a_per_tap) {
+            mbar_wait(a_empty(sa), pa ^ 1);
+            mbar_expect_tx(a_full(sa), prm.a_nbox * prm.a_box_rows * kRowBytes);
+            for (int bx = 0; bx < prm.a_nbox; ++bx)
+              tma_load_3d(a_base + sa * prm.a_stage_bytes + bx * prm.a_box_rows * kRowBytes, &tmap_a, a_full(sa),
+                          cb * kKBlock, q0 + prm.shift_min + bx * prm.a_box_rows, b);
+            if (++sa == prm.na) { sa = 0; pa ^= 1; }
+          }
+          for (int tap = 0; tap < p.taps; ++tap) {
+            if (prm.a_per_tap) {
+              mbar_wait(a_empty(sa), pa ^ 1);
+              mbar_expect_tx(a_full(sa), prm.a_nbox * prm.a_box_rows * kRowBytes);
+              for (int bx = 0; bx < prm.a_nbox; ++bx)
+                tma_load_3d(a_base + sa * prm.a_stage_bytes + bx * prm.a_box_rows * kRowBytes, &tmap_a, a_full(sa),
+                            cb * kKBlock, q0 + p.shift[tap] + bx * prm.a_box_rows, b);
+              if (++sa == prm.na) { sa = 0; pa ^= 1; }
+            }
+            mbar_wait(b_empty(sb), pb ^ 1);
+            mbar_expect_tx(b_full(sb), prm.b_stage_bytes);
+            const float* src = prm.wpacked +
+                               (static_cast<size_t>((nt * prm.cblocks + cb) * p.taps + tap)) * prm.n_tile * kKBlock;
+            bulk_load(b_base + sb * prm.b_stage_bytes, src, prm.b_stage_bytes, b_full(sb));
+            if (++sb == prm.nb) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int sa = 0, sb = 0, acc = 0;
+      uint32_t pa = 0, pb = 0, pacc = 0;
+      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
+        mbar_wait(acc_empty(acc), pacc ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + acc * prm.acc_stride;
+        for (int cb = 0; cb < prm.cblocks; ++cb) {
+          int rem = p.c_in - cb * kKBlock;
+          const int ksteps = rem >= kKBlock ? ksteps_full : (rem + 7) / 8;
+          if (!prm.a_per_tap) {
+            mbar_wait(a_full(sa), pa);
+            tc_fence_after();
+          }
+          for (int tap = 0; tap < p.taps; ++tap) {
+            if (prm.a_per_tap) {
+              mbar_wait(a_full(sa), pa);
+            }
+            mbar_wait(b_full(sb), pb);
+            tc_fence_after();
+            const uint32_t a_tile = a_base + sa * prm.a_stage_bytes;
+            const uint32_t b_tile = b_base + sb * prm.b_stage_bytes;
+            const int row_shift = prm.a_per_tap ? 0 : prm.rel_shift[tap];
+            for (int sub = 0; sub < prm.msub; ++sub) {
+              const uint32_t a_sub = a_tile + (sub * 128 + row_shift) * kRowBytes;
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t da = make_desc_sw128(a_sub + ks * 32, prm.base_offset_mode);
+                const uint64_t db = make_desc_sw128(b_tile + ks * 32, 0);
+                const uint32_t accum = (cb | tap | ks) ? 1u : 0u;
+                mma_tf32(tmem_acc + sub * prm.n_tile, da, db, prm.idesc, accum);
+              }
+            }
+            tc_commit(b_empty(sb));
+            if (++sb == prm.nb) { sb = 0; pb ^= 1; }
+            if (prm.a_per_tap) {
+              tc_commit(a_empty(sa));
+              if (++sa == prm.na) { sa = 0; pa ^= 1; }
+            }
+          }
+          if (!prm.a_per_tap) {
+            tc_commit(a_empty(sa));
+            if (++sa == prm.na) { sa = 0; pa ^= 1; }
+          }
+        }
+        tc_commit(acc_full(acc));
+        if (++acc == prm.nacc) { acc = 0; pacc ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const Epilogue& e = p.epi;
+    int acc = 0;
+    uint32_t pacc = 0;
+    for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
+      const int nt = tile % prm.n_tiles;
+      const int mt = (tile / prm.n_tiles) % prm.tiles_per_batch;
+      const int b = tile / (prm.n_tiles * prm.tiles_per_batch);
+      const int q0 = mt * prm.m_tile;
+      const int n0 = nt * prm.n_tile;
+      mbar_wait(acc_full(acc), pacc);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + acc * prm.acc_stride + (static_cast<uint32_t>(quad * 32) << 16);
+      for (int sub = 0; sub < prm.msub; ++sub) {
+        const int q = q0 + sub * 128 + quad * 32 + lane;
+        const bool row_ok = q < p.l_out;
+        const int drow = q + p.d_row_offset;
+        const bool valid = row_ok && epi_row_valid(e, b, row_ok ? drow : 0);
+        const size_t row_index = static_cast<size_t>(b) * p.d_batch_rows + drow;
+        float* drow_ptr = p.d + row_index * p.d_ld;
+        const float* rrow_ptr = e.res ? e.res + row_index * e.res_ld : nullptr;
+        const float* srow_ptr = e.accum ? e.accum + row_index * e.accum_ld : nullptr;
+        for (int c0 = 0; c0 < prm.n_tile; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_acc + sub * prm.n_tile + c0, r);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4) {
+              const int n = n0 + c0 + v4 * 4;
+              if (n < p.n) {
+                float4 bias4 = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + n)) : make_float4(0, 0, 0, 0);
+                float4 res4 = rrow_ptr ? *reinterpret_cast<const float4*>(rrow_ptr + n) : make_float4(0, 0, 0, 0);
+                float4 acc4 = srow_ptr ? *reinterpret_cast<const float4*>(srow_ptr + n) : make_float4(0, 0, 0, 0);
+                float4 o;
+                o.x = epi_apply(e, __uint_as_float(r[v4 * 4 + 0]), bias4.x, res4.x, acc4.x, valid);
+                o.y = epi_apply(e, __uint_as_float(r[v4 * 4 + 1]), bias4.y, res4.y, acc4.y, valid);
+                o.z = epi_apply(e, __uint_as_float(r[v4 * 4 + 2]), bias4.z, res4.z, acc4.z, valid);
+                o.w = epi_apply(e, __uint_as_float(r[v4 * 4 + 3]), bias4.w, res4.w, acc4.w, valid);
+                *reinterpret_cast<float4*>(drow_ptr + n) = o;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(acc));
+      if (++acc == prm.nacc) { acc = 0; pacc ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+
+}  // namespace
+
+EngineKnobs& engine_knobs() {
+  static EngineKnobs k = [] {
+    EngineKnobs x;
+    x.base_offset_mode = env_int("M2S_ENGINE_BASE_OFFSET", 0);
+    x.msub = env_int("M2S_ENGINE_MSUB", 0);
+    x.tmap_tf32 = env_int("M2S_ENGINE_TMAP_TF32", 0);
+    x.max_ctas = env_int("M2S_ENGINE_MAX_CTAS", 0);
+    x.a_per_tap = env_int("M2S_ENGINE_A_PER_TAP", 0);
+    return x;
+  }();
+  return k;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+void choose_n_tiling(int n, int* n_tile, int* n_tiles) {
+  // smallest number of tiles with n_tile a multiple of 16 and <= 256; prefer an even split.
+  int tiles = (n + 255) / 256;
+  int nt = (((n + tiles - 1) / tiles) + 15) / 16 * 16;
+  *n_tile = nt;
+  *n_tiles = tiles;
+}
+
+static float host_round_tf32(float v) {
+  uint32_t u;
+  std::memcpy(&u, &v, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return v;
+  u += 0x1000u;  // round to nearest, ties away (matches cvt.rna)
+  u &= 0xFFFFE000u;
+  float r;
+  std::memcpy(&r, &u, 4);
+  return r;
+}
+
+int pack_weights(const float* host_w, int taps, int n, int c_in, bool tf32_round, PackedWeights* out) {
+  PackedWeights w;
+  w.n = n; w.c_in = c_in; w.taps = taps;
+  choose_n_tiling(n, &w.n_tile, &w.n_tiles);
+  w.cblocks = (c_in + kKBlock - 1) / kKBlock;
+  w.packed_floats = static_cast<size_t>(w.n_tiles) * w.cblocks * taps * w.n_tile * kKBlock;
+  std::vector<float> packed(w.packed_floats, 0.f);
+  std::vector<float> plain(static_cast<size_t>(taps) * n * c_in);
+  for (int j = 0; j < taps; ++j)
+    for (int o = 0; o < n; ++o)
+      for (int c = 0; c < c_in; ++c) {
+        float v = host_w[(static_cast<size_t>(j) * n + o) * c_in + c];
+        if (tf32_round) v = host_round_tf32(v);
+        plain[(static_cast<size_t>(j) * n + o) * c_in + c] = v;
+        const int nt = o / w.n_tile, r = o % w.n_tile, cb = c / kKBlock, cc = c % kKBlock;
+        const size_t blk = (static_cast<size_t>(nt * w.cblocks + cb) * taps + j) * w.n_tile * kKBlock;
+        // 128B swizzle: 16-byte chunk index ^= (row & 7)
+        const int chunk = (cc >> 2) ^ (r & 7);
+        packed[blk + static_cast<size_t>(r) * kKBlock + chunk * 4 + (cc & 3)] = v;
+      }
+  M2S_CUDA_OK(cudaMalloc(&w.dev, packed.size() * sizeof(float)));
+  M2S_CUDA_OK(cudaMalloc(&w.plain, plain.size() * sizeof(float)));
+  M2S_CUDA_OK(cudaMemcpy(w.dev, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+  M2S_CUDA_OK(cudaMemcpy(w.plain, plain.data(), plain.size() * sizeof(float), cudaMemcpyHostToDevice));
+  *out = w;
+  return M2S_OK;
+}
+
+void free_weights(PackedWeights* w) {
+  if (w->dev) cudaFree(w->dev);
+  if (w->plain) cudaFree(w->plain);
+  *w = PackedWeights{};
+}
+
+int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stream) {
+  if (p.taps < 1 || p.taps > M2S_MAX_TAPS) return fail(M2S_ERR_BAD_ARG, "taps=%d out of range", p.taps);
+  if (p.c_in % 4 || p.a_ld % 4 || p.d_ld % 4 || p.n % 4)
+    return fail(M2S_ERR_UNSUPPORTED, "c_in/a_ld/d_ld/n must be multiples of 4 (got %d/%d/%d/%d)", p.c_in, p.a_ld,
+                p.d_ld, p.n);
+  if ((reinterpret_cast<uintptr_t>(p.a) & 15) || (reinterpret_cast<uintptr_t>(p.d) & 15))
+    return fail(M2S_ERR_BAD_ARG, "A and D must be 16-byte aligned");
+  if (w.n != p.n || w.c_in != p.c_in || w.taps != p.taps)
+    return fail(M2S_ERR_BAD_ARG, "packed weights do not match the problem");
+  if (p.batch <= 0 || p.l_out <= 0) return M2S_OK;
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(M2S_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  const EngineKnobs& knobs = engine_knobs();
+
+  EngineParams prm{};
+  prm.p = p;
+  prm.wpacked = w.dev;
+  prm.n_tile = w.n_tile;
+  prm.n_tiles = w.n_tiles;
+  prm.cblocks = w.cblocks;
+  prm.base_offset_mode = knobs.base_offset_mode;
+  prm.a_per_tap = knobs.a_per_tap;
+  int smin = p.shift[0], smax = p.shift[0];
+  for (int j = 1; j < p.taps; ++j) { smin = p.shift[j] < smin ? p.shift[j] : smin; smax = p.shift[j] > smax ? p.shift[j] : smax; }
+  prm.shift_min = smin;
+  for (int j = 0; j < p.taps; ++j) prm.rel_shift[j] = p.shift[j] - smin;
+  const int halo = prm.a_per_tap ? 0 : smax - smin;
+
+  // M sub-tiles per CTA: 2 halves the weight traffic per output row; use it when there is enough work.
+  int msub = knobs.msub;
+  if (msub != 1 && msub != 2) {
+    const long long tiles1 = static_cast<long long>(p.batch) * ((p.l_out + 127) / 128) * w.n_tiles;
+    msub = (tiles1 >= 4LL * sm_count() && 2 * w.n_tile <= kTmemCols) ? 2 : 1;
+  }
+  if (msub * w.n_tile > kTmemCols) msub = 1;
+  prm.msub = msub;
+  prm.m_tile = 128 * msub;
+  prm.tiles_per_batch = (p.l_out + prm.m_tile - 1) / prm.m_tile;
+  prm.total_tiles = p.batch * prm.tiles_per_batch * w.n_tiles;
+  prm.nacc = (2 * msub * w.n_tile <= kTmemCols) ? 2 : 1;
+  prm.acc_stride = prm.nacc == 2 ? kTmemCols / 2 : 0;
+
+  const int a_rows_needed = prm.m_tile + halo;
+  prm.a_nbox = (a_rows_needed + 255) / 256;
+  prm.a_box_rows = (((a_rows_needed + prm.a_nbox - 1) / prm.a_nbox) + 7) / 8 * 8;
+  prm.a_stage_bytes = static_cast<uint32_t>(prm.a_nbox * prm.a_box_rows * kRowBytes);
+  prm.a_stage_bytes = (prm.a_stage_bytes + 1023u) & ~1023u;
+  prm.b_stage_bytes = static_cast<uint32_t>(w.n_tile * kRowBytes);
+  const uint32_t b_stage_alloc = (prm.b_stage_bytes + 1023u) & ~1023u;
+  // stage counts inside the budget: at least 2 A + 2 B
+  const uint32_t bar_bytes = 1024;
+  int na = 2, nb = 2;
+  auto total = [&](int a, int b) { return a * prm.a_stage_bytes + b * b_stage_alloc + bar_bytes + 1024u; };
+  if (total(na, nb) > kSmemBudget + 24 * 1024)
+    return fail(M2S_ERR_UNSUPPORTED, "tile does not fit SMEM (A stage %u B, B stage %u B)", prm.a_stage_bytes,
+                b_stage_alloc);
+  while (nb < kMaxStagesB && nb < 4 && total(na, nb + 1) <= kSmemBudget) ++nb;
+  while (na < kMaxStagesA && na < 3 && total(na + 1, nb) <= kSmemBudget) ++na;
+  while (nb < kMaxStagesB && total(na, nb + 1) <= kSmemBudget) ++nb;
+  prm.na = na;
+  prm.nb = nb;
+  const uint32_t b_stage_bytes_copy = prm.b_stage_bytes;
+  prm.b_stage_bytes = b_stage_bytes_copy;  // bytes actually copied per stage
+  // NOTE: stage pitch in SMEM uses the 1024-aligned size
+  const uint32_t b_pitch = b_stage_alloc;
+  uint32_t smem_bytes = total(na, nb);
+  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;  // keep 1 CTA / SM (whole-TMEM allocation)
+
+  // instruction descriptor: D=f32, A=B=tf32, K-major both, N, M=128
+  prm.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(w.n_tile >> 3) << 17) |
+              (static_cast<uint32_t>(128 >> 4) << 24);
+
+  // tensor map over A: (c_in, a_rows, batch), box (32, a_box_rows, 1), 128B swizzle, OOB -> zero
+  CUtensorMap tmap;
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(p.c_in), static_cast<cuuint64_t>(p.a_rows),
+                        static_cast<cuuint64_t>(p.batch)};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(p.a_ld) * 4ull,
+                           static_cast<cuuint64_t>(p.a_batch_rows) * static_cast<cuuint64_t>(p.a_ld) * 4ull};
+  if (p.batch == 1) gstride[1] = gstride[0] * static_cast<cuuint64_t>(p.a_rows > 0 ? p.a_rows : 1);
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(kKBlock), static_cast<cuuint32_t>(prm.a_box_rows), 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult cr = enc(&tmap, knobs.tmap_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                    const_cast<float*>(p.a), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS)
+    return fail(M2S_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): c_in=%d rows=%d batch=%d ld=%d box_rows=%d",
+                static_cast<int>(cr), p.c_in, p.a_rows, p.batch, p.a_ld, prm.a_box_rows);
+
+  // B stage pitch must equal the copy size for the kernel's addressing: use the aligned pitch everywhere.
+  prm.b_stage_bytes = b_pitch;
+  // copy size = n_tile*128 which is already a multiple of 2048 for n_tile%16==0 -> equals pitch when n_tile%8==0
+  if (b_pitch != static_cast<uint32_t>(w.n_tile * kRowBytes))
+    return fail(M2S_ERR_UNSUPPORTED, "n_tile=%d gives a non-1024-aligned weight stage", w.n_tile);
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    M2S_CUDA_OK(cudaFuncSetAttribute(conv_engine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  int grid = knobs.max_ctas > 0 ? knobs.max_ctas : sm_count();
+  if (grid > prm.total_tiles) grid = prm.total_tiles;
+  conv_engine_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap, prm);
+  M2S_CUDA_OK(cudaGetLastError());
+  return M2S_OK;
+}
+
+}  // namespace m2s

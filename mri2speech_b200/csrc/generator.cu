@@ -1,0 +1,398 @@
+// HiFi-GAN Generator forward on the conv engine.
+//
+// Reference semantics (models.py:113-131, ResBlock1 models.py:35-49, utils.py:34-35):
+//   x = conv_pre(pad_right(mel, 6))
+//   for each upsample stage i: x = ConvTranspose1d(lrelu(x, .1)); x = mean_j ResBlock1_j(x)
+//   x = tanh(conv_post(pad_right(lrelu(x, .01), 6)))
+// with every ResBlock conv causal ((k-1)*d zeros on the left).
+//
+// Data layout in HBM: channels-last fp32 (B, L, C).  Activations are stored POST leaky-ReLU (and
+// TF32-rounded) because every consumer is a conv that wants lrelu(x) as its tensor-core operand; the
+// residual path recovers x = y >= 0 ? y : y / slope in the epilogue of the conv that needs it.
+//
+// Buffers (workspace): P, Q ping-pong between stages; R = ResBlock state, T = conv1 output,
+// S = MRF running sum.  Per stage:
+//   ups:     A=P -> Q = lrelu(convT(P)+b)                       (3-tap polyphase GEMM, N = u*C_out)
+//   block j: c1: A=state -> T = lrelu(c1+b); c2: A=T, res=state -> R (pairs 0,1)
+//            pair 2: j=0: S = x; j=1: S += x; j=2: P = mask(lrelu((S + x)/3, slope_next))
+#include "m2s_common.cuh"
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace m2s {
+
+int conv_post_tanh(const float* a, const float* w, float bias, float* out, int batch, int rows, int c, int k,
+                   long long a_batch_rows, long long out_batch_stride, cudaStream_t stream);
+int bct_to_btc(const float* in, float* out, int batch, int c, int t, const int32_t* lens, bool round,
+               cudaStream_t stream);
+
+namespace {
+
+struct HostTensor {
+  const float* data;
+  std::vector<int64_t> shape;
+  size_t numel() const {
+    size_t n = 1;
+    for (auto s : shape) n *= static_cast<size_t>(s);
+    return n;
+  }
+};
+
+using TensorMap = std::map<std::string, HostTensor>;
+
+TensorMap index_tensors(const m2s_tensor* t, int n) {
+  TensorMap m;
+  for (int i = 0; i < n; ++i) {
+    HostTensor h;
+    h.data = t[i].data;
+    for (int d = 0; d < t[i].ndim; ++d) h.shape.push_back(t[i].shape[d]);
+    m[t[i].name] = h;
+  }
+  return m;
+}
+
+// Effective weight of a (possibly weight-normed) conv: W = g * v / ||v||_2 over dims (1,2) per dim-0 slice.
+int folded_weight(const TensorMap& m, const std::string& prefix, std::vector<float>* w, std::vector<int64_t>* shape) {
+  auto it = m.find(prefix + ".weight");
+  if (it != m.end()) {
+    w->assign(it->second.data, it->second.data + it->second.numel());
+    *shape = it->second.shape;
+    return M2S_OK;
+  }
+  auto ig = m.find(prefix + ".weight_g");
+  auto iv = m.find(prefix + ".weight_v");
+  if (ig == m.end() || iv == m.end())
+    return fail(M2S_ERR_MISSING_TENSOR, "missing %s.weight or %s.weight_g/weight_v", prefix.c_str(), prefix.c_str());
+  const HostTensor& v = iv->second;
+  const HostTensor& g = ig->second;
+  if (v.shape.size() != 3 || g.numel() != static_cast<size_t>(v.shape[0]))
+    return fail(M2S_ERR_BAD_ARG, "%s: unexpected weight_g/weight_v shapes", prefix.c_str());
+  const size_t inner = static_cast<size_t>(v.shape[1] * v.shape[2]);
+  w->resize(v.numel());
+  for (int64_t o = 0; o < v.shape[0]; ++o) {
+    double ss = 0.0;
+    for (size_t i = 0; i < inner; ++i) ss += static_cast<double>(v.data[o * inner + i]) * v.data[o * inner + i];
+    const double s = static_cast<double>(g.data[o]) / std::sqrt(ss);
+    for (size_t i = 0; i < inner; ++i) (*w)[o * inner + i] = static_cast<float>(v.data[o * inner + i] * s);
+  }
+  *shape = v.shape;
+  return M2S_OK;
+}
+
+int get_bias(const TensorMap& m, const std::string& prefix, int n, std::vector<float>* b) {
+  auto it = m.find(prefix + ".bias");
+  if (it == m.end()) return fail(M2S_ERR_MISSING_TENSOR, "missing %s.bias", prefix.c_str());
+  if (it->second.numel() != static_cast<size_t>(n)) return fail(M2S_ERR_BAD_ARG, "%s.bias has wrong size", prefix.c_str());
+  b->assign(it->second.data, it->second.data + n);
+  return M2S_OK;
+}
+
+struct Layer {
+  PackedWeights w;
+  float* bias = nullptr;  // device [n]
+  int taps = 0;
+  int shift[M2S_MAX_TAPS] = {};
+};
+
+int upload(const std::vector<float>& h, float** dev) {
+  M2S_CUDA_OK(cudaMalloc(dev, h.size() * sizeof(float)));
+  M2S_CUDA_OK(cudaMemcpy(*dev, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return M2S_OK;
+}
+
+}  // namespace
+}  // namespace m2s
+
+using namespace m2s;
+
+struct m2s_generator {
+  m2s_generator_config cfg;
+  bool tf32 = true;
+  int hop = 1;
+  Layer pre;
+  std::vector<Layer> ups;
+  std::vector<int> ups_cout;
+  // resblocks[i*num_kernels + j] -> c1[3], c2[3]
+  std::vector<Layer> c1, c2;
+  float* post_w = nullptr;  // [k][c]
+  float post_bias = 0.f;
+  int post_k = 0, post_c = 0;
+  int launches = 0;
+};
+
+namespace {
+
+// Conv1d weight (C_out, C_in, k) -> engine layout [tap][n][c]
+int make_conv1d_layer(const TensorMap& m, const std::string& prefix, int c_out, int c_in, int k, bool causal,
+                      int dilation, bool tf32, Layer* L) {
+  std::vector<float> w;
+  std::vector<int64_t> shape;
+  M2S_TRY(folded_weight(m, prefix, &w, &shape));
+  if (shape.size() != 3 || shape[0] != c_out || shape[1] != c_in || shape[2] != k)
+    return fail(M2S_ERR_BAD_ARG, "%s: weight shape mismatch", prefix.c_str());
+  if (k > M2S_MAX_TAPS) return fail(M2S_ERR_UNSUPPORTED, "%s: kernel size %d > %d", prefix.c_str(), k, M2S_MAX_TAPS);
+  std::vector<float> e(static_cast<size_t>(k) * c_out * c_in);
+  for (int j = 0; j < k; ++j)
+    for (int o = 0; o < c_out; ++o)
+      for (int c = 0; c < c_in; ++c)
+        e[(static_cast<size_t>(j) * c_out + o) * c_in + c] = w[(static_cast<size_t>(o) * c_in + c) * k + j];
+  L->taps = k;
+  for (int j = 0; j < k; ++j) L->shift[j] = causal ? -(k - 1 - j) * dilation : j * dilation;
+  M2S_TRY(pack_weights(e.data(), k, c_out, c_in, tf32, &L->w));
+  std::vector<float> b;
+  M2S_TRY(get_bias(m, prefix, c_out, &b));
+  return upload(b, &L->bias);
+}
+
+// ConvTranspose1d weight (C_in, C_out, k), stride u, padding p -> polyphase GEMM:
+// row q, col r*C_out+co = sum_s sum_ci x[q - s, ci] * W[ci, co, s*u + r + p]
+int make_convT_layer(const TensorMap& m, const std::string& prefix, int c_in, int c_out, int k, int u, bool tf32,
+                     Layer* L) {
+  std::vector<float> w;
+  std::vector<int64_t> shape;
+  M2S_TRY(folded_weight(m, prefix, &w, &shape));
+  if (shape.size() != 3 || shape[0] != c_in || shape[1] != c_out || shape[2] != k)
+    return fail(M2S_ERR_BAD_ARG, "%s: weight shape mismatch", prefix.c_str());
+  if ((k - u) % 2) return fail(M2S_ERR_UNSUPPORTED, "%s: (kernel - stride) must be even", prefix.c_str());
+  const int p = (k - u) / 2;
+  int s_lo = 1 << 30, s_hi = -(1 << 30);
+  for (int r = 0; r < u; ++r)
+    for (int kk = 0; kk < k; ++kk)
+      if ((kk - r - p) % u == 0) {
+        const int s = (kk - r - p) / u;
+        s_lo = s < s_lo ? s : s_lo;
+        s_hi = s > s_hi ? s : s_hi;
+      }
+  const int taps = s_hi - s_lo + 1;
+  if (taps > M2S_MAX_TAPS) return fail(M2S_ERR_UNSUPPORTED, "%s: %d polyphase taps", prefix.c_str(), taps);
+  const int n = u * c_out;
+  std::vector<float> e(static_cast<size_t>(taps) * n * c_in, 0.f);
+  for (int t = 0; t < taps; ++t) {
+    const int s = s_lo + t;
+    for (int r = 0; r < u; ++r) {
+      const int kk = s * u + r + p;
+      if (kk < 0 || kk >= k) continue;
+      for (int co = 0; co < c_out; ++co)
+        for (int ci = 0; ci < c_in; ++ci)
+          e[(static_cast<size_t>(t) * n + r * c_out + co) * c_in + ci] = w[(static_cast<size_t>(ci) * c_out + co) * k + kk];
+    }
+  }
+  L->taps = taps;
+  for (int t = 0; t < taps; ++t) L->shift[t] = -(s_lo + t);
+  M2S_TRY(pack_weights(e.data(), taps, n, c_in, tf32, &L->w));
+  std::vector<float> b, be(n);
+  M2S_TRY(get_bias(m, prefix, c_out, &b));
+  for (int r = 0; r < u; ++r)
+    for (int co = 0; co < c_out; ++co) be[r * c_out + co] = b[co];
+  return upload(be, &L->bias);
+}
+
+void free_layer(Layer* L) {
+  free_weights(&L->w);
+  if (L->bias) cudaFree(L->bias);
+  L->bias = nullptr;
+}
+
+int run_conv(const m2s_generator* g, const ConvProblem& p, const Layer& L, cudaStream_t st) {
+  return g->tf32 ? conv_tcgen05(p, L.w, st) : conv_simt(p, L.w.plain, st);
+}
+
+ConvProblem base_problem(const float* a, int a_rows, int c_in, int batch, long long batch_rows_a, float* d,
+                         int d_ld, long long batch_rows_d, int l_out, const Layer& L) {
+  ConvProblem p{};
+  p.a = a; p.a_batch_rows = batch_rows_a; p.a_rows = a_rows; p.a_ld = c_in; p.c_in = c_in;
+  p.batch = batch; p.l_out = l_out; p.taps = L.taps;
+  for (int j = 0; j < L.taps; ++j) p.shift[j] = L.shift[j];
+  p.n = L.w.n; p.d = d; p.d_batch_rows = batch_rows_d; p.d_ld = d_ld; p.d_row_offset = 0;
+  p.epi.bias = L.bias; p.epi.out_scale = 1.f; p.epi.res_inv_slope = 1.f; p.epi.act = M2S_ACT_NONE;
+  return p;
+}
+
+}  // namespace
+
+extern "C" int m2s_generator_create(const m2s_generator_config* cfg, const m2s_tensor* tensors, int32_t n_tensors,
+                                    m2s_generator** out) {
+  if (!cfg || !tensors || !out) return fail(M2S_ERR_BAD_ARG, "null argument");
+  if (cfg->num_upsamples < 1 || cfg->num_upsamples > M2S_MAX_UPS || cfg->num_kernels < 1 ||
+      cfg->num_kernels > M2S_MAX_RBK)
+    return fail(M2S_ERR_BAD_ARG, "unsupported num_upsamples/num_kernels");
+  if (cfg->num_mels % 4 || (cfg->upsample_initial_channel >> cfg->num_upsamples) % 4)
+    return fail(M2S_ERR_UNSUPPORTED, "channel counts must stay multiples of 4");
+  M2S_TRY(m2s_device_check(-1));
+  TensorMap m = index_tensors(tensors, n_tensors);
+  auto* g = new m2s_generator();
+  g->cfg = *cfg;
+  g->tf32 = cfg->precision != M2S_PREC_FP32;
+  int st = M2S_OK;
+  auto bail = [&](int s) { m2s_generator_destroy(g); return s; };
+  const int c0 = cfg->upsample_initial_channel;
+  if ((st = make_conv1d_layer(m, "conv_pre", c0, cfg->num_mels, 7, false, 1, g->tf32, &g->pre)) != M2S_OK)
+    return bail(st);
+  g->hop = 1;
+  int ch = c0;
+  for (int i = 0; i < cfg->num_upsamples; ++i) {
+    const int cout = c0 >> (i + 1);
+    Layer L;
+    if ((st = make_convT_layer(m, "ups." + std::to_string(i), ch, cout, cfg->upsample_kernel_sizes[i],
+                               cfg->upsample_rates[i], g->tf32, &L)) != M2S_OK)
+      return bail(st);
+    g->ups.push_back(L);
+    g->ups_cout.push_back(cout);
+    g->hop *= cfg->upsample_rates[i];
+    for (int j = 0; j < cfg->num_kernels; ++j) {
+      const std::string p = "resblocks." + std::to_string(i * cfg->num_kernels + j);
+      const int k = cfg->resblock_kernel_sizes[j];
+      for (int d = 0; d < 3; ++d) {
+        Layer a, b;
+        if ((st = make_conv1d_layer(m, p + ".convs1." + std::to_string(d), cout, cout, k, true,
+                                    cfg->resblock_dilations[j][d], g->tf32, &a)) != M2S_OK)
+          return bail(st);
+        g->c1.push_back(a);
+        if ((st = make_conv1d_layer(m, p + ".convs2." + std::to_string(d), cout, cout, k, true, 1, g->tf32, &b)) !=
+            M2S_OK)
+          return bail(st);
+        g->c2.push_back(b);
+      }
+    }
+    ch = cout;
+  }
+  {
+    std::vector<float> w;
+    std::vector<int64_t> shape;
+    if ((st = folded_weight(m, "conv_post", &w, &shape)) != M2S_OK) return bail(st);
+    if (shape.size() != 3 || shape[0] != 1 || shape[1] != ch) return bail(fail(M2S_ERR_BAD_ARG, "conv_post shape"));
+    g->post_k = static_cast<int>(shape[2]);
+    g->post_c = ch;
+    std::vector<float> e(static_cast<size_t>(g->post_k) * ch);
+    for (int j = 0; j < g->post_k; ++j)
+      for (int c = 0; c < ch; ++c) e[static_cast<size_t>(j) * ch + c] = w[static_cast<size_t>(c) * g->post_k + j];
+    if ((st = upload(e, &g->post_w)) != M2S_OK) return bail(st);
+    std::vector<float> b;
+    if ((st = get_bias(m, "conv_post", 1, &b)) != M2S_OK) return bail(st);
+    g->post_bias = b[0];
+  }
+  g->launches = 2 + cfg->num_upsamples * (1 + cfg->num_kernels * 6) + 1;
+  *out = g;
+  return M2S_OK;
+}
+
+extern "C" void m2s_generator_destroy(m2s_generator* g) {
+  if (!g) return;
+  free_layer(&g->pre);
+  for (auto& L : g->ups) free_layer(&L);
+  for (auto& L : g->c1) free_layer(&L);
+  for (auto& L : g->c2) free_layer(&L);
+  if (g->post_w) cudaFree(g->post_w);
+  delete g;
+}
+
+extern "C" int m2s_generator_launches(const m2s_generator* g) { return g ? g->launches : 0; }
+
+namespace {
+struct GenBuffers {
+  size_t mel_floats, p_floats, q_floats;
+  size_t total_bytes;
+};
+GenBuffers plan_buffers(const m2s_generator* g, int batch, int frames) {
+  GenBuffers b{};
+  b.mel_floats = static_cast<size_t>(batch) * frames * g->cfg.num_mels;
+  size_t p = static_cast<size_t>(batch) * frames * g->cfg.upsample_initial_channel;
+  size_t q = 0;
+  size_t L = frames;
+  for (int i = 0; i < g->cfg.num_upsamples; ++i) {
+    L *= g->cfg.upsample_rates[i];
+    const size_t s = static_cast<size_t>(batch) * L * g->ups_cout[i];
+    p = s > p ? s : p;
+    q = s > q ? s : q;
+  }
+  auto al = [](size_t f) { return (f + 63) / 64 * 64; };
+  b.mel_floats = al(b.mel_floats);
+  b.p_floats = al(p);
+  b.q_floats = al(q);
+  b.total_bytes = (b.mel_floats + b.p_floats + 4 * b.q_floats) * sizeof(float) + 256;
+  return b;
+}
+}  // namespace
+
+extern "C" size_t m2s_generator_workspace_bytes(const m2s_generator* g, int32_t batch, int32_t frames) {
+  if (!g || batch <= 0 || frames <= 0) return 0;
+  return plan_buffers(g, batch, frames).total_bytes;
+}
+
+extern "C" int m2s_generator_forward(m2s_generator* g, const float* mel, int32_t batch, int32_t frames,
+                                     const int32_t* lengths, float* audio, void* workspace, size_t workspace_bytes,
+                                     m2s_stream_t stream) {
+  if (!g || !mel || !audio) return fail(M2S_ERR_BAD_ARG, "null argument");
+  if (batch <= 0 || frames <= 0) return M2S_OK;
+  const GenBuffers bufs = plan_buffers(g, batch, frames);
+  if (!workspace || workspace_bytes < bufs.total_bytes)
+    return fail(M2S_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", bufs.total_bytes, workspace_bytes);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  float* M0 = base;
+  float* P = M0 + bufs.mel_floats;
+  float* Q = P + bufs.p_floats;
+  float* R = Q + bufs.q_floats;
+  float* T = R + bufs.q_floats;
+  float* S = T + bufs.q_floats;
+  const m2s_generator_config& cfg = g->cfg;
+  const int mask = lengths ? M2S_MASK_LEN : M2S_MASK_NONE;
+  const int rnd = g->tf32 ? 1 : 0;
+
+  // (B, mels, T) -> channels-last, zero past lengths (conv_pre look-ahead must see zeros)
+  M2S_TRY(bct_to_btc(mel, M0, batch, cfg.num_mels, frames, lengths, g->tf32, st));
+
+  int L = frames;
+  int ch = cfg.upsample_initial_channel;
+  {  // conv_pre -> P = mask(lrelu(conv+b, .1))  (only consumer: ups[0])
+    ConvProblem p = base_problem(M0, L, cfg.num_mels, batch, L, P, ch, L, L, g->pre);
+    p.epi.act = M2S_ACT_LRELU; p.epi.act_slope = 0.1f; p.epi.round_tf32 = rnd;
+    p.epi.mask_mode = mask; p.epi.lens = lengths; p.epi.len_scale = 1;
+    M2S_TRY(run_conv(g, p, g->pre, st));
+  }
+  int scale = 1;
+  for (int i = 0; i < cfg.num_upsamples; ++i) {
+    const int u = cfg.upsample_rates[i];
+    const int cout = g->ups_cout[i];
+    {  // ups: rows = L, N = u*cout; D viewed as (B, L, u*cout) == (B, L*u, cout)
+      ConvProblem p = base_problem(P, L, ch, batch, L, Q, u * cout, L, L, g->ups[i]);
+      p.epi.act = M2S_ACT_LRELU; p.epi.act_slope = 0.1f; p.epi.round_tf32 = rnd;
+      M2S_TRY(run_conv(g, p, g->ups[i], st));
+    }
+    L *= u; scale *= u; ch = cout;
+    const bool last_stage = (i + 1 == cfg.num_upsamples);
+    for (int j = 0; j < cfg.num_kernels; ++j) {
+      const float* state = Q;
+      for (int d = 0; d < 3; ++d) {
+        const Layer& l1 = g->c1[(i * cfg.num_kernels + j) * 3 + d];
+        const Layer& l2 = g->c2[(i * cfg.num_kernels + j) * 3 + d];
+        ConvProblem p1 = base_problem(state, L, ch, batch, L, T, ch, L, L, l1);
+        p1.epi.act = M2S_ACT_LRELU; p1.epi.act_slope = 0.1f; p1.epi.round_tf32 = rnd;
+        M2S_TRY(run_conv(g, p1, l1, st));
+        ConvProblem p2 = base_problem(T, L, ch, batch, L, R, ch, L, L, l2);
+        p2.epi.res = state; p2.epi.res_ld = ch; p2.epi.res_inv_slope = 10.f;  // 1 / LRELU_SLOPE
+        if (d < 2) {
+          p2.epi.act = M2S_ACT_LRELU; p2.epi.act_slope = 0.1f; p2.epi.round_tf32 = rnd;
+        } else if (j + 1 < cfg.num_kernels) {
+          p2.d = S;
+          if (j > 0) { p2.epi.accum = S; p2.epi.accum_ld = ch; }
+        } else {
+          p2.d = P;
+          if (j > 0) { p2.epi.accum = S; p2.epi.accum_ld = ch; }
+          p2.epi.out_scale = 1.f / static_cast<float>(cfg.num_kernels);
+          p2.epi.act = M2S_ACT_LRELU; p2.epi.act_slope = last_stage ? 0.01f : 0.1f;
+          p2.epi.round_tf32 = last_stage ? 0 : rnd;
+          p2.epi.mask_mode = mask; p2.epi.lens = lengths; p2.epi.len_scale = scale;
+        }
+        M2S_TRY(run_conv(g, p2, l2, st));
+        state = R;
+      }
+    }
+  }
+  // conv_post + tanh: P holds mask(lrelu(x, .01)) as (B, L, ch)
+  M2S_TRY(conv_post_tanh(P, g->post_w, g->post_bias, audio, batch, L, g->post_c, g->post_k, L, L, st));
+  return M2S_OK;
+}

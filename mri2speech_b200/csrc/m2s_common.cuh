@@ -1,0 +1,143 @@
+// Shared host/device definitions for libm2s (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <string>
+#include "../../include/m2s.h"
+
+namespace m2s {
+
+// ---- error plumbing --------------------------------------------------------
+void set_error(const char* fmt, ...);
+int fail(int status, const char* fmt, ...);
+
+#define M2S_CUDA_OK(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return ::m2s::fail(M2S_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,         \
+                         cudaGetErrorString(_e));                                           \
+  } while (0)
+
+#define M2S_TRY(expr)             \
+  do {                            \
+    int _s = (expr);              \
+    if (_s != M2S_OK) return _s;  \
+  } while (0)
+
+// ---- the conv problem as the kernels see it ----------------------------------
+// D[b, q + d_row_offset, n] = epi(sum_j sum_c A[b, q + shift[j], c] * W[j][n][c])
+struct Epilogue {
+  const float* bias;
+  const float* res;
+  const float* accum;
+  const int32_t* lens;
+  int res_ld;
+  int accum_ld;
+  float res_inv_slope;
+  float out_scale;
+  float act_slope;
+  int act;
+  int round_tf32;
+  int mask_mode;
+  int len_scale;
+  int pitch, i_lo, i_hi, j_lo, j_hi;
+};
+
+struct ConvProblem {
+  const float* a;
+  long long a_batch_rows;
+  int a_rows, a_ld, c_in;
+  int batch, l_out;
+  int taps;
+  int shift[M2S_MAX_TAPS];
+  int n;
+  float* d;
+  long long d_batch_rows;
+  int d_ld, d_row_offset;
+  Epilogue epi;
+};
+
+inline ConvProblem problem_from_args(const m2s_conv_args& a) {
+  ConvProblem p{};
+  p.a = a.a; p.a_batch_rows = a.a_batch_rows; p.a_rows = a.a_rows; p.a_ld = a.a_ld; p.c_in = a.c_in;
+  p.batch = a.batch; p.l_out = a.l_out; p.taps = a.taps;
+  for (int i = 0; i < M2S_MAX_TAPS; ++i) p.shift[i] = a.shift[i];
+  p.n = a.n; p.d = a.d; p.d_batch_rows = a.d_batch_rows; p.d_ld = a.d_ld; p.d_row_offset = a.d_row_offset;
+  p.epi.bias = a.bias; p.epi.res = a.res; p.epi.res_ld = a.res_ld; p.epi.res_inv_slope = a.res_inv_slope;
+  p.epi.accum = a.accum; p.epi.accum_ld = a.accum_ld; p.epi.out_scale = a.out_scale; p.epi.act = a.act;
+  p.epi.act_slope = a.act_slope; p.epi.round_tf32 = a.round_tf32; p.epi.mask_mode = a.mask_mode;
+  p.epi.lens = a.lens; p.epi.len_scale = a.len_scale; p.epi.pitch = a.pitch; p.epi.i_lo = a.i_lo;
+  p.epi.i_hi = a.i_hi; p.epi.j_lo = a.j_lo; p.epi.j_hi = a.j_hi;
+  return p;
+}
+
+#ifdef __CUDACC__
+// Round-to-nearest (ties away) fp32 -> tf32, result kept in an fp32 register.
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+// Row validity for the fused output mask. `drow` = q + d_row_offset (row inside batch item b).
+__device__ __forceinline__ bool epi_row_valid(const Epilogue& e, int b, int drow) {
+  if (e.mask_mode == M2S_MASK_LEN) {
+    return drow < __ldg(e.lens + b) * e.len_scale;
+  } else if (e.mask_mode == M2S_MASK_PITCH) {
+    int i = drow / e.pitch, j = drow - i * e.pitch;
+    return i >= e.i_lo && i < e.i_hi && j >= e.j_lo && j < e.j_hi;
+  }
+  return true;
+}
+
+// One output element.  `roff` = element offset of (row, n) for ld == 1 scaling done by caller:
+// res/accum are addressed as base + row_index*ld + n by the caller, who passes the loaded values.
+__device__ __forceinline__ float epi_apply(const Epilogue& e, float acc, float bias, float res, float accum,
+                                           bool valid) {
+  float v = acc + bias;
+  if (e.res) v += (res >= 0.f ? res : res * e.res_inv_slope);
+  if (e.accum) v += accum;
+  v *= e.out_scale;
+  if (e.act == M2S_ACT_LRELU) v = v >= 0.f ? v : v * e.act_slope;
+  else if (e.act == M2S_ACT_SILU) v = v / (1.f + __expf(-v));
+  if (!valid) v = 0.f;
+  if (e.round_tf32) v = round_tf32(v);
+  return v;
+}
+#endif  // __CUDACC__
+
+// ---- engine entry points (host) ---------------------------------------------
+// Pre-packed weights for the tcgen05 engine: [n_tile][cblock][tap][n_tile_rows][32 floats, 128B-swizzled].
+struct PackedWeights {
+  float* dev = nullptr;   // packed, tcgen05 layout
+  float* plain = nullptr; // [taps][n][c_in] plain (SIMT path / tests)
+  int n = 0, c_in = 0, taps = 0;
+  int n_tile = 0, n_tiles = 0, cblocks = 0;
+  size_t packed_floats = 0;
+};
+
+// Choose N tiling for the tcgen05 engine (n_tile multiple of 16, <= 256).
+void choose_n_tiling(int n, int* n_tile, int* n_tiles);
+// Pack host weights [taps][n][c_in] (already folded) into both device layouts.  tf32_round: RNE-round values.
+int pack_weights(const float* host_w, int taps, int n, int c_in, bool tf32_round, PackedWeights* out);
+void free_weights(PackedWeights* w);
+
+int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stream);
+int conv_simt(const ConvProblem& p, const float* w_plain, cudaStream_t stream);
+
+// debug / probe knobs for the tcgen05 engine (environment-driven, read once)
+struct EngineKnobs {
+  int base_offset_mode = 0;  // 0: base_offset=0 ; 1: (start>>7)&7
+  int msub = 0;              // 0 = auto, else force 1 or 2
+  int tmap_tf32 = 0;         // encode the A tensor map as TFLOAT32
+  int max_ctas = 0;          // 0 = #SMs
+  int a_per_tap = 0;         // 1: reload the A tile per tap (no row-shifted descriptors; fallback)
+};
+EngineKnobs& engine_knobs();
+
+int sm_count();
+
+}  // namespace m2s

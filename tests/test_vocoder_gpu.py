@@ -1,0 +1,85 @@
+"""Generator.forward on the B200 path vs the reference's own outputs (golden vectors generated from
+/root/reference/models.py by oracle/gen_golden.py) and vs the CPU oracle on fresh seeded inputs.
+
+Gate (BASELINE.json north_star): waveform SNR >= 40 dB for the fp32/TF32 build.  Random-init weights
+give an almost-DC waveform, so the mean-removed SNR is asserted too (>= 40 dB)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import GOLDEN, load_config
+
+pytestmark = pytest.mark.gpu
+
+
+def _generator(precision):
+    from mri2speech_b200.vocoder import Generator
+    torch.manual_seed(1234)
+    return Generator(load_config(), precision=precision).cuda().eval()
+
+
+def _snr(ref, test, remove_mean=False):
+    from oracle.vocoder import snr_db
+    return snr_db(torch.as_tensor(ref), torch.as_tensor(test), remove_mean)
+
+
+@pytest.mark.parametrize("precision,min_snr,min_snr_ac", [("fp32", 90.0, 70.0), ("tf32", 40.0, 40.0)])
+def test_golden_reference_output(precision, min_snr, min_snr_ac):
+    z = np.load(os.path.join(GOLDEN, "vocoder_ref_seed1234_b2_t24.npz"))
+    g = _generator(precision)
+    with torch.no_grad():
+        wav = g(torch.from_numpy(z["mel"]).cuda()).cpu().numpy()
+    assert wav.shape == z["wav"].shape
+    snr, snr_ac = _snr(z["wav"], wav), _snr(z["wav"], wav, True)
+    print(f"[{precision}] SNR {snr:.1f} dB, mean-removed {snr_ac:.1f} dB, max-abs {np.abs(wav - z['wav']).max():.3e}")
+    assert snr >= min_snr and snr_ac >= min_snr_ac
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_ragged_batch_equals_b1(precision):
+    z = np.load(os.path.join(GOLDEN, "vocoder_ref_seed1234_ragged.npz"))
+    g = _generator(precision)
+    lens = torch.from_numpy(z["lens"]).cuda()
+    with torch.no_grad():
+        wav = g(torch.from_numpy(z["mel"]).cuda(), lengths=lens).cpu().numpy()
+    for b, key in enumerate(("wav0", "wav1")):
+        ref = z[key]
+        got = wav[b, 0, : ref.shape[0]]
+        assert _snr(ref, got, True) >= (70.0 if precision == "fp32" else 40.0)
+
+
+def test_unbatched_input_and_state_dict_roundtrip():
+    g = _generator("tf32")
+    mel = torch.randn(64, 9, generator=torch.Generator().manual_seed(1)).cuda()
+    with torch.no_grad():
+        y2 = g(mel)
+        y3 = g(mel.unsqueeze(0))
+    assert y2.shape == (1, 1, 9 * 420) and torch.equal(y2, y3)
+    # weight-norm removed checkpoints load and give the same waveform (run_mri_video_inference.py:105-115)
+    g2 = _generator("tf32")
+    g2.remove_weight_norm()
+    assert "ups.0.weight" in g2.state_dict()
+    with torch.no_grad():
+        y4 = g2(mel)
+    assert _snr(y2.cpu(), y4.cpu(), True) > 60.0
+
+
+def test_against_cpu_oracle_long_clip():
+    """T=150 (config 1 length), fresh seeded mel, oracle computed on the host in the same run."""
+    from oracle.vocoder import generator_forward
+    g = _generator("tf32")
+    mel = torch.randn(1, 64, 150, generator=torch.Generator().manual_seed(2024)) * 2.0 - 5.0
+    ref = generator_forward({k: v.cpu() for k, v in g.state_dict().items()}, load_config(), mel)
+    with torch.no_grad():
+        wav = g(mel.cuda()).cpu()
+    assert wav.shape == (1, 1, 63000)
+    assert _snr(ref, wav) >= 40.0 and _snr(ref, wav, True) >= 40.0
+
+
+def test_cpu_tensor_is_refused():
+    from mri2speech_b200._lib import M2SError
+    g = _generator("tf32")
+    with pytest.raises(M2SError):
+        g(torch.zeros(1, 64, 8))
