@@ -92,11 +92,13 @@ typedef struct {
   int64_t d_batch_rows;
   int32_t d_ld;
   int32_t d_row_offset;
-  /* fused epilogue: v = acc + bias[n] + inv_lrelu(res) + accum; v *= out_scale; v = act(v); mask; round */
+  /* fused epilogue: v = acc + bias[n] + inv_lrelu(res) + accum; v *= out_scale; v = act(v); mask; round
+   * (res_after_act != 0: the residual is added after the activation instead: v = act(..) + res) */
   const float* bias;     /* [n] or NULL */
   const float* res;      /* indexed like d (same rows), NULL = none */
   int32_t res_ld;
   float res_inv_slope;   /* res >= 0 ? res : res*res_inv_slope  (1 = plain residual) */
+  int32_t res_after_act;
   const float* accum;    /* indexed like d, NULL = none */
   int32_t accum_ld;
   float out_scale;
@@ -188,6 +190,14 @@ int m2s_acoustic_launches(const m2s_acoustic* m);
 int m2s_mel_glue(const float* pred_norm, const float* mean, const float* std, int32_t batch,
                  int32_t frames, int32_t n_mels, const int32_t* lengths, float* mel_db, float* mel_log,
                  float* voc_in, m2s_stream_t stream);
+
+/* Debug / probe knobs of the tcgen05 engine ("msub", "base_offset_mode", "a_per_tap", "tmap_tf32",
+ * "max_ctas").  Not part of the reference-facing surface. */
+int m2s_debug_set_knob(const char* name, int value);
+/* Per-launch CUDA-event timing of the conv engine: enable, run, then read (synchronises the device).
+ * ms[i] = duration of launch i, flops[i] = 2*M*N*K it executed. */
+int m2s_debug_profile(int enable);
+int m2s_debug_profile_read(float* ms, double* flops, int32_t cap, int32_t* n);
 
 #ifdef __cplusplus
 }

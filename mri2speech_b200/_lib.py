@@ -39,6 +39,7 @@ class ConvArgs(C.Structure):
         ("w", C.c_void_p), ("n", C.c_int32),
         ("d", C.c_void_p), ("d_batch_rows", C.c_int64), ("d_ld", C.c_int32), ("d_row_offset", C.c_int32),
         ("bias", C.c_void_p), ("res", C.c_void_p), ("res_ld", C.c_int32), ("res_inv_slope", C.c_float),
+        ("res_after_act", C.c_int32),
         ("accum", C.c_void_p), ("accum_ld", C.c_int32), ("out_scale", C.c_float),
         ("act", C.c_int32), ("act_slope", C.c_float), ("round_tf32", C.c_int32),
         ("mask_mode", C.c_int32), ("lens", C.c_void_p), ("len_scale", C.c_int32),
@@ -88,6 +89,9 @@ def lib() -> C.CDLL:
     L.m2s_device_check.argtypes = [C.c_int]
     L.m2s_conv_fwd.argtypes = [C.POINTER(ConvArgs), C.c_int, C.c_void_p]
     L.m2s_debug_set_knob.argtypes = [C.c_char_p, C.c_int]
+    L.m2s_debug_profile.argtypes = [C.c_int]
+    L.m2s_debug_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int32,
+                                         C.POINTER(C.c_int32)]
     L.m2s_generator_create.argtypes = [C.POINTER(GeneratorConfig), C.POINTER(Tensor), C.c_int32,
                                        C.POINTER(C.c_void_p)]
     L.m2s_generator_destroy.argtypes = [C.c_void_p]
@@ -97,6 +101,15 @@ def lib() -> C.CDLL:
     L.m2s_generator_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_size_t, C.c_void_p]
     L.m2s_generator_launches.argtypes = [C.c_void_p]
+    missing = [name for name in EXPORTS if not hasattr(L, name)]
+    if missing:
+        raise M2SError(f"{_LIB_PATH} is stale: missing exports {missing}; rebuild it")
+    _bind_acoustic(L)
+    _lib = L
+    return L
+
+
+def _bind_acoustic(L) -> None:
     L.m2s_acoustic_create.argtypes = [C.POINTER(AcousticConfig), C.POINTER(Tensor), C.c_int32,
                                       C.POINTER(C.c_void_p)]
     L.m2s_acoustic_destroy.argtypes = [C.c_void_p]
@@ -112,8 +125,6 @@ def lib() -> C.CDLL:
     L.m2s_acoustic_launches.argtypes = [C.c_void_p]
     L.m2s_mel_glue.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    _lib = L
-    return L
 
 
 def check(status: int) -> None:
@@ -166,7 +177,7 @@ def set_knob(name: str, value: int) -> None:
 
 
 def conv_fwd(a: torch.Tensor, w: torch.Tensor, shifts: Sequence[int], l_out: int, *, impl: int = IMPL_TCGEN05,
-             a_rows: Optional[int] = None, bias=None, res=None, res_inv_slope: float = 1.0, accum=None,
+             a_rows: Optional[int] = None, bias=None, res=None, res_inv_slope: float = 1.0, res_after_act: bool = False, accum=None,
              out_scale: float = 1.0, act: int = ACT_NONE, act_slope: float = 0.0, round_tf32: bool = False,
              lens=None, len_scale: int = 1, pitch_mask=None, d_row_offset: int = 0,
              d_rows: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -185,6 +196,7 @@ def conv_fwd(a: torch.Tensor, w: torch.Tensor, shifts: Sequence[int], l_out: int
     args.w = w.data_ptr(); args.n = N
     args.d = d.data_ptr(); args.d_batch_rows = d.shape[1]; args.d_ld = N; args.d_row_offset = d_row_offset
     args.bias = ptr(bias); args.res = ptr(res); args.res_ld = N; args.res_inv_slope = res_inv_slope
+    args.res_after_act = int(res_after_act)
     args.accum = ptr(accum); args.accum_ld = N; args.out_scale = out_scale
     args.act = act; args.act_slope = act_slope; args.round_tf32 = int(round_tf32)
     if lens is not None:
@@ -194,3 +206,16 @@ def conv_fwd(a: torch.Tensor, w: torch.Tensor, shifts: Sequence[int], l_out: int
         args.pitch, args.i_lo, args.i_hi, args.j_lo, args.j_hi = [int(v) for v in pitch_mask]
     check(lib().m2s_conv_fwd(C.byref(args), impl, current_stream()))
     return d
+
+
+def profile(enable: bool) -> None:
+    check(lib().m2s_debug_profile(int(enable)))
+
+
+def profile_read(cap: int = 65536):
+    """Per-launch (ms, executed flops) of the conv engine since the last read."""
+    ms = (C.c_float * cap)()
+    fl = (C.c_double * cap)()
+    n = C.c_int32(0)
+    check(lib().m2s_debug_profile_read(ms, fl, cap, C.byref(n)))
+    return list(ms[: n.value]), list(fl[: n.value])

@@ -84,3 +84,12 @@ extern "C" int m2s_mel_glue(const float* pred_norm, const float* mean, const flo
   return mel_glue(pred_norm, mean, std, batch, frames, n_mels, lengths, mel_db, mel_log, voc_in,
                   reinterpret_cast<cudaStream_t>(stream));
 }
+
+// Per-launch timing of the conv engine (CUDA events on the launching stream), for bench.py's roofline leg.
+extern "C" int m2s_debug_profile(int enable) { return profile_enable(enable); }
+extern "C" int m2s_debug_profile_read(float* ms, double* flops, int32_t cap, int32_t* n) {
+  int k = 0;
+  int s = profile_read(ms, flops, cap, &k);
+  if (n) *n = k;
+  return s;
+}

@@ -382,12 +382,50 @@ EngineKnobs& engine_knobs() {
     EngineKnobs x;
     x.base_offset_mode = env_int("M2S_ENGINE_BASE_OFFSET", 0);
     x.msub = env_int("M2S_ENGINE_MSUB", 0);
-    x.tmap_tf32 = env_int("M2S_ENGINE_TMAP_TF32", 0);
+    x.tmap_tf32 = env_int("M2S_ENGINE_TMAP_TF32", 1);
     x.max_ctas = env_int("M2S_ENGINE_MAX_CTAS", 0);
     x.a_per_tap = env_int("M2S_ENGINE_A_PER_TAP", 0);
     return x;
   }();
   return k;
+}
+
+// ---- optional per-launch timing (bench.py roofline leg) -----------------------------
+namespace {
+struct ProfileRing {
+  std::vector<cudaEvent_t> ev;
+  std::vector<double> flops;
+  int count = 0;
+  bool on = false;
+};
+ProfileRing& ring() {
+  static ProfileRing r;
+  return r;
+}
+}  // namespace
+
+int profile_enable(int on) {
+  ProfileRing& r = ring();
+  r.on = on != 0;
+  r.count = 0;
+  r.flops.clear();
+  return M2S_OK;
+}
+
+int profile_read(float* ms, double* flops, int cap, int* n_out) {
+  ProfileRing& r = ring();
+  M2S_CUDA_OK(cudaDeviceSynchronize());
+  int n = r.count < cap ? r.count : cap;
+  for (int i = 0; i < n; ++i) {
+    float t = 0.f;
+    M2S_CUDA_OK(cudaEventElapsedTime(&t, r.ev[2 * i], r.ev[2 * i + 1]));
+    ms[i] = t;
+    if (flops) flops[i] = r.flops[i];
+  }
+  *n_out = n;
+  r.count = 0;
+  r.flops.clear();
+  return M2S_OK;
 }
 
 int sm_count() {
@@ -555,8 +593,22 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
   }
   int grid = knobs.max_ctas > 0 ? knobs.max_ctas : sm_count();
   if (grid > prm.total_tiles) grid = prm.total_tiles;
+  ProfileRing& pr = ring();
+  if (pr.on) {
+    while (static_cast<int>(pr.ev.size()) < 2 * (pr.count + 1)) {
+      cudaEvent_t e;
+      M2S_CUDA_OK(cudaEventCreate(&e));
+      pr.ev.push_back(e);
+    }
+    M2S_CUDA_OK(cudaEventRecord(pr.ev[2 * pr.count], stream));
+  }
   conv_engine_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap, prm);
   M2S_CUDA_OK(cudaGetLastError());
+  if (pr.on) {
+    M2S_CUDA_OK(cudaEventRecord(pr.ev[2 * pr.count + 1], stream));
+    pr.flops.push_back(2.0 * p.batch * static_cast<double>(p.l_out) * p.n * p.c_in * p.taps);
+    ++pr.count;
+  }
   return M2S_OK;
 }
 

@@ -340,10 +340,10 @@ extern "C" int m2s_generator_forward(m2s_generator* g, const float* mel, int32_t
   float* S = T + bufs.q_floats;
   const m2s_generator_config& cfg = g->cfg;
   const int mask = lengths ? M2S_MASK_LEN : M2S_MASK_NONE;
-  const int rnd = g->tf32 ? 1 : 0;
+  const int rnd = 0;  // the A tensor map is TFLOAT32: TMA rounds on load, stored activations stay fp32
 
   // (B, mels, T) -> channels-last, zero past lengths (conv_pre look-ahead must see zeros)
-  M2S_TRY(bct_to_btc(mel, M0, batch, cfg.num_mels, frames, lengths, g->tf32, st));
+  M2S_TRY(bct_to_btc(mel, M0, batch, cfg.num_mels, frames, lengths, false, st));
 
   int L = frames;
   int ch = cfg.upsample_initial_channel;

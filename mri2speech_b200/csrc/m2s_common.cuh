@@ -40,6 +40,7 @@ struct Epilogue {
   float out_scale;
   float act_slope;
   int act;
+  int res_after_act;
   int round_tf32;
   int mask_mode;
   int len_scale;
@@ -66,7 +67,7 @@ inline ConvProblem problem_from_args(const m2s_conv_args& a) {
   p.batch = a.batch; p.l_out = a.l_out; p.taps = a.taps;
   for (int i = 0; i < M2S_MAX_TAPS; ++i) p.shift[i] = a.shift[i];
   p.n = a.n; p.d = a.d; p.d_batch_rows = a.d_batch_rows; p.d_ld = a.d_ld; p.d_row_offset = a.d_row_offset;
-  p.epi.bias = a.bias; p.epi.res = a.res; p.epi.res_ld = a.res_ld; p.epi.res_inv_slope = a.res_inv_slope;
+  p.epi.bias = a.bias; p.epi.res = a.res; p.epi.res_ld = a.res_ld; p.epi.res_inv_slope = a.res_inv_slope; p.epi.res_after_act = a.res_after_act;
   p.epi.accum = a.accum; p.epi.accum_ld = a.accum_ld; p.epi.out_scale = a.out_scale; p.epi.act = a.act;
   p.epi.act_slope = a.act_slope; p.epi.round_tf32 = a.round_tf32; p.epi.mask_mode = a.mask_mode;
   p.epi.lens = a.lens; p.epi.len_scale = a.len_scale; p.epi.pitch = a.pitch; p.epi.i_lo = a.i_lo;
@@ -98,11 +99,13 @@ __device__ __forceinline__ bool epi_row_valid(const Epilogue& e, int b, int drow
 __device__ __forceinline__ float epi_apply(const Epilogue& e, float acc, float bias, float res, float accum,
                                            bool valid) {
   float v = acc + bias;
-  if (e.res) v += (res >= 0.f ? res : res * e.res_inv_slope);
+  const float r = e.res ? (res >= 0.f ? res : res * e.res_inv_slope) : 0.f;
+  if (!e.res_after_act) v += r;
   if (e.accum) v += accum;
   v *= e.out_scale;
   if (e.act == M2S_ACT_LRELU) v = v >= 0.f ? v : v * e.act_slope;
   else if (e.act == M2S_ACT_SILU) v = v / (1.f + __expf(-v));
+  if (e.res_after_act) v += r;
   if (!valid) v = 0.f;
   if (e.round_tf32) v = round_tf32(v);
   return v;
@@ -132,12 +135,14 @@ int conv_simt(const ConvProblem& p, const float* w_plain, cudaStream_t stream);
 struct EngineKnobs {
   int base_offset_mode = 0;  // 0: base_offset=0 ; 1: (start>>7)&7
   int msub = 0;              // 0 = auto, else force 1 or 2
-  int tmap_tf32 = 0;         // encode the A tensor map as TFLOAT32
+  int tmap_tf32 = 1;         // encode the A tensor map as TFLOAT32 (TMA rounds fp32 -> tf32 on load)
   int max_ctas = 0;          // 0 = #SMs
   int a_per_tap = 0;         // 1: reload the A tile per tap (no row-shifted descriptors; fallback)
 };
 EngineKnobs& engine_knobs();
 
 int sm_count();
+int profile_enable(int on);
+int profile_read(float* ms, double* flops, int cap, int* n_out);
 
 }  // namespace m2s

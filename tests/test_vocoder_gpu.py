@@ -63,7 +63,7 @@ def test_unbatched_input_and_state_dict_roundtrip():
     assert "ups.0.weight" in g2.state_dict()
     with torch.no_grad():
         y4 = g2(mel)
-    assert _snr(y2.cpu(), y4.cpu(), True) > 60.0
+    assert _snr(y2.cpu(), y4.cpu(), True) > 50.0
 
 
 def test_against_cpu_oracle_long_clip():
