@@ -1,11 +1,579 @@
-// placeholder until the encoder lands (keeps the ABI complete)
+// Acoustic model forward: frame-CNN encoder (EfficientNetV2-B2 features) -> BiLSTM (sum merge) -> mel head.
+//
+// Reference semantics: OTNLikeCNNBiLSTM.forward (mri2speech_code/mri_acoustic_model.py:105-136):
+//   f = GAP(backbone(repeat3(x))[-1]) per frame; y = LSTM_fwd(f) + LSTM_bwd(f); out = Linear(y)
+// The backbone is timm's tf_efficientnetv2_b2 (un-vendored; topology in SURVEY.md 8a-1).  Eval-mode BatchNorm
+// is folded into the conv weights, the 3 identical input channels into the stem, fwd+bwd SUM into the head GEMM
+// (K = 2H with the head weight duplicated), b_ih + b_hh into the input-projection GEMM.
+//
+// Layouts: channels-last fp32.  Stages 0-2 keep a one-pixel zero border ("padded": pitch = W+2) so that a 3x3
+// stride-1 conv is 9 row-shifted taps on the conv engine; stages 3-5 are plain (frame, pixel) rows.
 #include "m2s_common.cuh"
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace m2s {
+int enc_stem(const float* frames, const int32_t* fmap, float* out, const float* w, const float* bias, int n, int H,
+             int W, cudaStream_t st);
+int enc_zero_rows(float* buf, int n, int rows_per_frame, int ld, int head_rows, int tail_start, cudaStream_t st);
+int enc_im2col_s2(const float* in, float* col, int n, int Hin, int Win, int C, cudaStream_t st);
+int enc_dwconv(const float* in, float* out, float* sums, const float* w, const float* bias, int n, int C, int Hin,
+               int Win, int pitch_in, int oy, int ox, int rows_in, int stride, cudaStream_t st);
+int enc_se(const float* sums, float* scales, const float* w1, const float* b1, const float* w2, const float* b2, int n,
+           int C, int rd, int hw, cudaStream_t st);
+int enc_se_scale(float* x, const float* scales, int n, int hw, int C, cudaStream_t st);
+int enc_gap(const float* x, const int32_t* fmap, float* feats, int n, int hw, int C, int feat_ld, cudaStream_t st);
+int lstm_recurrence(const float* gin, const float* w_hh_fwd, const float* w_hh_bwd, const int32_t* lens, float* hcat,
+                    unsigned int* counters, int batch, int frames, int max_len, int hidden, bool round_tf32,
+                    cudaStream_t stream);
+}  // namespace m2s
+
 using namespace m2s;
-struct m2s_acoustic { int dummy; };
-extern "C" int m2s_acoustic_create(const m2s_acoustic_config*, const m2s_tensor*, int32_t, m2s_acoustic**) { return fail(M2S_ERR_UNSUPPORTED, "acoustic model not built yet"); }
-extern "C" void m2s_acoustic_destroy(m2s_acoustic*) {}
-extern "C" size_t m2s_acoustic_workspace_bytes(const m2s_acoustic*, int32_t, int32_t) { return 0; }
-extern "C" int m2s_acoustic_forward(m2s_acoustic*, const float*, int32_t, int32_t, const int32_t*, const int32_t*, float*, void*, size_t, m2s_stream_t) { return fail(M2S_ERR_UNSUPPORTED, "acoustic model not built yet"); }
-extern "C" int m2s_acoustic_encode(m2s_acoustic*, const float*, int32_t, float*, void*, size_t, m2s_stream_t) { return fail(M2S_ERR_UNSUPPORTED, "acoustic model not built yet"); }
-extern "C" int m2s_acoustic_rnn_head(m2s_acoustic*, const float*, int32_t, int32_t, const int32_t*, const int32_t*, float*, void*, size_t, m2s_stream_t) { return fail(M2S_ERR_UNSUPPORTED, "acoustic model not built yet"); }
-extern "C" int m2s_acoustic_launches(const m2s_acoustic*) { return 0; }
+
+namespace {
+
+constexpr float kBnEps = 1e-3f;
+
+struct HT {
+  const float* data = nullptr;
+  std::vector<int64_t> shape;
+  size_t numel() const {
+    size_t n = 1;
+    for (auto s : shape) n *= static_cast<size_t>(s);
+    return n;
+  }
+};
+using TMap = std::map<std::string, HT>;
+
+int need(const TMap& m, const std::string& name, size_t numel, const HT** out) {
+  auto it = m.find(name);
+  if (it == m.end()) return fail(M2S_ERR_MISSING_TENSOR, "missing tensor %s", name.c_str());
+  if (numel && it->second.numel() != numel)
+    return fail(M2S_ERR_BAD_ARG, "%s has %zu elements, expected %zu", name.c_str(), it->second.numel(), numel);
+  *out = &it->second;
+  return M2S_OK;
+}
+
+// BN fold factors: y = s*(x) + t with s = g/sqrt(var+eps), t = b - mean*s
+int bn_fold(const TMap& m, const std::string& p, int ch, std::vector<float>* s, std::vector<float>* t) {
+  const HT *g, *b, *mu, *var;
+  M2S_TRY(need(m, p + ".weight", ch, &g));
+  M2S_TRY(need(m, p + ".bias", ch, &b));
+  M2S_TRY(need(m, p + ".running_mean", ch, &mu));
+  M2S_TRY(need(m, p + ".running_var", ch, &var));
+  s->resize(ch);
+  t->resize(ch);
+  for (int c = 0; c < ch; ++c) {
+    const double sc = static_cast<double>(g->data[c]) / std::sqrt(static_cast<double>(var->data[c]) + kBnEps);
+    (*s)[c] = static_cast<float>(sc);
+    (*t)[c] = static_cast<float>(b->data[c] - mu->data[c] * sc);
+  }
+  return M2S_OK;
+}
+
+int upload(const std::vector<float>& h, float** dev) {
+  M2S_CUDA_OK(cudaMalloc(dev, h.size() * sizeof(float)));
+  M2S_CUDA_OK(cudaMemcpy(*dev, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return M2S_OK;
+}
+
+struct GemmLayer {
+  PackedWeights w;
+  float* bias = nullptr;
+  int taps = 1;
+  int shift[M2S_MAX_TAPS] = {};
+};
+
+void free_gemm(GemmLayer* L) {
+  free_weights(&L->w);
+  if (L->bias) cudaFree(L->bias);
+  L->bias = nullptr;
+}
+
+// conv weight (cout, cin, k, k) + BN -> engine layer.  mode 0: k*k shifted taps (pitch given); mode 1: single tap
+// with K = k*k*cin (im2col order (dy*3+dx)*cin + c); 1x1 convs are mode 0 with one tap.
+int make_conv_layer(const TMap& m, const std::string& conv, const std::string& bn, int cout, int cin, int k,
+                    int pitch, int mode, bool tf32, GemmLayer* L) {
+  const HT* w;
+  M2S_TRY(need(m, conv + ".weight", static_cast<size_t>(cout) * cin * k * k, &w));
+  std::vector<float> s, t;
+  M2S_TRY(bn_fold(m, bn, cout, &s, &t));
+  const int kk = k * k;
+  std::vector<float> e(static_cast<size_t>(kk) * cout * cin);
+  for (int tap = 0; tap < kk; ++tap)
+    for (int o = 0; o < cout; ++o)
+      for (int c = 0; c < cin; ++c) {
+        const float v = w->data[(static_cast<size_t>(o) * cin + c) * kk + tap] * s[o];
+        if (mode == 0) e[(static_cast<size_t>(tap) * cout + o) * cin + c] = v;
+        else e[static_cast<size_t>(o) * kk * cin + static_cast<size_t>(tap) * cin + c] = v;
+      }
+  if (mode == 0) {
+    L->taps = kk;
+    for (int tap = 0; tap < kk; ++tap) L->shift[tap] = (tap / k) * pitch + (tap % k);
+    M2S_TRY(pack_weights(e.data(), kk, cout, cin, tf32, &L->w));
+  } else {
+    L->taps = 1;
+    L->shift[0] = 0;
+    M2S_TRY(pack_weights(e.data(), 1, cout, kk * cin, tf32, &L->w));
+  }
+  return upload(t, &L->bias);
+}
+
+enum BlockKind { CN, ER, IR };
+struct StageDef { BlockKind kind; int reps, stride, expand, cout, se; };
+const StageDef kStages[6] = {{CN, 2, 1, 1, 16, 0},  {ER, 3, 2, 4, 32, 0},   {ER, 3, 2, 4, 56, 0},
+                             {IR, 4, 2, 4, 104, 1}, {IR, 6, 1, 6, 120, 1}, {IR, 10, 2, 6, 208, 1}};
+constexpr int kStem = 32;
+constexpr int kFeat = 208;
+
+struct Block {
+  BlockKind kind;
+  int cin, cout, mid, stride, rd;
+  int hin, win;      // input spatial size
+  bool in_padded;    // input activation carries a zero border
+  bool out_padded;   // output activation carries a zero border
+  bool skip;
+  GemmLayer conv;    // CN conv / ER conv_exp / IR conv_pw
+  GemmLayer pwl;     // ER / IR projection
+  float *dw_w = nullptr, *dw_b = nullptr;                                   // IR depthwise [9][mid], [mid]
+  float *se_w1 = nullptr, *se_b1 = nullptr, *se_w2 = nullptr, *se_b2 = nullptr;
+};
+
+}  // namespace
+
+struct m2s_acoustic {
+  m2s_acoustic_config cfg;
+  bool tf32 = true;
+  float *stem_w = nullptr, *stem_b = nullptr;
+  std::vector<Block> blocks;
+  GemmLayer inproj, head;
+  float* w_hh[2] = {nullptr, nullptr};
+  int chunk = 64;  // frames per encoder pass
+  // per-frame buffer sizes (floats)
+  size_t x_floats = 0, e_floats = 0, e2_floats = 0, col_floats = 0;
+  int max_mid = 0;
+  int launches_encoder = 0;
+};
+
+namespace {
+
+void free_block(Block* b) {
+  free_gemm(&b->conv);
+  free_gemm(&b->pwl);
+  for (float** p : {&b->dw_w, &b->dw_b, &b->se_w1, &b->se_b1, &b->se_w2, &b->se_b2}) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+}
+
+size_t padded_rows(int h, int w) { return static_cast<size_t>(h + 2) * (w + 2); }
+
+int run_gemm(const m2s_acoustic* m, const ConvProblem& p, const GemmLayer& L, cudaStream_t st) {
+  return m->tf32 ? conv_tcgen05(p, L.w, st) : conv_simt(p, L.w.plain, st);
+}
+
+ConvProblem gemm_problem(const float* a, long long a_batch_rows, int a_rows, int c_in, int batch, int l_out, float* d,
+                         long long d_batch_rows, int d_ld, int d_row_offset, const GemmLayer& L) {
+  ConvProblem p{};
+  p.a = a; p.a_batch_rows = a_batch_rows; p.a_rows = a_rows; p.a_ld = c_in; p.c_in = c_in;
+  p.batch = batch; p.l_out = l_out; p.taps = L.taps;
+  for (int j = 0; j < L.taps; ++j) p.shift[j] = L.shift[j];
+  p.n = L.w.n; p.d = d; p.d_batch_rows = d_batch_rows; p.d_ld = d_ld; p.d_row_offset = d_row_offset;
+  p.epi.bias = L.bias; p.epi.out_scale = 1.f; p.epi.res_inv_slope = 1.f;
+  return p;
+}
+
+void set_pitch_mask(ConvProblem* p, int h, int w) {
+  p->epi.mask_mode = M2S_MASK_PITCH;
+  p->epi.pitch = w + 2; p->epi.i_lo = 1; p->epi.i_hi = h + 1; p->epi.j_lo = 1; p->epi.j_hi = w + 1;
+}
+
+struct EncBuffers {
+  float *x0, *x1, *e, *e2, *col, *sums, *scales;
+  int32_t* fmap;
+};
+
+size_t align64(size_t f) { return (f + 63) / 64 * 64; }
+
+struct AcWorkspace {
+  size_t enc_floats, feats_floats, gin_floats, hcat_floats, fmap_ints;
+  size_t total_bytes;
+};
+
+AcWorkspace plan_ws(const m2s_acoustic* m, int batch, int frames) {
+  AcWorkspace w{};
+  const size_t nf = static_cast<size_t>(batch) * frames;
+  const size_t nc = nf < static_cast<size_t>(m->chunk) ? nf : m->chunk;
+  w.enc_floats = align64(nc * m->x_floats) * 2 + align64(nc * m->e_floats) + align64(nc * m->e2_floats) +
+                 align64(nc * m->col_floats) + 2 * align64(nc * m->max_mid);
+  w.feats_floats = align64(nf * kFeat);
+  w.gin_floats = align64(nf * 8 * m->cfg.rnn_hidden);
+  w.hcat_floats = align64(nf * 2 * m->cfg.rnn_hidden);
+  w.fmap_ints = align64(nf);
+  w.total_bytes = (w.enc_floats + w.feats_floats + w.gin_floats + w.hcat_floats + w.fmap_ints + 64) * 4 + 512;
+  return w;
+}
+
+// encoder over `n` frames (compact list; fmap maps compact index -> source frame / feature row, or null)
+int encode_chunk(const m2s_acoustic* m, const float* frames, const int32_t* fmap, int n, float* feats, int feat_ld,
+                 const EncBuffers& B, cudaStream_t st) {
+  const int H = m->cfg.height, W = m->cfg.width;
+  float* x = B.x0;
+  float* y = B.x1;
+  M2S_TRY(enc_stem(frames, fmap, x, m->stem_w, m->stem_b, n, H, W, st));
+  for (const Block& b : m->blocks) {
+    const int hin = b.hin, win = b.win;
+    const int hout = hin / b.stride, wout = win / b.stride;
+    if (b.kind == CN) {
+      // 3x3 s1 conv on the padded layout -> padded layout, SiLU, (+ skip after the activation)
+      const int rows = static_cast<int>(padded_rows(hin, win));
+      ConvProblem p = gemm_problem(x, rows, rows, b.cin, n, hin * (win + 2), y, rows, b.cout, win + 3, b.conv);
+      p.epi.act = M2S_ACT_SILU;
+      set_pitch_mask(&p, hin, win);
+      if (b.skip) { p.epi.res = x; p.epi.res_ld = b.cin; p.epi.res_after_act = 1; }
+      M2S_TRY(run_gemm(m, p, b.conv, st));
+      M2S_TRY(enc_zero_rows(y, n, rows, b.cout, win + 3, hin * (win + 2) + win + 3, st));
+      std::swap(x, y);
+    } else if (b.kind == ER) {
+      const int rows_in = static_cast<int>(padded_rows(hin, win));
+      const int rows_out = static_cast<int>(padded_rows(hout, wout));
+      const int lq = hout * (wout + 2);  // rows in the (W+2)-pitch output space
+      if (b.stride == 2) {
+        M2S_TRY(enc_im2col_s2(x, B.col, n, hin, win, b.cin, st));
+        ConvProblem p = gemm_problem(B.col, lq, lq, 9 * b.cin, n, lq, B.e, lq, b.mid, 0, b.conv);
+        p.epi.act = M2S_ACT_SILU;
+        M2S_TRY(run_gemm(m, p, b.conv, st));
+      } else {
+        ConvProblem p = gemm_problem(x, rows_in, rows_in, b.cin, n, lq, B.e, lq, b.mid, 0, b.conv);
+        p.epi.act = M2S_ACT_SILU;
+        M2S_TRY(run_gemm(m, p, b.conv, st));
+      }
+      ConvProblem p = gemm_problem(B.e, lq, lq, b.mid, n, lq, y, rows_out, b.cout, wout + 3, b.pwl);
+      set_pitch_mask(&p, hout, wout);
+      if (b.skip) { p.epi.res = x; p.epi.res_ld = b.cin; }
+      M2S_TRY(run_gemm(m, p, b.pwl, st));
+      M2S_TRY(enc_zero_rows(y, n, rows_out, b.cout, wout + 3, hout * (wout + 2) + wout + 3, st));
+      std::swap(x, y);
+    } else {
+      // IR: 1x1 expand (+SiLU) -> depthwise 3x3 (+SiLU, squeeze) -> SE -> 1x1 project (+ skip)
+      const int rows_in = b.in_padded ? static_cast<int>(padded_rows(hin, win)) : hin * win;
+      {
+        ConvProblem p = gemm_problem(x, rows_in, rows_in, b.cin, n, rows_in, B.e, rows_in, b.mid, 0, b.conv);
+        p.epi.act = M2S_ACT_SILU;
+        M2S_TRY(run_gemm(m, p, b.conv, st));
+      }
+      const int pitch_in = b.in_padded ? win + 2 : win;
+      const int o = b.in_padded ? 1 : 0;
+      M2S_TRY(enc_dwconv(B.e, B.e2, B.sums, b.dw_w, b.dw_b, n, b.mid, hin, win, pitch_in, o, o, rows_in, b.stride, st));
+      const int hw = hout * wout;
+      M2S_TRY(enc_se(B.sums, B.scales, b.se_w1, b.se_b1, b.se_w2, b.se_b2, n, b.mid, b.rd, hw, st));
+      M2S_TRY(enc_se_scale(B.e2, B.scales, n, hw, b.mid, st));
+      ConvProblem p = gemm_problem(B.e2, hw, hw, b.mid, n, hw, y, hw, b.cout, 0, b.pwl);
+      if (b.skip) { p.epi.res = x; p.epi.res_ld = b.cin; }
+      M2S_TRY(run_gemm(m, p, b.pwl, st));
+      std::swap(x, y);
+    }
+  }
+  const Block& last = m->blocks.back();
+  const int hw = (last.hin / last.stride) * (last.win / last.stride);
+  return enc_gap(x, fmap, feats, n, hw, kFeat, feat_ld, st);
+}
+
+int encode_all(const m2s_acoustic* m, const float* frames, const int32_t* fmap_dev, int n_frames, float* feats,
+               float* enc_base, cudaStream_t st) {
+  const int nc = n_frames < m->chunk ? n_frames : m->chunk;
+  EncBuffers B{};
+  float* p = enc_base;
+  B.x0 = p; p += align64(static_cast<size_t>(nc) * m->x_floats);
+  B.x1 = p; p += align64(static_cast<size_t>(nc) * m->x_floats);
+  B.e = p; p += align64(static_cast<size_t>(nc) * m->e_floats);
+  B.e2 = p; p += align64(static_cast<size_t>(nc) * m->e2_floats);
+  B.col = p; p += align64(static_cast<size_t>(nc) * m->col_floats);
+  B.sums = p; p += align64(static_cast<size_t>(nc) * m->max_mid);
+  B.scales = p;
+  for (int f0 = 0; f0 < n_frames; f0 += nc) {
+    const int n = n_frames - f0 < nc ? n_frames - f0 : nc;
+    if (fmap_dev) {
+      M2S_TRY(encode_chunk(m, frames, fmap_dev + f0, n, feats, kFeat, B, st));
+    } else {
+      const size_t fsz = static_cast<size_t>(m->cfg.height) * m->cfg.width;
+      M2S_TRY(encode_chunk(m, frames + f0 * fsz, nullptr, n, feats + static_cast<size_t>(f0) * kFeat, kFeat, B, st));
+    }
+  }
+  return M2S_OK;
+}
+
+int rnn_head(const m2s_acoustic* m, const float* feats, int batch, int frames, const int32_t* lens,
+             const int32_t* lens_host, float* mel_norm, float* gin, float* hcat, unsigned int* counters,
+             cudaStream_t st) {
+  const int Hd = m->cfg.rnn_hidden;
+  const int rows = batch * frames;
+  int max_len = frames;
+  if (lens_host) {
+    max_len = 0;
+    for (int b = 0; b < batch; ++b) {
+      if (lens_host[b] < 0 || lens_host[b] > frames) return fail(M2S_ERR_BAD_ARG, "lengths[%d]=%d out of range", b, lens_host[b]);
+      max_len = lens_host[b] > max_len ? lens_host[b] : max_len;
+    }
+  }
+  {  // input projection for every timestep and both directions: (rows, 208) x (208, 8H) + (b_ih + b_hh)
+    ConvProblem p = gemm_problem(feats, rows, rows, kFeat, 1, rows, gin, rows, 8 * Hd, 0, m->inproj);
+    M2S_TRY(run_gemm(m, p, m->inproj, st));
+  }
+  M2S_CUDA_OK(cudaMemsetAsync(hcat, 0, static_cast<size_t>(rows) * 2 * Hd * sizeof(float), st));
+  M2S_TRY(lstm_recurrence(gin, m->w_hh[0], m->w_hh[1], lens, hcat, counters, batch, frames, max_len, Hd, false, st));
+  {  // head on [h_fwd | h_bwd] with the weight duplicated: y = W (h_fwd + h_bwd) + b ; rows past lens -> 0
+    ConvProblem p = gemm_problem(hcat, frames, frames, 2 * Hd, batch, frames, mel_norm, frames, m->cfg.n_mels, 0, m->head);
+    if (lens) { p.epi.mask_mode = M2S_MASK_LEN; p.epi.lens = lens; p.epi.len_scale = 1; }
+    M2S_TRY(run_gemm(m, p, m->head, st));
+  }
+  return M2S_OK;
+}
+
+}  // namespace
+
+extern "C" int m2s_acoustic_create(const m2s_acoustic_config* cfg, const m2s_tensor* tensors, int32_t n_tensors,
+                                   m2s_acoustic** out) {
+  if (!cfg || !tensors || !out) return fail(M2S_ERR_BAD_ARG, "null argument");
+  if (cfg->height % 32 || cfg->width % 32 || cfg->height <= 0 || cfg->width <= 0)
+    return fail(M2S_ERR_UNSUPPORTED, "frame size %dx%d must be a positive multiple of 32", cfg->height, cfg->width);
+  if (cfg->n_mels % 4) return fail(M2S_ERR_UNSUPPORTED, "n_mels must be a multiple of 4");
+  M2S_TRY(m2s_device_check(-1));
+  TMap tm;
+  for (int i = 0; i < n_tensors; ++i) {
+    HT h;
+    h.data = tensors[i].data;
+    for (int d = 0; d < tensors[i].ndim; ++d) h.shape.push_back(tensors[i].shape[d]);
+    tm[tensors[i].name] = h;
+  }
+  auto* m = new m2s_acoustic();
+  m->cfg = *cfg;
+  m->tf32 = cfg->precision != M2S_PREC_FP32;
+  if (const char* c = std::getenv("M2S_ENCODER_CHUNK")) m->chunk = std::max(1, std::atoi(c));
+  int st = M2S_OK;
+  auto bail = [&](int s) { m2s_acoustic_destroy(m); return s; };
+  const std::string bb = "cnn.backbone.";
+
+  {  // stem: fold the 3 identical input channels and BN
+    const HT* w;
+    if ((st = need(tm, bb + "conv_stem.weight", static_cast<size_t>(kStem) * 27, &w)) != M2S_OK) return bail(st);
+    std::vector<float> s, t;
+    if ((st = bn_fold(tm, bb + "bn1", kStem, &s, &t)) != M2S_OK) return bail(st);
+    std::vector<float> e(9 * kStem);
+    for (int o = 0; o < kStem; ++o)
+      for (int tap = 0; tap < 9; ++tap) {
+        float v = 0.f;
+        for (int c = 0; c < 3; ++c) v += w->data[(static_cast<size_t>(o) * 3 + c) * 9 + tap];
+        e[tap * kStem + o] = v * s[o];
+      }
+    if ((st = upload(e, &m->stem_w)) != M2S_OK || (st = upload(t, &m->stem_b)) != M2S_OK) return bail(st);
+  }
+
+  int cin = kStem, h = cfg->height / 2, w = cfg->width / 2;
+  bool padded = true;  // the stem writes a padded layout
+  m->x_floats = padded_rows(h, w) * kStem;
+  int launches = 1;
+  for (int s = 0; s < 6; ++s) {
+    const StageDef& sd = kStages[s];
+    for (int r = 0; r < sd.reps; ++r) {
+      Block b{};
+      b.kind = sd.kind; b.cin = cin; b.cout = sd.cout; b.stride = r == 0 ? sd.stride : 1;
+      b.mid = cin * sd.expand; b.hin = h; b.win = w; b.in_padded = padded;
+      b.skip = (b.stride == 1 && cin == sd.cout);
+      b.rd = sd.se ? static_cast<int>(std::lround(cin * 0.25)) : 0;
+      const std::string p = bb + "blocks." + std::to_string(s) + "." + std::to_string(r);
+      const int ho = h / b.stride, wo = w / b.stride;
+      if (sd.kind == CN) {
+        b.out_padded = true;
+        if ((st = make_conv_layer(tm, p + ".conv", p + ".bn1", b.cout, cin, 3, w + 2, 0, m->tf32, &b.conv)) != M2S_OK)
+          return bail(st);
+        m->x_floats = std::max(m->x_floats, padded_rows(ho, wo) * b.cout);
+        launches += 2;
+      } else if (sd.kind == ER) {
+        b.out_padded = true;
+        if ((st = make_conv_layer(tm, p + ".conv_exp", p + ".bn1", b.mid, cin, 3, w + 2, b.stride == 2 ? 1 : 0,
+                                  m->tf32, &b.conv)) != M2S_OK)
+          return bail(st);
+        if ((st = make_conv_layer(tm, p + ".conv_pwl", p + ".bn2", b.cout, b.mid, 1, 0, 0, m->tf32, &b.pwl)) != M2S_OK)
+          return bail(st);
+        const size_t lq = static_cast<size_t>(ho) * (wo + 2);
+        m->e_floats = std::max(m->e_floats, lq * b.mid);
+        if (b.stride == 2) m->col_floats = std::max(m->col_floats, lq * 9 * cin);
+        m->x_floats = std::max(m->x_floats, padded_rows(ho, wo) * b.cout);
+        launches += b.stride == 2 ? 4 : 3;
+      } else {
+        b.out_padded = false;
+        if ((st = make_conv_layer(tm, p + ".conv_pw", p + ".bn1", b.mid, cin, 1, 0, 0, m->tf32, &b.conv)) != M2S_OK)
+          return bail(st);
+        if ((st = make_conv_layer(tm, p + ".conv_pwl", p + ".bn3", b.cout, b.mid, 1, 0, 0, m->tf32, &b.pwl)) != M2S_OK)
+          return bail(st);
+        {  // depthwise (mid,1,3,3) + bn2 -> [9][mid]
+          const HT* dw;
+          if ((st = need(tm, p + ".conv_dw.weight", static_cast<size_t>(b.mid) * 9, &dw)) != M2S_OK) return bail(st);
+          std::vector<float> s2, t2;
+          if ((st = bn_fold(tm, p + ".bn2", b.mid, &s2, &t2)) != M2S_OK) return bail(st);
+          std::vector<float> e(static_cast<size_t>(9) * b.mid);
+          for (int c = 0; c < b.mid; ++c)
+            for (int tap = 0; tap < 9; ++tap) e[static_cast<size_t>(tap) * b.mid + c] = dw->data[c * 9 + tap] * s2[c];
+          if ((st = upload(e, &b.dw_w)) != M2S_OK || (st = upload(t2, &b.dw_b)) != M2S_OK) return bail(st);
+        }
+        {
+          const HT *w1, *b1, *w2, *b2;
+          if ((st = need(tm, p + ".se.conv_reduce.weight", static_cast<size_t>(b.rd) * b.mid, &w1)) != M2S_OK ||
+              (st = need(tm, p + ".se.conv_reduce.bias", b.rd, &b1)) != M2S_OK ||
+              (st = need(tm, p + ".se.conv_expand.weight", static_cast<size_t>(b.mid) * b.rd, &w2)) != M2S_OK ||
+              (st = need(tm, p + ".se.conv_expand.bias", b.mid, &b2)) != M2S_OK)
+            return bail(st);
+          auto up = [&](const HT* t, float** d) { return upload(std::vector<float>(t->data, t->data + t->numel()), d); };
+          if ((st = up(w1, &b.se_w1)) != M2S_OK || (st = up(b1, &b.se_b1)) != M2S_OK ||
+              (st = up(w2, &b.se_w2)) != M2S_OK || (st = up(b2, &b.se_b2)) != M2S_OK)
+            return bail(st);
+        }
+        const size_t rows_in = padded ? padded_rows(h, w) : static_cast<size_t>(h) * w;
+        m->e_floats = std::max(m->e_floats, rows_in * b.mid);
+        m->e2_floats = std::max(m->e2_floats, static_cast<size_t>(ho) * wo * b.mid);
+        m->x_floats = std::max(m->x_floats, static_cast<size_t>(ho) * wo * b.cout);
+        m->max_mid = std::max(m->max_mid, b.mid);
+        launches += 5;
+      }
+      m->blocks.push_back(b);
+      padded = b.out_padded;
+      cin = sd.cout; h = ho; w = wo;
+    }
+  }
+  m->launches_encoder = launches + 1;  // + GAP
+  if (cin != kFeat) return bail(fail(M2S_ERR_BAD_ARG, "unexpected feature width %d", cin));
+
+  {  // LSTM input projection (both directions) + recurrent weights + head
+    const int Hd = cfg->rnn_hidden;
+    const std::string l = "rnn.lstm.";
+    const HT *wi[2], *wh[2], *bi[2], *bh[2];
+    const char* sfx[2] = {"", "_reverse"};
+    for (int d = 0; d < 2; ++d) {
+      if ((st = need(tm, l + "weight_ih_l0" + sfx[d], static_cast<size_t>(4) * Hd * kFeat, &wi[d])) != M2S_OK ||
+          (st = need(tm, l + "weight_hh_l0" + sfx[d], static_cast<size_t>(4) * Hd * Hd, &wh[d])) != M2S_OK ||
+          (st = need(tm, l + "bias_ih_l0" + sfx[d], static_cast<size_t>(4) * Hd, &bi[d])) != M2S_OK ||
+          (st = need(tm, l + "bias_hh_l0" + sfx[d], static_cast<size_t>(4) * Hd, &bh[d])) != M2S_OK)
+        return bail(st);
+    }
+    std::vector<float> wcat(static_cast<size_t>(8) * Hd * kFeat), bcat(static_cast<size_t>(8) * Hd);
+    for (int d = 0; d < 2; ++d) {
+      std::memcpy(wcat.data() + static_cast<size_t>(d) * 4 * Hd * kFeat, wi[d]->data, sizeof(float) * 4 * Hd * kFeat);
+      for (int i = 0; i < 4 * Hd; ++i) bcat[d * 4 * Hd + i] = bi[d]->data[i] + bh[d]->data[i];
+      if ((st = upload(std::vector<float>(wh[d]->data, wh[d]->data + wh[d]->numel()), &m->w_hh[d])) != M2S_OK)
+        return bail(st);
+    }
+    if ((st = pack_weights(wcat.data(), 1, 8 * Hd, kFeat, m->tf32, &m->inproj.w)) != M2S_OK ||
+        (st = upload(bcat, &m->inproj.bias)) != M2S_OK)
+      return bail(st);
+    const HT *hw, *hb;
+    if ((st = need(tm, "head.weight", static_cast<size_t>(cfg->n_mels) * Hd, &hw)) != M2S_OK ||
+        (st = need(tm, "head.bias", cfg->n_mels, &hb)) != M2S_OK)
+      return bail(st);
+    std::vector<float> hcat(static_cast<size_t>(cfg->n_mels) * 2 * Hd);
+    for (int o = 0; o < cfg->n_mels; ++o)
+      for (int k = 0; k < Hd; ++k) hcat[static_cast<size_t>(o) * 2 * Hd + k] = hcat[static_cast<size_t>(o) * 2 * Hd + Hd + k] = hw->data[o * Hd + k];
+    if ((st = pack_weights(hcat.data(), 1, cfg->n_mels, 2 * Hd, m->tf32, &m->head.w)) != M2S_OK ||
+        (st = upload(std::vector<float>(hb->data, hb->data + cfg->n_mels), &m->head.bias)) != M2S_OK)
+      return bail(st);
+  }
+  *out = m;
+  return M2S_OK;
+}
+
+extern "C" void m2s_acoustic_destroy(m2s_acoustic* m) {
+  if (!m) return;
+  if (m->stem_w) cudaFree(m->stem_w);
+  if (m->stem_b) cudaFree(m->stem_b);
+  for (auto& b : m->blocks) free_block(&b);
+  free_gemm(&m->inproj);
+  free_gemm(&m->head);
+  for (int d = 0; d < 2; ++d)
+    if (m->w_hh[d]) cudaFree(m->w_hh[d]);
+  delete m;
+}
+
+extern "C" int m2s_acoustic_launches(const m2s_acoustic* m) { return m ? m->launches_encoder + 5 : 0; }
+
+extern "C" size_t m2s_acoustic_workspace_bytes(const m2s_acoustic* m, int32_t batch, int32_t frames) {
+  if (!m || batch <= 0 || frames <= 0) return 0;
+  return plan_ws(m, batch, frames).total_bytes;
+}
+
+namespace {
+struct WsPtrs {
+  float *enc, *feats, *gin, *hcat;
+  int32_t* fmap;
+  unsigned int* counters;
+};
+int carve(const m2s_acoustic* m, int batch, int frames, void* ws, size_t ws_bytes, WsPtrs* o) {
+  const AcWorkspace w = plan_ws(m, batch, frames);
+  if (!ws || ws_bytes < w.total_bytes)
+    return fail(M2S_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total_bytes, ws_bytes);
+  float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  o->enc = base;
+  o->feats = o->enc + w.enc_floats;
+  o->gin = o->feats + w.feats_floats;
+  o->hcat = o->gin + w.gin_floats;
+  o->fmap = reinterpret_cast<int32_t*>(o->hcat + w.hcat_floats);
+  o->counters = reinterpret_cast<unsigned int*>(o->fmap + w.fmap_ints);
+  return M2S_OK;
+}
+}  // namespace
+
+extern "C" int m2s_acoustic_encode(m2s_acoustic* m, const float* frames_dev, int32_t n_frames, float* feats,
+                                   void* workspace, size_t workspace_bytes, m2s_stream_t stream) {
+  if (!m || !frames_dev || !feats) return fail(M2S_ERR_BAD_ARG, "null argument");
+  if (n_frames <= 0) return M2S_OK;
+  WsPtrs w;
+  M2S_TRY(carve(m, 1, n_frames, workspace, workspace_bytes, &w));
+  return encode_all(m, frames_dev, nullptr, n_frames, feats, w.enc, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int m2s_acoustic_rnn_head(m2s_acoustic* m, const float* feats, int32_t batch, int32_t frames,
+                                     const int32_t* lengths, const int32_t* lengths_host, float* mel_norm,
+                                     void* workspace, size_t workspace_bytes, m2s_stream_t stream) {
+  if (!m || !feats || !mel_norm) return fail(M2S_ERR_BAD_ARG, "null argument");
+  if ((lengths == nullptr) != (lengths_host == nullptr))
+    return fail(M2S_ERR_BAD_ARG, "lengths and lengths_host must be given together");
+  if (batch <= 0 || frames <= 0) return M2S_OK;
+  WsPtrs w;
+  M2S_TRY(carve(m, batch, frames, workspace, workspace_bytes, &w));
+  return rnn_head(m, feats, batch, frames, lengths, lengths_host, mel_norm, w.gin, w.hcat, w.counters,
+                  reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int m2s_acoustic_forward(m2s_acoustic* m, const float* frames_dev, int32_t batch, int32_t frames,
+                                    const int32_t* lengths, const int32_t* lengths_host, float* mel_norm,
+                                    void* workspace, size_t workspace_bytes, m2s_stream_t stream) {
+  if (!m || !frames_dev || !mel_norm) return fail(M2S_ERR_BAD_ARG, "null argument");
+  if ((lengths == nullptr) != (lengths_host == nullptr))
+    return fail(M2S_ERR_BAD_ARG, "lengths and lengths_host must be given together");
+  if (batch <= 0 || frames <= 0) return M2S_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  WsPtrs w;
+  M2S_TRY(carve(m, batch, frames, workspace, workspace_bytes, &w));
+  const int total = batch * frames;
+  if (lengths_host) {
+    // encode only the valid frames of a ragged batch: compact list of (b, t) source indices
+    std::vector<int32_t> fmap;
+    fmap.reserve(total);
+    for (int b = 0; b < batch; ++b) {
+      if (lengths_host[b] < 0 || lengths_host[b] > frames)
+        return fail(M2S_ERR_BAD_ARG, "lengths[%d]=%d out of range", b, lengths_host[b]);
+      for (int t = 0; t < lengths_host[b]; ++t) fmap.push_back(b * frames + t);
+    }
+    M2S_CUDA_OK(cudaMemsetAsync(w.feats, 0, static_cast<size_t>(total) * kFeat * sizeof(float), st));
+    if (!fmap.empty()) {
+      M2S_CUDA_OK(cudaMemcpyAsync(w.fmap, fmap.data(), fmap.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      M2S_CUDA_OK(cudaStreamSynchronize(st));  // fmap is a stack-lifetime host buffer
+      M2S_TRY(encode_all(m, frames_dev, w.fmap, static_cast<int>(fmap.size()), w.feats, w.enc, st));
+    }
+  } else {
+    M2S_TRY(encode_all(m, frames_dev, nullptr, total, w.feats, w.enc, st));
+  }
+  return rnn_head(m, w.feats, batch, frames, lengths, lengths_host, mel_norm, w.gin, w.hcat, w.counters, st);
+}

@@ -1,0 +1,269 @@
+// CUDA-core kernels of the frame-CNN encoder (the parts that are not GEMM-shaped).
+//
+// Reference: timm tf_efficientnetv2_b2 (features_only) as called by EffNetV2B2Backbone.forward
+// (mri2speech_code/mri_acoustic_model.py:28-48); topology restated in SURVEY.md 8a-1.
+//   * stem 3x3 s2 conv (the 3 identical input channels folded into 1) + BN + SiLU
+//   * im2col for the two stride-2 3x3 convs (TF "same": pad right/bottom only)
+//   * depthwise 3x3 (+BN+SiLU) with the squeeze (spatial sum) fused
+//   * squeeze-excite MLP, excite scale, global average pool
+// All activations are channels-last.  "Padded" layouts carry a one-pixel zero border so that the
+// tensor-core engine can treat a 3x3 stride-1 conv as 9 row-shifted taps over the flattened image.
+#include "m2s_common.cuh"
+
+namespace m2s {
+
+namespace {
+
+__device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); }
+
+// frames (n, H, W) -> out padded ((H/2+2) x (W/2+2) rows, 32 ch); one block per padded output row.
+__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ frames, const int32_t* __restrict__ fmap,
+                                                   float* __restrict__ out, const float* __restrict__ w /*[9][32]*/,
+                                                   const float* __restrict__ bias, int H, int W) {
+  const int Ho = H / 2, Wo = W / 2, pitch = Wo + 2;
+  const int n = blockIdx.y;
+  const int i = blockIdx.x;  // padded row 0..Ho+1
+  float* orow = out + (static_cast<size_t>(n) * (Ho + 2) * pitch + static_cast<size_t>(i) * pitch) * 32;
+  if (i == 0 || i == Ho + 1) {
+    for (int k = threadIdx.x; k < pitch * 8; k += blockDim.x) reinterpret_cast<float4*>(orow)[k] = make_float4(0, 0, 0, 0);
+    return;
+  }
+  extern __shared__ float srow[];  // 3 x (W + 1) input pixels
+  __shared__ float sw[9 * 32 + 32];
+  const int y = i - 1;
+  const float* f = frames + static_cast<size_t>(fmap ? fmap[n] : n) * H * W;
+  for (int k = threadIdx.x; k < 3 * (W + 1); k += blockDim.x) {
+    const int r = k / (W + 1), x = k % (W + 1);
+    const int yy = 2 * y + r;
+    srow[k] = (yy < H && x < W) ? f[static_cast<size_t>(yy) * W + x] : 0.f;
+  }
+  for (int k = threadIdx.x; k < 9 * 32 + 32; k += blockDim.x) sw[k] = k < 288 ? w[k] : bias[k - 288];
+  __syncthreads();
+  // thread -> (x, 8-channel group)
+  for (int k = threadIdx.x; k < pitch * 4; k += blockDim.x) {
+    const int j = k >> 2, cg = (k & 3) * 8;
+    float v[8];
+    if (j == 0 || j == Wo + 1) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c] = 0.f;
+    } else {
+      const int x = j - 1;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c] = sw[288 + cg + c];
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float px = srow[dy * (W + 1) + 2 * x + dx];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[c] = fmaf(px, sw[(dy * 3 + dx) * 32 + cg + c], v[c]);
+        }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c] = silu(v[c]);
+    }
+    float4* o = reinterpret_cast<float4*>(orow + static_cast<size_t>(j) * 32 + cg);
+    o[0] = make_float4(v[0], v[1], v[2], v[3]);
+    o[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+// Zero the rows of a padded layout that the engine's masked epilogue never writes:
+// [0, head_rows) and [tail_start, rows_per_frame) of every frame.
+__global__ void zero_rows_kernel(float* __restrict__ buf, int rows_per_frame, int ld4, int head_rows, int tail_start) {
+  const int n = blockIdx.y;
+  const int nz = head_rows + (rows_per_frame - tail_start);
+  float4* base = reinterpret_cast<float4*>(buf) + static_cast<size_t>(n) * rows_per_frame * ld4;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nz * ld4; k += gridDim.x * blockDim.x) {
+    int r = k / ld4;
+    const int c = k % ld4;
+    if (r >= head_rows) r = tail_start + (r - head_rows);
+    base[static_cast<size_t>(r) * ld4 + c] = make_float4(0, 0, 0, 0);
+  }
+}
+
+// im2col for a 3x3 stride-2 TF-"same" conv.  Input: padded layout (pitch_in = W_in + 2, origin (1,1));
+// output rows q = y*(Wo+2) + x (x >= Wo rows are zero), columns (dy*3+dx)*C + c.
+__global__ void im2col_s2_kernel(const float* __restrict__ in, float* __restrict__ col, int Hin, int Win, int C) {
+  const int Ho = Hin / 2, Wo = Win / 2, pitch_in = Win + 2, pitch_o = Wo + 2;
+  const int n = blockIdx.y;
+  const int c4n = C / 4;
+  const size_t total = static_cast<size_t>(Ho) * pitch_o * 9 * c4n;
+  const float4* src = reinterpret_cast<const float4*>(in) + static_cast<size_t>(n) * (Hin + 2) * pitch_in * c4n;
+  float4* dst = reinterpret_cast<float4*>(col) + static_cast<size_t>(n) * Ho * pitch_o * 9 * c4n;
+  for (size_t k = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < total;
+       k += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c4 = k % c4n;
+    const int tap = (k / c4n) % 9;
+    const int q = k / (static_cast<size_t>(c4n) * 9);
+    const int y = q / pitch_o, x = q % pitch_o;
+    float4 v = make_float4(0, 0, 0, 0);
+    if (x < Wo) {
+      const int dy = tap / 3, dx = tap % 3;
+      // input pixel (2y+dy, 2x+dx) lives at padded (2y+dy+1, 2x+dx+1); index Hin / Win hits the zero border
+      v = src[(static_cast<size_t>(2 * y + dy + 1) * pitch_in + (2 * x + dx + 1)) * c4n + c4];
+    }
+    dst[k] = v;
+  }
+}
+
+// Depthwise 3x3 + bias (folded BN) + SiLU, with the SE squeeze (per-frame channel sums) fused.
+// Input pixel (y, x) is row (y + oy) * pitch_in + (x + ox); pixels outside [0,Hin)x[0,Win) are zero.
+// grid = (C / 32, frames); block = 32 channels x 8 pixel lanes.
+__global__ void __launch_bounds__(256) dwconv_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                     float* __restrict__ sums, const float* __restrict__ w /*[9][C]*/,
+                                                     const float* __restrict__ bias, int C, int Hin, int Win,
+                                                     int pitch_in, int oy, int ox, int rows_in, int stride) {
+  const int Ho = Hin / stride, Wo = Win / stride;
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int lane_p = threadIdx.x >> 5;
+  __shared__ float red[8][33];
+  float wv[9], b = 0.f, acc_sum = 0.f;
+  if (c < C) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wv[t] = w[t * C + c];
+    b = bias[c];
+  }
+  const float* src = in + static_cast<size_t>(n) * rows_in * C;
+  const int off = stride == 1 ? -1 : 0;  // TF same: stride 1 pads 1/1, stride 2 pads 0/1
+  if (c < C) {
+    for (int p = lane_p; p < Ho * Wo; p += 8) {
+      const int y = p / Wo, x = p % Wo;
+      float v = b;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const int yy = y * stride + dy + off;
+        if (yy < 0 || yy >= Hin) continue;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const int xx = x * stride + dx + off;
+          if (xx < 0 || xx >= Win) continue;
+          v = fmaf(src[(static_cast<size_t>(yy + oy) * pitch_in + (xx + ox)) * C + c], wv[dy * 3 + dx], v);
+        }
+      }
+      v = silu(v);
+      out[(static_cast<size_t>(n) * Ho * Wo + p) * C + c] = v;
+      acc_sum += v;
+    }
+  }
+  red[lane_p][threadIdx.x & 31] = acc_sum;
+  __syncthreads();
+  if (lane_p == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+    sums[static_cast<size_t>(n) * C + c] = s;
+  }
+}
+
+// Squeeze-excite MLP: scale[n][c] = sigmoid(W2 silu(W1 mean + b1) + b2).  One block per frame.
+__global__ void __launch_bounds__(256) se_kernel(const float* __restrict__ sums, float* __restrict__ scales,
+                                                 const float* __restrict__ w1 /*[rd][C]*/, const float* __restrict__ b1,
+                                                 const float* __restrict__ w2 /*[C][rd]*/, const float* __restrict__ b2,
+                                                 int C, int rd, float inv_hw) {
+  extern __shared__ float sm[];  // mean[C] + r[rd]
+  float* mean = sm;
+  float* r = sm + C;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = sums[static_cast<size_t>(n) * C + c] * inv_hw;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < rd; j += 8) {
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a = fmaf(w1[static_cast<size_t>(j) * C + c], mean[c], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) {
+      a += b1[j];
+      r[j] = a / (1.f + expf(-a));
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = b2[c];
+    for (int j = 0; j < rd; ++j) a = fmaf(w2[static_cast<size_t>(c) * rd + j], r[j], a);
+    scales[static_cast<size_t>(n) * C + c] = 1.f / (1.f + expf(-a));
+  }
+}
+
+// x[n][p][c] *= scale[n][c]
+__global__ void se_scale_kernel(float* __restrict__ x, const float* __restrict__ scales, int hw, int c4n, size_t total4) {
+  for (size_t k = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < total4;
+       k += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c4 = k % c4n;
+    const size_t n = k / (static_cast<size_t>(c4n) * hw);
+    float4 v = reinterpret_cast<float4*>(x)[k];
+    const float4 s = reinterpret_cast<const float4*>(scales)[n * c4n + c4];
+    v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
+    reinterpret_cast<float4*>(x)[k] = v;
+  }
+}
+
+// feats[dst(n)][c] = mean_p x[n][p][c]
+__global__ void gap_kernel(const float* __restrict__ x, const int32_t* __restrict__ fmap, float* __restrict__ feats,
+                           int hw, int C, int feat_ld) {
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < hw; ++p) s += x[(static_cast<size_t>(n) * hw + p) * C + c];
+    feats[static_cast<size_t>(fmap ? fmap[n] : n) * feat_ld + c] = s / static_cast<float>(hw);
+  }
+}
+
+}  // namespace
+
+int enc_stem(const float* frames, const int32_t* fmap, float* out, const float* w, const float* bias, int n, int H,
+             int W, cudaStream_t st) {
+  dim3 grid(H / 2 + 2, n);
+  stem_kernel<<<grid, 256, 3 * (W + 1) * sizeof(float), st>>>(frames, fmap, out, w, bias, H, W);
+  M2S_CUDA_OK(cudaGetLastError());
+  return M2S_OK;
+}
+
+int enc_zero_rows(float* buf, int n, int rows_per_frame, int ld, int head_rows, int tail_start, cudaStream_t st) {
+  const int nz = (head_rows + rows_per_frame - tail_start) * (ld / 4);
+  dim3 grid((nz + 255) / 256, n);
+  zero_rows_kernel<<<grid, 256, 0, st>>>(buf, rows_per_frame, ld / 4, head_rows, tail_start);
+  M2S_CUDA_OK(cudaGetLastError());
+  return M2S_OK;
+}
+
+int enc_im2col_s2(const float* in, float* col, int n, int Hin, int Win, int C, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(Hin / 2) * (Win / 2 + 2) * 9 * (C / 4);
+  dim3 grid(static_cast<unsigned>((total + 255) / 256), n);
+  im2col_s2_kernel<<<grid, 256, 0, st>>>(in, col, Hin, Win, C);
+  M2S_CUDA_OK(cudaGetLastError());
+  return M2S_OK;
+}
+
+int enc_dwconv(const float* in, float* out, float* sums, const float* w, const float* bias, int n, int C, int Hin,
+               int Win, int pitch_in, int oy, int ox, int rows_in, int stride, cudaStream_t st) {
+  dim3 grid((C + 31) / 32, n);
+  dwconv_kernel<<<grid, 256, 0, st>>>(in, out, sums, w, bias, C, Hin, Win, pitch_in, oy, ox, rows_in, stride);
+  M2S_CUDA_OK(cudaGetLastError());
+  return M2S_OK;
+}
+
+int enc_se(const float* sums, float* scales, const float* w1, const float* b1, const float* w2, const float* b2, int n,
+           int C, int rd, int hw, cudaStream_t st) {
+  se_kernel<<<n, 256, (C + rd) * sizeof(float), st>>>(sums, scales, w1, b1, w2, b2, C, rd, 1.f / hw);
+  M2S_CUDA_OK(cudaGetLastError());
+  return M2S_OK;
+}
+
+int enc_se_scale(float* x, const float* scales, int n, int hw, int C, cudaStream_t st) {
+  const size_t total4 = static_cast<size_t>(n) * hw * (C / 4);
+  unsigned blocks = static_cast<unsigned>((total4 + 255) / 256);
+  if (blocks > 148u * 16u) blocks = 148u * 16u;
+  se_scale_kernel<<<blocks, 256, 0, st>>>(x, scales, hw, C / 4, total4);
+  M2S_CUDA_OK(cudaGetLastError());
+  return M2S_OK;
+}
+
+int enc_gap(const float* x, const int32_t* fmap, float* feats, int n, int hw, int C, int feat_ld, cudaStream_t st) {
+  gap_kernel<<<n, 256, 0, st>>>(x, fmap, feats, hw, C, feat_ld);
+  M2S_CUDA_OK(cudaGetLastError());
+  return M2S_OK;
+}
+
+}  // namespace m2s
