@@ -92,7 +92,7 @@ typedef struct {
   int64_t d_batch_rows;
   int32_t d_ld;
   int32_t d_row_offset;
-  /* fused epilogue: v = acc + bias[n] + inv_lrelu(res) + accum; v *= out_scale; v = act(v); mask; round
+  /* fused epilogue: v = acc + bias[n] + inv_lrelu(res) + accum; v *= out_scale; v = act(v); mask
    * (res_after_act != 0: the residual is added after the activation instead: v = act(..) + res) */
   const float* bias;     /* [n] or NULL */
   const float* res;      /* indexed like d (same rows), NULL = none */
@@ -104,7 +104,6 @@ typedef struct {
   float out_scale;
   int32_t act;
   float act_slope;
-  int32_t round_tf32;    /* store RNE-rounded-to-TF32 values (operand of a later tcgen05 layer) */
   int32_t mask_mode;
   const int32_t* lens;   /* M2S_MASK_LEN: row valid iff (q + d_row_offset) < lens[b]*len_scale */
   int32_t len_scale;
@@ -198,6 +197,8 @@ int m2s_debug_set_knob(const char* name, int value);
  * ms[i] = duration of launch i, flops[i] = 2*M*N*K it executed. */
 int m2s_debug_profile(int enable);
 int m2s_debug_profile_read(float* ms, double* flops, int32_t cap, int32_t* n);
+/* clock64 timeline of CTA 0 (producer / MMA / epilogue stamps, 9 per tile) into a device buffer; NULL = off. */
+int m2s_debug_trace(unsigned long long* buf, int32_t tiles);
 
 #ifdef __cplusplus
 }

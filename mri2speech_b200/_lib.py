@@ -41,7 +41,7 @@ class ConvArgs(C.Structure):
         ("bias", C.c_void_p), ("res", C.c_void_p), ("res_ld", C.c_int32), ("res_inv_slope", C.c_float),
         ("res_after_act", C.c_int32),
         ("accum", C.c_void_p), ("accum_ld", C.c_int32), ("out_scale", C.c_float),
-        ("act", C.c_int32), ("act_slope", C.c_float), ("round_tf32", C.c_int32),
+        ("act", C.c_int32), ("act_slope", C.c_float),
         ("mask_mode", C.c_int32), ("lens", C.c_void_p), ("len_scale", C.c_int32),
         ("pitch", C.c_int32), ("i_lo", C.c_int32), ("i_hi", C.c_int32), ("j_lo", C.c_int32), ("j_hi", C.c_int32),
     ]
@@ -89,6 +89,7 @@ def lib() -> C.CDLL:
     L.m2s_device_check.argtypes = [C.c_int]
     L.m2s_conv_fwd.argtypes = [C.POINTER(ConvArgs), C.c_int, C.c_void_p]
     L.m2s_debug_set_knob.argtypes = [C.c_char_p, C.c_int]
+    L.m2s_debug_trace.argtypes = [C.c_void_p, C.c_int32]
     L.m2s_debug_profile.argtypes = [C.c_int]
     L.m2s_debug_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int32,
                                          C.POINTER(C.c_int32)]
@@ -178,7 +179,7 @@ def set_knob(name: str, value: int) -> None:
 
 def conv_fwd(a: torch.Tensor, w: torch.Tensor, shifts: Sequence[int], l_out: int, *, impl: int = IMPL_TCGEN05,
              a_rows: Optional[int] = None, bias=None, res=None, res_inv_slope: float = 1.0, res_after_act: bool = False, accum=None,
-             out_scale: float = 1.0, act: int = ACT_NONE, act_slope: float = 0.0, round_tf32: bool = False,
+             out_scale: float = 1.0, act: int = ACT_NONE, act_slope: float = 0.0,
              lens=None, len_scale: int = 1, pitch_mask=None, d_row_offset: int = 0,
              d_rows: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Test helper around m2s_conv_fwd.  a: (B, L_in, C) cuda fp32; w: (taps, N, C) cuda fp32."""
@@ -198,7 +199,7 @@ def conv_fwd(a: torch.Tensor, w: torch.Tensor, shifts: Sequence[int], l_out: int
     args.bias = ptr(bias); args.res = ptr(res); args.res_ld = N; args.res_inv_slope = res_inv_slope
     args.res_after_act = int(res_after_act)
     args.accum = ptr(accum); args.accum_ld = N; args.out_scale = out_scale
-    args.act = act; args.act_slope = act_slope; args.round_tf32 = int(round_tf32)
+    args.act = act; args.act_slope = act_slope
     if lens is not None:
         args.mask_mode = MASK_LEN; args.lens = lens.data_ptr(); args.len_scale = len_scale
     elif pitch_mask is not None:

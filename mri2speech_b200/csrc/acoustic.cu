@@ -27,7 +27,7 @@ int enc_se(const float* sums, float* scales, const float* w1, const float* b1, c
 int enc_se_scale(float* x, const float* scales, int n, int hw, int C, cudaStream_t st);
 int enc_gap(const float* x, const int32_t* fmap, float* feats, int n, int hw, int C, int feat_ld, cudaStream_t st);
 int lstm_recurrence(const float* gin, const float* w_hh_fwd, const float* w_hh_bwd, const int32_t* lens, float* hcat,
-                    unsigned int* counters, int batch, int frames, int max_len, int hidden, bool round_tf32,
+                    unsigned int* counters, int batch, int frames, int max_len, int hidden,
                     cudaStream_t stream);
 }  // namespace m2s
 
@@ -324,7 +324,7 @@ int rnn_head(const m2s_acoustic* m, const float* feats, int batch, int frames, c
     M2S_TRY(run_gemm(m, p, m->inproj, st));
   }
   M2S_CUDA_OK(cudaMemsetAsync(hcat, 0, static_cast<size_t>(rows) * 2 * Hd * sizeof(float), st));
-  M2S_TRY(lstm_recurrence(gin, m->w_hh[0], m->w_hh[1], lens, hcat, counters, batch, frames, max_len, Hd, false, st));
+  M2S_TRY(lstm_recurrence(gin, m->w_hh[0], m->w_hh[1], lens, hcat, counters, batch, frames, max_len, Hd, st));
   {  // head on [h_fwd | h_bwd] with the weight duplicated: y = W (h_fwd + h_bwd) + b ; rows past lens -> 0
     ConvProblem p = gemm_problem(hcat, frames, frames, 2 * Hd, batch, frames, mel_norm, frames, m->cfg.n_mels, 0, m->head);
     if (lens) { p.epi.mask_mode = M2S_MASK_LEN; p.epi.lens = lens; p.epi.len_scale = 1; }

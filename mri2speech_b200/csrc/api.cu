@@ -53,6 +53,7 @@ extern "C" int m2s_debug_set_knob(const char* name, int value) {
   else if (!std::strcmp(name, "tmap_tf32")) k.tmap_tf32 = value;
   else if (!std::strcmp(name, "max_ctas")) k.max_ctas = value;
   else if (!std::strcmp(name, "a_per_tap")) k.a_per_tap = value;
+  else if (!std::strcmp(name, "dbg")) k.dbg = value;
   else return fail(M2S_ERR_BAD_ARG, "unknown knob %s", name);
   return M2S_OK;
 }
@@ -92,4 +93,12 @@ extern "C" int m2s_debug_profile_read(float* ms, double* flops, int32_t cap, int
   int s = profile_read(ms, flops, cap, &k);
   if (n) *n = k;
   return s;
+}
+
+// Debug timeline of CTA 0 of the conv engine: buf = device uint64[tiles * 9] (null disables).
+extern "C" int m2s_debug_trace(unsigned long long* buf, int32_t tiles) {
+  EngineKnobs& k = engine_knobs();
+  k.trace = buf;
+  k.trace_tiles = tiles;
+  return M2S_OK;
 }

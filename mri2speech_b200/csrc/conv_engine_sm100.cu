@@ -18,11 +18,11 @@
 // rel_shift[j] rows.  Weights are pre-packed on the host in the exact swizzled SMEM image and
 // streamed per (channel block, tap) with 1-D bulk copies.
 //
-// Warp roles (192 threads, 1 CTA / SM, persistent over tiles):
+// Warp roles (320 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0   : TMA producer (one lane)
 //   warp 1   : TMEM allocator + MMA issuer (one lane)
-//   warps 2-5: epilogue (TMEM lane quadrant = warp_idx % 4): tcgen05.ld -> bias / residual /
-//              MRF accumulate / scale / activation / mask / TF32 rounding -> global
+//   warps 2-9: epilogue (two per TMEM lane quadrant): tcgen05.ld -> SMEM transpose -> bias / residual /
+//              MRF accumulate / scale / activation / mask -> coalesced global stores
 #include "m2s_common.cuh"
 #include <cuda.h>
 #include <cstdlib>
@@ -34,7 +34,8 @@ namespace m2s {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kKBlock = 32;     // tf32 elements per 128-byte swizzle row
 constexpr int kRowBytes = 128;
 constexpr int kTmemCols = 512;
@@ -56,6 +57,9 @@ struct EngineParams {
   int base_offset_mode;
   int a_per_tap;
   int rel_shift[M2S_MAX_TAPS];
+  unsigned long long* trace;  // debug: per-role clock64 stamps of CTA 0 (null = off)
+  int trace_tiles;
+  int dbg;  // debug: bit0 skip global stores, bit1 skip TMEM loads, bit2 skip SMEM transpose, bit3 skip MMA issue
 };
 
 // ---- PTX wrappers ------------------------------------------------------------
@@ -160,17 +164,60 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, int base_off
   return d;
 }
 
+// debug timeline: slot = role*3 + k ; layout trace[tile_iter][9]
+__device__ __forceinline__ void trace_stamp(const EngineParams& prm, int it, int slot) {
+  if (prm.trace && blockIdx.x == 0 && it < prm.trace_tiles) prm.trace[it * 9 + slot] = clock64();
+}
+
+// One lane of a converged warp (the compiler then knows the region is warp-uniform and keeps descriptors /
+// barrier addresses in uniform registers instead of emitting per-lane R2UR loops).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// Four consecutive K-steps (4 x 8 tf32 = one 128-byte swizzle row) of one (sub-tile, tap).
+__device__ __forceinline__ void mma_tf32_k4(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum0,
+                                            int ksteps) {
+  mma_tf32(tmem_d, da, db, idesc, accum0);
+  if (ksteps > 1) mma_tf32(tmem_d, da + 2, db + 2, idesc, 1u);
+  if (ksteps > 2) mma_tf32(tmem_d, da + 4, db + 4, idesc, 1u);
+  if (ksteps > 3) mma_tf32(tmem_d, da + 6, db + 6, idesc, 1u);
+}
+
+struct EpiConsts {
+  float inv_slope, pre_w, post_w, out_scale, act_slope;
+};
+
+template <bool kSilu>
+__device__ __forceinline__ float epi_elem(const EpiConsts& c, float acc, float bias, float res, float accum, bool valid) {
+  const float rt = res >= 0.f ? res : res * c.inv_slope;
+  float v = acc + bias;
+  v = fmaf(rt, c.pre_w, v);
+  v += accum;
+  v *= c.out_scale;
+  if (kSilu) v = v / (1.f + __expf(-v));
+  else v = v >= 0.f ? v : v * c.act_slope;
+  v = fmaf(rt, c.post_w, v);
+  return valid ? v : 0.f;
+}
+
 // ---- the kernel ----------------------------------------------------------------
+// 320 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue (two warps per
+// TMEM lane quadrant; a pair splits the (sub-tile, 32-column chunk) units of a tile).
+template <bool kSilu>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ EngineParams prm) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [A stages][B stages][barriers][tmem ptr]
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + prm.na * prm.a_stage_bytes;
   const uint32_t bar_base = b_base + prm.nb * prm.b_stage_bytes;
-  // barrier slots (8 B each)
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (kMaxStagesA + s); };
   auto b_full = [&](int s) { return bar_base + 8u * (2 * kMaxStagesA + s); };
@@ -178,8 +225,7 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   auto acc_full = [&](int s) { return bar_base + 8u * (2 * kMaxStagesA + 2 * kMaxStagesB + s); };
   auto acc_empty = [&](int s) { return bar_base + 8u * (2 * kMaxStagesA + 2 * kMaxStagesB + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStagesA + 2 * kMaxStagesB + 4);
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
+  const uint32_t stage_base = bar_base + 1024u;  // 8 epilogue warps x 4 KB transpose staging
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -188,7 +234,7 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < prm.na; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < prm.nb; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    for (int s = 0; s < prm.nacc; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 4); }
+    for (int s = 0; s < prm.nacc; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), kEpiWarps); }
     fence_barrier_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
   }
@@ -196,149 +242,209 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int ksteps_full = kKBlock / 8;
+  const int taps = p.taps;
+  const int cblocks = prm.cblocks;
+  const int msub = prm.msub;
+  const int n_tile = prm.n_tile;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
-        const int nt = tile % prm.n_tiles;
-        const int mt = (tile / prm.n_tiles) % prm.tiles_per_batch;
-        const int b = tile / (prm.n_tiles * prm.tiles_per_batch);
-        const int q0 = mt * prm.m_tile;
-        for (int cb = 0; cb < prm.cblocks; ++cb) {
-          if (!prm.a_per_tap) {
-            mbar_wait(a_empty(sa), pa ^ 1);
-            mbar_expect_tx(a_full(sa), prm.a_nbox * prm.a_box_rows * kRowBytes);
-            for (int bx = 0; bx < prm.a_nbox; ++bx)
-              tma_load_3d(a_base + sa * prm.a_stage_bytes + bx * prm.a_box_rows * kRowBytes, &tmap_a, a_full(sa),
-                          cb * kKBlock, q0 + prm.shift_min + bx * prm.a_box_rows, b);
-            if (++sa == prm.na) { sa = 0; pa ^= 1; }
-          }
-          for (int tap = 0; tap < p.taps; ++tap) {
-            if (prm.a_per_tap) {
-              mbar_wait(a_empty(sa), pa ^ 1);
-              mbar_expect_tx(a_full(sa), prm.a_nbox * prm.a_box_rows * kRowBytes);
-              for (int bx = 0; bx < prm.a_nbox; ++bx)
-                tma_load_3d(a_base + sa * prm.a_stage_bytes + bx * prm.a_box_rows * kRowBytes, &tmap_a, a_full(sa),
-                            cb * kKBlock, q0 + p.shift[tap] + bx * prm.a_box_rows, b);
-              if (++sa == prm.na) { sa = 0; pa ^= 1; }
-            }
-            mbar_wait(b_empty(sb), pb ^ 1);
-            mbar_expect_tx(b_full(sb), prm.b_stage_bytes);
-            const float* src = prm.wpacked +
-                               (static_cast<size_t>((nt * prm.cblocks + cb) * p.taps + tap)) * prm.n_tile * kKBlock;
-            bulk_load(b_base + sb * prm.b_stage_bytes, src, prm.b_stage_bytes, b_full(sb));
-            if (++sb == prm.nb) { sb = 0; pb ^= 1; }
-          }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int sa = 0, sb = 0, acc = 0;
-      uint32_t pa = 0, pb = 0, pacc = 0;
-      for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
-        mbar_wait(acc_empty(acc), pacc ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + acc * prm.acc_stride;
-        for (int cb = 0; cb < prm.cblocks; ++cb) {
-          int rem = p.c_in - cb * kKBlock;
-          const int ksteps = rem >= kKBlock ? ksteps_full : (rem + 7) / 8;
-          if (!prm.a_per_tap) {
-            mbar_wait(a_full(sa), pa);
-            tc_fence_after();
-          }
-          for (int tap = 0; tap < p.taps; ++tap) {
-            if (prm.a_per_tap) {
-              mbar_wait(a_full(sa), pa);
-            }
-            mbar_wait(b_full(sb), pb);
-            tc_fence_after();
-            const uint32_t a_tile = a_base + sa * prm.a_stage_bytes;
-            const uint32_t b_tile = b_base + sb * prm.b_stage_bytes;
-            const int row_shift = prm.a_per_tap ? 0 : prm.rel_shift[tap];
-            for (int sub = 0; sub < prm.msub; ++sub) {
-              const uint32_t a_sub = a_tile + (sub * 128 + row_shift) * kRowBytes;
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint64_t da = make_desc_sw128(a_sub + ks * 32, prm.base_offset_mode);
-                const uint64_t db = make_desc_sw128(b_tile + ks * 32, 0);
-                const uint32_t accum = (cb | tap | ks) ? 1u : 0u;
-                mma_tf32(tmem_acc + sub * prm.n_tile, da, db, prm.idesc, accum);
-              }
-            }
-            tc_commit(b_empty(sb));
-            if (++sb == prm.nb) { sb = 0; pb ^= 1; }
-            if (prm.a_per_tap) {
-              tc_commit(a_empty(sa));
-              if (++sa == prm.na) { sa = 0; pa ^= 1; }
-            }
-          }
-          if (!prm.a_per_tap) {
-            tc_commit(a_empty(sa));
-            if (++sa == prm.na) { sa = 0; pa ^= 1; }
-          }
-        }
-        tc_commit(acc_full(acc));
-        if (++acc == prm.nacc) { acc = 0; pacc ^= 1; }
-      }
-    }
-    __syncwarp();
-  } else {
-    // ===================== epilogue warps =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    const Epilogue& e = p.epi;
-    int acc = 0;
-    uint32_t pacc = 0;
-    for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
+    // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    int it = 0;
+    const uint32_t a_bytes = prm.a_nbox * prm.a_box_rows * kRowBytes;
+    for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x, ++it) {
       const int nt = tile % prm.n_tiles;
       const int mt = (tile / prm.n_tiles) % prm.tiles_per_batch;
       const int b = tile / (prm.n_tiles * prm.tiles_per_batch);
       const int q0 = mt * prm.m_tile;
-      const int n0 = nt * prm.n_tile;
-      mbar_wait(acc_full(acc), pacc);
-      tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + acc * prm.acc_stride + (static_cast<uint32_t>(quad * 32) << 16);
-      for (int sub = 0; sub < prm.msub; ++sub) {
-        const int q = q0 + sub * 128 + quad * 32 + lane;
-        const bool row_ok = q < p.l_out;
-        const int drow = q + p.d_row_offset;
-        const bool valid = row_ok && epi_row_valid(e, b, row_ok ? drow : 0);
-        const size_t row_index = static_cast<size_t>(b) * p.d_batch_rows + drow;
-        float* drow_ptr = p.d + row_index * p.d_ld;
-        const float* rrow_ptr = e.res ? e.res + row_index * e.res_ld : nullptr;
-        const float* srow_ptr = e.accum ? e.accum + row_index * e.accum_ld : nullptr;
-        for (int c0 = 0; c0 < prm.n_tile; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(tmem_acc + sub * prm.n_tile + c0, r);
-          tmem_ld_wait();
-          if (row_ok) {
-#pragma unroll
-            for (int v4 = 0; v4 < 4; ++v4) {
-              const int n = n0 + c0 + v4 * 4;
-              if (n < p.n) {
-                float4 bias4 = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + n)) : make_float4(0, 0, 0, 0);
-                float4 res4 = rrow_ptr ? *reinterpret_cast<const float4*>(rrow_ptr + n) : make_float4(0, 0, 0, 0);
-                float4 acc4 = srow_ptr ? *reinterpret_cast<const float4*>(srow_ptr + n) : make_float4(0, 0, 0, 0);
-                float4 o;
-                o.x = epi_apply(e, __uint_as_float(r[v4 * 4 + 0]), bias4.x, res4.x, acc4.x, valid);
-                o.y = epi_apply(e, __uint_as_float(r[v4 * 4 + 1]), bias4.y, res4.y, acc4.y, valid);
-                o.z = epi_apply(e, __uint_as_float(r[v4 * 4 + 2]), bias4.z, res4.z, acc4.z, valid);
-                o.w = epi_apply(e, __uint_as_float(r[v4 * 4 + 3]), bias4.w, res4.w, acc4.w, valid);
-                *reinterpret_cast<float4*>(drow_ptr + n) = o;
-              }
+      if (lane == 0) trace_stamp(prm, it, 0);
+      for (int cb = 0; cb < cblocks; ++cb) {
+        if (!prm.a_per_tap) {
+          mbar_wait(a_empty(sa), pa ^ 1);
+          if (cb == 0 && lane == 0) trace_stamp(prm, it, 1);
+          if (elect_one()) {
+            mbar_expect_tx(a_full(sa), a_bytes);
+            for (int bx = 0; bx < prm.a_nbox; ++bx)
+              tma_load_3d(a_base + sa * prm.a_stage_bytes + bx * prm.a_box_rows * kRowBytes, &tmap_a, a_full(sa),
+                          cb * kKBlock, q0 + prm.shift_min + bx * prm.a_box_rows, b);
+          }
+          __syncwarp();
+          if (++sa == prm.na) { sa = 0; pa ^= 1; }
+        }
+        for (int tap = 0; tap < taps; ++tap) {
+          if (prm.a_per_tap) {
+            mbar_wait(a_empty(sa), pa ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(a_full(sa), a_bytes);
+              for (int bx = 0; bx < prm.a_nbox; ++bx)
+                tma_load_3d(a_base + sa * prm.a_stage_bytes + bx * prm.a_box_rows * kRowBytes, &tmap_a, a_full(sa),
+                            cb * kKBlock, q0 + p.shift[tap] + bx * prm.a_box_rows, b);
             }
+            __syncwarp();
+            if (++sa == prm.na) { sa = 0; pa ^= 1; }
+          }
+          mbar_wait(b_empty(sb), pb ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(b_full(sb), prm.b_stage_bytes);
+            const float* src =
+                prm.wpacked + (static_cast<size_t>((nt * cblocks + cb) * taps + tap)) * n_tile * kKBlock;
+            bulk_load(b_base + sb * prm.b_stage_bytes, src, prm.b_stage_bytes, b_full(sb));
+          }
+          __syncwarp();
+          if (++sb == prm.nb) { sb = 0; pb ^= 1; }
+        }
+      }
+      if (lane == 0) trace_stamp(prm, it, 2);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+    int sa = 0, sb = 0, acc = 0;
+    uint32_t pa = 0, pb = 0, pacc = 0;
+    const uint64_t desc_hi = make_desc_sw128(0, 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x, ++it) {
+      if (lane == 0) trace_stamp(prm, it, 3);
+      mbar_wait(acc_empty(acc), pacc ^ 1);
+      tc_fence_after();
+      if (lane == 0) trace_stamp(prm, it, 4);
+      const uint32_t tmem_acc = tmem_base + acc * prm.acc_stride;
+      for (int cb = 0; cb < cblocks; ++cb) {
+        const int rem = p.c_in - cb * kKBlock;
+        const int ksteps = rem >= kKBlock ? 4 : (rem + 7) / 8;
+        if (!prm.a_per_tap) {
+          mbar_wait(a_full(sa), pa);
+        }
+        for (int tap = 0; tap < taps; ++tap) {
+          if (prm.a_per_tap) mbar_wait(a_full(sa), pa);
+          mbar_wait(b_full(sb), pb);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_tile = a_base + sa * prm.a_stage_bytes;
+            const uint32_t b_tile = b_base + sb * prm.b_stage_bytes;
+            const int row_shift = prm.a_per_tap ? 0 : prm.rel_shift[tap];
+            const uint64_t db = desc_hi | ((b_tile & 0x3FFFF) >> 4);
+            const uint32_t first = (cb | tap) ? 1u : 0u;
+            if (!(prm.dbg & 8)) {
+              const uint64_t da0 = desc_hi | (((a_tile + row_shift * kRowBytes) & 0x3FFFF) >> 4);
+              mma_tf32_k4(tmem_acc, da0, db, prm.idesc, first, ksteps);
+              if (msub > 1) mma_tf32_k4(tmem_acc + n_tile, da0 + ((128 * kRowBytes) >> 4), db, prm.idesc, first, ksteps);
+            }
+            tc_commit(b_empty(sb));
+            if (prm.a_per_tap || tap == taps - 1) tc_commit(a_empty(sa));
+            if (cb == cblocks - 1 && tap == taps - 1) tc_commit(acc_full(acc));
+          }
+          __syncwarp();
+          if (++sb == prm.nb) { sb = 0; pb ^= 1; }
+          if (prm.a_per_tap) {
+            if (++sa == prm.na) { sa = 0; pa ^= 1; }
           }
         }
+        if (!prm.a_per_tap) {
+          if (++sa == prm.na) { sa = 0; pa ^= 1; }
+        }
+      }
+      if (lane == 0) trace_stamp(prm, it, 5);
+      if (++acc == prm.nacc) { acc = 0; pacc ^= 1; }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    // TMEM -> registers (row per thread) -> SMEM transpose (XOR-swizzled, conflict-free) -> coalesced global
+    // traffic: 8 lanes cover one 128-byte row segment, a warp instruction covers 4 rows.
+    const int ew = warp - 2;      // 0..7
+    const int quad = warp & 3;    // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;     // which of the two warps of the quadrant
+    const Epilogue& e = p.epi;
+    const uint32_t stage = stage_base + ew * 4096;  // 32 rows x 128 B
+    const int rr0 = lane >> 3, cc = lane & 7;
+    const bool has_res = e.res != nullptr, has_acc = e.accum != nullptr;
+    EpiConsts ec;
+    ec.inv_slope = e.res_inv_slope;
+    ec.pre_w = (has_res && !e.res_after_act) ? 1.f : 0.f;
+    ec.post_w = (has_res && e.res_after_act) ? 1.f : 0.f;
+    ec.out_scale = e.out_scale;
+    ec.act_slope = e.act == M2S_ACT_LRELU ? e.act_slope : 1.f;
+    const int mask_mode = e.mask_mode;
+    const int nchunks = (n_tile + 31) >> 5;
+    const int units = msub * nchunks;
+    int acc = 0;
+    uint32_t pacc = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x, ++it) {
+      const int nt = tile % prm.n_tiles;
+      const int mt = (tile / prm.n_tiles) % prm.tiles_per_batch;
+      const int b = tile / (prm.n_tiles * prm.tiles_per_batch);
+      const int q0 = mt * prm.m_tile;
+      const int n0 = nt * n_tile;
+      int len_rows = 0x7fffffff;
+      if (mask_mode == M2S_MASK_LEN) len_rows = __ldg(e.lens + b) * e.len_scale;
+      const size_t d_base = static_cast<size_t>(b) * p.d_batch_rows + p.d_row_offset;
+      if (ew == 0 && lane == 0) trace_stamp(prm, it, 6);
+      mbar_wait(acc_full(acc), pacc);
+      tc_fence_after();
+      if (ew == 0 && lane == 0) trace_stamp(prm, it, 7);
+      const uint32_t tmem_acc = tmem_base + acc * prm.acc_stride + (static_cast<uint32_t>(quad * 32) << 16);
+      for (int u = half; u < units; u += 2) {
+        const int sub = u / nchunks;
+        const int c0 = (u - sub * nchunks) << 5;
+        const int qw = q0 + sub * 128 + quad * 32;  // first row of this warp's 32-row slab
+        uint32_t r[32];
+        tmem_ld16(tmem_acc + sub * n_tile + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+        if (c0 + 16 < n_tile) tmem_ld16(tmem_acc + sub * n_tile + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+        // overlap the TMEM read with the residual / accumulate / bias loads of this unit (the output may alias
+        // them in place, so every load is issued before the first store)
+        const int n = n0 + c0 + cc * 4;
+        const bool col_ok = (c0 + cc * 4 < n_tile) && n < p.n;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok && e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+        float4 res4[8], acc4[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int q = qw + i * 4 + rr0;
+          res4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (col_ok && q < p.l_out) {
+            const size_t row_index = d_base + q;
+            if (has_res) res4[i] = *reinterpret_cast<const float4*>(e.res + row_index * e.res_ld + n);
+            if (has_acc) acc4[i] = *reinterpret_cast<const float4*>(e.accum + row_index * e.accum_ld + n);
+          }
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + lane * 128 + ((j ^ (lane & 7)) << 4)),
+                       "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                       : "memory");
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + rr0;
+          const int q = qw + rr;
+          if (col_ok && q < p.l_out) {
+            float4 a4;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w)
+                         : "r"(stage + rr * 128 + ((cc ^ (rr & 7)) << 4)));
+            const int drow = q + p.d_row_offset;
+            bool valid = true;
+            if (mask_mode == M2S_MASK_LEN) valid = drow < len_rows;
+            else if (mask_mode == M2S_MASK_PITCH) valid = epi_row_valid(e, b, drow);
+            float4 o;
+            o.x = epi_elem<kSilu>(ec, a4.x, bias4.x, res4[i].x, acc4[i].x, valid);
+            o.y = epi_elem<kSilu>(ec, a4.y, bias4.y, res4[i].y, acc4[i].y, valid);
+            o.z = epi_elem<kSilu>(ec, a4.z, bias4.z, res4[i].z, acc4[i].z, valid);
+            o.w = epi_elem<kSilu>(ec, a4.w, bias4.w, res4[i].w, acc4[i].w, valid);
+            if (!(prm.dbg & 1)) *reinterpret_cast<float4*>(p.d + (d_base + q) * p.d_ld + n) = o;
+          }
+        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
+      if (ew == 0 && lane == 0) trace_stamp(prm, it, 8);
       if (lane == 0) mbar_arrive(acc_empty(acc));
       if (++acc == prm.nacc) { acc = 0; pacc ^= 1; }
     }
@@ -440,7 +546,7 @@ int sm_count() {
 
 void choose_n_tiling(int n, int* n_tile, int* n_tiles) {
   // smallest number of tiles with n_tile a multiple of 16 and <= 256; prefer an even split.
-  int tiles = (n + 255) / 256;
+  int tiles = n >= 256 ? (n + 127) / 128 : 1;
   int nt = (((n + tiles - 1) / tiles) + 15) / 16 * 16;
   *n_tile = nt;
   *n_tiles = tiles;
@@ -512,6 +618,9 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
   prm.n_tiles = w.n_tiles;
   prm.cblocks = w.cblocks;
   prm.base_offset_mode = knobs.base_offset_mode;
+  prm.dbg = knobs.dbg;
+  prm.trace = knobs.trace;
+  prm.trace_tiles = knobs.trace_tiles;
   prm.a_per_tap = knobs.a_per_tap;
   int smin = p.shift[0], smax = p.shift[0];
   for (int j = 1; j < p.taps; ++j) { smin = p.shift[j] < smin ? p.shift[j] : smin; smax = p.shift[j] > smax ? p.shift[j] : smax; }
@@ -523,7 +632,9 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
   int msub = knobs.msub;
   if (msub != 1 && msub != 2) {
     const long long tiles1 = static_cast<long long>(p.batch) * ((p.l_out + 127) / 128) * w.n_tiles;
-    msub = (tiles1 >= 4LL * sm_count() && 2 * w.n_tile <= kTmemCols) ? 2 : 1;
+    // two M sub-tiles halve the weight traffic per output row; keep TWO accumulator buffers so that the
+    // epilogue of tile i overlaps the MMAs of tile i+1
+    msub = (tiles1 >= 2LL * sm_count() && 4 * w.n_tile <= kTmemCols) ? 2 : 1;
   }
   if (msub * w.n_tile > kTmemCols) msub = 1;
   prm.msub = msub;
@@ -541,7 +652,7 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
   prm.b_stage_bytes = static_cast<uint32_t>(w.n_tile * kRowBytes);
   const uint32_t b_stage_alloc = (prm.b_stage_bytes + 1023u) & ~1023u;
   // stage counts inside the budget: at least 2 A + 2 B
-  const uint32_t bar_bytes = 1024;
+  const uint32_t bar_bytes = 1024 + kEpiWarps * 4096;  // barriers + epilogue staging
   int na = 2, nb = 2;
   auto total = [&](int a, int b) { return a * prm.a_stage_bytes + b * b_stage_alloc + bar_bytes + 1024u; };
   if (total(na, nb) > kSmemBudget + 24 * 1024)
@@ -588,7 +699,8 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
 
   static bool attr_set = false;
   if (!attr_set) {
-    M2S_CUDA_OK(cudaFuncSetAttribute(conv_engine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    M2S_CUDA_OK(cudaFuncSetAttribute(conv_engine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    M2S_CUDA_OK(cudaFuncSetAttribute(conv_engine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   int grid = knobs.max_ctas > 0 ? knobs.max_ctas : sm_count();
@@ -602,7 +714,8 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
     }
     M2S_CUDA_OK(cudaEventRecord(pr.ev[2 * pr.count], stream));
   }
-  conv_engine_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap, prm);
+  if (p.epi.act == M2S_ACT_SILU) conv_engine_kernel<true><<<grid, kThreads, smem_bytes, stream>>>(tmap, prm);
+  else conv_engine_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(tmap, prm);
   M2S_CUDA_OK(cudaGetLastError());
   if (pr.on) {
     M2S_CUDA_OK(cudaEventRecord(pr.ev[2 * pr.count + 1], stream));

@@ -340,7 +340,6 @@ extern "C" int m2s_generator_forward(m2s_generator* g, const float* mel, int32_t
   float* S = T + bufs.q_floats;
   const m2s_generator_config& cfg = g->cfg;
   const int mask = lengths ? M2S_MASK_LEN : M2S_MASK_NONE;
-  const int rnd = 0;  // the A tensor map is TFLOAT32: TMA rounds on load, stored activations stay fp32
 
   // (B, mels, T) -> channels-last, zero past lengths (conv_pre look-ahead must see zeros)
   M2S_TRY(bct_to_btc(mel, M0, batch, cfg.num_mels, frames, lengths, false, st));
@@ -349,7 +348,7 @@ extern "C" int m2s_generator_forward(m2s_generator* g, const float* mel, int32_t
   int ch = cfg.upsample_initial_channel;
   {  // conv_pre -> P = mask(lrelu(conv+b, .1))  (only consumer: ups[0])
     ConvProblem p = base_problem(M0, L, cfg.num_mels, batch, L, P, ch, L, L, g->pre);
-    p.epi.act = M2S_ACT_LRELU; p.epi.act_slope = 0.1f; p.epi.round_tf32 = rnd;
+    p.epi.act = M2S_ACT_LRELU; p.epi.act_slope = 0.1f;
     p.epi.mask_mode = mask; p.epi.lens = lengths; p.epi.len_scale = 1;
     M2S_TRY(run_conv(g, p, g->pre, st));
   }
@@ -359,7 +358,7 @@ extern "C" int m2s_generator_forward(m2s_generator* g, const float* mel, int32_t
     const int cout = g->ups_cout[i];
     {  // ups: rows = L, N = u*cout; D viewed as (B, L, u*cout) == (B, L*u, cout)
       ConvProblem p = base_problem(P, L, ch, batch, L, Q, u * cout, L, L, g->ups[i]);
-      p.epi.act = M2S_ACT_LRELU; p.epi.act_slope = 0.1f; p.epi.round_tf32 = rnd;
+      p.epi.act = M2S_ACT_LRELU; p.epi.act_slope = 0.1f;
       M2S_TRY(run_conv(g, p, g->ups[i], st));
     }
     L *= u; scale *= u; ch = cout;
@@ -370,12 +369,12 @@ extern "C" int m2s_generator_forward(m2s_generator* g, const float* mel, int32_t
         const Layer& l1 = g->c1[(i * cfg.num_kernels + j) * 3 + d];
         const Layer& l2 = g->c2[(i * cfg.num_kernels + j) * 3 + d];
         ConvProblem p1 = base_problem(state, L, ch, batch, L, T, ch, L, L, l1);
-        p1.epi.act = M2S_ACT_LRELU; p1.epi.act_slope = 0.1f; p1.epi.round_tf32 = rnd;
+        p1.epi.act = M2S_ACT_LRELU; p1.epi.act_slope = 0.1f;
         M2S_TRY(run_conv(g, p1, l1, st));
         ConvProblem p2 = base_problem(T, L, ch, batch, L, R, ch, L, L, l2);
         p2.epi.res = state; p2.epi.res_ld = ch; p2.epi.res_inv_slope = 10.f;  // 1 / LRELU_SLOPE
         if (d < 2) {
-          p2.epi.act = M2S_ACT_LRELU; p2.epi.act_slope = 0.1f; p2.epi.round_tf32 = rnd;
+          p2.epi.act = M2S_ACT_LRELU; p2.epi.act_slope = 0.1f;
         } else if (j + 1 < cfg.num_kernels) {
           p2.d = S;
           if (j > 0) { p2.epi.accum = S; p2.epi.accum_ld = ch; }
@@ -384,7 +383,6 @@ extern "C" int m2s_generator_forward(m2s_generator* g, const float* mel, int32_t
           if (j > 0) { p2.epi.accum = S; p2.epi.accum_ld = ch; }
           p2.epi.out_scale = 1.f / static_cast<float>(cfg.num_kernels);
           p2.epi.act = M2S_ACT_LRELU; p2.epi.act_slope = last_stage ? 0.01f : 0.1f;
-          p2.epi.round_tf32 = last_stage ? 0 : rnd;
           p2.epi.mask_mode = mask; p2.epi.lens = lengths; p2.epi.len_scale = scale;
         }
         M2S_TRY(run_conv(g, p2, l2, st));

@@ -36,7 +36,6 @@ struct LstmParams {
   float* hcat;           // (B, T, 2H): forward h in [0,H), backward h in [H,2H)
   unsigned int* counters;  // [2] arrive counters, zeroed before launch
   int batch, frames, max_len;
-  int round_tf32;
 };
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + expf(-x)); }
@@ -160,7 +159,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_recurrence_kernel(LstmParams
 
 // hcat must be zero-initialised by the caller where rows past lens[b] are expected to read as zero.
 int lstm_recurrence(const float* gin, const float* w_hh_fwd, const float* w_hh_bwd, const int32_t* lens, float* hcat,
-                    unsigned int* counters, int batch, int frames, int max_len, int hidden, bool round_tf32,
+                    unsigned int* counters, int batch, int frames, int max_len, int hidden,
                     cudaStream_t stream) {
   if (hidden != kHidden) return fail(M2S_ERR_UNSUPPORTED, "LSTM recurrence is specialised for hidden=640 (got %d)", hidden);
   if (batch <= 0 || max_len <= 0) return M2S_OK;
@@ -169,7 +168,6 @@ int lstm_recurrence(const float* gin, const float* w_hh_fwd, const float* w_hh_b
   LstmParams prm{};
   prm.gin = gin; prm.w_hh[0] = w_hh_fwd; prm.w_hh[1] = w_hh_bwd; prm.lens = lens; prm.hcat = hcat;
   prm.counters = counters; prm.batch = batch; prm.frames = frames; prm.max_len = max_len;
-  prm.round_tf32 = round_tf32 ? 1 : 0;
   static bool attr = false;
   if (!attr) {
     M2S_CUDA_OK(cudaFuncSetAttribute(lstm_recurrence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));

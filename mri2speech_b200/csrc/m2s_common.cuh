@@ -41,7 +41,6 @@ struct Epilogue {
   float act_slope;
   int act;
   int res_after_act;
-  int round_tf32;
   int mask_mode;
   int len_scale;
   int pitch, i_lo, i_hi, j_lo, j_hi;
@@ -69,7 +68,7 @@ inline ConvProblem problem_from_args(const m2s_conv_args& a) {
   p.n = a.n; p.d = a.d; p.d_batch_rows = a.d_batch_rows; p.d_ld = a.d_ld; p.d_row_offset = a.d_row_offset;
   p.epi.bias = a.bias; p.epi.res = a.res; p.epi.res_ld = a.res_ld; p.epi.res_inv_slope = a.res_inv_slope; p.epi.res_after_act = a.res_after_act;
   p.epi.accum = a.accum; p.epi.accum_ld = a.accum_ld; p.epi.out_scale = a.out_scale; p.epi.act = a.act;
-  p.epi.act_slope = a.act_slope; p.epi.round_tf32 = a.round_tf32; p.epi.mask_mode = a.mask_mode;
+  p.epi.act_slope = a.act_slope; p.epi.mask_mode = a.mask_mode;
   p.epi.lens = a.lens; p.epi.len_scale = a.len_scale; p.epi.pitch = a.pitch; p.epi.i_lo = a.i_lo;
   p.epi.i_hi = a.i_hi; p.epi.j_lo = a.j_lo; p.epi.j_hi = a.j_hi;
   return p;
@@ -107,7 +106,6 @@ __device__ __forceinline__ float epi_apply(const Epilogue& e, float acc, float b
   else if (e.act == M2S_ACT_SILU) v = v / (1.f + __expf(-v));
   if (e.res_after_act) v += r;
   if (!valid) v = 0.f;
-  if (e.round_tf32) v = round_tf32(v);
   return v;
 }
 #endif  // __CUDACC__
@@ -138,6 +136,9 @@ struct EngineKnobs {
   int tmap_tf32 = 1;         // encode the A tensor map as TFLOAT32 (TMA rounds fp32 -> tf32 on load)
   int max_ctas = 0;          // 0 = #SMs
   int a_per_tap = 0;         // 1: reload the A tile per tap (no row-shifted descriptors; fallback)
+  unsigned long long* trace = nullptr;  // debug timeline buffer (device), trace_tiles x 9 stamps of CTA 0
+  int trace_tiles = 0;
+  int dbg = 0;
 };
 EngineKnobs& engine_knobs();
 
