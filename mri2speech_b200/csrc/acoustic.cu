@@ -151,7 +151,7 @@ struct m2s_acoustic {
   std::vector<Block> blocks;
   GemmLayer inproj, head;
   float* w_hh[2] = {nullptr, nullptr};
-  int chunk = 64;  // frames per encoder pass
+  int chunk = 256;  // frames per encoder pass (M2S_ENCODER_CHUNK)
   // per-frame buffer sizes (floats)
   size_t x_floats = 0, e_floats = 0, e2_floats = 0, col_floats = 0;
   int max_mid = 0;
@@ -428,8 +428,11 @@ extern "C" int m2s_acoustic_create(const m2s_acoustic_config* cfg, const m2s_ten
               (st = need(tm, p + ".se.conv_expand.bias", b.mid, &b2)) != M2S_OK)
             return bail(st);
           auto up = [&](const HT* t, float** d) { return upload(std::vector<float>(t->data, t->data + t->numel()), d); };
+          std::vector<float> w2t(static_cast<size_t>(b.rd) * b.mid);  // (mid, rd) -> (rd, mid): coalesced over channels
+          for (int c = 0; c < b.mid; ++c)
+            for (int j = 0; j < b.rd; ++j) w2t[static_cast<size_t>(j) * b.mid + c] = w2->data[static_cast<size_t>(c) * b.rd + j];
           if ((st = up(w1, &b.se_w1)) != M2S_OK || (st = up(b1, &b.se_b1)) != M2S_OK ||
-              (st = up(w2, &b.se_w2)) != M2S_OK || (st = up(b2, &b.se_b2)) != M2S_OK)
+              (st = upload(w2t, &b.se_w2)) != M2S_OK || (st = up(b2, &b.se_b2)) != M2S_OK)
             return bail(st);
         }
         const size_t rows_in = padded ? padded_rows(h, w) : static_cast<size_t>(h) * w;

@@ -57,6 +57,8 @@ struct EngineParams {
   int base_offset_mode;
   int a_per_tap;
   int rel_shift[M2S_MAX_TAPS];
+  int tg;               // taps per weight stage
+  uint32_t b_tap_bytes; // bytes of one tap's weight block (n_tile x 128)
   unsigned long long* trace;  // debug: per-role clock64 stamps of CTA 0 (null = off)
   int trace_tiles;
   int dbg;  // debug: bit0 skip global stores, bit1 skip TMEM loads, bit2 skip SMEM transpose, bit3 skip MMA issue
@@ -194,23 +196,32 @@ struct EpiConsts {
   float inv_slope, pre_w, post_w, out_scale, act_slope;
 };
 
-template <bool kSilu>
-__device__ __forceinline__ float epi_elem(const EpiConsts& c, float acc, float bias, float res, float accum, bool valid) {
-  const float rt = res >= 0.f ? res : res * c.inv_slope;
+// Epilogue programs (compile-time): the common cases drop every unused instruction -- with 256-column-wide tiles the
+// epilogue is ALU-issue-bound (32K outputs per tile on 8 warps), so instructions per output are what matters.
+enum { EPI_FULL = 0, EPI_FULL_SILU = 1, EPI_BIAS = 2, EPI_LRELU = 3, EPI_SILU = 4, EPI_RES = 5 };
+
+__device__ __forceinline__ float fast_silu(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+
+template <int kEpi>
+__device__ __forceinline__ float epi_elem(const EpiConsts& c, float acc, float bias, float res, float accum) {
   float v = acc + bias;
+  if (kEpi == EPI_BIAS) return v;
+  if (kEpi == EPI_LRELU) return v >= 0.f ? v : v * c.act_slope;
+  if (kEpi == EPI_SILU) return fast_silu(v);
+  if (kEpi == EPI_RES) return v + res;
+  const float rt = res >= 0.f ? res : res * c.inv_slope;
   v = fmaf(rt, c.pre_w, v);
   v += accum;
   v *= c.out_scale;
-  if (kSilu) v = v / (1.f + __expf(-v));
+  if (kEpi == EPI_FULL_SILU) v = fast_silu(v);
   else v = v >= 0.f ? v : v * c.act_slope;
-  v = fmaf(rt, c.post_w, v);
-  return valid ? v : 0.f;
+  return fmaf(rt, c.post_w, v);
 }
 
 // ---- the kernel ----------------------------------------------------------------
 // 320 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue (two warps per
 // TMEM lane quadrant; a pair splits the (sub-tile, 32-column chunk) units of a tile).
-template <bool kSilu>
+template <int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ EngineParams prm) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -275,24 +286,26 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           __syncwarp();
           if (++sa == prm.na) { sa = 0; pa ^= 1; }
         }
-        for (int tap = 0; tap < taps; ++tap) {
+        for (int tap0 = 0; tap0 < taps; tap0 += prm.tg) {
+          const int cnt = min(prm.tg, taps - tap0);
           if (prm.a_per_tap) {
             mbar_wait(a_empty(sa), pa ^ 1);
             if (elect_one()) {
               mbar_expect_tx(a_full(sa), a_bytes);
               for (int bx = 0; bx < prm.a_nbox; ++bx)
                 tma_load_3d(a_base + sa * prm.a_stage_bytes + bx * prm.a_box_rows * kRowBytes, &tmap_a, a_full(sa),
-                            cb * kKBlock, q0 + p.shift[tap] + bx * prm.a_box_rows, b);
+                            cb * kKBlock, q0 + p.shift[tap0] + bx * prm.a_box_rows, b);
             }
             __syncwarp();
             if (++sa == prm.na) { sa = 0; pa ^= 1; }
           }
           mbar_wait(b_empty(sb), pb ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(b_full(sb), prm.b_stage_bytes);
+            const uint32_t bytes = cnt * prm.b_tap_bytes;
+            mbar_expect_tx(b_full(sb), bytes);
             const float* src =
-                prm.wpacked + (static_cast<size_t>((nt * cblocks + cb) * taps + tap)) * n_tile * kKBlock;
-            bulk_load(b_base + sb * prm.b_stage_bytes, src, prm.b_stage_bytes, b_full(sb));
+                prm.wpacked + (static_cast<size_t>((nt * cblocks + cb) * taps + tap0)) * n_tile * kKBlock;
+            bulk_load(b_base + sb * prm.b_stage_bytes, src, bytes, b_full(sb));
           }
           __syncwarp();
           if (++sb == prm.nb) { sb = 0; pb ^= 1; }
@@ -318,24 +331,28 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         if (!prm.a_per_tap) {
           mbar_wait(a_full(sa), pa);
         }
-        for (int tap = 0; tap < taps; ++tap) {
+        for (int tap0 = 0; tap0 < taps; tap0 += prm.tg) {
+          const int cnt = min(prm.tg, taps - tap0);
           if (prm.a_per_tap) mbar_wait(a_full(sa), pa);
           mbar_wait(b_full(sb), pb);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t a_tile = a_base + sa * prm.a_stage_bytes;
             const uint32_t b_tile = b_base + sb * prm.b_stage_bytes;
-            const int row_shift = prm.a_per_tap ? 0 : prm.rel_shift[tap];
-            const uint64_t db = desc_hi | ((b_tile & 0x3FFFF) >> 4);
-            const uint32_t first = (cb | tap) ? 1u : 0u;
             if (!(prm.dbg & 8)) {
-              const uint64_t da0 = desc_hi | (((a_tile + row_shift * kRowBytes) & 0x3FFFF) >> 4);
-              mma_tf32_k4(tmem_acc, da0, db, prm.idesc, first, ksteps);
-              if (msub > 1) mma_tf32_k4(tmem_acc + n_tile, da0 + ((128 * kRowBytes) >> 4), db, prm.idesc, first, ksteps);
+              for (int t = 0; t < cnt; ++t) {
+                const int row_shift = prm.a_per_tap ? 0 : prm.rel_shift[tap0 + t];
+                const uint64_t db = desc_hi | (((b_tile + t * prm.b_tap_bytes) & 0x3FFFF) >> 4);
+                const uint32_t first = (cb | tap0 | t) ? 1u : 0u;
+                const uint64_t da0 = desc_hi | (((a_tile + row_shift * kRowBytes) & 0x3FFFF) >> 4);
+                mma_tf32_k4(tmem_acc, da0, db, prm.idesc, first, ksteps);
+                if (msub > 1) mma_tf32_k4(tmem_acc + n_tile, da0 + ((128 * kRowBytes) >> 4), db, prm.idesc, first, ksteps);
+              }
             }
+            const bool last_group = tap0 + cnt >= taps;
             tc_commit(b_empty(sb));
-            if (prm.a_per_tap || tap == taps - 1) tc_commit(a_empty(sa));
-            if (cb == cblocks - 1 && tap == taps - 1) tc_commit(acc_full(acc));
+            if (prm.a_per_tap || last_group) tc_commit(a_empty(sa));
+            if (cb == cblocks - 1 && last_group) tc_commit(acc_full(acc));
           }
           __syncwarp();
           if (++sb == prm.nb) { sb = 0; pb ^= 1; }
@@ -408,8 +425,12 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (col_ok && q < p.l_out) {
             const size_t row_index = d_base + q;
-            if (has_res) res4[i] = *reinterpret_cast<const float4*>(e.res + row_index * e.res_ld + n);
-            if (has_acc) acc4[i] = *reinterpret_cast<const float4*>(e.accum + row_index * e.accum_ld + n);
+            if (kEpi == EPI_FULL || kEpi == EPI_FULL_SILU || kEpi == EPI_RES) {
+              if (has_res) res4[i] = *reinterpret_cast<const float4*>(e.res + row_index * e.res_ld + n);
+            }
+            if (kEpi == EPI_FULL || kEpi == EPI_FULL_SILU) {
+              if (has_acc) acc4[i] = *reinterpret_cast<const float4*>(e.accum + row_index * e.accum_ld + n);
+            }
           }
         }
         tmem_ld_wait();
@@ -432,11 +453,13 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             bool valid = true;
             if (mask_mode == M2S_MASK_LEN) valid = drow < len_rows;
             else if (mask_mode == M2S_MASK_PITCH) valid = epi_row_valid(e, b, drow);
-            float4 o;
-            o.x = epi_elem<kSilu>(ec, a4.x, bias4.x, res4[i].x, acc4[i].x, valid);
-            o.y = epi_elem<kSilu>(ec, a4.y, bias4.y, res4[i].y, acc4[i].y, valid);
-            o.z = epi_elem<kSilu>(ec, a4.z, bias4.z, res4[i].z, acc4[i].z, valid);
-            o.w = epi_elem<kSilu>(ec, a4.w, bias4.w, res4[i].w, acc4[i].w, valid);
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+              o.x = epi_elem<kEpi>(ec, a4.x, bias4.x, res4[i].x, acc4[i].x);
+              o.y = epi_elem<kEpi>(ec, a4.y, bias4.y, res4[i].y, acc4[i].y);
+              o.z = epi_elem<kEpi>(ec, a4.z, bias4.z, res4[i].z, acc4[i].z);
+              o.w = epi_elem<kEpi>(ec, a4.w, bias4.w, res4[i].w, acc4[i].w);
+            }
             if (!(prm.dbg & 1)) *reinterpret_cast<float4*>(p.d + (d_base + q) * p.d_ld + n) = o;
           }
         }
@@ -491,6 +514,7 @@ EngineKnobs& engine_knobs() {
     x.tmap_tf32 = env_int("M2S_ENGINE_TMAP_TF32", 1);
     x.max_ctas = env_int("M2S_ENGINE_MAX_CTAS", 0);
     x.a_per_tap = env_int("M2S_ENGINE_A_PER_TAP", 0);
+    x.n_tile_max = env_int("M2S_ENGINE_NTILE_MAX", 128);
     return x;
   }();
   return k;
@@ -546,7 +570,8 @@ int sm_count() {
 
 void choose_n_tiling(int n, int* n_tile, int* n_tiles) {
   // smallest number of tiles with n_tile a multiple of 16 and <= 256; prefer an even split.
-  int tiles = n >= 256 ? (n + 127) / 128 : 1;
+  const int cap = engine_knobs().n_tile_max;
+  int tiles = n > cap ? (n + cap - 1) / cap : 1;
   int nt = (((n + tiles - 1) / tiles) + 15) / 16 * 16;
   *n_tile = nt;
   *n_tiles = tiles;
@@ -649,7 +674,14 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
   prm.a_box_rows = (((a_rows_needed + prm.a_nbox - 1) / prm.a_nbox) + 7) / 8 * 8;
   prm.a_stage_bytes = static_cast<uint32_t>(prm.a_nbox * prm.a_box_rows * kRowBytes);
   prm.a_stage_bytes = (prm.a_stage_bytes + 1023u) & ~1023u;
-  prm.b_stage_bytes = static_cast<uint32_t>(w.n_tile * kRowBytes);
+  prm.b_tap_bytes = static_cast<uint32_t>(w.n_tile * kRowBytes);
+  // several taps share one weight stage when the per-tap block is small (amortises barrier round trips)
+  int tg = static_cast<int>(32768u / prm.b_tap_bytes);
+  if (tg < 1) tg = 1;
+  if (tg > p.taps) tg = p.taps;
+  if (knobs.a_per_tap) tg = 1;
+  prm.tg = tg;
+  prm.b_stage_bytes = static_cast<uint32_t>(tg) * prm.b_tap_bytes;
   const uint32_t b_stage_alloc = (prm.b_stage_bytes + 1023u) & ~1023u;
   // stage counts inside the budget: at least 2 A + 2 B
   const uint32_t bar_bytes = 1024 + kEpiWarps * 4096;  // barriers + epilogue staging
@@ -694,15 +726,23 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
   // B stage pitch must equal the copy size for the kernel's addressing: use the aligned pitch everywhere.
   prm.b_stage_bytes = b_pitch;
   // copy size = n_tile*128 which is already a multiple of 2048 for n_tile%16==0 -> equals pitch when n_tile%8==0
-  if (b_pitch != static_cast<uint32_t>(w.n_tile * kRowBytes))
+  if (b_pitch != static_cast<uint32_t>(tg) * prm.b_tap_bytes)
     return fail(M2S_ERR_UNSUPPORTED, "n_tile=%d gives a non-1024-aligned weight stage", w.n_tile);
 
+  using KernelFn = void (*)(const CUtensorMap, const EngineParams);
+  static const KernelFn kernels[6] = {conv_engine_kernel<EPI_FULL>, conv_engine_kernel<EPI_FULL_SILU>,
+                                      conv_engine_kernel<EPI_BIAS>, conv_engine_kernel<EPI_LRELU>,
+                                      conv_engine_kernel<EPI_SILU>, conv_engine_kernel<EPI_RES>};
   static bool attr_set = false;
   if (!attr_set) {
-    M2S_CUDA_OK(cudaFuncSetAttribute(conv_engine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    M2S_CUDA_OK(cudaFuncSetAttribute(conv_engine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    for (KernelFn k : kernels)
+      M2S_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
+  int epi = p.epi.act == M2S_ACT_SILU ? EPI_FULL_SILU : EPI_FULL;
+  const bool plain = !p.epi.accum && p.epi.out_scale == 1.f;
+  if (plain && !p.epi.res) epi = p.epi.act == M2S_ACT_SILU ? EPI_SILU : (p.epi.act == M2S_ACT_LRELU ? EPI_LRELU : EPI_BIAS);
+  else if (plain && p.epi.act == M2S_ACT_NONE && p.epi.res_inv_slope == 1.f) epi = EPI_RES;
   int grid = knobs.max_ctas > 0 ? knobs.max_ctas : sm_count();
   if (grid > prm.total_tiles) grid = prm.total_tiles;
   ProfileRing& pr = ring();
@@ -714,8 +754,7 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
     }
     M2S_CUDA_OK(cudaEventRecord(pr.ev[2 * pr.count], stream));
   }
-  if (p.epi.act == M2S_ACT_SILU) conv_engine_kernel<true><<<grid, kThreads, smem_bytes, stream>>>(tmap, prm);
-  else conv_engine_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(tmap, prm);
+  kernels[epi]<<<grid, kThreads, smem_bytes, stream>>>(tmap, prm);
   M2S_CUDA_OK(cudaGetLastError());
   if (pr.on) {
     M2S_CUDA_OK(cudaEventRecord(pr.ev[2 * pr.count + 1], stream));

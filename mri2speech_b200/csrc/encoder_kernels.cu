@@ -108,58 +108,68 @@ __global__ void im2col_s2_kernel(const float* __restrict__ in, float* __restrict
 
 // Depthwise 3x3 + bias (folded BN) + SiLU, with the SE squeeze (per-frame channel sums) fused.
 // Input pixel (y, x) is row (y + oy) * pitch_in + (x + ox); pixels outside [0,Hin)x[0,Win) are zero.
-// grid = (C / 32, frames); block = 32 channels x 8 pixel lanes.
+// grid = (C / 32, frames); block = 8 channel quads x 32 pixel lanes, float4 everywhere.  The (frame, 32-channel)
+// input slab is staged in SMEM once (a quarter-warp reads one 128-byte pixel row: coalesced and conflict-free).
 __global__ void __launch_bounds__(256) dwconv_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                      float* __restrict__ sums, const float* __restrict__ w /*[9][C]*/,
                                                      const float* __restrict__ bias, int C, int Hin, int Win,
                                                      int pitch_in, int oy, int ox, int rows_in, int stride) {
+  extern __shared__ float4 slab[];  // [Hin*Win][8 quads]
+  __shared__ float4 red[32][8];
   const int Ho = Hin / stride, Wo = Win / stride;
   const int n = blockIdx.y;
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int lane_p = threadIdx.x >> 5;
-  __shared__ float red[8][33];
-  float wv[9], b = 0.f, acc_sum = 0.f;
-  if (c < C) {
-#pragma unroll
-    for (int t = 0; t < 9; ++t) wv[t] = w[t * C + c];
-    b = bias[c];
-  }
+  const int cq = threadIdx.x & 7;   // channel quad inside the 32-channel slab
+  const int pl = threadIdx.x >> 3;  // pixel lane 0..31
+  const int c = blockIdx.x * 32 + cq * 4;
+  const bool c_ok = c < C;          // C is a multiple of 4
   const float* src = in + static_cast<size_t>(n) * rows_in * C;
-  const int off = stride == 1 ? -1 : 0;  // TF same: stride 1 pads 1/1, stride 2 pads 0/1
-  if (c < C) {
-    for (int p = lane_p; p < Ho * Wo; p += 8) {
-      const int y = p / Wo, x = p % Wo;
-      float v = b;
-#pragma unroll
-      for (int dy = 0; dy < 3; ++dy) {
-        const int yy = y * stride + dy + off;
-        if (yy < 0 || yy >= Hin) continue;
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          const int xx = x * stride + dx + off;
-          if (xx < 0 || xx >= Win) continue;
-          v = fmaf(src[(static_cast<size_t>(yy + oy) * pitch_in + (xx + ox)) * C + c], wv[dy * 3 + dx], v);
-        }
-      }
-      v = silu(v);
-      out[(static_cast<size_t>(n) * Ho * Wo + p) * C + c] = v;
-      acc_sum += v;
-    }
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int pix = pl; pix < Hin * Win; pix += 32) {
+    const int y = pix / Win, x = pix - y * Win;
+    slab[pix * 8 + cq] =
+        c_ok ? *reinterpret_cast<const float4*>(src + (static_cast<size_t>(y + oy) * pitch_in + (x + ox)) * C + c) : z4;
   }
-  red[lane_p][threadIdx.x & 31] = acc_sum;
-  __syncthreads();
-  if (lane_p == 0 && c < C) {
-    float s = 0.f;
+  float4 wv[9], b4 = z4, acc_sum = z4;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
-    sums[static_cast<size_t>(n) * C + c] = s;
+  for (int t = 0; t < 9; ++t) wv[t] = c_ok ? *reinterpret_cast<const float4*>(w + static_cast<size_t>(t) * C + c) : z4;
+  if (c_ok) b4 = *reinterpret_cast<const float4*>(bias + c);
+  __syncthreads();
+  const int off = stride == 1 ? -1 : 0;  // TF same: stride 1 pads 1/1, stride 2 pads 0/1
+  for (int p = pl; p < Ho * Wo; p += 32) {
+    const int y = p / Wo, x = p - y * Wo;
+    float4 v = b4;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = y * stride + dy + off;
+      if (yy < 0 || yy >= Hin) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int xx = x * stride + dx + off;
+        if (xx < 0 || xx >= Win) continue;
+        const float4 a = slab[(yy * Win + xx) * 8 + cq];
+        const float4 ww = wv[dy * 3 + dx];
+        v.x = fmaf(a.x, ww.x, v.x); v.y = fmaf(a.y, ww.y, v.y); v.z = fmaf(a.z, ww.z, v.z); v.w = fmaf(a.w, ww.w, v.w);
+      }
+    }
+    v.x = silu(v.x); v.y = silu(v.y); v.z = silu(v.z); v.w = silu(v.w);
+    if (c_ok) *reinterpret_cast<float4*>(out + (static_cast<size_t>(n) * Ho * Wo + p) * C + c) = v;
+    acc_sum.x += v.x; acc_sum.y += v.y; acc_sum.z += v.z; acc_sum.w += v.w;
+  }
+  red[pl][cq] = acc_sum;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int ch = threadIdx.x;  // channel inside the slab
+    float s = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) s += reinterpret_cast<const float*>(&red[k][0])[ch];
+    if (blockIdx.x * 32 + ch < C) sums[static_cast<size_t>(n) * C + blockIdx.x * 32 + ch] = s;
   }
 }
 
 // Squeeze-excite MLP: scale[n][c] = sigmoid(W2 silu(W1 mean + b1) + b2).  One block per frame.
 __global__ void __launch_bounds__(256) se_kernel(const float* __restrict__ sums, float* __restrict__ scales,
                                                  const float* __restrict__ w1 /*[rd][C]*/, const float* __restrict__ b1,
-                                                 const float* __restrict__ w2 /*[C][rd]*/, const float* __restrict__ b2,
+                                                 const float* __restrict__ w2t /*[rd][C]*/, const float* __restrict__ b2,
                                                  int C, int rd, float inv_hw) {
   extern __shared__ float sm[];  // mean[C] + r[rd]
   float* mean = sm;
@@ -181,7 +191,7 @@ __global__ void __launch_bounds__(256) se_kernel(const float* __restrict__ sums,
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float a = b2[c];
-    for (int j = 0; j < rd; ++j) a = fmaf(w2[static_cast<size_t>(c) * rd + j], r[j], a);
+    for (int j = 0; j < rd; ++j) a = fmaf(w2t[static_cast<size_t>(j) * C + c], r[j], a);
     scales[static_cast<size_t>(n) * C + c] = 1.f / (1.f + expf(-a));
   }
 }
@@ -239,7 +249,14 @@ int enc_im2col_s2(const float* in, float* col, int n, int Hin, int Win, int C, c
 int enc_dwconv(const float* in, float* out, float* sums, const float* w, const float* bias, int n, int C, int Hin,
                int Win, int pitch_in, int oy, int ox, int rows_in, int stride, cudaStream_t st) {
   dim3 grid((C + 31) / 32, n);
-  dwconv_kernel<<<grid, 256, 0, st>>>(in, out, sums, w, bias, C, Hin, Win, pitch_in, oy, ox, rows_in, stride);
+  const size_t smem = static_cast<size_t>(Hin) * Win * 32 * sizeof(float);
+  if (smem > 200 * 1024) return fail(M2S_ERR_UNSUPPORTED, "depthwise input %dx%d too large for the SMEM slab", Hin, Win);
+  static bool attr = false;
+  if (!attr) {
+    M2S_CUDA_OK(cudaFuncSetAttribute(dwconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  dwconv_kernel<<<grid, 256, smem, st>>>(in, out, sums, w, bias, C, Hin, Win, pitch_in, oy, ox, rows_in, stride);
   M2S_CUDA_OK(cudaGetLastError());
   return M2S_OK;
 }

@@ -139,6 +139,7 @@ struct EngineKnobs {
   unsigned long long* trace = nullptr;  // debug timeline buffer (device), trace_tiles x 9 stamps of CTA 0
   int trace_tiles = 0;
   int dbg = 0;
+  int n_tile_max = 128;      // N columns per tile once N exceeds it (weights are packed accordingly)
 };
 EngineKnobs& engine_knobs();
 

@@ -1,0 +1,17 @@
+"""Run the encoder once on synthetic frames (for ncu launch lists)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from mri2speech_b200.acoustic import build_acoustic_model
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+torch.manual_seed(1234)
+ac = build_acoustic_model().cuda().eval()
+frames = torch.rand(n, 256, 256, device="cuda")
+for _ in range(3):
+    f = ac.encode_frames(frames)
+torch.cuda.synchronize()
+print("ok", f.shape, float(f.abs().max()))
