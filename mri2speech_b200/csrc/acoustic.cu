@@ -258,10 +258,13 @@ int encode_chunk(const m2s_acoustic* m, const float* frames, const int32_t* fmap
       M2S_TRY(enc_zero_rows(y, n, rows_out, b.cout, wout + 3, hout * (wout + 2) + wout + 3, st));
       std::swap(x, y);
     } else {
-      // IR: 1x1 expand (+SiLU) -> depthwise 3x3 (+SiLU, squeeze) -> SE -> 1x1 project (+ skip)
+      // IR: 1x1 expand (+SiLU) -> depthwise 3x3 (+SiLU, squeeze) -> SE -> 1x1 project (+ skip).
+      // The 1x1 convs have no halo, so all frames of the chunk are flattened into ONE batch item: tiles then
+      // span frame boundaries (a per-frame batch would waste 3/4 of every 256-row tile at 8x8 = 64 rows/frame).
       const int rows_in = b.in_padded ? static_cast<int>(padded_rows(hin, win)) : hin * win;
       {
-        ConvProblem p = gemm_problem(x, rows_in, rows_in, b.cin, n, rows_in, B.e, rows_in, b.mid, 0, b.conv);
+        const int rows = n * rows_in;
+        ConvProblem p = gemm_problem(x, rows, rows, b.cin, 1, rows, B.e, rows, b.mid, 0, b.conv);
         p.epi.act = M2S_ACT_SILU;
         M2S_TRY(run_gemm(m, p, b.conv, st));
       }
@@ -271,7 +274,8 @@ int encode_chunk(const m2s_acoustic* m, const float* frames, const int32_t* fmap
       const int hw = hout * wout;
       M2S_TRY(enc_se(B.sums, B.scales, b.se_w1, b.se_b1, b.se_w2, b.se_b2, n, b.mid, b.rd, hw, st));
       M2S_TRY(enc_se_scale(B.e2, B.scales, n, hw, b.mid, st));
-      ConvProblem p = gemm_problem(B.e2, hw, hw, b.mid, n, hw, y, hw, b.cout, 0, b.pwl);
+      const int rows_out = n * hw;
+      ConvProblem p = gemm_problem(B.e2, rows_out, rows_out, b.mid, 1, rows_out, y, rows_out, b.cout, 0, b.pwl);
       if (b.skip) { p.epi.res = x; p.epi.res_ld = b.cin; }
       M2S_TRY(run_gemm(m, p, b.pwl, st));
       std::swap(x, y);

@@ -106,17 +106,21 @@ __global__ void im2col_s2_kernel(const float* __restrict__ in, float* __restrict
   }
 }
 
+__device__ __forceinline__ float fsilu(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+
 // Depthwise 3x3 + bias (folded BN) + SiLU, with the SE squeeze (per-frame channel sums) fused.
-// Input pixel (y, x) is row (y + oy) * pitch_in + (x + ox); pixels outside [0,Hin)x[0,Win) are zero.
-// grid = (C / 32, frames); block = 8 channel quads x 32 pixel lanes, float4 everywhere.  The (frame, 32-channel)
-// input slab is staged in SMEM once (a quarter-warp reads one 128-byte pixel row: coalesced and conflict-free).
-__global__ void __launch_bounds__(256) dwconv_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                     float* __restrict__ sums, const float* __restrict__ w /*[9][C]*/,
-                                                     const float* __restrict__ bias, int C, int Hin, int Win,
-                                                     int pitch_in, int oy, int ox, int rows_in, int stride) {
-  extern __shared__ float4 slab[];  // [Hin*Win][8 quads]
+// Input pixel (y, x) is row (y + oy) * pitch_in + (x + ox) of the frame.  TF "same" padding: stride 1 pads 1/1,
+// stride 2 pads 0/1 -- both are served by ONE zero-bordered SMEM slab ((Hin+2) x (Win+2) pixels x 32 channels),
+// so the tap loop has no boundary checks.  grid = (C / 32, frames); block = 8 channel quads x 32 pixel lanes,
+// float4 everywhere (a quarter-warp touches one 128-byte pixel row: coalesced in HBM, conflict-free in SMEM).
+template <int kStride>
+__global__ void __launch_bounds__(256, 3) dwconv_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                        float* __restrict__ sums, const float* __restrict__ w /*[9][C]*/,
+                                                        const float* __restrict__ bias, int C, int Hin, int Win,
+                                                        int pitch_in, int oy, int ox, int rows_in, int wo_shift) {
+  extern __shared__ float4 slab[];  // [(Hin+2)*(Win+2)][8 quads]
   __shared__ float4 red[32][8];
-  const int Ho = Hin / stride, Wo = Win / stride;
+  const int Ho = Hin / kStride, Wo = Win / kStride, Wp = Win + 2;
   const int n = blockIdx.y;
   const int cq = threadIdx.x & 7;   // channel quad inside the 32-channel slab
   const int pl = threadIdx.x >> 3;  // pixel lane 0..31
@@ -124,34 +128,34 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const float* __restrict__ i
   const bool c_ok = c < C;          // C is a multiple of 4
   const float* src = in + static_cast<size_t>(n) * rows_in * C;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int pix = pl; pix < Hin * Win; pix += 32) {
-    const int y = pix / Win, x = pix - y * Win;
+  for (int pix = pl; pix < (Hin + 2) * Wp; pix += 32) {
+    const int yp = pix / Wp, xp = pix - yp * Wp;
+    const bool inside = c_ok && yp >= 1 && yp <= Hin && xp >= 1 && xp <= Win;
     slab[pix * 8 + cq] =
-        c_ok ? *reinterpret_cast<const float4*>(src + (static_cast<size_t>(y + oy) * pitch_in + (x + ox)) * C + c) : z4;
+        inside ? *reinterpret_cast<const float4*>(src + (static_cast<size_t>(yp - 1 + oy) * pitch_in + (xp - 1 + ox)) * C + c)
+               : z4;
   }
   float4 wv[9], b4 = z4, acc_sum = z4;
 #pragma unroll
   for (int t = 0; t < 9; ++t) wv[t] = c_ok ? *reinterpret_cast<const float4*>(w + static_cast<size_t>(t) * C + c) : z4;
   if (c_ok) b4 = *reinterpret_cast<const float4*>(bias + c);
   __syncthreads();
-  const int off = stride == 1 ? -1 : 0;  // TF same: stride 1 pads 1/1, stride 2 pads 0/1
+  // padded coordinate of tap (dy, dx) for output (y, x): stride 1 -> (y + dy, x + dx); stride 2 -> (2y + dy + 1, 2x + dx + 1)
+  constexpr int kOff = kStride == 1 ? 0 : 1;
   for (int p = pl; p < Ho * Wo; p += 32) {
-    const int y = p / Wo, x = p - y * Wo;
+    const int y = wo_shift >= 0 ? (p >> wo_shift) : p / Wo;
+    const int x = p - y * Wo;
+    const float4* base = slab + ((y * kStride + kOff) * Wp + x * kStride + kOff) * 8 + cq;
     float4 v = b4;
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      const int yy = y * stride + dy + off;
-      if (yy < 0 || yy >= Hin) continue;
+    for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
-        const int xx = x * stride + dx + off;
-        if (xx < 0 || xx >= Win) continue;
-        const float4 a = slab[(yy * Win + xx) * 8 + cq];
+        const float4 a = base[(dy * Wp + dx) * 8];
         const float4 ww = wv[dy * 3 + dx];
         v.x = fmaf(a.x, ww.x, v.x); v.y = fmaf(a.y, ww.y, v.y); v.z = fmaf(a.z, ww.z, v.z); v.w = fmaf(a.w, ww.w, v.w);
       }
-    }
-    v.x = silu(v.x); v.y = silu(v.y); v.z = silu(v.z); v.w = silu(v.w);
+    v.x = fsilu(v.x); v.y = fsilu(v.y); v.z = fsilu(v.z); v.w = fsilu(v.w);
     if (c_ok) *reinterpret_cast<float4*>(out + (static_cast<size_t>(n) * Ho * Wo + p) * C + c) = v;
     acc_sum.x += v.x; acc_sum.y += v.y; acc_sum.z += v.z; acc_sum.w += v.w;
   }
@@ -166,21 +170,28 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const float* __restrict__ i
   }
 }
 
-// Squeeze-excite MLP: scale[n][c] = sigmoid(W2 silu(W1 mean + b1) + b2).  One block per frame.
-__global__ void __launch_bounds__(256) se_kernel(const float* __restrict__ sums, float* __restrict__ scales,
-                                                 const float* __restrict__ w1 /*[rd][C]*/, const float* __restrict__ b1,
-                                                 const float* __restrict__ w2t /*[rd][C]*/, const float* __restrict__ b2,
-                                                 int C, int rd, float inv_hw) {
+// Squeeze-excite MLP: scale[n][c] = sigmoid(W2 silu(W1 mean + b1) + b2).  One 1024-thread block per frame:
+// phase 1 = one warp per reduced unit (float4 over channels), phase 2 = one thread per channel (coalesced over W2^T).
+__global__ void __launch_bounds__(1024) se_kernel(const float* __restrict__ sums, float* __restrict__ scales,
+                                                  const float* __restrict__ w1 /*[rd][C]*/, const float* __restrict__ b1,
+                                                  const float* __restrict__ w2t /*[rd][C]*/, const float* __restrict__ b2,
+                                                  int C, int rd, float inv_hw) {
   extern __shared__ float sm[];  // mean[C] + r[rd]
   float* mean = sm;
   float* r = sm + C;
   const int n = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = sums[static_cast<size_t>(n) * C + c] * inv_hw;
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int j = warp; j < rd; j += 8) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int c4n = C >> 2;
+  for (int j = warp; j < rd; j += nwarps) {
+    const float4* wr = reinterpret_cast<const float4*>(w1 + static_cast<size_t>(j) * C);
     float a = 0.f;
-    for (int c = lane; c < C; c += 32) a = fmaf(w1[static_cast<size_t>(j) * C + c], mean[c], a);
+    for (int k = lane; k < c4n; k += 32) {
+      const float4 wv = __ldg(wr + k);
+      const float4 mv = reinterpret_cast<const float4*>(mean)[k];
+      a = fmaf(wv.x, mv.x, a); a = fmaf(wv.y, mv.y, a); a = fmaf(wv.z, mv.z, a); a = fmaf(wv.w, mv.w, a);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     if (lane == 0) {
@@ -190,8 +201,16 @@ __global__ void __launch_bounds__(256) se_kernel(const float* __restrict__ sums,
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = b2[c];
-    for (int j = 0; j < rd; ++j) a = fmaf(w2t[static_cast<size_t>(j) * C + c], r[j], a);
+    float a0 = b2[c], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int j = 0;
+    for (; j + 4 <= rd; j += 4) {
+      a0 = fmaf(__ldg(w2t + static_cast<size_t>(j) * C + c), r[j], a0);
+      a1 = fmaf(__ldg(w2t + static_cast<size_t>(j + 1) * C + c), r[j + 1], a1);
+      a2 = fmaf(__ldg(w2t + static_cast<size_t>(j + 2) * C + c), r[j + 2], a2);
+      a3 = fmaf(__ldg(w2t + static_cast<size_t>(j + 3) * C + c), r[j + 3], a3);
+    }
+    for (; j < rd; ++j) a0 = fmaf(__ldg(w2t + static_cast<size_t>(j) * C + c), r[j], a0);
+    const float a = (a0 + a1) + (a2 + a3);
     scales[static_cast<size_t>(n) * C + c] = 1.f / (1.f + expf(-a));
   }
 }
@@ -249,21 +268,30 @@ int enc_im2col_s2(const float* in, float* col, int n, int Hin, int Win, int C, c
 int enc_dwconv(const float* in, float* out, float* sums, const float* w, const float* bias, int n, int C, int Hin,
                int Win, int pitch_in, int oy, int ox, int rows_in, int stride, cudaStream_t st) {
   dim3 grid((C + 31) / 32, n);
-  const size_t smem = static_cast<size_t>(Hin) * Win * 32 * sizeof(float);
+  const size_t smem = static_cast<size_t>(Hin + 2) * (Win + 2) * 32 * sizeof(float);
   if (smem > 200 * 1024) return fail(M2S_ERR_UNSUPPORTED, "depthwise input %dx%d too large for the SMEM slab", Hin, Win);
+  if (stride != 1 && stride != 2) return fail(M2S_ERR_UNSUPPORTED, "depthwise stride %d", stride);
   static bool attr = false;
   if (!attr) {
-    M2S_CUDA_OK(cudaFuncSetAttribute(dwconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    M2S_CUDA_OK(cudaFuncSetAttribute(dwconv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    M2S_CUDA_OK(cudaFuncSetAttribute(dwconv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  dwconv_kernel<<<grid, 256, smem, st>>>(in, out, sums, w, bias, C, Hin, Win, pitch_in, oy, ox, rows_in, stride);
+  const int wo = Win / stride;
+  int wo_shift = -1;
+  for (int k = 0; k < 16; ++k)
+    if ((1 << k) == wo) wo_shift = k;
+  if (stride == 1)
+    dwconv_kernel<1><<<grid, 256, smem, st>>>(in, out, sums, w, bias, C, Hin, Win, pitch_in, oy, ox, rows_in, wo_shift);
+  else
+    dwconv_kernel<2><<<grid, 256, smem, st>>>(in, out, sums, w, bias, C, Hin, Win, pitch_in, oy, ox, rows_in, wo_shift);
   M2S_CUDA_OK(cudaGetLastError());
   return M2S_OK;
 }
 
 int enc_se(const float* sums, float* scales, const float* w1, const float* b1, const float* w2, const float* b2, int n,
            int C, int rd, int hw, cudaStream_t st) {
-  se_kernel<<<n, 256, (C + rd) * sizeof(float), st>>>(sums, scales, w1, b1, w2, b2, C, rd, 1.f / hw);
+  se_kernel<<<n, 1024, (C + rd) * sizeof(float), st>>>(sums, scales, w1, b1, w2, b2, C, rd, 1.f / hw);
   M2S_CUDA_OK(cudaGetLastError());
   return M2S_OK;
 }

@@ -49,6 +49,8 @@ def main():
                       "rnn_head_ms": t_rnn, "vocoder_ms": t_voc,
                       "e2e_audio_s_per_s": audio_s / ((t_enc + t_rnn + t_voc) * 1e-3),
                       "us_per_frame_encoder": t_enc * 1e3 / (B * T)}))
+    per = len(ms) // max(1, (B * T + 255) // 256)
+    print("engine launches of the first chunk (us, TF/s):", [(i, round(ms[i] * 1e3), round(fl[i] / ms[i] / 1e9)) for i in range(min(per, 60))])
     # slowest engine launches of the encoder
     order = sorted(range(len(ms)), key=lambda i: -ms[i])[:12]
     print("top encoder engine launches (idx, ms, TF/s):", [(i, round(ms[i], 3), round(fl[i] / ms[i] / 1e9, 1)) for i in order])

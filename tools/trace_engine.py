@@ -8,43 +8,44 @@ import torch
 from mri2speech_b200 import _lib
 
 
-def run(B, L, C, k, d, res=False, tiles=40, knobs=None):
+def run(B, L, C, k, d, res=False, tiles=40, knobs=None, N=None, act=None, shifts=None):
     for kk, v in (knobs or {}).items():
         _lib.set_knob(kk, v)
+    N = N or C
+    act = _lib.ACT_LRELU if act is None else act
     a = torch.randn(B, L, C, device="cuda")
-    w = torch.randn(k, C, C, device="cuda") / (C * k) ** 0.5
-    bias = torch.randn(C, device="cuda")
-    r = torch.randn(B, L, C, device="cuda") if res else None
-    shifts = [-(k - 1 - j) * d for j in range(k)]
-    out = torch.empty(B, L, C, device="cuda")
+    w = torch.randn(k, N, C, device="cuda") / (C * k) ** 0.5
+    bias = torch.randn(N, device="cuda")
+    r = torch.randn(B, L, N, device="cuda") if res else None
+    shifts = shifts or [-(k - 1 - j) * d for j in range(k)]
+    out = torch.empty(B, L, N, device="cuda")
     buf = torch.zeros(tiles * 9, dtype=torch.int64, device="cuda")
-    _lib.conv_fwd(a, w, shifts, L, bias=bias, res=r, res_inv_slope=10.0, act=_lib.ACT_LRELU, act_slope=0.1, out=out)
+    kw = dict(bias=bias, res=r, res_inv_slope=10.0 if res else 1.0, act=act, act_slope=0.1, out=out)
+    _lib.conv_fwd(a, w, shifts, L, **kw)
     _lib.check(_lib.lib().m2s_debug_trace(buf.data_ptr(), tiles))
-    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-    e0.record()
-    _lib.conv_fwd(a, w, shifts, L, bias=bias, res=r, res_inv_slope=10.0, act=_lib.ACT_LRELU, act_slope=0.1, out=out)
-    e1.record()
+    _lib.conv_fwd(a, w, shifts, L, **kw)
     torch.cuda.synchronize()
     _lib.check(_lib.lib().m2s_debug_trace(None, 0))
     t = buf.cpu().view(tiles, 9)
+    valid = int((t[:, 8] > 0).sum())
+    t = t[:valid]
+    tiles = valid
     t0 = int(t[0, 0])
-    print(f"--- B={B} L={L} C={C} k={k} d={d} res={res} knobs={knobs}: {e0.elapsed_time(e1)*1e3:.0f} us (incl. weight packing)")
-    print("tile |  P:start  a_empty  issued |  M:start acc_empty  mma_done |  E:start acc_full  done   (cycles since t0)")
-    for i in range(min(tiles, 6)):
+    print(f"--- B={B} L={L} C={C} N={N} k={k} d={d} res={res} act={act} knobs={knobs}: CTA0 ran {tiles} tiles")
+    for i in range(min(tiles, 4)):
         print(f"{i:4d} | " + " ".join(f"{int(v) - t0:8d}" for v in t[i, 0:3]) + " | " +
               " ".join(f"{int(v) - t0:8d}" for v in t[i, 3:6]) + " | " + " ".join(f"{int(v) - t0:8d}" for v in t[i, 6:9]))
-    n = tiles - 4 if tiles > 4 else 1
-    per_tile = (int(t[tiles - 1, 8]) - int(t[3, 8])) / n
-    print(f"steady-state cycles/tile: {per_tile:.0f}; epilogue busy {float((t[4:, 8] - t[4:, 7]).float().mean()):.0f}; "
-          f"epilogue wait {float((t[4:, 7] - t[4:, 6]).float().mean()):.0f}; mma issue {float((t[4:, 5] - t[4:, 4]).float().mean()):.0f}; "
-          f"mma wait acc {float((t[4:, 4] - t[4:, 3]).float().mean()):.0f}; producer a_empty wait {float((t[4:, 1] - t[4:, 0]).float().mean()):.0f}; "
-          f"producer issue {float((t[4:, 2] - t[4:, 1]).float().mean()):.0f}")
+    s0 = 1 if tiles > 2 else 0
+    n = max(tiles - 1 - s0, 1)
+    per_tile = (int(t[tiles - 1, 8]) - int(t[s0, 8])) / n
+    f = lambda x: float(x.float().mean())
+    print(f"steady-state cycles/tile: {per_tile:.0f}; epilogue busy {f(t[s0:, 8] - t[s0:, 7]):.0f}; "
+          f"epilogue wait {f(t[s0:, 7] - t[s0:, 6]):.0f}; mma issue {f(t[s0:, 5] - t[s0:, 4]):.0f}; "
+          f"mma wait acc {f(t[s0:, 4] - t[s0:, 3]):.0f}; producer a_empty wait {f(t[s0:, 1] - t[s0:, 0]):.0f}; "
+          f"producer issue {f(t[s0:, 2] - t[s0:, 1]):.0f}; total {int(t[tiles-1, 8]) - t0} cycles")
 
 
 if __name__ == "__main__":
-    run(32, 107520, 32, 3, 1, tiles=40)
-    run(32, 107520, 32, 3, 1, res=True, tiles=40)
-    run(32, 107520, 32, 11, 5, tiles=40)
-    run(32, 53760, 64, 7, 3, tiles=40)
-    run(32, 17920, 128, 7, 3, tiles=12)
-    run(32, 2560, 256, 11, 5, tiles=4)
+    S = _lib.ACT_SILU
+    for dbg in (0, 1, 2, 4, 7, 16, 23):
+        run(1, 16384, 208, 1, 0, N=1248, act=S, shifts=[0], knobs={"dbg": dbg})       # stage 5 expand
