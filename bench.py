@@ -320,6 +320,10 @@ def main():
         "engine_share_of_step": engine_ms_per_step / ms_per_step,
         "executed_tflop_per_step": sum(launch_flops) / max(args.steps, 1) / 1e12,
         "algorithmic_tflop_per_step": ENGINE_FLOP_PER_FRAME * B * T / 1e12,
+        # mean duration of each of the engine launches of one forward, in launch order (conv_pre, then per stage:
+        # ups, 3 ResBlocks x 3 x (conv1, conv2)), microseconds
+        "per_launch_us": [round(1e3 * sum(launch_ms[i::per_step_launches]) / max(args.steps, 1), 1)
+                          for i in range(per_step_launches)] if per_step_launches else [],
     }
 
     cpu = None

@@ -409,45 +409,61 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         const int c0 = (u - sub * nchunks) << 5;
         const int qw = q0 + sub * 128 + quad * 32;  // first row of this warp's 32-row slab
         uint32_t r[32];
-        if (!(prm.dbg & 2)) {
-          tmem_ld16(tmem_acc + sub * n_tile + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-          if (c0 + 16 < n_tile) tmem_ld16(tmem_acc + sub * n_tile + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0x3f800000u;
-        }
-        // overlap the TMEM read with the residual / accumulate / bias loads of this unit (the output may alias
-        // them in place, so every load is issued before the first store)
+        tmem_ld16(tmem_acc + sub * n_tile + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+        if (c0 + 16 < n_tile) tmem_ld16(tmem_acc + sub * n_tile + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+        // While the TMEM read is in flight: bias / residual / accumulate loads of this unit (the output may alias
+        // them in place, so every load is issued before the first store).  Thread (rr0, cc) owns rows rr0 + 4i,
+        // columns n .. n+3; all row predicates reduce to "4i + rr0 < bound".
         const int n = n0 + c0 + cc * 4;
         const bool col_ok = (c0 + cc * 4 < n_tile) && n < p.n;
+        const int rows_ok = col_ok ? min(32, p.l_out - qw) : 0;                 // rows that exist
+        int rows_valid = 32;                                                    // rows that survive the mask
+        if (mask_mode == M2S_MASK_LEN) rows_valid = len_rows - (qw + p.d_row_offset);
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (col_ok && e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+        const size_t row0 = d_base + qw + rr0;
+        float* dptr = p.d + row0 * p.d_ld + n;
+        const size_t d_step = static_cast<size_t>(4) * p.d_ld;
         float4 res4[8], acc4[8];
-        bool ok[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int q = qw + i * 4 + rr0;
-          ok[i] = col_ok && q < p.l_out;
           res4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          const size_t row_index = d_base + q;
-          if (kEpi == EPI_FULL || kEpi == EPI_FULL_SILU || kEpi == EPI_RES) {
-            if (has_res && ok[i]) res4[i] = *reinterpret_cast<const float4*>(e.res + row_index * e.res_ld + n);
-          }
-          if (kEpi == EPI_FULL || kEpi == EPI_FULL_SILU) {
-            if (has_acc && ok[i]) acc4[i] = *reinterpret_cast<const float4*>(e.accum + row_index * e.accum_ld + n);
+        }
+        if (kEpi == EPI_FULL || kEpi == EPI_FULL_SILU || kEpi == EPI_RES) {
+          if (has_res) {
+            const float* rptr = e.res + row0 * e.res_ld + n;
+            const size_t r_step = static_cast<size_t>(4) * e.res_ld;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (i * 4 + rr0 < rows_ok) res4[i] = *reinterpret_cast<const float4*>(rptr + i * r_step);
           }
         }
-        if (!(prm.dbg & 2)) tmem_ld_wait();
-        if (!(prm.dbg & 4))
+        if (kEpi == EPI_FULL || kEpi == EPI_FULL_SILU) {
+          if (has_acc) {
+            const float* aptr = e.accum + row0 * e.accum_ld + n;
+            const size_t a_step = static_cast<size_t>(4) * e.accum_ld;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (i * 4 + rr0 < rows_ok) acc4[i] = *reinterpret_cast<const float4*>(aptr + i * a_step);
+          }
+        }
+        // image-border mask: (i, j) = divmod(row, pitch) once, then stepped by 4 rows
+        int mi = 0, mj = 0;
+        if (mask_mode == M2S_MASK_PITCH) {
+          const int drow = qw + rr0 + p.d_row_offset;
+          mi = drow / e.pitch;
+          mj = drow - mi * e.pitch;
+        }
+        tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + lane * 128 + ((j ^ (lane & 7)) << 4)),
                        "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
                        : "memory");
         __syncwarp();
-        // branch-free: all 8 rows' (32 independent) element chains are computed unconditionally so the scheduler
-        // can interleave them; only the store is predicated
+        // all 8 rows' (32 independent) element chains are computed unconditionally so the scheduler can interleave
+        // them; only the stores are predicated
         float4 o[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -456,22 +472,27 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                        : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w)
                        : "r"(stage + rr * 128 + ((cc ^ (rr & 7)) << 4)));
-          if (prm.dbg & 16) { o[i] = a4; continue; }
           o[i].x = epi_elem<kEpi>(ec, a4.x, bias4.x, res4[i].x, acc4[i].x);
           o[i].y = epi_elem<kEpi>(ec, a4.y, bias4.y, res4[i].y, acc4[i].y);
           o[i].z = epi_elem<kEpi>(ec, a4.z, bias4.z, res4[i].z, acc4[i].z);
           o[i].w = epi_elem<kEpi>(ec, a4.w, bias4.w, res4[i].w, acc4[i].w);
         }
+        if (mask_mode == M2S_MASK_PITCH) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int q = qw + i * 4 + rr0;
-          const int drow = q + p.d_row_offset;
-          bool valid = true;
-          if (mask_mode == M2S_MASK_LEN) valid = drow < len_rows;
-          else if (mask_mode == M2S_MASK_PITCH) valid = epi_row_valid(e, b, drow);
-          if (!valid) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok[i] && !(prm.dbg & 1)) *reinterpret_cast<float4*>(p.d + (d_base + q) * p.d_ld + n) = o[i];
+          for (int i = 0; i < 8; ++i) {
+            const bool valid = mi >= e.i_lo && mi < e.i_hi && mj >= e.j_lo && mj < e.j_hi;
+            if (!valid) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            mj += 4;
+            if (mj >= e.pitch) { mj -= e.pitch; ++mi; }
+          }
+        } else if (mask_mode == M2S_MASK_LEN) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i * 4 + rr0 >= rows_valid) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i * 4 + rr0 < rows_ok) *reinterpret_cast<float4*>(dptr + i * d_step) = o[i];
         __syncwarp();
       }
       tc_fence_before();

@@ -113,60 +113,72 @@ __device__ __forceinline__ float fsilu(float v) { return __fdividef(v, 1.f + __e
 // stride 2 pads 0/1 -- both are served by ONE zero-bordered SMEM slab ((Hin+2) x (Win+2) pixels x 32 channels),
 // so the tap loop has no boundary checks.  grid = (C / 32, frames); block = 8 channel quads x 32 pixel lanes,
 // float4 everywhere (a quarter-warp touches one 128-byte pixel row: coalesced in HBM, conflict-free in SMEM).
-template <int kStride>
+template <int kStride, int kF>
 __global__ void __launch_bounds__(256, 3) dwconv_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                         float* __restrict__ sums, const float* __restrict__ w /*[9][C]*/,
                                                         const float* __restrict__ bias, int C, int Hin, int Win,
-                                                        int pitch_in, int oy, int ox, int rows_in, int wo_shift) {
-  extern __shared__ float4 slab[];  // [(Hin+2)*(Win+2)][8 quads]
+                                                        int pitch_in, int oy, int ox, int rows_in, int wo_shift,
+                                                        int n_frames) {
+  extern __shared__ float4 slab[];  // [kF][(Hin+2)*(Win+2)][8 quads]
   __shared__ float4 red[32][8];
   const int Ho = Hin / kStride, Wo = Win / kStride, Wp = Win + 2;
-  const int n = blockIdx.y;
-  const int cq = threadIdx.x & 7;   // channel quad inside the 32-channel slab
-  const int pl = threadIdx.x >> 3;  // pixel lane 0..31
+  const int hw = Ho * Wo, spix = (Hin + 2) * Wp;
+  const int f0 = blockIdx.y * kF;    // first frame of this block (kF frames share the weights and the launch)
+  const int cq = threadIdx.x & 7;    // channel quad inside the 32-channel slab
+  const int pl = threadIdx.x >> 3;   // pixel lane 0..31
   const int c = blockIdx.x * 32 + cq * 4;
-  const bool c_ok = c < C;          // C is a multiple of 4
-  const float* src = in + static_cast<size_t>(n) * rows_in * C;
+  const bool c_ok = c < C;           // C is a multiple of 4
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int pix = pl; pix < (Hin + 2) * Wp; pix += 32) {
-    const int yp = pix / Wp, xp = pix - yp * Wp;
-    const bool inside = c_ok && yp >= 1 && yp <= Hin && xp >= 1 && xp <= Win;
-    slab[pix * 8 + cq] =
-        inside ? *reinterpret_cast<const float4*>(src + (static_cast<size_t>(yp - 1 + oy) * pitch_in + (xp - 1 + ox)) * C + c)
-               : z4;
+#pragma unroll
+  for (int f = 0; f < kF; ++f) {
+    const bool f_ok = f0 + f < n_frames;
+    const float* src = in + static_cast<size_t>(f0 + f) * rows_in * C;
+    for (int pix = pl; pix < spix; pix += 32) {
+      const int yp = pix / Wp, xp = pix - yp * Wp;
+      const bool inside = f_ok && c_ok && yp >= 1 && yp <= Hin && xp >= 1 && xp <= Win;
+      slab[(f * spix + pix) * 8 + cq] =
+          inside ? *reinterpret_cast<const float4*>(src + (static_cast<size_t>(yp - 1 + oy) * pitch_in + (xp - 1 + ox)) * C + c)
+                 : z4;
+    }
   }
-  float4 wv[9], b4 = z4, acc_sum = z4;
+  float4 wv[9], b4 = z4;
 #pragma unroll
   for (int t = 0; t < 9; ++t) wv[t] = c_ok ? *reinterpret_cast<const float4*>(w + static_cast<size_t>(t) * C + c) : z4;
   if (c_ok) b4 = *reinterpret_cast<const float4*>(bias + c);
   __syncthreads();
   // padded coordinate of tap (dy, dx) for output (y, x): stride 1 -> (y + dy, x + dx); stride 2 -> (2y + dy + 1, 2x + dx + 1)
   constexpr int kOff = kStride == 1 ? 0 : 1;
-  for (int p = pl; p < Ho * Wo; p += 32) {
-    const int y = wo_shift >= 0 ? (p >> wo_shift) : p / Wo;
-    const int x = p - y * Wo;
-    const float4* base = slab + ((y * kStride + kOff) * Wp + x * kStride + kOff) * 8 + cq;
-    float4 v = b4;
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
+  for (int f = 0; f < kF; ++f) {
+    if (f0 + f >= n_frames) break;
+    float4 acc_sum = z4;
+    for (int p = pl; p < hw; p += 32) {
+      const int y = wo_shift >= 0 ? (p >> wo_shift) : p / Wo;
+      const int x = p - y * Wo;
+      const float4* base = slab + (f * spix + (y * kStride + kOff) * Wp + x * kStride + kOff) * 8 + cq;
+      float4 v = b4;
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const float4 a = base[(dy * Wp + dx) * 8];
-        const float4 ww = wv[dy * 3 + dx];
-        v.x = fmaf(a.x, ww.x, v.x); v.y = fmaf(a.y, ww.y, v.y); v.z = fmaf(a.z, ww.z, v.z); v.w = fmaf(a.w, ww.w, v.w);
-      }
-    v.x = fsilu(v.x); v.y = fsilu(v.y); v.z = fsilu(v.z); v.w = fsilu(v.w);
-    if (c_ok) *reinterpret_cast<float4*>(out + (static_cast<size_t>(n) * Ho * Wo + p) * C + c) = v;
-    acc_sum.x += v.x; acc_sum.y += v.y; acc_sum.z += v.z; acc_sum.w += v.w;
-  }
-  red[pl][cq] = acc_sum;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const int ch = threadIdx.x;  // channel inside the slab
-    float s = 0.f;
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float4 a = base[(dy * Wp + dx) * 8];
+          const float4 ww = wv[dy * 3 + dx];
+          v.x = fmaf(a.x, ww.x, v.x); v.y = fmaf(a.y, ww.y, v.y); v.z = fmaf(a.z, ww.z, v.z); v.w = fmaf(a.w, ww.w, v.w);
+        }
+      v.x = fsilu(v.x); v.y = fsilu(v.y); v.z = fsilu(v.z); v.w = fsilu(v.w);
+      if (c_ok) *reinterpret_cast<float4*>(out + (static_cast<size_t>(f0 + f) * hw + p) * C + c) = v;
+      acc_sum.x += v.x; acc_sum.y += v.y; acc_sum.z += v.z; acc_sum.w += v.w;
+    }
+    red[pl][cq] = acc_sum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int ch = threadIdx.x;  // channel inside the slab
+      float s = 0.f;
 #pragma unroll 8
-    for (int k = 0; k < 32; ++k) s += reinterpret_cast<const float*>(&red[k][0])[ch];
-    if (blockIdx.x * 32 + ch < C) sums[static_cast<size_t>(n) * C + blockIdx.x * 32 + ch] = s;
+      for (int k = 0; k < 32; ++k) s += reinterpret_cast<const float*>(&red[k][0])[ch];
+      if (blockIdx.x * 32 + ch < C) sums[static_cast<size_t>(f0 + f) * C + blockIdx.x * 32 + ch] = s;
+    }
+    __syncthreads();
   }
 }
 
@@ -267,24 +279,26 @@ int enc_im2col_s2(const float* in, float* col, int n, int Hin, int Win, int C, c
 
 int enc_dwconv(const float* in, float* out, float* sums, const float* w, const float* bias, int n, int C, int Hin,
                int Win, int pitch_in, int oy, int ox, int rows_in, int stride, cudaStream_t st) {
-  dim3 grid((C + 31) / 32, n);
-  const size_t smem = static_cast<size_t>(Hin + 2) * (Win + 2) * 32 * sizeof(float);
-  if (smem > 200 * 1024) return fail(M2S_ERR_UNSUPPORTED, "depthwise input %dx%d too large for the SMEM slab", Hin, Win);
+  const size_t slab = static_cast<size_t>(Hin + 2) * (Win + 2) * 32 * sizeof(float);
+  if (slab > 200 * 1024) return fail(M2S_ERR_UNSUPPORTED, "depthwise input %dx%d too large for the SMEM slab", Hin, Win);
   if (stride != 1 && stride != 2) return fail(M2S_ERR_UNSUPPORTED, "depthwise stride %d", stride);
+  // small images: several frames per block (amortises weight loads / block launch; more pixels per thread)
+  const int kf = (stride == 1 && slab * 4 <= 64 * 1024) ? 4 : 1;
+  using Fn = void (*)(const float*, float*, float*, const float*, const float*, int, int, int, int, int, int, int, int, int);
+  Fn fn = stride == 2 ? dwconv_kernel<2, 1> : (kf == 4 ? dwconv_kernel<1, 4> : dwconv_kernel<1, 1>);
   static bool attr = false;
   if (!attr) {
-    M2S_CUDA_OK(cudaFuncSetAttribute(dwconv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    M2S_CUDA_OK(cudaFuncSetAttribute(dwconv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    M2S_CUDA_OK(cudaFuncSetAttribute(dwconv_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    M2S_CUDA_OK(cudaFuncSetAttribute(dwconv_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    M2S_CUDA_OK(cudaFuncSetAttribute(dwconv_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
   const int wo = Win / stride;
   int wo_shift = -1;
   for (int k = 0; k < 16; ++k)
     if ((1 << k) == wo) wo_shift = k;
-  if (stride == 1)
-    dwconv_kernel<1><<<grid, 256, smem, st>>>(in, out, sums, w, bias, C, Hin, Win, pitch_in, oy, ox, rows_in, wo_shift);
-  else
-    dwconv_kernel<2><<<grid, 256, smem, st>>>(in, out, sums, w, bias, C, Hin, Win, pitch_in, oy, ox, rows_in, wo_shift);
+  dim3 grid((C + 31) / 32, (n + kf - 1) / kf);
+  fn<<<grid, 256, slab * kf, st>>>(in, out, sums, w, bias, C, Hin, Win, pitch_in, oy, ox, rows_in, wo_shift, n);
   M2S_CUDA_OK(cudaGetLastError());
   return M2S_OK;
 }
