@@ -1,0 +1,335 @@
+// Device-side building blocks shared by the conv engine kernels (single-CTA and CTA-pair variants):
+// PTX wrappers (mbarrier, TMA, tcgen05 / TMEM), the 128B-swizzle SMEM descriptor, and the fused epilogue.
+#pragma once
+#include "m2s_common.cuh"
+#include <cuda.h>
+
+namespace m2s {
+namespace engine {
+
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kKBlock = 32;     // tf32 elements per 128-byte swizzle row
+constexpr int kRowBytes = 128;
+constexpr int kTmemCols = 512;
+constexpr int kMaxStagesA = 4;
+constexpr int kMaxStagesB = 8;
+constexpr uint32_t kSmemBudget = 200 * 1024;  // > 114 KB forces 1 CTA / SM (TMEM is allocated whole)
+
+struct EngineParams {
+  ConvProblem p;
+  const float* wpacked;
+  int n_tile, n_tiles, msub, m_tile;
+  int tiles_per_batch, total_tiles;
+  int cblocks;
+  int a_box_rows, a_nbox, shift_min;
+  int na, nb;
+  uint32_t a_stage_bytes, b_stage_bytes;
+  int nacc, acc_stride;
+  uint32_t idesc;
+  int base_offset_mode;
+  int a_per_tap;
+  int rel_shift[M2S_MAX_TAPS];
+  int tg;               // taps per weight stage
+  uint32_t b_tap_bytes; // bytes of one tap's weight block (n_tile x 128)
+  unsigned long long* trace;  // debug: per-role clock64 stamps of CTA 0 (null = off)
+  int trace_tiles;
+  int dbg;  // debug: bit0 skip global stores, bit1 skip TMEM loads, bit2 skip SMEM transpose, bit3 skip MMA issue
+};
+
+// ---- PTX wrappers ------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug must trap, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("m2s conv engine: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// SMEM matrix descriptor, K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, int base_offset_mode) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);        // start address  [0,14)
+  d |= static_cast<uint64_t>(1) << 16;                       // LBO (unused for swizzled K-major) [16,30)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;               // SBO = 1024 B   [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                       // descriptor version (Blackwell) [46,48)
+  if (base_offset_mode) d |= static_cast<uint64_t>((saddr >> 7) & 7) << 49;  // base offset [49,52)
+  d |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B    [61,64)
+  return d;
+}
+
+// debug timeline: slot = role*3 + k ; layout trace[tile_iter][9]
+__device__ __forceinline__ void trace_stamp(const EngineParams& prm, int it, int slot) {
+  if (prm.trace && blockIdx.x == 0 && it < prm.trace_tiles) prm.trace[it * 9 + slot] = clock64();
+}
+
+// One lane of a converged warp (the compiler then knows the region is warp-uniform and keeps descriptors /
+// barrier addresses in uniform registers instead of emitting per-lane R2UR loops).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// Four consecutive K-steps (4 x 8 tf32 = one 128-byte swizzle row) of one (sub-tile, tap).
+__device__ __forceinline__ void mma_tf32_k4(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum0,
+                                            int ksteps) {
+  mma_tf32(tmem_d, da, db, idesc, accum0);
+  if (ksteps > 1) mma_tf32(tmem_d, da + 2, db + 2, idesc, 1u);
+  if (ksteps > 2) mma_tf32(tmem_d, da + 4, db + 4, idesc, 1u);
+  if (ksteps > 3) mma_tf32(tmem_d, da + 6, db + 6, idesc, 1u);
+}
+
+struct EpiConsts {
+  float inv_slope, pre_w, post_w, out_scale, act_slope;
+};
+
+// Epilogue programs (compile-time): the common cases drop every unused instruction -- with 256-column-wide tiles the
+// epilogue is ALU-issue-bound (32K outputs per tile on 8 warps), so instructions per output are what matters.
+enum { EPI_FULL = 0, EPI_FULL_SILU = 1, EPI_BIAS = 2, EPI_LRELU = 3, EPI_SILU = 4, EPI_RES = 5 };
+
+__device__ __forceinline__ float fast_silu(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+
+template <int kEpi>
+__device__ __forceinline__ float epi_elem(const EpiConsts& c, float acc, float bias, float res, float accum) {
+  float v = acc + bias;
+  if (kEpi == EPI_BIAS) return v;
+  if (kEpi == EPI_LRELU) return v >= 0.f ? v : v * c.act_slope;
+  if (kEpi == EPI_SILU) return fast_silu(v);
+  if (kEpi == EPI_RES) return v + res;
+  const float rt = res >= 0.f ? res : res * c.inv_slope;
+  v = fmaf(rt, c.pre_w, v);
+  v += accum;
+  v *= c.out_scale;
+  if (kEpi == EPI_FULL_SILU) v = fast_silu(v);
+  else v = v >= 0.f ? v : v * c.act_slope;
+  return fmaf(rt, c.post_w, v);
+}
+
+
+// Per-warp epilogue state that does not change across tiles.
+struct EpiWarp {
+  EpiConsts ec;
+  uint32_t stage;  // this warp's 4 KB transpose staging (shared::cta address)
+  int quad, half, lane, rr0, cc;
+  int mask_mode;
+  bool has_res, has_acc;
+};
+
+__device__ __forceinline__ EpiWarp make_epi_warp(const Epilogue& e, uint32_t stage_base, int ew, int warp, int lane) {
+  EpiWarp w;
+  w.quad = warp & 3;  // TMEM lane quadrant this warp may access
+  w.half = ew >> 2;   // which of the two warps of the quadrant
+  w.lane = lane;
+  w.rr0 = lane >> 3;
+  w.cc = lane & 7;
+  w.stage = stage_base + ew * 4096;
+  w.has_res = e.res != nullptr;
+  w.has_acc = e.accum != nullptr;
+  w.ec.inv_slope = e.res_inv_slope;
+  w.ec.pre_w = (w.has_res && !e.res_after_act) ? 1.f : 0.f;
+  w.ec.post_w = (w.has_res && e.res_after_act) ? 1.f : 0.f;
+  w.ec.out_scale = e.out_scale;
+  w.ec.act_slope = e.act == M2S_ACT_LRELU ? e.act_slope : 1.f;
+  w.mask_mode = e.mask_mode;
+  return w;
+}
+
+// Epilogue of one accumulator tile for one warp: rows [q0, q0 + 128*msub) of batch item b, columns [n0, n0+n_tile).
+// TMEM -> registers (row per thread) -> SMEM transpose (XOR-swizzled, conflict-free) -> coalesced global traffic:
+// 8 lanes cover one 128-byte row segment, a warp instruction covers 4 rows.  `tmem_acc` already carries this warp's
+// lane-quadrant offset.
+template <int kEpi>
+__device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWarp& ew_, uint32_t tmem_acc, int b, int q0,
+                                              int n0, int msub, int n_tile) {
+  const Epilogue& e = p.epi;
+  const EpiConsts& ec = ew_.ec;
+  const uint32_t stage = ew_.stage;
+  const int quad = ew_.quad, half = ew_.half, lane = ew_.lane, rr0 = ew_.rr0, cc = ew_.cc;
+  const int mask_mode = ew_.mask_mode;
+  const bool has_res = ew_.has_res, has_acc = ew_.has_acc;
+  const int nchunks = (n_tile + 31) >> 5;
+  const int units = msub * nchunks;
+  int len_rows = 0x7fffffff;
+  if (mask_mode == M2S_MASK_LEN) len_rows = __ldg(e.lens + b) * e.len_scale;
+  const size_t d_base = static_cast<size_t>(b) * p.d_batch_rows + p.d_row_offset;
+  for (int u = half; u < units; u += 2) {
+    const int sub = u / nchunks;
+    const int c0 = (u - sub * nchunks) << 5;
+    const int qw = q0 + sub * 128 + quad * 32;  // first row of this warp's 32-row slab
+    uint32_t r[32];
+    tmem_ld16(tmem_acc + sub * n_tile + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+    if (c0 + 16 < n_tile) tmem_ld16(tmem_acc + sub * n_tile + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+    // While the TMEM read is in flight: bias / residual / accumulate loads of this unit (the output may alias
+    // them in place, so every load is issued before the first store).  Thread (rr0, cc) owns rows rr0 + 4i,
+    // columns n .. n+3; all row predicates reduce to "4i + rr0 < bound".
+    const int n = n0 + c0 + cc * 4;
+    const bool col_ok = (c0 + cc * 4 < n_tile) && n < p.n;
+    const int rows_ok = col_ok ? min(32, p.l_out - qw) : 0;                 // rows that exist
+    int rows_valid = 32;                                                    // rows that survive the mask
+    if (mask_mode == M2S_MASK_LEN) rows_valid = len_rows - (qw + p.d_row_offset);
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col_ok && e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+    const size_t row0 = d_base + qw + rr0;
+    float* dptr = p.d + row0 * p.d_ld + n;
+    const size_t d_step = static_cast<size_t>(4) * p.d_ld;
+    float4 res4[8], acc4[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      res4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (kEpi == EPI_FULL || kEpi == EPI_FULL_SILU || kEpi == EPI_RES) {
+      if (has_res) {
+        const float* rptr = e.res + row0 * e.res_ld + n;
+        const size_t r_step = static_cast<size_t>(4) * e.res_ld;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i * 4 + rr0 < rows_ok) res4[i] = *reinterpret_cast<const float4*>(rptr + i * r_step);
+      }
+    }
+    if (kEpi == EPI_FULL || kEpi == EPI_FULL_SILU) {
+      if (has_acc) {
+        const float* aptr = e.accum + row0 * e.accum_ld + n;
+        const size_t a_step = static_cast<size_t>(4) * e.accum_ld;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i * 4 + rr0 < rows_ok) acc4[i] = *reinterpret_cast<const float4*>(aptr + i * a_step);
+      }
+    }
+    // image-border mask: (i, j) = divmod(row, pitch) once, then stepped by 4 rows
+    int mi = 0, mj = 0;
+    if (mask_mode == M2S_MASK_PITCH) {
+      const int drow = qw + rr0 + p.d_row_offset;
+      mi = drow / e.pitch;
+      mj = drow - mi * e.pitch;
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + lane * 128 + ((j ^ (lane & 7)) << 4)),
+                   "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                   : "memory");
+    __syncwarp();
+    // all 8 rows' (32 independent) element chains are computed unconditionally so the scheduler can interleave
+    // them; only the stores are predicated
+    float4 o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rr = i * 4 + rr0;
+      float4 a4;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w)
+                   : "r"(stage + rr * 128 + ((cc ^ (rr & 7)) << 4)));
+      o[i].x = epi_elem<kEpi>(ec, a4.x, bias4.x, res4[i].x, acc4[i].x);
+      o[i].y = epi_elem<kEpi>(ec, a4.y, bias4.y, res4[i].y, acc4[i].y);
+      o[i].z = epi_elem<kEpi>(ec, a4.z, bias4.z, res4[i].z, acc4[i].z);
+      o[i].w = epi_elem<kEpi>(ec, a4.w, bias4.w, res4[i].w, acc4[i].w);
+    }
+    if (mask_mode == M2S_MASK_PITCH) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool valid = mi >= e.i_lo && mi < e.i_hi && mj >= e.j_lo && mj < e.j_hi;
+        if (!valid) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        mj += 4;
+        if (mj >= e.pitch) { mj -= e.pitch; ++mi; }
+      }
+    } else if (mask_mode == M2S_MASK_LEN) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i * 4 + rr0 >= rows_valid) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i * 4 + rr0 < rows_ok) *reinterpret_cast<float4*>(dptr + i * d_step) = o[i];
+    __syncwarp();
+  }
+}
+
+}  // namespace engine
+}  // namespace m2s

@@ -118,6 +118,10 @@ struct PackedWeights {
   int n = 0, c_in = 0, taps = 0;
   int n_tile = 0, n_tiles = 0, cblocks = 0;
   size_t packed_floats = 0;
+  // CTA-pair layout (cta_group::2, wide layers only): rows of 32 floats, unswizzled,
+  // [n_tile][cblock][half][tap][n_tile/2]; nullptr when the layer is too narrow
+  float* dev_pair = nullptr;
+  int n_tile_pair = 0, n_tiles_pair = 0;
 };
 
 // Choose N tiling for the tcgen05 engine (n_tile multiple of 16, <= 256).
@@ -127,6 +131,9 @@ int pack_weights(const float* host_w, int taps, int n, int c_in, bool tf32_round
 void free_weights(PackedWeights* w);
 
 int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stream);
+int conv_tcgen05_pair(const ConvProblem& p, const PackedWeights& w, cudaStream_t stream);
+int profile_before(cudaStream_t stream);
+int profile_after(cudaStream_t stream, double flops);
 int conv_simt(const ConvProblem& p, const float* w_plain, cudaStream_t stream);
 
 // debug / probe knobs for the tcgen05 engine (environment-driven, read once)
@@ -139,6 +146,7 @@ struct EngineKnobs {
   unsigned long long* trace = nullptr;  // debug timeline buffer (device), trace_tiles x 9 stamps of CTA 0
   int trace_tiles = 0;
   int dbg = 0;
+  int pair = 1;              // 1: use the CTA-pair (cta_group::2) kernel for wide layers, 0: never
   int n_tile_max = 128;      // N columns per tile once N exceeds it (weights are packed accordingly)
 };
 EngineKnobs& engine_knobs();

@@ -19,6 +19,11 @@ CASES = [
     (2, 1500, 256, 256, [-50, -45, -40, -35, -30, -25, -20, -15, -10, -5, 0]),
     (2, 100, 64, 512, [0, 1, 2, 3, 4, 5, 6]),
     (2, 500, 64, 320, [1, 0, -1]),
+    (4, 4000, 256, 256, [-50, -45, -40, -35, -30, -25, -20, -15, -10, -5, 0]),   # CTA-pair kernel, N = 256
+    (1, 20000, 128, 128, [-6, -3, 0]),                                           # CTA-pair kernel, N = 128
+    (2, 3000, 64, 512, [0, 1, 2, 3, 4, 5, 6]),                                    # CTA-pair kernel, 2 N-tiles
+    (2, 5003, 64, 320, [1, 0, -1]),                                               # CTA-pair, N = 320 -> 2 x 160, ragged M
+    (1, 20001, 208, 208, [0]),                                                    # CTA-pair GEMM, odd channel counts
     (1, 5, 32, 32, [-2, -1, 0]),          # shorter than one tile
     (2, 129, 56, 104, [0]),               # odd encoder channel counts (N padded to 16 inside)
 ]
@@ -65,6 +70,34 @@ def test_fused_epilogue(impl):
                       act=_lib.ACT_LRELU, act_slope=0.01, lens=lens, len_scale=4)
     err = (d.double().cpu() - ref).abs().max().item()
     assert err < (5e-5 if impl == "simt" else 6e-3), err
+
+
+def test_pair_kernel_fused_epilogue_and_matches_single_cta():
+    """cta_group::2 kernel with residual + accumulate + scale + activation + length mask; must agree with the
+    single-CTA kernel to fp32 accumulation-order noise."""
+    from mri2speech_b200 import _lib
+    B, L, C, N, shifts = 3, 6000, 128, 128, [-18, -15, -12, -9, -6, -3, 0]
+    a, w, bias = _inputs(B, L, C, N, len(shifts), seed=9)
+    g = torch.Generator().manual_seed(10)
+    x = torch.randn(B, L, N, generator=g)
+    res = torch.nn.functional.leaky_relu(x, 0.1).cuda()
+    acc = torch.randn(B, L, N, generator=g).cuda()
+    lens = torch.tensor([1500, 40, 777], dtype=torch.int32).cuda()
+    kw = dict(bias=bias, res=res, res_inv_slope=10.0, accum=acc, out_scale=1.0 / 3.0, act=_lib.ACT_LRELU,
+              act_slope=0.01, lens=lens, len_scale=4)
+    ref = multi_tap_reference(a, w, shifts, L) + bias.double().cpu() + x.double() + acc.double().cpu()
+    ref = torch.nn.functional.leaky_relu(ref / 3.0, 0.01)
+    t = torch.arange(L).view(1, L, 1)
+    ref = ref * (t < (lens.cpu().view(-1, 1, 1) * 4)).double()
+    _lib.set_knob("pair", 1)
+    d_pair = _lib.conv_fwd(a, w, shifts, L, **kw).cpu()
+    _lib.set_knob("pair", 0)
+    try:
+        d_single = _lib.conv_fwd(a, w, shifts, L, **kw).cpu()
+    finally:
+        _lib.set_knob("pair", 1)
+    assert (d_pair.double() - ref).abs().max().item() < 6e-3
+    assert (d_pair - d_single).abs().max().item() < 1e-4
 
 
 def test_pitch_mask_and_row_offset():
