@@ -254,6 +254,7 @@ EngineKnobs& engine_knobs() {
     x.a_per_tap = env_int("M2S_ENGINE_A_PER_TAP", 0);
     x.n_tile_max = env_int("M2S_ENGINE_NTILE_MAX", 128);
     x.pair = env_int("M2S_ENGINE_PAIR", 1);
+    x.pair_min_n = env_int("M2S_ENGINE_PAIR_MIN_N", 32);
     return x;
   }();
   return k;
@@ -368,7 +369,7 @@ int pack_weights(const float* host_w, int taps, int n, int c_in, bool tf32_round
         const int chunk = (cc >> 2) ^ (r & 7);
         packed[blk + static_cast<size_t>(r) * kKBlock + chunk * 4 + (cc & 3)] = v;
       }
-  if (n >= 128 && engine_knobs().pair) {
+  if (n >= engine_knobs().pair_min_n && n % 16 == 0 && engine_knobs().pair) {
     // CTA-pair layout: [nt][cb][half][tap][nh rows][32], unswizzled (TMA applies the 128B swizzle)
     const int tiles = (n + 255) / 256;
     w.n_tile_pair = (((n + tiles - 1) / tiles) + 15) / 16 * 16;
@@ -412,9 +413,18 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
     return fail(M2S_ERR_BAD_ARG, "packed weights do not match the problem");
   if (p.batch <= 0 || p.l_out <= 0) return M2S_OK;
   if (w.dev_pair && engine_knobs().pair && !engine_knobs().a_per_tap && !engine_knobs().trace) {
-    // wide layer with enough 256-row tiles to occupy the CTA pairs: cta_group::2 kernel
+    // CTA-pair (cta_group::2) kernel when the layer is wide, or narrow but bound by the MMA's SMEM operand fetch
+    // rather than by HBM (measured model: ~75 B/clk/SM of operand fetch, ~23 B/clk/SM of HBM).
     const long long pair_tiles = static_cast<long long>(p.batch) * ((p.l_out + 255) / 256) * w.n_tiles_pair;
-    if (pair_tiles >= sm_count() / 4) return conv_tcgen05_pair(p, w, stream);
+    bool use_pair = p.n >= 128;
+    if (!use_pair) {
+      const double mma_clk = static_cast<double>(p.taps) * ((p.c_in + 7) / 8) * (4096.0 + 32.0 * w.n_tile) / 75.0;
+      const int streams = 1 + (p.epi.res ? 1 : 0) + (p.epi.accum ? 1 : 0);
+      const double hbm_clk = 128.0 * 4.0 * (p.c_in + static_cast<double>(p.n) * streams) / 23.0;
+      use_pair = mma_clk > 1.5 * hbm_clk;
+    }
+    if (engine_knobs().pair == 2) use_pair = true;
+    if (use_pair && pair_tiles >= sm_count() / 4) return conv_tcgen05_pair(p, w, stream);
   }
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(M2S_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");

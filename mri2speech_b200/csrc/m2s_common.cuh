@@ -146,7 +146,8 @@ struct EngineKnobs {
   unsigned long long* trace = nullptr;  // debug timeline buffer (device), trace_tiles x 9 stamps of CTA 0
   int trace_tiles = 0;
   int dbg = 0;
-  int pair = 1;              // 1: use the CTA-pair (cta_group::2) kernel for wide layers, 0: never
+  int pair = 1;              // CTA-pair (cta_group::2) kernel: 0 never, 1 heuristic, 2 whenever packed
+  int pair_min_n = 32;       // narrowest layer whose weights are also packed for the CTA-pair kernel
   int n_tile_max = 128;      // N columns per tile once N exceeds it (weights are packed accordingly)
 };
 EngineKnobs& engine_knobs();
