@@ -150,5 +150,6 @@ def acoustic_forward(sd: dict, x: torch.Tensor, lengths=None) -> torch.Tensor:
             return bilstm_head_forward(sd, f)
         out = torch.zeros(B, T, sd["head.weight"].shape[0])
         for b, ln in enumerate(lengths):
-            out[b, :ln] = bilstm_head_forward(sd, f[b:b + 1, :ln])[0]
+            if ln > 0:
+                out[b, :ln] = bilstm_head_forward(sd, f[b:b + 1, :ln])[0]
         return out
