@@ -170,6 +170,15 @@ size_t m2s_acoustic_workspace_bytes(const m2s_acoustic* m, int32_t batch, int32_
 int m2s_acoustic_forward(m2s_acoustic* m, const float* frames_dev, int32_t batch, int32_t frames,
                          const int32_t* lengths, const int32_t* lengths_host, float* mel_norm,
                          void* workspace, size_t workspace_bytes, m2s_stream_t stream);
+/* Fused ingest: frames are the raw uint8 gray frames (batch, frames, height, width).
+ * Replaces the host-side chain of the reference CLI: scripts/run_mri_video_inference.py:34-53
+ * (_preprocess_frame: z-score then min-max == per-frame min-max; a constant frame maps to zeros) and, when
+ * mask != NULL, scripts/mask_rtmri_video.py:96-98 first (masked = uint8(clip(frame * mask, 0, 255)),
+ * truncating).  mask: device float32 (height, width) shared by the batch, or NULL.  The min-max pass and
+ * the stem conv read the uint8 frames directly: the float32 frames never exist in HBM. */
+int m2s_acoustic_forward_u8(m2s_acoustic* m, const uint8_t* frames_dev, const float* mask, int32_t batch,
+                            int32_t frames, const int32_t* lengths, const int32_t* lengths_host,
+                            float* mel_norm, void* workspace, size_t workspace_bytes, m2s_stream_t stream);
 /* Encoder only: (n_frames, height, width) -> (n_frames, 208) features. */
 int m2s_acoustic_encode(m2s_acoustic* m, const float* frames_dev, int32_t n_frames, float* feats,
                         void* workspace, size_t workspace_bytes, m2s_stream_t stream);

@@ -215,7 +215,11 @@ class OTNLikeCNNBiLSTM(nn.Module):
         return int(_lib.lib().m2s_acoustic_launches(self._handle)) if self._handle else 0
 
     # -- the drop-in call -----------------------------------------------------------------
-    def forward(self, x: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, lengths: Optional[torch.Tensor] = None,
+                mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x float32: frames already normalised to [0,1] (the reference call, mri_acoustic_model.py:116-136).
+        x uint8: raw gray frames; the per-frame min-max of run_mri_video_inference.py:34-53 and, with ``mask``
+        (H,W) float32, the articulator masking of mask_rtmri_video.py:96-98 run fused into the stem load."""
         _lib.require_device(x)
         if x.dim() == 5:
             if x.size(2) != 1:
@@ -223,7 +227,10 @@ class OTNLikeCNNBiLSTM(nn.Module):
             x = x[:, :, 0]
         if x.dim() != 4:
             raise ValueError(f"expected (B,T,1,H,W) or (B,T,H,W), got {tuple(x.shape)}")
-        x = x.contiguous().float()
+        raw = x.dtype == torch.uint8
+        if mask is not None and not raw:
+            raise ValueError("mask applies to raw uint8 frames (it is applied before normalisation)")
+        x = x.contiguous() if raw else x.contiguous().float()
         B, T, H, W = x.shape
         with torch.cuda.device(x.device):
             self._prepare(x, B, T, (H, W))
@@ -232,10 +239,19 @@ class OTNLikeCNNBiLSTM(nn.Module):
             if lengths is not None:
                 lens_host = lengths.detach().to("cpu", torch.int32).contiguous()
                 lens_dev = lens_host.to(x.device)
-            _lib.check(_lib.lib().m2s_acoustic_forward(
-                self._handle, x.data_ptr(), B, T, _lib.ptr(lens_dev),
-                lens_host.data_ptr() if lens_host is not None else None, out.data_ptr(),
-                self._workspace.data_ptr(), self._workspace.numel(), _lib.current_stream()))
+            lens_host_ptr = lens_host.data_ptr() if lens_host is not None else None
+            if raw:
+                if mask is not None:
+                    if tuple(mask.shape) != (H, W):
+                        raise ValueError(f"Mask shape {tuple(mask.shape)} != frame shape {(H, W)}")
+                    mask = mask.to(x.device, torch.float32).contiguous()
+                _lib.check(_lib.lib().m2s_acoustic_forward_u8(
+                    self._handle, x.data_ptr(), _lib.ptr(mask), B, T, _lib.ptr(lens_dev), lens_host_ptr,
+                    out.data_ptr(), self._workspace.data_ptr(), self._workspace.numel(), _lib.current_stream()))
+            else:
+                _lib.check(_lib.lib().m2s_acoustic_forward(
+                    self._handle, x.data_ptr(), B, T, _lib.ptr(lens_dev), lens_host_ptr, out.data_ptr(),
+                    self._workspace.data_ptr(), self._workspace.numel(), _lib.current_stream()))
         return out
 
     def encode_frames(self, frames: torch.Tensor) -> torch.Tensor:

@@ -18,6 +18,8 @@
 namespace m2s {
 int enc_stem(const float* frames, const int32_t* fmap, float* out, const float* w, const float* bias, int n, int H,
              int W, cudaStream_t st);
+int enc_stem_u8(const uint8_t* frames, const int32_t* fmap, const float* mask, float2* norm, float* out, const float* w,
+                const float* bias, int n, int H, int W, cudaStream_t st);
 int enc_zero_rows(float* buf, int n, int rows_per_frame, int ld, int head_rows, int tail_start, cudaStream_t st);
 int enc_im2col_s2(const float* in, float* col, int n, int Hin, int Win, int C, cudaStream_t st);
 int enc_dwconv(const float* in, float* out, float* sums, const float* w, const float* bias, int n, int C, int Hin,
@@ -193,6 +195,7 @@ void set_pitch_mask(ConvProblem* p, int h, int w) {
 
 struct EncBuffers {
   float *x0, *x1, *e, *e2, *col, *sums, *scales;
+  float2* norm;  // per-frame (min, 1/range) of the uint8 ingest
   int32_t* fmap;
 };
 
@@ -208,7 +211,7 @@ AcWorkspace plan_ws(const m2s_acoustic* m, int batch, int frames) {
   const size_t nf = static_cast<size_t>(batch) * frames;
   const size_t nc = nf < static_cast<size_t>(m->chunk) ? nf : m->chunk;
   w.enc_floats = align64(nc * m->x_floats) * 2 + align64(nc * m->e_floats) + align64(nc * m->e2_floats) +
-                 align64(nc * m->col_floats) + 2 * align64(nc * m->max_mid);
+                 align64(nc * m->col_floats) + 2 * align64(nc * m->max_mid) + align64(2 * nc);
   w.feats_floats = align64(nf * kFeat);
   w.gin_floats = align64(nf * 8 * m->cfg.rnn_hidden);
   w.hcat_floats = align64(nf * 2 * m->cfg.rnn_hidden);
@@ -218,12 +221,15 @@ AcWorkspace plan_ws(const m2s_acoustic* m, int batch, int frames) {
 }
 
 // encoder over `n` frames (compact list; fmap maps compact index -> source frame / feature row, or null)
-int encode_chunk(const m2s_acoustic* m, const float* frames, const int32_t* fmap, int n, float* feats, int feat_ld,
-                 const EncBuffers& B, cudaStream_t st) {
+int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float* mask, const int32_t* fmap, int n,
+                 float* feats, int feat_ld, const EncBuffers& B, cudaStream_t st) {
   const int H = m->cfg.height, W = m->cfg.width;
   float* x = B.x0;
   float* y = B.x1;
-  M2S_TRY(enc_stem(frames, fmap, x, m->stem_w, m->stem_b, n, H, W, st));
+  if (u8)
+    M2S_TRY(enc_stem_u8(static_cast<const uint8_t*>(frames), fmap, mask, B.norm, x, m->stem_w, m->stem_b, n, H, W, st));
+  else
+    M2S_TRY(enc_stem(static_cast<const float*>(frames), fmap, x, m->stem_w, m->stem_b, n, H, W, st));
   for (const Block& b : m->blocks) {
     const int hin = b.hin, win = b.win;
     const int hout = hin / b.stride, wout = win / b.stride;
@@ -286,8 +292,8 @@ int encode_chunk(const m2s_acoustic* m, const float* frames, const int32_t* fmap
   return enc_gap(x, fmap, feats, n, hw, kFeat, feat_ld, st);
 }
 
-int encode_all(const m2s_acoustic* m, const float* frames, const int32_t* fmap_dev, int n_frames, float* feats,
-               float* enc_base, cudaStream_t st) {
+int encode_all(const m2s_acoustic* m, const void* frames, bool u8, const float* mask, const int32_t* fmap_dev,
+               int n_frames, float* feats, float* enc_base, cudaStream_t st) {
   const int nc = n_frames < m->chunk ? n_frames : m->chunk;
   EncBuffers B{};
   float* p = enc_base;
@@ -297,14 +303,16 @@ int encode_all(const m2s_acoustic* m, const float* frames, const int32_t* fmap_d
   B.e2 = p; p += align64(static_cast<size_t>(nc) * m->e2_floats);
   B.col = p; p += align64(static_cast<size_t>(nc) * m->col_floats);
   B.sums = p; p += align64(static_cast<size_t>(nc) * m->max_mid);
-  B.scales = p;
+  B.scales = p; p += align64(static_cast<size_t>(nc) * m->max_mid);
+  B.norm = reinterpret_cast<float2*>(p);
   for (int f0 = 0; f0 < n_frames; f0 += nc) {
     const int n = n_frames - f0 < nc ? n_frames - f0 : nc;
     if (fmap_dev) {
-      M2S_TRY(encode_chunk(m, frames, fmap_dev + f0, n, feats, kFeat, B, st));
+      M2S_TRY(encode_chunk(m, frames, u8, mask, fmap_dev + f0, n, feats, kFeat, B, st));
     } else {
-      const size_t fsz = static_cast<size_t>(m->cfg.height) * m->cfg.width;
-      M2S_TRY(encode_chunk(m, frames + f0 * fsz, nullptr, n, feats + static_cast<size_t>(f0) * kFeat, kFeat, B, st));
+      const size_t fsz = static_cast<size_t>(m->cfg.height) * m->cfg.width * (u8 ? 1 : 4);
+      M2S_TRY(encode_chunk(m, static_cast<const char*>(frames) + f0 * fsz, u8, mask, nullptr, n,
+                           feats + static_cast<size_t>(f0) * kFeat, kFeat, B, st));
     }
   }
   return M2S_OK;
@@ -537,7 +545,7 @@ extern "C" int m2s_acoustic_encode(m2s_acoustic* m, const float* frames_dev, int
   if (n_frames <= 0) return M2S_OK;
   WsPtrs w;
   M2S_TRY(carve(m, 1, n_frames, workspace, workspace_bytes, &w));
-  return encode_all(m, frames_dev, nullptr, n_frames, feats, w.enc, reinterpret_cast<cudaStream_t>(stream));
+  return encode_all(m, frames_dev, false, nullptr, nullptr, n_frames, feats, w.enc, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int m2s_acoustic_rnn_head(m2s_acoustic* m, const float* feats, int32_t batch, int32_t frames,
@@ -553,9 +561,10 @@ extern "C" int m2s_acoustic_rnn_head(m2s_acoustic* m, const float* feats, int32_
                   reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int m2s_acoustic_forward(m2s_acoustic* m, const float* frames_dev, int32_t batch, int32_t frames,
-                                    const int32_t* lengths, const int32_t* lengths_host, float* mel_norm,
-                                    void* workspace, size_t workspace_bytes, m2s_stream_t stream) {
+namespace {
+int acoustic_forward_impl(m2s_acoustic* m, const void* frames_dev, bool u8, const float* mask, int32_t batch,
+                          int32_t frames, const int32_t* lengths, const int32_t* lengths_host, float* mel_norm,
+                          void* workspace, size_t workspace_bytes, m2s_stream_t stream) {
   if (!m || !frames_dev || !mel_norm) return fail(M2S_ERR_BAD_ARG, "null argument");
   if ((lengths == nullptr) != (lengths_host == nullptr))
     return fail(M2S_ERR_BAD_ARG, "lengths and lengths_host must be given together");
@@ -577,10 +586,25 @@ extern "C" int m2s_acoustic_forward(m2s_acoustic* m, const float* frames_dev, in
     if (!fmap.empty()) {
       M2S_CUDA_OK(cudaMemcpyAsync(w.fmap, fmap.data(), fmap.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
       M2S_CUDA_OK(cudaStreamSynchronize(st));  // fmap is a stack-lifetime host buffer
-      M2S_TRY(encode_all(m, frames_dev, w.fmap, static_cast<int>(fmap.size()), w.feats, w.enc, st));
+      M2S_TRY(encode_all(m, frames_dev, u8, mask, w.fmap, static_cast<int>(fmap.size()), w.feats, w.enc, st));
     }
   } else {
-    M2S_TRY(encode_all(m, frames_dev, nullptr, total, w.feats, w.enc, st));
+    M2S_TRY(encode_all(m, frames_dev, u8, mask, nullptr, total, w.feats, w.enc, st));
   }
   return rnn_head(m, w.feats, batch, frames, lengths, lengths_host, mel_norm, w.gin, w.hcat, w.counters, st);
+}
+}  // namespace
+
+extern "C" int m2s_acoustic_forward(m2s_acoustic* m, const float* frames_dev, int32_t batch, int32_t frames,
+                                    const int32_t* lengths, const int32_t* lengths_host, float* mel_norm,
+                                    void* workspace, size_t workspace_bytes, m2s_stream_t stream) {
+  return acoustic_forward_impl(m, frames_dev, false, nullptr, batch, frames, lengths, lengths_host, mel_norm, workspace,
+                               workspace_bytes, stream);
+}
+
+extern "C" int m2s_acoustic_forward_u8(m2s_acoustic* m, const uint8_t* frames_dev, const float* mask, int32_t batch,
+                                       int32_t frames, const int32_t* lengths, const int32_t* lengths_host,
+                                       float* mel_norm, void* workspace, size_t workspace_bytes, m2s_stream_t stream) {
+  return acoustic_forward_impl(m, frames_dev, true, mask, batch, frames, lengths, lengths_host, mel_norm, workspace,
+                               workspace_bytes, stream);
 }

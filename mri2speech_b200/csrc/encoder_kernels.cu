@@ -16,8 +16,45 @@ namespace {
 
 __device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); }
 
+// Per-frame min / max of (optionally masked) uint8 frames -> norm[n] = (min, 1 / (max - min)) (scale 0 for a
+// constant frame, which then maps to all zeros like run_mri_video_inference.py:50-53).  The reference's z-score
+// followed by min-max (:41-51) is an affine map followed by min-max, i.e. plain per-frame min-max.
+// Masking (scripts/mask_rtmri_video.py:96-98): masked = uint8(clip(frame * mask, 0, 255)) (truncation).
+__device__ __forceinline__ float masked_u8(uint8_t v, float m) {
+  return static_cast<float>(static_cast<uint8_t>(fminf(fmaxf(static_cast<float>(v) * m, 0.f), 255.f)));
+}
+
+__global__ void __launch_bounds__(256) frame_minmax_kernel(const uint8_t* __restrict__ frames,
+                                                           const int32_t* __restrict__ fmap,
+                                                           const float* __restrict__ mask, float2* __restrict__ norm,
+                                                           int hw) {
+  __shared__ float smin[8], smax[8];
+  const int n = blockIdx.x;
+  const uint8_t* f = frames + static_cast<size_t>(fmap ? fmap[n] : n) * hw;
+  float mn = 1e30f, mx = -1e30f;
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+    const float v = mask ? masked_u8(f[i], mask[i]) : static_cast<float>(f[i]);
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = mn; smax[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) { mn = fminf(mn, smin[k]); mx = fmaxf(mx, smax[k]); }
+    norm[n] = make_float2(mn, mx > mn ? 1.f / (mx - mn) : 0.f);
+  }
+}
+
 // frames (n, H, W) -> out padded ((H/2+2) x (W/2+2) rows, 32 ch); one block per padded output row.
-__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ frames, const int32_t* __restrict__ fmap,
+// kU8: frames are uint8 and are masked / min-max normalised on the fly (the fused ingest of SURVEY.md 8f-1).
+template <bool kU8>
+__global__ void __launch_bounds__(256) stem_kernel(const void* __restrict__ frames_v, const int32_t* __restrict__ fmap,
+                                                   const float* __restrict__ mask, const float2* __restrict__ norm,
                                                    float* __restrict__ out, const float* __restrict__ w /*[9][32]*/,
                                                    const float* __restrict__ bias, int H, int W) {
   const int Ho = H / 2, Wo = W / 2, pitch = Wo + 2;
@@ -31,11 +68,23 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ fra
   extern __shared__ float srow[];  // 3 x (W + 1) input pixels
   __shared__ float sw[9 * 32 + 32];
   const int y = i - 1;
-  const float* f = frames + static_cast<size_t>(fmap ? fmap[n] : n) * H * W;
+  const size_t foff = static_cast<size_t>(fmap ? fmap[n] : n) * H * W;
+  float2 nm = make_float2(0.f, 1.f);
+  if (kU8) nm = norm[n];
   for (int k = threadIdx.x; k < 3 * (W + 1); k += blockDim.x) {
     const int r = k / (W + 1), x = k % (W + 1);
     const int yy = 2 * y + r;
-    srow[k] = (yy < H && x < W) ? f[static_cast<size_t>(yy) * W + x] : 0.f;
+    float v = 0.f;
+    if (yy < H && x < W) {
+      const size_t idx = static_cast<size_t>(yy) * W + x;
+      if (kU8) {
+        const uint8_t u = static_cast<const uint8_t*>(frames_v)[foff + idx];
+        v = ((mask ? masked_u8(u, mask[idx]) : static_cast<float>(u)) - nm.x) * nm.y;
+      } else {
+        v = static_cast<const float*>(frames_v)[foff + idx];
+      }
+    }
+    srow[k] = v;
   }
   for (int k = threadIdx.x; k < 9 * 32 + 32; k += blockDim.x) sw[k] = k < 288 ? w[k] : bias[k - 288];
   __syncthreads();
@@ -256,7 +305,18 @@ __global__ void gap_kernel(const float* __restrict__ x, const int32_t* __restric
 int enc_stem(const float* frames, const int32_t* fmap, float* out, const float* w, const float* bias, int n, int H,
              int W, cudaStream_t st) {
   dim3 grid(H / 2 + 2, n);
-  stem_kernel<<<grid, 256, 3 * (W + 1) * sizeof(float), st>>>(frames, fmap, out, w, bias, H, W);
+  stem_kernel<false><<<grid, 256, 3 * (W + 1) * sizeof(float), st>>>(frames, fmap, nullptr, nullptr, out, w, bias, H, W);
+  M2S_CUDA_OK(cudaGetLastError());
+  return M2S_OK;
+}
+
+// uint8 ingest: per-frame min-max (after the optional articulator mask) fused into the stem load.
+int enc_stem_u8(const uint8_t* frames, const int32_t* fmap, const float* mask, float2* norm, float* out, const float* w,
+                const float* bias, int n, int H, int W, cudaStream_t st) {
+  frame_minmax_kernel<<<n, 256, 0, st>>>(frames, fmap, mask, norm, H * W);
+  M2S_CUDA_OK(cudaGetLastError());
+  dim3 grid(H / 2 + 2, n);
+  stem_kernel<true><<<grid, 256, 3 * (W + 1) * sizeof(float), st>>>(frames, fmap, mask, norm, out, w, bias, H, W);
   M2S_CUDA_OK(cudaGetLastError());
   return M2S_OK;
 }

@@ -73,16 +73,21 @@ class MriToSpeech:
         self.hop = generator.hop
 
     @torch.no_grad()
-    def infer_padded(self, frames: torch.Tensor, lengths: Optional[torch.Tensor]):
-        """frames (B,T,H,W) cuda, lengths int32[B] (cpu or cuda) or None -> dict of padded device tensors."""
-        pred = self.acoustic(frames, lengths=lengths)
+    def infer_padded(self, frames: torch.Tensor, lengths: Optional[torch.Tensor],
+                     mask: Optional[torch.Tensor] = None):
+        """frames (B,T,H,W) cuda -- float32 in [0,1], or raw uint8 (min-max normalised on the device, after the
+        optional (H,W) articulator ``mask``); lengths int32[B] (cpu or cuda) or None -> dict of padded tensors."""
+        pred = self.acoustic(frames, lengths=lengths, mask=mask) if mask is not None else \
+            self.acoustic(frames, lengths=lengths)
         mel_db, mel_log, voc_in = mel_glue(pred, self.mean, self.std, lengths)
         wav = self.generator(voc_in, lengths=lengths)
         return {"mel_norm": pred, "mel_db": mel_db, "mel_log": mel_log, "audio": wav}
 
     @torch.no_grad()
-    def infer(self, clips: Sequence[torch.Tensor], max_batch_frames: int = 4096) -> List[Dict[str, torch.Tensor]]:
-        """clips: list of (T_i,H,W) float32 tensors (host or device).  Returns one dict per clip, in order.
+    def infer(self, clips: Sequence[torch.Tensor], max_batch_frames: int = 4096,
+              mask: Optional[torch.Tensor] = None) -> List[Dict[str, torch.Tensor]]:
+        """clips: list of (T_i,H,W) tensors (host or device), all float32 in [0,1] or all raw uint8 (4x fewer
+        bytes over PCIe / HBM; normalised on the device).  Returns one dict per clip, in order.
 
         Clips are sorted by length and packed into micro-batches of at most ``max_batch_frames`` padded
         frames so that padding waste stays small; every clip equals its own B=1 run (ragged parity)."""
@@ -95,10 +100,11 @@ class MriToSpeech:
             idx = order[i:i + nb]
             lens = [int(clips[j].shape[0]) for j in idx]
             H, W = clips[idx[0]].shape[-2:]
-            batch = torch.zeros(nb, tmax, H, W, device=self.device, dtype=torch.float32)
+            dtype = torch.uint8 if clips[idx[0]].dtype == torch.uint8 else torch.float32
+            batch = torch.zeros(nb, tmax, H, W, device=self.device, dtype=dtype)
             for b, j in enumerate(idx):
                 batch[b, :lens[b]].copy_(clips[j], non_blocking=True)
-            out = self.infer_padded(batch, torch.tensor(lens, dtype=torch.int32))
+            out = self.infer_padded(batch, torch.tensor(lens, dtype=torch.int32), mask=mask)
             for b, j in enumerate(idx):
                 n = lens[b]
                 results[j] = {"mel_norm": out["mel_norm"][b, :n], "mel_db": out["mel_db"][b, :n],

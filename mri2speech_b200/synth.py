@@ -38,6 +38,17 @@ def synthetic_clip(clip_id: int, frames: int, size: int = 256) -> torch.Tensor:
     return ((x - mn) / (mx - mn).clamp_min(1e-12)).contiguous()
 
 
+def synthetic_clip_u8(clip_id: int, frames: int, size: int = 256) -> torch.Tensor:
+    """(frames, size, size) uint8 raw gray frames as a video decoder delivers them: the smooth field of
+    ``synthetic_clip`` scaled to a per-frame dynamic range that does NOT span 0..255, so that the device
+    min-max normalisation is exercised."""
+    x = synthetic_clip(clip_id, frames, size)
+    g = torch.Generator().manual_seed(4321 + clip_id)
+    lo = torch.randint(0, 40, (frames, 1, 1), generator=g).float()
+    hi = torch.randint(150, 256, (frames, 1, 1), generator=g).float()
+    return (lo + x * (hi - lo)).round().clamp(0, 255).to(torch.uint8).contiguous()
+
+
 def synthetic_lengths(n_clips: int, lo: int = 150, hi: int = 600, seed: int = 4321) -> List[int]:
     g = torch.Generator().manual_seed(seed)
     return torch.randint(lo, hi + 1, (n_clips,), generator=g).tolist()

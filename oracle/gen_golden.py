@@ -64,8 +64,62 @@ def acoustic_goldens():
     print("acoustic goldens written")
 
 
+def _reference_preprocess_frame():
+    """``_preprocess_frame`` exactly as the reference defines it (scripts/run_mri_video_inference.py:34-53).
+    The script itself cannot be imported (soundfile / matplotlib at module import), so the function is cut out
+    of the file with ``ast`` and executed with cv2 / numpy in scope."""
+    import ast
+    import cv2
+    path = os.path.join("/root/reference", "scripts", "run_mri_video_inference.py")
+    src = open(path, "r", encoding="utf-8").read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "_preprocess_frame")
+    scope = {"np": np, "cv2": cv2}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), scope)
+    return scope["_preprocess_frame"]
+
+
+def _reference_mask_module():
+    import importlib.util
+    path = os.path.join("/root/reference", "scripts", "mask_rtmri_video.py")
+    spec = importlib.util.spec_from_file_location("_ref_mask_rtmri_video", path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = mod  # dataclass needs the module registered
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def ingest_goldens():
+    """Outputs of the REFERENCE's frame normalisation and mask construction on synthetic uint8 frames."""
+    from mri2speech_b200 import synth
+    from oracle import ingest
+    pre = _reference_preprocess_frame()
+    ref_mask = _reference_mask_module()
+    clip = synth.synthetic_clip_u8(7, 3).numpy()
+    clip[2] = 93  # constant frame -> zeros (:50-53)
+    norm = np.stack([pre(f) for f in clip]).astype(np.float32)
+    out = {"clip_u8": clip, "norm": norm}
+    presets = {"lip": ref_mask.LIP_MASK, "tongue": ref_mask.TONGUE_MASK}
+    for name, preset in presets.items():
+        for alpha in (0.0, 0.3, 1.0):
+            m = ref_mask.build_mask((256, 256), preset.scaled((256, 256)), alpha, 11)
+            out[f"mask_{name}_{alpha}"] = m.astype(np.float32)
+    m = out["mask_tongue_0.3"]
+    masked = (clip.astype(np.float32) * m[None]).clip(0.0, 255.0).astype(np.uint8)  # mask_rtmri_video.py:96-98
+    out["masked_tongue_0.3"] = masked
+    out["masked_norm_tongue_0.3"] = np.stack([pre(f) for f in masked]).astype(np.float32)
+    np.savez_compressed(os.path.join(GOLDEN, "ingest_ref.npz"), **out)
+    # cross-check the restatement against the reference while we are here
+    assert np.array_equal(ingest.preprocess_clip(clip), norm)
+    assert np.array_equal(ingest.apply_mask(clip, m), masked)
+    print("ingest goldens written")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
+    if "--ingest-only" in sys.argv:
+        ingest_goldens()
+        sys.exit(0)
     vocoder_goldens()
     if "--vocoder-only" not in sys.argv:
         acoustic_goldens()
+        ingest_goldens()
