@@ -45,7 +45,9 @@ typedef enum {
 /* arithmetic of the GEMM-shaped layers */
 enum {
   M2S_PREC_TF32 = 0, /* tcgen05 kind::tf32, fp32 accumulate in TMEM (default build) */
-  M2S_PREC_FP32 = 1  /* CUDA-core fp32 FMA kernels (exact-fp32 build, slow)          */
+  M2S_PREC_FP32 = 1, /* CUDA-core fp32 FMA kernels (exact-fp32 build, slow)          */
+  M2S_PREC_FP16 = 2  /* tcgen05 kind::f16: fp16 operands (10-bit mantissa, the same as tf32), fp32 accumulate,
+                        fp32 residual / MRF streams; layers whose c_in is not a multiple of 32 stay on tf32 */
 };
 
 const char* m2s_version(void);
@@ -108,6 +110,10 @@ typedef struct {
   const int32_t* lens;   /* M2S_MASK_LEN: row valid iff (q + d_row_offset) < lens[b]*len_scale */
   int32_t len_scale;
   int32_t pitch, i_lo, i_hi, j_lo, j_hi; /* M2S_MASK_PITCH: (i,j)=divmod(row,pitch) inside the box */
+  /* fp16 operands (M2S_IMPL_TCGEN05 only): a holds __half rows (a_ld, c_in in elements, multiples of 8) and the
+   * weights are rounded to fp16; d16 = optional second output in fp16, indexed like d (d may then be NULL) */
+  int32_t a_half;
+  void* d16;
 } m2s_conv_args;
 
 int m2s_conv_fwd(const m2s_conv_args* args, int impl, m2s_stream_t stream);

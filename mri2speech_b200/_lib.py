@@ -17,7 +17,8 @@ _lib: Optional[C.CDLL] = None
 M2S_MAX_TAPS = 16
 M2S_MAX_UPS = 8
 M2S_MAX_RBK = 8
-PREC_TF32, PREC_FP32 = 0, 1
+PREC_TF32, PREC_FP32, PREC_FP16 = 0, 1, 2
+PRECISIONS = {"tf32": PREC_TF32, "fp32": PREC_FP32, "fp16": PREC_FP16}
 ACT_NONE, ACT_LRELU, ACT_SILU = 0, 1, 2
 MASK_NONE, MASK_LEN, MASK_PITCH = 0, 1, 2
 IMPL_TCGEN05, IMPL_SIMT = 0, 1
@@ -44,6 +45,7 @@ class ConvArgs(C.Structure):
         ("act", C.c_int32), ("act_slope", C.c_float),
         ("mask_mode", C.c_int32), ("lens", C.c_void_p), ("len_scale", C.c_int32),
         ("pitch", C.c_int32), ("i_lo", C.c_int32), ("i_hi", C.c_int32), ("j_lo", C.c_int32), ("j_hi", C.c_int32),
+        ("a_half", C.c_int32), ("d16", C.c_void_p),
     ]
 
 
@@ -183,8 +185,10 @@ def conv_fwd(a: torch.Tensor, w: torch.Tensor, shifts: Sequence[int], l_out: int
              a_rows: Optional[int] = None, bias=None, res=None, res_inv_slope: float = 1.0, res_after_act: bool = False, accum=None,
              out_scale: float = 1.0, act: int = ACT_NONE, act_slope: float = 0.0,
              lens=None, len_scale: int = 1, pitch_mask=None, d_row_offset: int = 0,
-             d_rows: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Test helper around m2s_conv_fwd.  a: (B, L_in, C) cuda fp32; w: (taps, N, C) cuda fp32."""
+             d_rows: Optional[int] = None, out: Optional[torch.Tensor] = None,
+             out16: Optional[torch.Tensor] = None, want_d32: bool = True) -> torch.Tensor:
+    """Test helper around m2s_conv_fwd.  a: (B, L_in, C) cuda fp32 (tf32 operands) or fp16 (kind::f16 operands);
+    w: (taps, N, C) cuda fp32.  ``out16``: optional fp16 second output (same shape as the fp32 one)."""
     require_device(a)
     B, L_in, Cin = a.shape
     taps, N, Cw = w.shape
@@ -192,12 +196,15 @@ def conv_fwd(a: torch.Tensor, w: torch.Tensor, shifts: Sequence[int], l_out: int
     d_rows = d_rows if d_rows is not None else l_out + d_row_offset
     d = out if out is not None else torch.zeros(B, d_rows, N, device=a.device, dtype=torch.float32)
     args = ConvArgs()
+    args.a_half = int(a.dtype == torch.float16)
+    args.d16 = ptr(out16)
     args.a = a.data_ptr(); args.a_batch_rows = L_in; args.a_rows = a_rows if a_rows is not None else L_in
     args.a_ld = Cin; args.c_in = Cin; args.batch = B; args.l_out = l_out; args.taps = taps
     for i, s in enumerate(shifts):
         args.shift[i] = int(s)
     args.w = w.data_ptr(); args.n = N
-    args.d = d.data_ptr(); args.d_batch_rows = d.shape[1]; args.d_ld = N; args.d_row_offset = d_row_offset
+    args.d = d.data_ptr() if want_d32 else None
+    args.d_batch_rows = d.shape[1]; args.d_ld = N; args.d_row_offset = d_row_offset
     args.bias = ptr(bias); args.res = ptr(res); args.res_ld = N; args.res_inv_slope = res_inv_slope
     args.res_after_act = int(res_after_act)
     args.accum = ptr(accum); args.accum_ld = N; args.out_scale = out_scale

@@ -30,7 +30,7 @@ int mel_glue(const float* pred, const float* mean, const float* stdv, int batch,
 
 using namespace m2s;
 
-extern "C" const char* m2s_version(void) { return "m2s 0.1.0 (sm_100a; tcgen05 tf32 conv engine)"; }
+extern "C" const char* m2s_version(void) { return "m2s 0.2.0 (sm_100a; tcgen05 tf32 / f16 conv engine)"; }
 
 extern "C" const char* m2s_last_error_string(void) { return g_error; }
 
@@ -63,17 +63,20 @@ extern "C" int m2s_debug_set_knob(const char* name, int value) {
 
 // Test entry: weights arrive as a plain device array [taps][n][c_in]; the tcgen05 path packs them on the fly.
 extern "C" int m2s_conv_fwd(const m2s_conv_args* args, int impl, m2s_stream_t stream) {
-  if (!args || !args->a || !args->w || !args->d) return fail(M2S_ERR_BAD_ARG, "null argument");
+  if (!args || !args->a || !args->w || (!args->d && !args->d16)) return fail(M2S_ERR_BAD_ARG, "null argument");
   M2S_TRY(m2s_device_check(-1));
   ConvProblem p = problem_from_args(*args);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (impl == M2S_IMPL_SIMT) return conv_simt(p, args->w, st);
+  if (impl == M2S_IMPL_SIMT) {
+    if (p.a_half || p.d16) return fail(M2S_ERR_UNSUPPORTED, "the CUDA-core path is fp32 only");
+    return conv_simt(p, args->w, st);
+  }
   if (impl != M2S_IMPL_TCGEN05) return fail(M2S_ERR_BAD_ARG, "unknown impl %d", impl);
   const size_t nw = static_cast<size_t>(p.taps) * p.n * p.c_in;
   std::vector<float> hw(nw);
   M2S_CUDA_OK(cudaMemcpy(hw.data(), args->w, nw * sizeof(float), cudaMemcpyDeviceToHost));
   PackedWeights w;
-  M2S_TRY(pack_weights(hw.data(), p.taps, p.n, p.c_in, false, &w));
+  M2S_TRY(pack_weights(hw.data(), p.taps, p.n, p.c_in, p.a_half ? PACK_FP16 : PACK_FP32, &w));
   int s = conv_tcgen05(p, w, st);
   cudaError_t e = cudaStreamSynchronize(st);
   free_weights(&w);

@@ -75,6 +75,22 @@ __device__ __forceinline__ void mma2_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void mma2_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma2_f16_k4(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum0,
+                                            int ksteps) {
+  mma2_f16(tmem_d, da, db, idesc, accum0);
+  if (ksteps > 1) mma2_f16(tmem_d, da + 2, db + 2, idesc, 1u);
+  if (ksteps > 2) mma2_f16(tmem_d, da + 4, db + 4, idesc, 1u);
+  if (ksteps > 3) mma2_f16(tmem_d, da + 6, db + 6, idesc, 1u);
+}
 __device__ __forceinline__ void mma2_tf32_k4(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum0,
                                              int ksteps) {
   mma2_tf32(tmem_d, da, db, idesc, accum0);
@@ -134,7 +150,8 @@ conv_engine_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     // ===================== TMA producer (both CTAs; signals land on the LEADER's full barriers) =====================
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
-    const uint32_t a_bytes = prm.a_nbox * prm.a_box_rows * kRowBytes;
+    const uint32_t row_bytes = prm.row_bytes;
+    const uint32_t a_bytes = prm.a_nbox * prm.a_box_rows * row_bytes;
     for (int tile = pair; tile < prm.total_tiles; tile += npairs) {
       const int nt = tile % prm.n_tiles;
       const int mt = (tile / prm.n_tiles) % prm.tiles_per_batch;
@@ -145,8 +162,8 @@ conv_engine_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         if (elect_one()) {
           if (leader) mbar_expect_tx(a_full(sa), 2 * a_bytes);
           for (int bx = 0; bx < prm.a_nbox; ++bx)
-            tma2_load_3d(a_base + sa * prm.a_stage_bytes + bx * prm.a_box_rows * kRowBytes, &tmap_a,
-                         mapa(a_full(sa), 0), cb * kKBlock, q0 + prm.shift_min + bx * prm.a_box_rows, b);
+            tma2_load_3d(a_base + sa * prm.a_stage_bytes + bx * prm.a_box_rows * row_bytes, &tmap_a,
+                         mapa(a_full(sa), 0), cb * prm.kblock, q0 + prm.shift_min + bx * prm.a_box_rows, b);
         }
         __syncwarp();
         if (++sa == prm.na) { sa = 0; pa ^= 1; }
@@ -168,14 +185,16 @@ conv_engine_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     if (leader) {
       int sa = 0, sb = 0, acc = 0;
       uint32_t pa = 0, pb = 0, pacc = 0;
-      const uint64_t desc_hi = make_desc_sw128(0, 0);
+      const uint64_t desc_hi = prm.desc_hi;
+      const uint32_t row_bytes = prm.row_bytes;
+      const int ksteps_full = prm.row_bytes >> 5;
       for (int tile = pair; tile < prm.total_tiles; tile += npairs) {
         mbar_wait(acc_empty(acc), pacc ^ 1);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + acc * prm.acc_stride;
         for (int cb = 0; cb < cblocks; ++cb) {
-          const int rem = p.c_in - cb * kKBlock;
-          const int ksteps = rem >= kKBlock ? 4 : (rem + 7) / 8;
+          const int rem = p.c_in - cb * prm.kblock;
+          const int ksteps = rem >= prm.kblock ? ksteps_full : (rem + prm.kstep_elems - 1) / prm.kstep_elems;
           mbar_wait(a_full(sa), pa);
           for (int tap0 = 0; tap0 < taps; tap0 += prm.tg) {
             const int cnt = min(prm.tg, taps - tap0);
@@ -186,11 +205,15 @@ conv_engine_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
               const uint32_t b_tile = b_base + sb * prm.b_stage_bytes;
               for (int t = 0; t < cnt; ++t) {
                 const uint64_t db = desc_hi | (((b_tile + t * prm.b_tap_bytes) & 0x3FFFF) >> 4);
-                const uint64_t da = desc_hi | (((a_tile + prm.rel_shift[tap0 + t] * kRowBytes) & 0x3FFFF) >> 4);
-                mma2_tf32_k4(tmem_acc, da, db, prm.idesc, (cb | tap0 | t) ? 1u : 0u, ksteps);
-                if (prm.msub > 1)
-                  mma2_tf32_k4(tmem_acc + n_tile, da + ((128 * kRowBytes) >> 4), db, prm.idesc, (cb | tap0 | t) ? 1u : 0u,
-                               ksteps);
+                const uint64_t da = desc_hi | (((a_tile + prm.rel_shift[tap0 + t] * row_bytes) & 0x3FFFF) >> 4);
+                const uint32_t first = (cb | tap0 | t) ? 1u : 0u;
+                if (prm.half) {
+                  mma2_f16_k4(tmem_acc, da, db, prm.idesc, first, ksteps);
+                  if (prm.msub > 1) mma2_f16_k4(tmem_acc + n_tile, da + ((128 * row_bytes) >> 4), db, prm.idesc, first, ksteps);
+                } else {
+                  mma2_tf32_k4(tmem_acc, da, db, prm.idesc, first, ksteps);
+                  if (prm.msub > 1) mma2_tf32_k4(tmem_acc + n_tile, da + ((128 * row_bytes) >> 4), db, prm.idesc, first, ksteps);
+                }
               }
               const bool last_group = tap0 + cnt >= taps;
               tc_commit2(b_empty(sb));
@@ -274,6 +297,11 @@ int conv_tcgen05_pair(const ConvProblem& p, const PackedWeights& w, cudaStream_t
   prm.n_tile = w.n_tile_pair;
   prm.n_tiles = w.n_tiles_pair;
   prm.cblocks = w.cblocks;
+  prm.half = w.half;
+  prm.kblock = w.kblock;
+  prm.row_bytes = w.row_bytes;
+  prm.kstep_elems = w.half ? 16 : 8;
+  prm.desc_hi = make_desc_hi(w.row_bytes);
   int smin = p.shift[0], smax = p.shift[0];
   for (int j = 1; j < p.taps; ++j) { smin = p.shift[j] < smin ? p.shift[j] : smin; smax = p.shift[j] > smax ? p.shift[j] : smax; }
   prm.shift_min = smin;
@@ -296,10 +324,12 @@ int conv_tcgen05_pair(const ConvProblem& p, const PackedWeights& w, cudaStream_t
   const int a_rows_needed = 128 * msub + halo;
   prm.a_nbox = (a_rows_needed + 255) / 256;
   prm.a_box_rows = (((a_rows_needed + prm.a_nbox - 1) / prm.a_nbox) + 7) / 8 * 8;
-  prm.a_stage_bytes = (static_cast<uint32_t>(prm.a_nbox * prm.a_box_rows * kRowBytes) + 1023u) & ~1023u;
+  prm.a_stage_bytes = (static_cast<uint32_t>(prm.a_nbox * prm.a_box_rows * w.row_bytes) + 1023u) & ~1023u;
   const int nh = prm.n_tile / 2;
-  prm.b_tap_bytes = static_cast<uint32_t>(nh * kRowBytes);
+  prm.b_tap_bytes = static_cast<uint32_t>(nh * w.row_bytes);
   prm.tg = pair_taps_per_stage(prm.n_tile, p.taps);
+  // a tap's block must keep the 8-row swizzle phase: nh * row_bytes multiple of 1 KB (64-byte rows: nh % 16 == 0)
+  while (prm.tg > 1 && ((prm.tg * prm.b_tap_bytes) & 1023u)) --prm.tg;
   prm.b_stage_bytes = static_cast<uint32_t>(prm.tg) * prm.b_tap_bytes;
   if (prm.b_stage_bytes & 1023u) return fail(M2S_ERR_UNSUPPORTED, "pair mode: weight stage not 1 KB aligned");
   const uint32_t bar_bytes = 1024 + kEpiWarps * 4096;
@@ -314,7 +344,7 @@ int conv_tcgen05_pair(const ConvProblem& p, const PackedWeights& w, cudaStream_t
   uint32_t smem_bytes = total(na, nb);
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
   // instruction descriptor: D=f32, A=B=tf32, K-major both, N = n_tile, M = 256 (two CTAs x 128)
-  prm.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(prm.n_tile >> 3) << 17) |
+  prm.idesc = (1u << 4) | (w.half ? 0u : ((2u << 7) | (2u << 10))) | (static_cast<uint32_t>(prm.n_tile >> 3) << 17) |
               (static_cast<uint32_t>(256 >> 4) << 24);
   prm.trace = nullptr;
   prm.dbg = knobs.dbg;
@@ -323,25 +353,29 @@ int conv_tcgen05_pair(const ConvProblem& p, const PackedWeights& w, cudaStream_t
   {
     cuuint64_t gdim[3] = {static_cast<cuuint64_t>(p.c_in), static_cast<cuuint64_t>(p.a_rows),
                           static_cast<cuuint64_t>(p.batch)};
-    cuuint64_t gstride[2] = {static_cast<cuuint64_t>(p.a_ld) * 4ull,
-                             static_cast<cuuint64_t>(p.a_batch_rows) * static_cast<cuuint64_t>(p.a_ld) * 4ull};
+    const cuuint64_t esize = w.half ? 2ull : 4ull;
+    cuuint64_t gstride[2] = {static_cast<cuuint64_t>(p.a_ld) * esize,
+                             static_cast<cuuint64_t>(p.a_batch_rows) * static_cast<cuuint64_t>(p.a_ld) * esize};
     if (p.batch == 1) gstride[1] = gstride[0] * static_cast<cuuint64_t>(p.a_rows > 0 ? p.a_rows : 1);
-    cuuint32_t box[3] = {static_cast<cuuint32_t>(kKBlock), static_cast<cuuint32_t>(prm.a_box_rows), 1u};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(w.kblock), static_cast<cuuint32_t>(prm.a_box_rows), 1u};
     cuuint32_t estr[3] = {1u, 1u, 1u};
-    CUresult cr = enc(&tmap_a, knobs.tmap_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
-                      const_cast<float*>(p.a), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUtensorMapDataType dt = w.half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                          : (knobs.tmap_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+    CUresult cr = enc(&tmap_a, dt, 3, const_cast<float*>(p.a), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      w.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(M2S_ERR_CUDA, "pair mode: A tensor map failed (%d)", static_cast<int>(cr));
   }
   {
     const cuuint64_t rows = static_cast<cuuint64_t>(w.n_tiles_pair) * w.cblocks * 2 * p.taps * nh;
-    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(kKBlock), rows};
-    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(kRowBytes)};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(kKBlock), static_cast<cuuint32_t>(prm.tg * nh)};
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(w.kblock), rows};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(w.row_bytes)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(w.kblock), static_cast<cuuint32_t>(prm.tg * nh)};
     cuuint32_t estr[2] = {1u, 1u};
-    CUresult cr = enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, w.dev_pair, gdim, gstride, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult cr = enc(&tmap_w, w.half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, w.dev_pair,
+                      gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      w.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(M2S_ERR_CUDA, "pair mode: W tensor map failed (%d)", static_cast<int>(cr));
   }
 

@@ -83,7 +83,8 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
     int it = 0;
-    const uint32_t a_bytes = prm.a_nbox * prm.a_box_rows * kRowBytes;
+    const uint32_t row_bytes = prm.row_bytes;
+    const uint32_t a_bytes = prm.a_nbox * prm.a_box_rows * row_bytes;
     for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x, ++it) {
       const int nt = tile % prm.n_tiles;
       const int mt = (tile / prm.n_tiles) % prm.tiles_per_batch;
@@ -97,8 +98,8 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           if (elect_one()) {
             mbar_expect_tx(a_full(sa), a_bytes);
             for (int bx = 0; bx < prm.a_nbox; ++bx)
-              tma_load_3d(a_base + sa * prm.a_stage_bytes + bx * prm.a_box_rows * kRowBytes, &tmap_a, a_full(sa),
-                          cb * kKBlock, q0 + prm.shift_min + bx * prm.a_box_rows, b);
+              tma_load_3d(a_base + sa * prm.a_stage_bytes + bx * prm.a_box_rows * row_bytes, &tmap_a, a_full(sa),
+                          cb * prm.kblock, q0 + prm.shift_min + bx * prm.a_box_rows, b);
           }
           __syncwarp();
           if (++sa == prm.na) { sa = 0; pa ^= 1; }
@@ -110,8 +111,8 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             if (elect_one()) {
               mbar_expect_tx(a_full(sa), a_bytes);
               for (int bx = 0; bx < prm.a_nbox; ++bx)
-                tma_load_3d(a_base + sa * prm.a_stage_bytes + bx * prm.a_box_rows * kRowBytes, &tmap_a, a_full(sa),
-                            cb * kKBlock, q0 + p.shift[tap0] + bx * prm.a_box_rows, b);
+                tma_load_3d(a_base + sa * prm.a_stage_bytes + bx * prm.a_box_rows * row_bytes, &tmap_a, a_full(sa),
+                            cb * prm.kblock, q0 + p.shift[tap0] + bx * prm.a_box_rows, b);
             }
             __syncwarp();
             if (++sa == prm.na) { sa = 0; pa ^= 1; }
@@ -120,8 +121,8 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           if (elect_one()) {
             const uint32_t bytes = cnt * prm.b_tap_bytes;
             mbar_expect_tx(b_full(sb), bytes);
-            const float* src =
-                prm.wpacked + (static_cast<size_t>((nt * cblocks + cb) * taps + tap0)) * n_tile * kKBlock;
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(prm.wpacked) +
+                                 (static_cast<size_t>((nt * cblocks + cb) * taps + tap0)) * prm.b_tap_bytes;
             bulk_load(b_base + sb * prm.b_stage_bytes, src, bytes, b_full(sb));
           }
           __syncwarp();
@@ -134,7 +135,9 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
     int sa = 0, sb = 0, acc = 0;
     uint32_t pa = 0, pb = 0, pacc = 0;
-    const uint64_t desc_hi = make_desc_sw128(0, 0);
+    const uint64_t desc_hi = prm.desc_hi;
+    const uint32_t row_bytes = prm.row_bytes;
+    const int ksteps_full = prm.row_bytes >> 5;  // a K-step covers 32 bytes of every row
     int it = 0;
     for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x, ++it) {
       if (lane == 0) trace_stamp(prm, it, 3);
@@ -143,8 +146,8 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       if (lane == 0) trace_stamp(prm, it, 4);
       const uint32_t tmem_acc = tmem_base + acc * prm.acc_stride;
       for (int cb = 0; cb < cblocks; ++cb) {
-        const int rem = p.c_in - cb * kKBlock;
-        const int ksteps = rem >= kKBlock ? 4 : (rem + 7) / 8;
+        const int rem = p.c_in - cb * prm.kblock;
+        const int ksteps = rem >= prm.kblock ? ksteps_full : (rem + prm.kstep_elems - 1) / prm.kstep_elems;
         if (!prm.a_per_tap) {
           mbar_wait(a_full(sa), pa);
         }
@@ -161,9 +164,14 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 const int row_shift = prm.a_per_tap ? 0 : prm.rel_shift[tap0 + t];
                 const uint64_t db = desc_hi | (((b_tile + t * prm.b_tap_bytes) & 0x3FFFF) >> 4);
                 const uint32_t first = (cb | tap0 | t) ? 1u : 0u;
-                const uint64_t da0 = desc_hi | (((a_tile + row_shift * kRowBytes) & 0x3FFFF) >> 4);
-                mma_tf32_k4(tmem_acc, da0, db, prm.idesc, first, ksteps);
-                if (msub > 1) mma_tf32_k4(tmem_acc + n_tile, da0 + ((128 * kRowBytes) >> 4), db, prm.idesc, first, ksteps);
+                const uint64_t da0 = desc_hi | (((a_tile + row_shift * row_bytes) & 0x3FFFF) >> 4);
+                if (prm.half) {
+                  mma_f16_k4(tmem_acc, da0, db, prm.idesc, first, ksteps);
+                  if (msub > 1) mma_f16_k4(tmem_acc + n_tile, da0 + ((128 * row_bytes) >> 4), db, prm.idesc, first, ksteps);
+                } else {
+                  mma_tf32_k4(tmem_acc, da0, db, prm.idesc, first, ksteps);
+                  if (msub > 1) mma_tf32_k4(tmem_acc + n_tile, da0 + ((128 * row_bytes) >> 4), db, prm.idesc, first, ksteps);
+                }
               }
             }
             const bool last_group = tap0 + cnt >= taps;
@@ -349,47 +357,65 @@ static float host_round_tf32(float v) {
   return r;
 }
 
-int pack_weights(const float* host_w, int taps, int n, int c_in, bool tf32_round, PackedWeights* out) {
+static float host_round_fp16(float v) { return __half2float(__float2half_rn(v)); }
+
+int pack_weights(const float* host_w, int taps, int n, int c_in, int mode, PackedWeights* out) {
   PackedWeights w;
   w.n = n; w.c_in = c_in; w.taps = taps;
+  int esize = 4;
+  if (mode == PACK_FP16) {
+    if (c_in % 8) return fail(M2S_ERR_UNSUPPORTED, "fp16 operands need c_in %% 8 == 0 (got %d)", c_in);
+    esize = 2;
+    if (c_in <= 32) { w.half = 2; w.kblock = 32; w.row_bytes = 64; }
+    else { w.half = 1; w.kblock = 64; w.row_bytes = 128; }
+  }
   choose_n_tiling(n, &w.n_tile, &w.n_tiles);
-  w.cblocks = (c_in + kKBlock - 1) / kKBlock;
-  w.packed_floats = static_cast<size_t>(w.n_tiles) * w.cblocks * taps * w.n_tile * kKBlock;
-  std::vector<float> packed(w.packed_floats, 0.f);
+  w.cblocks = (c_in + w.kblock - 1) / w.kblock;
+  const size_t tap_bytes = static_cast<size_t>(w.n_tile) * w.row_bytes;
+  const size_t packed_bytes = static_cast<size_t>(w.n_tiles) * w.cblocks * taps * tap_bytes;
+  w.packed_floats = packed_bytes / 4;
+  std::vector<uint8_t> packed(packed_bytes, 0);
   std::vector<float> plain(static_cast<size_t>(taps) * n * c_in);
+  auto put = [&](uint8_t* dst, float v) {
+    if (esize == 4) std::memcpy(dst, &v, 4);
+    else { const __half h = __float2half_rn(v); std::memcpy(dst, &h, 2); }
+  };
   for (int j = 0; j < taps; ++j)
     for (int o = 0; o < n; ++o)
       for (int c = 0; c < c_in; ++c) {
         float v = host_w[(static_cast<size_t>(j) * n + o) * c_in + c];
-        if (tf32_round) v = host_round_tf32(v);
+        if (mode == PACK_TF32) v = host_round_tf32(v);
+        else if (mode == PACK_FP16) v = host_round_fp16(v);
         plain[(static_cast<size_t>(j) * n + o) * c_in + c] = v;
-        const int nt = o / w.n_tile, r = o % w.n_tile, cb = c / kKBlock, cc = c % kKBlock;
-        const size_t blk = (static_cast<size_t>(nt * w.cblocks + cb) * taps + j) * w.n_tile * kKBlock;
-        // 128B swizzle: 16-byte chunk index ^= (row & 7)
-        const int chunk = (cc >> 2) ^ (r & 7);
-        packed[blk + static_cast<size_t>(r) * kKBlock + chunk * 4 + (cc & 3)] = v;
+        const int nt = o / w.n_tile, r = o % w.n_tile, cb = c / w.kblock, cc = c % w.kblock;
+        const size_t blk = (static_cast<size_t>(nt * w.cblocks + cb) * taps + j) * tap_bytes;
+        // swizzle on (absolute = stage-relative, stages are 1 KB aligned) address bits: 128-byte rows XOR the
+        // 16-byte chunk index with (row & 7); 64-byte rows XOR it with ((row >> 1) & 3)
+        const int off = cc * esize;
+        const int chunk = (off >> 4) ^ (w.row_bytes == 128 ? (r & 7) : ((r >> 1) & 3));
+        put(&packed[blk + static_cast<size_t>(r) * w.row_bytes + chunk * 16 + (off & 15)], v);
       }
   if (n >= engine_knobs().pair_min_n && n % 16 == 0 && engine_knobs().pair) {
-    // CTA-pair layout: [nt][cb][half][tap][nh rows][32], unswizzled (TMA applies the 128B swizzle)
+    // CTA-pair layout: [nt][cb][half][tap][nh rows][row_bytes], unswizzled (TMA applies the swizzle)
     const int tiles = (n + 255) / 256;
     w.n_tile_pair = (((n + tiles - 1) / tiles) + 15) / 16 * 16;
     w.n_tiles_pair = tiles;
     const int nh = w.n_tile_pair / 2;
-    std::vector<float> pk(static_cast<size_t>(tiles) * w.cblocks * 2 * taps * nh * kKBlock, 0.f);
+    std::vector<uint8_t> pk(static_cast<size_t>(tiles) * w.cblocks * 2 * taps * nh * w.row_bytes, 0);
     for (int j = 0; j < taps; ++j)
       for (int o = 0; o < n; ++o)
         for (int c = 0; c < c_in; ++c) {
           const int nt = o / w.n_tile_pair, rr = o % w.n_tile_pair, half = rr / nh, r = rr % nh;
-          const int cb = c / kKBlock, cc = c % kKBlock;
+          const int cb = c / w.kblock, cc = c % w.kblock;
           const size_t row = ((static_cast<size_t>(nt * w.cblocks + cb) * 2 + half) * taps + j) * nh + r;
-          pk[row * kKBlock + cc] = plain[(static_cast<size_t>(j) * n + o) * c_in + c];
+          put(&pk[row * w.row_bytes + static_cast<size_t>(cc) * esize], plain[(static_cast<size_t>(j) * n + o) * c_in + c]);
         }
-    M2S_CUDA_OK(cudaMalloc(&w.dev_pair, pk.size() * sizeof(float)));
-    M2S_CUDA_OK(cudaMemcpy(w.dev_pair, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice));
+    M2S_CUDA_OK(cudaMalloc(&w.dev_pair, pk.size()));
+    M2S_CUDA_OK(cudaMemcpy(w.dev_pair, pk.data(), pk.size(), cudaMemcpyHostToDevice));
   }
-  M2S_CUDA_OK(cudaMalloc(&w.dev, packed.size() * sizeof(float)));
+  M2S_CUDA_OK(cudaMalloc(&w.dev, packed.size()));
   M2S_CUDA_OK(cudaMalloc(&w.plain, plain.size() * sizeof(float)));
-  M2S_CUDA_OK(cudaMemcpy(w.dev, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+  M2S_CUDA_OK(cudaMemcpy(w.dev, packed.data(), packed.size(), cudaMemcpyHostToDevice));
   M2S_CUDA_OK(cudaMemcpy(w.plain, plain.data(), plain.size() * sizeof(float), cudaMemcpyHostToDevice));
   *out = w;
   return M2S_OK;
@@ -407,7 +433,14 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
   if (p.c_in % 4 || p.a_ld % 4 || p.d_ld % 4 || p.n % 4)
     return fail(M2S_ERR_UNSUPPORTED, "c_in/a_ld/d_ld/n must be multiples of 4 (got %d/%d/%d/%d)", p.c_in, p.a_ld,
                 p.d_ld, p.n);
-  if ((reinterpret_cast<uintptr_t>(p.a) & 15) || (reinterpret_cast<uintptr_t>(p.d) & 15))
+  if ((p.a_half != 0) != (w.half != 0))
+    return fail(M2S_ERR_BAD_ARG, "operand format mismatch: A is %s but the weights are packed as %s",
+                p.a_half ? "fp16" : "fp32", w.half ? "fp16" : "tf32");
+  if (p.a_half && (p.c_in % 8 || p.a_ld % 8))
+    return fail(M2S_ERR_UNSUPPORTED, "fp16 operands need c_in/a_ld multiples of 8 (got %d/%d)", p.c_in, p.a_ld);
+  if (!p.d && !p.d16) return fail(M2S_ERR_BAD_ARG, "no output pointer");
+  if ((reinterpret_cast<uintptr_t>(p.a) & 15) || (reinterpret_cast<uintptr_t>(p.d) & 15) ||
+      (reinterpret_cast<uintptr_t>(p.d16) & 7))
     return fail(M2S_ERR_BAD_ARG, "A and D must be 16-byte aligned");
   if (w.n != p.n || w.c_in != p.c_in || w.taps != p.taps)
     return fail(M2S_ERR_BAD_ARG, "packed weights do not match the problem");
@@ -418,9 +451,11 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
     const long long pair_tiles = static_cast<long long>(p.batch) * ((p.l_out + 255) / 256) * w.n_tiles_pair;
     bool use_pair = p.n >= 128;
     if (!use_pair) {
-      const double mma_clk = static_cast<double>(p.taps) * ((p.c_in + 7) / 8) * (4096.0 + 32.0 * w.n_tile) / 75.0;
-      const int streams = 1 + (p.epi.res ? 1 : 0) + (p.epi.accum ? 1 : 0);
-      const double hbm_clk = 128.0 * 4.0 * (p.c_in + static_cast<double>(p.n) * streams) / 23.0;
+      const int kstep = w.half ? 16 : 8;
+      const double mma_clk =
+          static_cast<double>(p.taps) * ((p.c_in + kstep - 1) / kstep) * (4096.0 + 32.0 * w.n_tile) / 75.0;
+      const double out_bytes = (p.d ? 4.0 : 0.0) + (p.d16 ? 2.0 : 0.0) + (p.epi.res ? 4.0 : 0.0) + (p.epi.accum ? 4.0 : 0.0);
+      const double hbm_clk = 128.0 * (p.c_in * (w.half ? 2.0 : 4.0) + static_cast<double>(p.n) * out_bytes) / 23.0;
       use_pair = mma_clk > 1.5 * hbm_clk;
     }
     if (engine_knobs().pair == 2) use_pair = true;
@@ -436,6 +471,11 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
   prm.n_tile = w.n_tile;
   prm.n_tiles = w.n_tiles;
   prm.cblocks = w.cblocks;
+  prm.half = w.half;
+  prm.kblock = w.kblock;
+  prm.row_bytes = w.row_bytes;
+  prm.kstep_elems = w.half ? 16 : 8;
+  prm.desc_hi = make_desc_hi(w.row_bytes);
   prm.base_offset_mode = knobs.base_offset_mode;
   prm.dbg = knobs.dbg;
   prm.trace = knobs.trace;
@@ -466,9 +506,9 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
   const int a_rows_needed = prm.m_tile + halo;
   prm.a_nbox = (a_rows_needed + 255) / 256;
   prm.a_box_rows = (((a_rows_needed + prm.a_nbox - 1) / prm.a_nbox) + 7) / 8 * 8;
-  prm.a_stage_bytes = static_cast<uint32_t>(prm.a_nbox * prm.a_box_rows * kRowBytes);
+  prm.a_stage_bytes = static_cast<uint32_t>(prm.a_nbox * prm.a_box_rows * w.row_bytes);
   prm.a_stage_bytes = (prm.a_stage_bytes + 1023u) & ~1023u;
-  prm.b_tap_bytes = static_cast<uint32_t>(w.n_tile * kRowBytes);
+  prm.b_tap_bytes = static_cast<uint32_t>(w.n_tile * w.row_bytes);
   // several taps share one weight stage when the per-tap block is small (amortises barrier round trips)
   int tg = static_cast<int>(32768u / prm.b_tap_bytes);
   if (tg < 1) tg = 1;
@@ -496,23 +536,25 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
   uint32_t smem_bytes = total(na, nb);
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;  // keep 1 CTA / SM (whole-TMEM allocation)
 
-  // instruction descriptor: D=f32, A=B=tf32, K-major both, N, M=128
-  prm.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(w.n_tile >> 3) << 17) |
+  // instruction descriptor: D=f32, A=B=tf32 (format 2) or f16 (format 0), K-major both, N, M=128
+  prm.idesc = (1u << 4) | (w.half ? 0u : ((2u << 7) | (2u << 10))) | (static_cast<uint32_t>(w.n_tile >> 3) << 17) |
               (static_cast<uint32_t>(128 >> 4) << 24);
 
   // tensor map over A: (c_in, a_rows, batch), box (32, a_box_rows, 1), 128B swizzle, OOB -> zero
   CUtensorMap tmap;
   cuuint64_t gdim[3] = {static_cast<cuuint64_t>(p.c_in), static_cast<cuuint64_t>(p.a_rows),
                         static_cast<cuuint64_t>(p.batch)};
-  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(p.a_ld) * 4ull,
-                           static_cast<cuuint64_t>(p.a_batch_rows) * static_cast<cuuint64_t>(p.a_ld) * 4ull};
+  const cuuint64_t esize = w.half ? 2ull : 4ull;
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(p.a_ld) * esize,
+                           static_cast<cuuint64_t>(p.a_batch_rows) * static_cast<cuuint64_t>(p.a_ld) * esize};
   if (p.batch == 1) gstride[1] = gstride[0] * static_cast<cuuint64_t>(p.a_rows > 0 ? p.a_rows : 1);
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(kKBlock), static_cast<cuuint32_t>(prm.a_box_rows), 1u};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(w.kblock), static_cast<cuuint32_t>(prm.a_box_rows), 1u};
   cuuint32_t estr[3] = {1u, 1u, 1u};
-  CUresult cr = enc(&tmap, knobs.tmap_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
-                    const_cast<float*>(p.a), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dt = w.half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                        : (knobs.tmap_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+  CUresult cr = enc(&tmap, dt, 3, const_cast<float*>(p.a), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    w.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS)
     return fail(M2S_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): c_in=%d rows=%d batch=%d ld=%d box_rows=%d",
                 static_cast<int>(cr), p.c_in, p.a_rows, p.batch, p.a_ld, prm.a_box_rows);

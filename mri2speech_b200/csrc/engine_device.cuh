@@ -3,14 +3,15 @@
 #pragma once
 #include "m2s_common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 namespace m2s {
 namespace engine {
 
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
-constexpr int kKBlock = 32;     // tf32 elements per 128-byte swizzle row
-constexpr int kRowBytes = 128;
+constexpr int kKBlock = 32;     // tf32 elements per 128-byte swizzle row (fp16: EngineParams::kblock = 64 or 32)
+constexpr int kRowBytes = 128;  // tf32 / wide fp16 rows; narrow fp16 layers (c_in <= 32) use 64-byte rows (SWIZZLE_64B)
 constexpr int kTmemCols = 512;
 constexpr int kMaxStagesA = 4;
 constexpr int kMaxStagesB = 8;
@@ -32,6 +33,10 @@ struct EngineParams {
   int rel_shift[M2S_MAX_TAPS];
   int tg;               // taps per weight stage
   uint32_t b_tap_bytes; // bytes of one tap's weight block (n_tile x 128)
+  // operand format: half = 0 tf32 (kblock 32, 128-byte rows, K = 8 per MMA), 1 fp16 (kblock 64, 128-byte rows,
+  // K = 16), 2 fp16 narrow (kblock 32, 64-byte rows, SWIZZLE_64B).  A K-step always advances 32 bytes.
+  int half, kblock, row_bytes, kstep_elems;
+  uint64_t desc_hi;           // SMEM matrix descriptor without the start address
   unsigned long long* trace;  // debug: per-role clock64 stamps of CTA 0 (null = off)
   int trace_tiles;
   int dbg;  // debug: bit0 skip global stores, bit1 skip TMEM loads, bit2 skip SMEM transpose, bit3 skip MMA issue
@@ -139,6 +144,16 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, int base_off
   return d;
 }
 
+// Same for rows of `row_bytes` (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B); 8-row groups are 8 * row_bytes apart.
+inline uint64_t make_desc_hi(int row_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((8 * row_bytes) >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(row_bytes == 128 ? 2 : 4) << 61;
+  return d;
+}
+
 // debug timeline: slot = role*3 + k ; layout trace[tile_iter][9]
 __device__ __forceinline__ void trace_stamp(const EngineParams& prm, int it, int slot) {
   if (prm.trace && blockIdx.x == 0 && it < prm.trace_tiles) prm.trace[it * 9 + slot] = clock64();
@@ -163,6 +178,24 @@ __device__ __forceinline__ void mma_tf32_k4(uint32_t tmem_d, uint64_t da, uint64
   if (ksteps > 1) mma_tf32(tmem_d, da + 2, db + 2, idesc, 1u);
   if (ksteps > 2) mma_tf32(tmem_d, da + 4, db + 4, idesc, 1u);
   if (ksteps > 3) mma_tf32(tmem_d, da + 6, db + 6, idesc, 1u);
+}
+
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-steps of one (sub-tile, tap) over one SMEM row block, fp16 operands (K = 16 per instruction, 32 bytes per step).
+__device__ __forceinline__ void mma_f16_k4(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum0,
+                                           int ksteps) {
+  mma_f16(tmem_d, da, db, idesc, accum0);
+  if (ksteps > 1) mma_f16(tmem_d, da + 2, db + 2, idesc, 1u);
+  if (ksteps > 2) mma_f16(tmem_d, da + 4, db + 4, idesc, 1u);
+  if (ksteps > 3) mma_f16(tmem_d, da + 6, db + 6, idesc, 1u);
 }
 
 struct EpiConsts {
@@ -257,6 +290,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
     if (col_ok && e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
     const size_t row0 = d_base + qw + rr0;
     float* dptr = p.d + row0 * p.d_ld + n;
+    __half* hptr = static_cast<__half*>(p.d16) + row0 * p.d_ld + n;
     const size_t d_step = static_cast<size_t>(4) * p.d_ld;
     float4 res4[8], acc4[8];
 #pragma unroll
@@ -324,9 +358,23 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
       for (int i = 0; i < 8; ++i)
         if (i * 4 + rr0 >= rows_valid) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    if (p.d) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i * 4 + rr0 < rows_ok) *reinterpret_cast<float4*>(dptr + i * d_step) = o[i];
+      for (int i = 0; i < 8; ++i)
+        if (i * 4 + rr0 < rows_ok) *reinterpret_cast<float4*>(dptr + i * d_step) = o[i];
+    }
+    if (p.d16) {  // fp16 copy of the tile: the tensor-core operand of the next conv (saturating, never inf)
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i * 4 + rr0 < rows_ok) {
+          const __half2 lo = __floats2half2_rn(fminf(fmaxf(o[i].x, -65504.f), 65504.f), fminf(fmaxf(o[i].y, -65504.f), 65504.f));
+          const __half2 hi = __floats2half2_rn(fminf(fmaxf(o[i].z, -65504.f), 65504.f), fminf(fmaxf(o[i].w, -65504.f), 65504.f));
+          uint2 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(hptr + i * d_step) = pk;
+        }
+    }
     __syncwarp();
   }
 }

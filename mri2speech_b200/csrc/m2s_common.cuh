@@ -47,17 +47,19 @@ struct Epilogue {
 };
 
 struct ConvProblem {
-  const float* a;
+  const float* a;      // fp32 rows, or __half rows when a_half != 0 (a_ld / c_in count elements either way)
   long long a_batch_rows;
   int a_rows, a_ld, c_in;
   int batch, l_out;
   int taps;
   int shift[M2S_MAX_TAPS];
   int n;
-  float* d;
+  float* d;            // fp32 output (may be null when d16 is set)
   long long d_batch_rows;
   int d_ld, d_row_offset;
   Epilogue epi;
+  int a_half;          // A operand is fp16 (tcgen05 kind::f16); 0 = fp32 rounded to tf32 by TMA
+  void* d16;           // optional second output, fp16, indexed like d (same d_ld in elements); null = none
 };
 
 inline ConvProblem problem_from_args(const m2s_conv_args& a) {
@@ -71,6 +73,7 @@ inline ConvProblem problem_from_args(const m2s_conv_args& a) {
   p.epi.act_slope = a.act_slope; p.epi.mask_mode = a.mask_mode;
   p.epi.lens = a.lens; p.epi.len_scale = a.len_scale; p.epi.pitch = a.pitch; p.epi.i_lo = a.i_lo;
   p.epi.i_hi = a.i_hi; p.epi.j_lo = a.j_lo; p.epi.j_hi = a.j_hi;
+  p.a_half = a.a_half; p.d16 = a.d16;
   return p;
 }
 
@@ -112,8 +115,15 @@ __device__ __forceinline__ float epi_apply(const Epilogue& e, float acc, float b
 
 // ---- engine entry points (host) ---------------------------------------------
 // Pre-packed weights for the tcgen05 engine: [n_tile][cblock][tap][n_tile_rows][32 floats, 128B-swizzled].
+enum { PACK_FP32 = 0, PACK_TF32 = 1, PACK_FP16 = 2 };
+
 struct PackedWeights {
-  float* dev = nullptr;   // packed, tcgen05 layout
+  // operand format of the tcgen05 layouts: 0 = tf32 (32 floats per 128-byte SMEM row), 1 = fp16 with 64 halves per
+  // 128-byte row (SWIZZLE_128B, c_in > 32), 2 = fp16 with 32 halves per 64-byte row (SWIZZLE_64B, c_in <= 32)
+  int half = 0;
+  int kblock = 32;        // channels per SMEM row
+  int row_bytes = 128;
+  float* dev = nullptr;   // packed, tcgen05 layout (fp16 layouts are stored in the same allocation type)
   float* plain = nullptr; // [taps][n][c_in] plain (SIMT path / tests)
   int n = 0, c_in = 0, taps = 0;
   int n_tile = 0, n_tiles = 0, cblocks = 0;
@@ -126,8 +136,12 @@ struct PackedWeights {
 
 // Choose N tiling for the tcgen05 engine (n_tile multiple of 16, <= 256).
 void choose_n_tiling(int n, int* n_tile, int* n_tiles);
-// Pack host weights [taps][n][c_in] (already folded) into both device layouts.  tf32_round: RNE-round values.
-int pack_weights(const float* host_w, int taps, int n, int c_in, bool tf32_round, PackedWeights* out);
+// Pack host weights [taps][n][c_in] (already folded) into both device layouts.  mode = PACK_FP32 (values kept),
+// PACK_TF32 (RNE-rounded to tf32) or PACK_FP16 (fp16 operands for tcgen05 kind::f16; `plain` keeps the rounded fp32).
+int pack_weights(const float* host_w, int taps, int n, int c_in, int mode, PackedWeights* out);
+inline int pack_weights(const float* host_w, int taps, int n, int c_in, bool tf32_round, PackedWeights* out) {
+  return pack_weights(host_w, taps, n, c_in, tf32_round ? PACK_TF32 : PACK_FP32, out);
+}
 void free_weights(PackedWeights* w);
 
 int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stream);
