@@ -186,6 +186,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--frames", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default=os.environ.get("M2S_BENCH_PRECISION", "tf32"), choices=["tf32", "fp16"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -212,7 +213,7 @@ def main():
     from mri2speech_b200.vocoder import Generator
 
     torch.manual_seed(1234)
-    gen = Generator(load_h(), precision="tf32").to(device).eval()
+    gen = Generator(load_h(), precision=args.precision).to(device).eval()
     B, T = args.batch, args.frames
     mel_host = synth.synthetic_mels(B, T, seed=2024 + rank).pin_memory()
     mel = mel_host.to(device)

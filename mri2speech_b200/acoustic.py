@@ -182,7 +182,7 @@ class OTNLikeCNNBiLSTM(nn.Module):
         cfg.n_mels = self.n_mels
         cfg.rnn_hidden = self.rnn_hidden
         cfg.height, cfg.width = height, width
-        cfg.precision = {"tf32": _lib.PREC_TF32, "fp32": _lib.PREC_FP32}[self.precision]
+        cfg.precision = _lib.PRECISIONS[self.precision]
         handle = C.c_void_p()
         _lib.check(_lib.lib().m2s_acoustic_create(C.byref(cfg), arr, n, C.byref(handle)))
         del keep

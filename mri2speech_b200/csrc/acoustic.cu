@@ -16,17 +16,18 @@
 #include <vector>
 
 namespace m2s {
-int enc_stem(const float* frames, const int32_t* fmap, float* out, const float* w, const float* bias, int n, int H,
-             int W, cudaStream_t st);
-int enc_stem_u8(const uint8_t* frames, const int32_t* fmap, const float* mask, float2* norm, float* out, const float* w,
-                const float* bias, int n, int H, int W, cudaStream_t st);
-int enc_zero_rows(float* buf, int n, int rows_per_frame, int ld, int head_rows, int tail_start, cudaStream_t st);
-int enc_im2col_s2(const float* in, float* col, int n, int Hin, int Win, int C, cudaStream_t st);
-int enc_dwconv(const float* in, float* out, float* sums, const float* w, const float* bias, int n, int C, int Hin,
+int enc_stem(const float* frames, const int32_t* fmap, void* out, int half, const float* w, const float* bias, int n,
+             int H, int W, cudaStream_t st);
+int enc_stem_u8(const uint8_t* frames, const int32_t* fmap, const float* mask, float2* norm, void* out, int half,
+                const float* w, const float* bias, int n, int H, int W, cudaStream_t st);
+int enc_zero_rows(void* buf, int esize, int n, int rows_per_frame, int ld, int head_rows, int tail_start,
+                  cudaStream_t st);
+int enc_im2col_s2(const void* in, void* col, int esize, int n, int Hin, int Win, int C, cudaStream_t st);
+int enc_dwconv(const void* in, void* out, int half, float* sums, const float* w, const float* bias, int n, int C, int Hin,
                int Win, int pitch_in, int oy, int ox, int rows_in, int stride, cudaStream_t st);
 int enc_se(const float* sums, float* scales, const float* w1, const float* b1, const float* w2, const float* b2, int n,
            int C, int rd, int hw, cudaStream_t st);
-int enc_se_scale(float* x, const float* scales, int n, int hw, int C, cudaStream_t st);
+int enc_se_scale(void* x, int half, const float* scales, int n, int hw, int C, cudaStream_t st);
 int enc_gap(const float* x, const int32_t* fmap, float* feats, int n, int hw, int C, int feat_ld, cudaStream_t st);
 int lstm_recurrence(const float* gin, const float* w_hh_fwd, const float* w_hh_bwd, const int32_t* lens, float* hcat,
                     unsigned int* counters, int batch, int frames, int max_len, int hidden,
@@ -98,7 +99,7 @@ void free_gemm(GemmLayer* L) {
 // conv weight (cout, cin, k, k) + BN -> engine layer.  mode 0: k*k shifted taps (pitch given); mode 1: single tap
 // with K = k*k*cin (im2col order (dy*3+dx)*cin + c); 1x1 convs are mode 0 with one tap.
 int make_conv_layer(const TMap& m, const std::string& conv, const std::string& bn, int cout, int cin, int k,
-                    int pitch, int mode, bool tf32, GemmLayer* L) {
+                    int pitch, int mode, int pack, GemmLayer* L) {
   const HT* w;
   M2S_TRY(need(m, conv + ".weight", static_cast<size_t>(cout) * cin * k * k, &w));
   std::vector<float> s, t;
@@ -115,11 +116,11 @@ int make_conv_layer(const TMap& m, const std::string& conv, const std::string& b
   if (mode == 0) {
     L->taps = kk;
     for (int tap = 0; tap < kk; ++tap) L->shift[tap] = (tap / k) * pitch + (tap % k);
-    M2S_TRY(pack_weights(e.data(), kk, cout, cin, tf32, &L->w));
+    M2S_TRY(pack_weights(e.data(), kk, cout, cin, pack, &L->w));
   } else {
     L->taps = 1;
     L->shift[0] = 0;
-    M2S_TRY(pack_weights(e.data(), 1, cout, kk * cin, tf32, &L->w));
+    M2S_TRY(pack_weights(e.data(), 1, cout, kk * cin, pack, &L->w));
   }
   return upload(t, &L->bias);
 }
@@ -148,7 +149,8 @@ struct Block {
 
 struct m2s_acoustic {
   m2s_acoustic_config cfg;
-  bool tf32 = true;
+  bool tf32 = true;   // tensor-core build (tf32 or fp16 operands); false = CUDA-core fp32 build
+  bool fp16 = false;  // M2S_PREC_FP16: encoder GEMMs run kind::f16, operand-only activations live in HBM as fp16
   float *stem_w = nullptr, *stem_b = nullptr;
   std::vector<Block> blocks;
   GemmLayer inproj, head;
@@ -177,10 +179,11 @@ int run_gemm(const m2s_acoustic* m, const ConvProblem& p, const GemmLayer& L, cu
   return m->tf32 ? conv_tcgen05(p, L.w, st) : conv_simt(p, L.w.plain, st);
 }
 
-ConvProblem gemm_problem(const float* a, long long a_batch_rows, int a_rows, int c_in, int batch, int l_out, float* d,
+// `a` holds fp16 rows when the layer is packed for kind::f16 (L.w.half), fp32 rows otherwise.
+ConvProblem gemm_problem(const void* a, long long a_batch_rows, int a_rows, int c_in, int batch, int l_out, float* d,
                          long long d_batch_rows, int d_ld, int d_row_offset, const GemmLayer& L) {
   ConvProblem p{};
-  p.a = a; p.a_batch_rows = a_batch_rows; p.a_rows = a_rows; p.a_ld = c_in; p.c_in = c_in;
+  p.a = static_cast<const float*>(a); p.a_half = L.w.half != 0; p.a_batch_rows = a_batch_rows; p.a_rows = a_rows; p.a_ld = c_in; p.c_in = c_in;
   p.batch = batch; p.l_out = l_out; p.taps = L.taps;
   for (int j = 0; j < L.taps; ++j) p.shift[j] = L.shift[j];
   p.n = L.w.n; p.d = d; p.d_batch_rows = d_batch_rows; p.d_ld = d_ld; p.d_row_offset = d_row_offset;
@@ -195,6 +198,7 @@ void set_pitch_mask(ConvProblem* p, int h, int w) {
 
 struct EncBuffers {
   float *x0, *x1, *e, *e2, *col, *sums, *scales;
+  float *x0h, *x1h;  // fp16 copies of the block outputs (fp16 build)
   float2* norm;  // per-frame (min, 1/range) of the uint8 ingest
   int32_t* fmap;
 };
@@ -211,7 +215,8 @@ AcWorkspace plan_ws(const m2s_acoustic* m, int batch, int frames) {
   const size_t nf = static_cast<size_t>(batch) * frames;
   const size_t nc = nf < static_cast<size_t>(m->chunk) ? nf : m->chunk;
   w.enc_floats = align64(nc * m->x_floats) * 2 + align64(nc * m->e_floats) + align64(nc * m->e2_floats) +
-                 align64(nc * m->col_floats) + 2 * align64(nc * m->max_mid) + align64(2 * nc);
+                 align64(nc * m->col_floats) + 2 * align64(nc * m->max_mid) + align64(2 * nc) +
+                 (m->fp16 ? 2 * align64(nc * m->x_floats / 2 + 64) : 0);
   w.feats_floats = align64(nf * kFeat);
   w.gin_floats = align64(nf * 8 * m->cfg.rnn_hidden);
   w.hcat_floats = align64(nf * 2 * m->cfg.rnn_hidden);
@@ -220,48 +225,84 @@ AcWorkspace plan_ws(const m2s_acoustic* m, int batch, int frames) {
   return w;
 }
 
+// One activation tensor of the encoder: the fp32 copy (residual source / GAP input) and/or the fp16 copy (tensor-core
+// operand of the fp16 build); either may be absent (null).
+struct Act {
+  float* f32;
+  void* f16;
+};
+
 // encoder over `n` frames (compact list; fmap maps compact index -> source frame / feature row, or null)
 int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float* mask, const int32_t* fmap, int n,
                  float* feats, int feat_ld, const EncBuffers& B, cudaStream_t st) {
   const int H = m->cfg.height, W = m->cfg.width;
-  float* x = B.x0;
-  float* y = B.x1;
-  if (u8)
-    M2S_TRY(enc_stem_u8(static_cast<const uint8_t*>(frames), fmap, mask, B.norm, x, m->stem_w, m->stem_b, n, H, W, st));
-  else
-    M2S_TRY(enc_stem(static_cast<const float*>(frames), fmap, x, m->stem_w, m->stem_b, n, H, W, st));
-  for (const Block& b : m->blocks) {
+  const bool h = m->fp16;
+  const int esz = h ? 2 : 4;
+  Act x{B.x0, B.x0h}, y{B.x1, B.x1h};
+  // operand view of an activation / of the scratch tensors e, e2, col (fp16 build: fp16 data in the same buffers)
+  auto op = [&](const Act& a) { return h ? static_cast<const void*>(a.f16) : static_cast<const void*>(a.f32); };
+  // a GEMM output that is only ever an operand (e, e2): fp16 in the fp16 build
+  auto set_operand_out = [&](ConvProblem* p, float* buf) {
+    if (h) { p->d = nullptr; p->d16 = buf; } else { p->d = buf; }
+  };
+  {  // the stem's only consumer is block 0.0 (no skip): operand copy only in the fp16 build
+    void* out = h ? x.f16 : static_cast<void*>(x.f32);
+    if (u8)
+      M2S_TRY(enc_stem_u8(static_cast<const uint8_t*>(frames), fmap, mask, B.norm, out, h, m->stem_w, m->stem_b, n, H, W, st));
+    else
+      M2S_TRY(enc_stem(static_cast<const float*>(frames), fmap, out, h, m->stem_w, m->stem_b, n, H, W, st));
+  }
+  for (size_t bi = 0; bi < m->blocks.size(); ++bi) {
+    const Block& b = m->blocks[bi];
+    const bool last = bi + 1 == m->blocks.size();
+    // block output copies: fp32 when the next block adds it as a shortcut (or the GAP reads it), fp16 when the next
+    // consumer is a GEMM of the fp16 build
+    const bool out32 = !h || last || m->blocks[bi + 1].skip;
+    const bool out16 = h && !last;
+    auto set_block_out = [&](ConvProblem* p) {
+      p->d = out32 ? y.f32 : nullptr;
+      p->d16 = out16 ? y.f16 : nullptr;
+    };
+    auto zero_border = [&](int rows, int ld, int head, int tail) -> int {
+      if (out32) M2S_TRY(enc_zero_rows(y.f32, 4, n, rows, ld, head, tail, st));
+      if (out16) M2S_TRY(enc_zero_rows(y.f16, 2, n, rows, ld, head, tail, st));
+      return M2S_OK;
+    };
     const int hin = b.hin, win = b.win;
     const int hout = hin / b.stride, wout = win / b.stride;
     if (b.kind == CN) {
       // 3x3 s1 conv on the padded layout -> padded layout, SiLU, (+ skip after the activation)
       const int rows = static_cast<int>(padded_rows(hin, win));
-      ConvProblem p = gemm_problem(x, rows, rows, b.cin, n, hin * (win + 2), y, rows, b.cout, win + 3, b.conv);
+      ConvProblem p = gemm_problem(op(x), rows, rows, b.cin, n, hin * (win + 2), y.f32, rows, b.cout, win + 3, b.conv);
+      set_block_out(&p);
       p.epi.act = M2S_ACT_SILU;
       set_pitch_mask(&p, hin, win);
-      if (b.skip) { p.epi.res = x; p.epi.res_ld = b.cin; p.epi.res_after_act = 1; }
+      if (b.skip) { p.epi.res = x.f32; p.epi.res_ld = b.cin; p.epi.res_after_act = 1; }
       M2S_TRY(run_gemm(m, p, b.conv, st));
-      M2S_TRY(enc_zero_rows(y, n, rows, b.cout, win + 3, hin * (win + 2) + win + 3, st));
+      M2S_TRY(zero_border(rows, b.cout, win + 3, hin * (win + 2) + win + 3));
       std::swap(x, y);
     } else if (b.kind == ER) {
       const int rows_in = static_cast<int>(padded_rows(hin, win));
       const int rows_out = static_cast<int>(padded_rows(hout, wout));
       const int lq = hout * (wout + 2);  // rows in the (W+2)-pitch output space
       if (b.stride == 2) {
-        M2S_TRY(enc_im2col_s2(x, B.col, n, hin, win, b.cin, st));
+        M2S_TRY(enc_im2col_s2(op(x), B.col, esz, n, hin, win, b.cin, st));
         ConvProblem p = gemm_problem(B.col, lq, lq, 9 * b.cin, n, lq, B.e, lq, b.mid, 0, b.conv);
+        set_operand_out(&p, B.e);
         p.epi.act = M2S_ACT_SILU;
         M2S_TRY(run_gemm(m, p, b.conv, st));
       } else {
-        ConvProblem p = gemm_problem(x, rows_in, rows_in, b.cin, n, lq, B.e, lq, b.mid, 0, b.conv);
+        ConvProblem p = gemm_problem(op(x), rows_in, rows_in, b.cin, n, lq, B.e, lq, b.mid, 0, b.conv);
+        set_operand_out(&p, B.e);
         p.epi.act = M2S_ACT_SILU;
         M2S_TRY(run_gemm(m, p, b.conv, st));
       }
-      ConvProblem p = gemm_problem(B.e, lq, lq, b.mid, n, lq, y, rows_out, b.cout, wout + 3, b.pwl);
+      ConvProblem p = gemm_problem(B.e, lq, lq, b.mid, n, lq, y.f32, rows_out, b.cout, wout + 3, b.pwl);
+      set_block_out(&p);
       set_pitch_mask(&p, hout, wout);
-      if (b.skip) { p.epi.res = x; p.epi.res_ld = b.cin; }
+      if (b.skip) { p.epi.res = x.f32; p.epi.res_ld = b.cin; }
       M2S_TRY(run_gemm(m, p, b.pwl, st));
-      M2S_TRY(enc_zero_rows(y, n, rows_out, b.cout, wout + 3, hout * (wout + 2) + wout + 3, st));
+      M2S_TRY(zero_border(rows_out, b.cout, wout + 3, hout * (wout + 2) + wout + 3));
       std::swap(x, y);
     } else {
       // IR: 1x1 expand (+SiLU) -> depthwise 3x3 (+SiLU, squeeze) -> SE -> 1x1 project (+ skip).
@@ -270,26 +311,28 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
       const int rows_in = b.in_padded ? static_cast<int>(padded_rows(hin, win)) : hin * win;
       {
         const int rows = n * rows_in;
-        ConvProblem p = gemm_problem(x, rows, rows, b.cin, 1, rows, B.e, rows, b.mid, 0, b.conv);
+        ConvProblem p = gemm_problem(op(x), rows, rows, b.cin, 1, rows, B.e, rows, b.mid, 0, b.conv);
+        set_operand_out(&p, B.e);
         p.epi.act = M2S_ACT_SILU;
         M2S_TRY(run_gemm(m, p, b.conv, st));
       }
       const int pitch_in = b.in_padded ? win + 2 : win;
       const int o = b.in_padded ? 1 : 0;
-      M2S_TRY(enc_dwconv(B.e, B.e2, B.sums, b.dw_w, b.dw_b, n, b.mid, hin, win, pitch_in, o, o, rows_in, b.stride, st));
+      M2S_TRY(enc_dwconv(B.e, B.e2, h, B.sums, b.dw_w, b.dw_b, n, b.mid, hin, win, pitch_in, o, o, rows_in, b.stride, st));
       const int hw = hout * wout;
       M2S_TRY(enc_se(B.sums, B.scales, b.se_w1, b.se_b1, b.se_w2, b.se_b2, n, b.mid, b.rd, hw, st));
-      M2S_TRY(enc_se_scale(B.e2, B.scales, n, hw, b.mid, st));
+      M2S_TRY(enc_se_scale(B.e2, h, B.scales, n, hw, b.mid, st));
       const int rows_out = n * hw;
-      ConvProblem p = gemm_problem(B.e2, rows_out, rows_out, b.mid, 1, rows_out, y, rows_out, b.cout, 0, b.pwl);
-      if (b.skip) { p.epi.res = x; p.epi.res_ld = b.cin; }
+      ConvProblem p = gemm_problem(B.e2, rows_out, rows_out, b.mid, 1, rows_out, y.f32, rows_out, b.cout, 0, b.pwl);
+      set_block_out(&p);
+      if (b.skip) { p.epi.res = x.f32; p.epi.res_ld = b.cin; }
       M2S_TRY(run_gemm(m, p, b.pwl, st));
       std::swap(x, y);
     }
   }
-  const Block& last = m->blocks.back();
-  const int hw = (last.hin / last.stride) * (last.win / last.stride);
-  return enc_gap(x, fmap, feats, n, hw, kFeat, feat_ld, st);
+  const Block& lastb = m->blocks.back();
+  const int hw = (lastb.hin / lastb.stride) * (lastb.win / lastb.stride);
+  return enc_gap(x.f32, fmap, feats, n, hw, kFeat, feat_ld, st);
 }
 
 int encode_all(const m2s_acoustic* m, const void* frames, bool u8, const float* mask, const int32_t* fmap_dev,
@@ -304,7 +347,12 @@ int encode_all(const m2s_acoustic* m, const void* frames, bool u8, const float* 
   B.col = p; p += align64(static_cast<size_t>(nc) * m->col_floats);
   B.sums = p; p += align64(static_cast<size_t>(nc) * m->max_mid);
   B.scales = p; p += align64(static_cast<size_t>(nc) * m->max_mid);
-  B.norm = reinterpret_cast<float2*>(p);
+  B.norm = reinterpret_cast<float2*>(p); p += align64(2 * static_cast<size_t>(nc));
+  B.x0h = B.x1h = nullptr;
+  if (m->fp16) {
+    B.x0h = p; p += align64(static_cast<size_t>(nc) * m->x_floats / 2 + 64);
+    B.x1h = p;
+  }
   for (int f0 = 0; f0 < n_frames; f0 += nc) {
     const int n = n_frames - f0 < nc ? n_frames - f0 : nc;
     if (fmap_dev) {
@@ -364,6 +412,10 @@ extern "C" int m2s_acoustic_create(const m2s_acoustic_config* cfg, const m2s_ten
   auto* m = new m2s_acoustic();
   m->cfg = *cfg;
   m->tf32 = cfg->precision != M2S_PREC_FP32;
+  m->fp16 = cfg->precision == M2S_PREC_FP16;
+  // encoder GEMMs: fp16 operands in the fp16 build (every c_in of the topology is a multiple of 8); the BiLSTM input
+  // projection and the head stay on tf32 (fp32 features / hidden states, 0.2 % of the FLOPs)
+  const int enc_pack = !m->tf32 ? PACK_FP32 : (m->fp16 ? PACK_FP16 : PACK_TF32);
   if (const char* c = std::getenv("M2S_ENCODER_CHUNK")) m->chunk = std::max(1, std::atoi(c));
   int st = M2S_OK;
   auto bail = [&](int s) { m2s_acoustic_destroy(m); return s; };
@@ -400,16 +452,16 @@ extern "C" int m2s_acoustic_create(const m2s_acoustic_config* cfg, const m2s_ten
       const int ho = h / b.stride, wo = w / b.stride;
       if (sd.kind == CN) {
         b.out_padded = true;
-        if ((st = make_conv_layer(tm, p + ".conv", p + ".bn1", b.cout, cin, 3, w + 2, 0, m->tf32, &b.conv)) != M2S_OK)
+        if ((st = make_conv_layer(tm, p + ".conv", p + ".bn1", b.cout, cin, 3, w + 2, 0, enc_pack, &b.conv)) != M2S_OK)
           return bail(st);
         m->x_floats = std::max(m->x_floats, padded_rows(ho, wo) * b.cout);
         launches += 2;
       } else if (sd.kind == ER) {
         b.out_padded = true;
         if ((st = make_conv_layer(tm, p + ".conv_exp", p + ".bn1", b.mid, cin, 3, w + 2, b.stride == 2 ? 1 : 0,
-                                  m->tf32, &b.conv)) != M2S_OK)
+                                  enc_pack, &b.conv)) != M2S_OK)
           return bail(st);
-        if ((st = make_conv_layer(tm, p + ".conv_pwl", p + ".bn2", b.cout, b.mid, 1, 0, 0, m->tf32, &b.pwl)) != M2S_OK)
+        if ((st = make_conv_layer(tm, p + ".conv_pwl", p + ".bn2", b.cout, b.mid, 1, 0, 0, enc_pack, &b.pwl)) != M2S_OK)
           return bail(st);
         const size_t lq = static_cast<size_t>(ho) * (wo + 2);
         m->e_floats = std::max(m->e_floats, lq * b.mid);
@@ -418,9 +470,9 @@ extern "C" int m2s_acoustic_create(const m2s_acoustic_config* cfg, const m2s_ten
         launches += b.stride == 2 ? 4 : 3;
       } else {
         b.out_padded = false;
-        if ((st = make_conv_layer(tm, p + ".conv_pw", p + ".bn1", b.mid, cin, 1, 0, 0, m->tf32, &b.conv)) != M2S_OK)
+        if ((st = make_conv_layer(tm, p + ".conv_pw", p + ".bn1", b.mid, cin, 1, 0, 0, enc_pack, &b.conv)) != M2S_OK)
           return bail(st);
-        if ((st = make_conv_layer(tm, p + ".conv_pwl", p + ".bn3", b.cout, b.mid, 1, 0, 0, m->tf32, &b.pwl)) != M2S_OK)
+        if ((st = make_conv_layer(tm, p + ".conv_pwl", p + ".bn3", b.cout, b.mid, 1, 0, 0, enc_pack, &b.pwl)) != M2S_OK)
           return bail(st);
         {  // depthwise (mid,1,3,3) + bn2 -> [9][mid]
           const HT* dw;

@@ -203,7 +203,7 @@ conv_engine_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             if (elect_one()) {
               const uint32_t a_tile = a_base + sa * prm.a_stage_bytes;
               const uint32_t b_tile = b_base + sb * prm.b_stage_bytes;
-              for (int t = 0; t < cnt; ++t) {
+              for (int t = 0; t < cnt && !(prm.dbg & 8); ++t) {
                 const uint64_t db = desc_hi | (((b_tile + t * prm.b_tap_bytes) & 0x3FFFF) >> 4);
                 const uint64_t da = desc_hi | (((a_tile + prm.rel_shift[tap0 + t] * row_bytes) & 0x3FFFF) >> 4);
                 const uint32_t first = (cb | tap0 | t) ? 1u : 0u;
@@ -231,7 +231,7 @@ conv_engine_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   } else {
     // ===================== epilogue warps (each CTA drains its own 128 TMEM lanes) =====================
     const int ew = warp - 2;
-    const EpiWarp epw = make_epi_warp(p.epi, stage_base, ew, warp, lane);
+    const EpiWarp epw = make_epi_warp(p.epi, stage_base, ew, warp, lane, prm.dbg);
     int acc = 0;
     uint32_t pacc = 0;
     for (int tile = pair; tile < prm.total_tiles; tile += npairs) {
@@ -380,9 +380,9 @@ int conv_tcgen05_pair(const ConvProblem& p, const PackedWeights& w, cudaStream_t
   }
 
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const EngineParams);
-  static const KernelFn kernels[6] = {conv_engine_pair_kernel<EPI_FULL>, conv_engine_pair_kernel<EPI_FULL_SILU>,
-                                      conv_engine_pair_kernel<EPI_BIAS>, conv_engine_pair_kernel<EPI_LRELU>,
-                                      conv_engine_pair_kernel<EPI_SILU>, conv_engine_pair_kernel<EPI_RES>};
+  static const KernelFn kernels[EPI_COUNT] = {conv_engine_pair_kernel<EPI_FULL>,  conv_engine_pair_kernel<EPI_FULL_SILU>, conv_engine_pair_kernel<EPI_BIAS>,
+                                              conv_engine_pair_kernel<EPI_LRELU>, conv_engine_pair_kernel<EPI_SILU>,      conv_engine_pair_kernel<EPI_RES>,
+                                              conv_engine_pair_kernel<EPI_RB>,    conv_engine_pair_kernel<EPI_RB_ACC>};
   static bool attr_set = false;
   if (!attr_set) {
     for (KernelFn k : kernels) {
@@ -390,10 +390,7 @@ int conv_tcgen05_pair(const ConvProblem& p, const PackedWeights& w, cudaStream_t
     }
     attr_set = true;
   }
-  int epi = p.epi.act == M2S_ACT_SILU ? EPI_FULL_SILU : EPI_FULL;
-  const bool plain = !p.epi.accum && p.epi.out_scale == 1.f;
-  if (plain && !p.epi.res) epi = p.epi.act == M2S_ACT_SILU ? EPI_SILU : (p.epi.act == M2S_ACT_LRELU ? EPI_LRELU : EPI_BIAS);
-  else if (plain && p.epi.act == M2S_ACT_NONE && p.epi.res_inv_slope == 1.f) epi = EPI_RES;
+  const int epi = choose_epilogue(p.epi);
 
   int pairs = (knobs.max_ctas > 0 ? knobs.max_ctas : sm_count()) / 2;
   if (pairs > prm.total_tiles) pairs = prm.total_tiles;

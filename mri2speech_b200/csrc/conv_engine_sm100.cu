@@ -197,7 +197,7 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     // TMEM -> registers (row per thread) -> SMEM transpose (XOR-swizzled, conflict-free) -> coalesced global
     // traffic: 8 lanes cover one 128-byte row segment, a warp instruction covers 4 rows.
     const int ew = warp - 2;  // 0..7
-    const EpiWarp epw = make_epi_warp(p.epi, stage_base, ew, warp, lane);
+    const EpiWarp epw = make_epi_warp(p.epi, stage_base, ew, warp, lane, prm.dbg);
     int acc = 0;
     uint32_t pacc = 0;
     int it = 0;
@@ -566,19 +566,16 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
     return fail(M2S_ERR_UNSUPPORTED, "n_tile=%d gives a non-1024-aligned weight stage", w.n_tile);
 
   using KernelFn = void (*)(const CUtensorMap, const EngineParams);
-  static const KernelFn kernels[6] = {conv_engine_kernel<EPI_FULL>, conv_engine_kernel<EPI_FULL_SILU>,
-                                      conv_engine_kernel<EPI_BIAS>, conv_engine_kernel<EPI_LRELU>,
-                                      conv_engine_kernel<EPI_SILU>, conv_engine_kernel<EPI_RES>};
+  static const KernelFn kernels[EPI_COUNT] = {conv_engine_kernel<EPI_FULL>,  conv_engine_kernel<EPI_FULL_SILU>, conv_engine_kernel<EPI_BIAS>,
+                                              conv_engine_kernel<EPI_LRELU>, conv_engine_kernel<EPI_SILU>,      conv_engine_kernel<EPI_RES>,
+                                              conv_engine_kernel<EPI_RB>,    conv_engine_kernel<EPI_RB_ACC>};
   static bool attr_set = false;
   if (!attr_set) {
     for (KernelFn k : kernels)
       M2S_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  int epi = p.epi.act == M2S_ACT_SILU ? EPI_FULL_SILU : EPI_FULL;
-  const bool plain = !p.epi.accum && p.epi.out_scale == 1.f;
-  if (plain && !p.epi.res) epi = p.epi.act == M2S_ACT_SILU ? EPI_SILU : (p.epi.act == M2S_ACT_LRELU ? EPI_LRELU : EPI_BIAS);
-  else if (plain && p.epi.act == M2S_ACT_NONE && p.epi.res_inv_slope == 1.f) epi = EPI_RES;
+  const int epi = choose_epilogue(p.epi);
   int grid = knobs.max_ctas > 0 ? knobs.max_ctas : sm_count();
   if (grid > prm.total_tiles) grid = prm.total_tiles;
   M2S_TRY(profile_before(stream));

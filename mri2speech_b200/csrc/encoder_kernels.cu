@@ -8,13 +8,33 @@
 //   * squeeze-excite MLP, excite scale, global average pool
 // All activations are channels-last.  "Padded" layouts carry a one-pixel zero border so that the
 // tensor-core engine can treat a 3x3 stride-1 conv as 9 row-shifted taps over the flattened image.
+// Every kernel that touches an activation is a template over its element type: float (tf32 / fp32 builds) or __half
+// (fp16 build: activations that are only tensor-core operands live in HBM as fp16, halving the traffic of these
+// memory-bound kernels; the arithmetic stays fp32).
 #include "m2s_common.cuh"
+#include <cuda_fp16.h>
 
 namespace m2s {
 
 namespace {
 
 __device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); }
+
+// 4 consecutive channels <-> float4
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const __half* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(__half* p, float4 v) {
+  uint2 u;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.x) : "f"(v.y), "f"(v.x));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.y) : "f"(v.w), "f"(v.z));
+  *reinterpret_cast<uint2*>(p) = u;
+}
 
 // Per-frame min / max of (optionally masked) uint8 frames -> norm[n] = (min, 1 / (max - min)) (scale 0 for a
 // constant frame, which then maps to all zeros like run_mri_video_inference.py:50-53).  The reference's z-score
@@ -52,17 +72,17 @@ __global__ void __launch_bounds__(256) frame_minmax_kernel(const uint8_t* __rest
 
 // frames (n, H, W) -> out padded ((H/2+2) x (W/2+2) rows, 32 ch); one block per padded output row.
 // kU8: frames are uint8 and are masked / min-max normalised on the fly (the fused ingest of SURVEY.md 8f-1).
-template <bool kU8>
+template <bool kU8, typename T>
 __global__ void __launch_bounds__(256) stem_kernel(const void* __restrict__ frames_v, const int32_t* __restrict__ fmap,
                                                    const float* __restrict__ mask, const float2* __restrict__ norm,
-                                                   float* __restrict__ out, const float* __restrict__ w /*[9][32]*/,
+                                                   T* __restrict__ out, const float* __restrict__ w /*[9][32]*/,
                                                    const float* __restrict__ bias, int H, int W) {
   const int Ho = H / 2, Wo = W / 2, pitch = Wo + 2;
   const int n = blockIdx.y;
   const int i = blockIdx.x;  // padded row 0..Ho+1
-  float* orow = out + (static_cast<size_t>(n) * (Ho + 2) * pitch + static_cast<size_t>(i) * pitch) * 32;
+  T* orow = out + (static_cast<size_t>(n) * (Ho + 2) * pitch + static_cast<size_t>(i) * pitch) * 32;
   if (i == 0 || i == Ho + 1) {
-    for (int k = threadIdx.x; k < pitch * 8; k += blockDim.x) reinterpret_cast<float4*>(orow)[k] = make_float4(0, 0, 0, 0);
+    for (int k = threadIdx.x; k < pitch * 8; k += blockDim.x) store4(orow + 4 * k, make_float4(0, 0, 0, 0));
     return;
   }
   extern __shared__ float srow[];  // 3 x (W + 1) input pixels
@@ -110,14 +130,15 @@ __global__ void __launch_bounds__(256) stem_kernel(const void* __restrict__ fram
 #pragma unroll
       for (int c = 0; c < 8; ++c) v[c] = silu(v[c]);
     }
-    float4* o = reinterpret_cast<float4*>(orow + static_cast<size_t>(j) * 32 + cg);
-    o[0] = make_float4(v[0], v[1], v[2], v[3]);
-    o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    T* o = orow + static_cast<size_t>(j) * 32 + cg;
+    store4(o, make_float4(v[0], v[1], v[2], v[3]));
+    store4(o + 4, make_float4(v[4], v[5], v[6], v[7]));
   }
 }
 
 // Zero the rows of a padded layout that the engine's masked epilogue never writes:
 // [0, head_rows) and [tail_start, rows_per_frame) of every frame.
+// (Type-agnostic: `ld4` = 16-byte vectors per row.)
 __global__ void zero_rows_kernel(float* __restrict__ buf, int rows_per_frame, int ld4, int head_rows, int tail_start) {
   const int n = blockIdx.y;
   const int nz = head_rows + (rows_per_frame - tail_start);
@@ -132,10 +153,10 @@ __global__ void zero_rows_kernel(float* __restrict__ buf, int rows_per_frame, in
 
 // im2col for a 3x3 stride-2 TF-"same" conv.  Input: padded layout (pitch_in = W_in + 2, origin (1,1));
 // output rows q = y*(Wo+2) + x (x >= Wo rows are zero), columns (dy*3+dx)*C + c.
-__global__ void im2col_s2_kernel(const float* __restrict__ in, float* __restrict__ col, int Hin, int Win, int C) {
+// (Type-agnostic copy: `c4n` = 16-byte vectors per pixel = C * sizeof(element) / 16.)
+__global__ void im2col_s2_kernel(const float* __restrict__ in, float* __restrict__ col, int Hin, int Win, int c4n) {
   const int Ho = Hin / 2, Wo = Win / 2, pitch_in = Win + 2, pitch_o = Wo + 2;
   const int n = blockIdx.y;
-  const int c4n = C / 4;
   const size_t total = static_cast<size_t>(Ho) * pitch_o * 9 * c4n;
   const float4* src = reinterpret_cast<const float4*>(in) + static_cast<size_t>(n) * (Hin + 2) * pitch_in * c4n;
   float4* dst = reinterpret_cast<float4*>(col) + static_cast<size_t>(n) * Ho * pitch_o * 9 * c4n;
@@ -162,8 +183,8 @@ __device__ __forceinline__ float fsilu(float v) { return __fdividef(v, 1.f + __e
 // stride 2 pads 0/1 -- both are served by ONE zero-bordered SMEM slab ((Hin+2) x (Win+2) pixels x 32 channels),
 // so the tap loop has no boundary checks.  grid = (C / 32, frames); block = 8 channel quads x 32 pixel lanes,
 // float4 everywhere (a quarter-warp touches one 128-byte pixel row: coalesced in HBM, conflict-free in SMEM).
-template <int kStride, int kF>
-__global__ void __launch_bounds__(256, 3) dwconv_kernel(const float* __restrict__ in, float* __restrict__ out,
+template <int kStride, int kF, typename T>
+__global__ void __launch_bounds__(256, 3) dwconv_kernel(const T* __restrict__ in, T* __restrict__ out,
                                                         float* __restrict__ sums, const float* __restrict__ w /*[9][C]*/,
                                                         const float* __restrict__ bias, int C, int Hin, int Win,
                                                         int pitch_in, int oy, int ox, int rows_in, int wo_shift,
@@ -181,13 +202,12 @@ __global__ void __launch_bounds__(256, 3) dwconv_kernel(const float* __restrict_
 #pragma unroll
   for (int f = 0; f < kF; ++f) {
     const bool f_ok = f0 + f < n_frames;
-    const float* src = in + static_cast<size_t>(f0 + f) * rows_in * C;
+    const T* src = in + static_cast<size_t>(f0 + f) * rows_in * C;
     for (int pix = pl; pix < spix; pix += 32) {
       const int yp = pix / Wp, xp = pix - yp * Wp;
       const bool inside = f_ok && c_ok && yp >= 1 && yp <= Hin && xp >= 1 && xp <= Win;
       slab[(f * spix + pix) * 8 + cq] =
-          inside ? *reinterpret_cast<const float4*>(src + (static_cast<size_t>(yp - 1 + oy) * pitch_in + (xp - 1 + ox)) * C + c)
-                 : z4;
+          inside ? load4(src + (static_cast<size_t>(yp - 1 + oy) * pitch_in + (xp - 1 + ox)) * C + c) : z4;
     }
   }
   float4 wv[9], b4 = z4;
@@ -215,7 +235,7 @@ __global__ void __launch_bounds__(256, 3) dwconv_kernel(const float* __restrict_
           v.x = fmaf(a.x, ww.x, v.x); v.y = fmaf(a.y, ww.y, v.y); v.z = fmaf(a.z, ww.z, v.z); v.w = fmaf(a.w, ww.w, v.w);
         }
       v.x = fsilu(v.x); v.y = fsilu(v.y); v.z = fsilu(v.z); v.w = fsilu(v.w);
-      if (c_ok) *reinterpret_cast<float4*>(out + (static_cast<size_t>(f0 + f) * hw + p) * C + c) = v;
+      if (c_ok) store4(out + (static_cast<size_t>(f0 + f) * hw + p) * C + c, v);
       acc_sum.x += v.x; acc_sum.y += v.y; acc_sum.z += v.z; acc_sum.w += v.w;
     }
     red[pl][cq] = acc_sum;
@@ -277,15 +297,16 @@ __global__ void __launch_bounds__(1024) se_kernel(const float* __restrict__ sums
 }
 
 // x[n][p][c] *= scale[n][c]
-__global__ void se_scale_kernel(float* __restrict__ x, const float* __restrict__ scales, int hw, int c4n, size_t total4) {
+template <typename T>
+__global__ void se_scale_kernel(T* __restrict__ x, const float* __restrict__ scales, int hw, int c4n, size_t total4) {
   for (size_t k = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < total4;
        k += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int c4 = k % c4n;
     const size_t n = k / (static_cast<size_t>(c4n) * hw);
-    float4 v = reinterpret_cast<float4*>(x)[k];
+    float4 v = load4(x + 4 * k);
     const float4 s = reinterpret_cast<const float4*>(scales)[n * c4n + c4];
     v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
-    reinterpret_cast<float4*>(x)[k] = v;
+    store4(x + 4 * k, v);
   }
 }
 
@@ -302,55 +323,70 @@ __global__ void gap_kernel(const float* __restrict__ x, const int32_t* __restric
 
 }  // namespace
 
-int enc_stem(const float* frames, const int32_t* fmap, float* out, const float* w, const float* bias, int n, int H,
-             int W, cudaStream_t st) {
+// `half` selects the activation element type: 0 = float, 1 = __half (`out` / `in` are then __half buffers).
+int enc_stem(const float* frames, const int32_t* fmap, void* out, int half, const float* w, const float* bias, int n,
+             int H, int W, cudaStream_t st) {
   dim3 grid(H / 2 + 2, n);
-  stem_kernel<false><<<grid, 256, 3 * (W + 1) * sizeof(float), st>>>(frames, fmap, nullptr, nullptr, out, w, bias, H, W);
+  const size_t sm = 3 * (W + 1) * sizeof(float);
+  if (half)
+    stem_kernel<false, __half><<<grid, 256, sm, st>>>(frames, fmap, nullptr, nullptr, static_cast<__half*>(out), w, bias, H, W);
+  else
+    stem_kernel<false, float><<<grid, 256, sm, st>>>(frames, fmap, nullptr, nullptr, static_cast<float*>(out), w, bias, H, W);
   M2S_CUDA_OK(cudaGetLastError());
   return M2S_OK;
 }
 
 // uint8 ingest: per-frame min-max (after the optional articulator mask) fused into the stem load.
-int enc_stem_u8(const uint8_t* frames, const int32_t* fmap, const float* mask, float2* norm, float* out, const float* w,
-                const float* bias, int n, int H, int W, cudaStream_t st) {
+int enc_stem_u8(const uint8_t* frames, const int32_t* fmap, const float* mask, float2* norm, void* out, int half,
+                const float* w, const float* bias, int n, int H, int W, cudaStream_t st) {
   frame_minmax_kernel<<<n, 256, 0, st>>>(frames, fmap, mask, norm, H * W);
   M2S_CUDA_OK(cudaGetLastError());
   dim3 grid(H / 2 + 2, n);
-  stem_kernel<true><<<grid, 256, 3 * (W + 1) * sizeof(float), st>>>(frames, fmap, mask, norm, out, w, bias, H, W);
+  const size_t sm = 3 * (W + 1) * sizeof(float);
+  if (half)
+    stem_kernel<true, __half><<<grid, 256, sm, st>>>(frames, fmap, mask, norm, static_cast<__half*>(out), w, bias, H, W);
+  else
+    stem_kernel<true, float><<<grid, 256, sm, st>>>(frames, fmap, mask, norm, static_cast<float*>(out), w, bias, H, W);
   M2S_CUDA_OK(cudaGetLastError());
   return M2S_OK;
 }
 
-int enc_zero_rows(float* buf, int n, int rows_per_frame, int ld, int head_rows, int tail_start, cudaStream_t st) {
-  const int nz = (head_rows + rows_per_frame - tail_start) * (ld / 4);
+// `ld` counts elements of `esize` bytes (rows are multiples of 16 bytes).
+int enc_zero_rows(void* buf, int esize, int n, int rows_per_frame, int ld, int head_rows, int tail_start,
+                  cudaStream_t st) {
+  const int ld4 = ld * esize / 16;
+  const int nz = (head_rows + rows_per_frame - tail_start) * ld4;
   dim3 grid((nz + 255) / 256, n);
-  zero_rows_kernel<<<grid, 256, 0, st>>>(buf, rows_per_frame, ld / 4, head_rows, tail_start);
+  zero_rows_kernel<<<grid, 256, 0, st>>>(static_cast<float*>(buf), rows_per_frame, ld4, head_rows, tail_start);
   M2S_CUDA_OK(cudaGetLastError());
   return M2S_OK;
 }
 
-int enc_im2col_s2(const float* in, float* col, int n, int Hin, int Win, int C, cudaStream_t st) {
-  const size_t total = static_cast<size_t>(Hin / 2) * (Win / 2 + 2) * 9 * (C / 4);
+int enc_im2col_s2(const void* in, void* col, int esize, int n, int Hin, int Win, int C, cudaStream_t st) {
+  const int c4n = C * esize / 16;
+  const size_t total = static_cast<size_t>(Hin / 2) * (Win / 2 + 2) * 9 * c4n;
   dim3 grid(static_cast<unsigned>((total + 255) / 256), n);
-  im2col_s2_kernel<<<grid, 256, 0, st>>>(in, col, Hin, Win, C);
+  im2col_s2_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(in), static_cast<float*>(col), Hin, Win, c4n);
   M2S_CUDA_OK(cudaGetLastError());
   return M2S_OK;
 }
 
-int enc_dwconv(const float* in, float* out, float* sums, const float* w, const float* bias, int n, int C, int Hin,
-               int Win, int pitch_in, int oy, int ox, int rows_in, int stride, cudaStream_t st) {
+namespace {
+template <typename T>
+int dwconv_launch(const T* in, T* out, float* sums, const float* w, const float* bias, int n, int C, int Hin, int Win,
+                  int pitch_in, int oy, int ox, int rows_in, int stride, cudaStream_t st) {
   const size_t slab = static_cast<size_t>(Hin + 2) * (Win + 2) * 32 * sizeof(float);
   if (slab > 200 * 1024) return fail(M2S_ERR_UNSUPPORTED, "depthwise input %dx%d too large for the SMEM slab", Hin, Win);
   if (stride != 1 && stride != 2) return fail(M2S_ERR_UNSUPPORTED, "depthwise stride %d", stride);
   // small images: several frames per block (amortises weight loads / block launch; more pixels per thread)
   const int kf = (stride == 1 && slab * 4 <= 64 * 1024) ? 4 : 1;
-  using Fn = void (*)(const float*, float*, float*, const float*, const float*, int, int, int, int, int, int, int, int, int);
-  Fn fn = stride == 2 ? dwconv_kernel<2, 1> : (kf == 4 ? dwconv_kernel<1, 4> : dwconv_kernel<1, 1>);
+  using Fn = void (*)(const T*, T*, float*, const float*, const float*, int, int, int, int, int, int, int, int, int);
+  Fn fn = stride == 2 ? dwconv_kernel<2, 1, T> : (kf == 4 ? dwconv_kernel<1, 4, T> : dwconv_kernel<1, 1, T>);
   static bool attr = false;
   if (!attr) {
-    M2S_CUDA_OK(cudaFuncSetAttribute(dwconv_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    M2S_CUDA_OK(cudaFuncSetAttribute(dwconv_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    M2S_CUDA_OK(cudaFuncSetAttribute(dwconv_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    M2S_CUDA_OK(cudaFuncSetAttribute(dwconv_kernel<1, 1, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    M2S_CUDA_OK(cudaFuncSetAttribute(dwconv_kernel<1, 4, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    M2S_CUDA_OK(cudaFuncSetAttribute(dwconv_kernel<2, 1, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
   const int wo = Win / stride;
@@ -362,6 +398,16 @@ int enc_dwconv(const float* in, float* out, float* sums, const float* w, const f
   M2S_CUDA_OK(cudaGetLastError());
   return M2S_OK;
 }
+}  // namespace
+
+int enc_dwconv(const void* in, void* out, int half, float* sums, const float* w, const float* bias, int n, int C, int Hin,
+               int Win, int pitch_in, int oy, int ox, int rows_in, int stride, cudaStream_t st) {
+  if (half)
+    return dwconv_launch(static_cast<const __half*>(in), static_cast<__half*>(out), sums, w, bias, n, C, Hin, Win,
+                         pitch_in, oy, ox, rows_in, stride, st);
+  return dwconv_launch(static_cast<const float*>(in), static_cast<float*>(out), sums, w, bias, n, C, Hin, Win, pitch_in,
+                       oy, ox, rows_in, stride, st);
+}
 
 int enc_se(const float* sums, float* scales, const float* w1, const float* b1, const float* w2, const float* b2, int n,
            int C, int rd, int hw, cudaStream_t st) {
@@ -370,11 +416,12 @@ int enc_se(const float* sums, float* scales, const float* w1, const float* b1, c
   return M2S_OK;
 }
 
-int enc_se_scale(float* x, const float* scales, int n, int hw, int C, cudaStream_t st) {
+int enc_se_scale(void* x, int half, const float* scales, int n, int hw, int C, cudaStream_t st) {
   const size_t total4 = static_cast<size_t>(n) * hw * (C / 4);
   unsigned blocks = static_cast<unsigned>((total4 + 255) / 256);
   if (blocks > 148u * 16u) blocks = 148u * 16u;
-  se_scale_kernel<<<blocks, 256, 0, st>>>(x, scales, hw, C / 4, total4);
+  if (half) se_scale_kernel<<<blocks, 256, 0, st>>>(static_cast<__half*>(x), scales, hw, C / 4, total4);
+  else se_scale_kernel<<<blocks, 256, 0, st>>>(static_cast<float*>(x), scales, hw, C / 4, total4);
   M2S_CUDA_OK(cudaGetLastError());
   return M2S_OK;
 }

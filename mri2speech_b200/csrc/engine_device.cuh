@@ -204,7 +204,25 @@ struct EpiConsts {
 
 // Epilogue programs (compile-time): the common cases drop every unused instruction -- with 256-column-wide tiles the
 // epilogue is ALU-issue-bound (32K outputs per tile on 8 warps), so instructions per output are what matters.
-enum { EPI_FULL = 0, EPI_FULL_SILU = 1, EPI_BIAS = 2, EPI_LRELU = 3, EPI_SILU = 4, EPI_RES = 5 };
+// EPI_RB / EPI_RB_ACC are the two ResBlock conv2 programs of the vocoder (residual stored post-leaky-ReLU and recovered
+// with min(y, y/slope); leaky-ReLU as max(v, slope*v), which also covers "no activation" with slope = 1).
+enum { EPI_FULL = 0, EPI_FULL_SILU = 1, EPI_BIAS = 2, EPI_LRELU = 3, EPI_SILU = 4, EPI_RES = 5, EPI_RB = 6, EPI_RB_ACC = 7,
+       EPI_COUNT = 8 };
+
+// Host-side choice of the epilogue program for a problem (shared by both kernels).
+inline int choose_epilogue(const Epilogue& e) {
+  const bool lrelu_ok = (e.act == M2S_ACT_LRELU && e.act_slope > 0.f && e.act_slope <= 1.f);
+  const bool plain = !e.accum && e.out_scale == 1.f;
+  if (plain && !e.res) {
+    if (e.act == M2S_ACT_SILU) return EPI_SILU;
+    if (lrelu_ok) return EPI_LRELU;
+    if (e.act == M2S_ACT_NONE) return EPI_BIAS;
+  }
+  if (plain && e.res && e.act == M2S_ACT_NONE && e.res_inv_slope == 1.f) return EPI_RES;
+  if (e.res && !e.res_after_act && e.res_inv_slope >= 1.f && (lrelu_ok || e.act == M2S_ACT_NONE))
+    return plain && lrelu_ok ? EPI_RB : EPI_RB_ACC;
+  return e.act == M2S_ACT_SILU ? EPI_FULL_SILU : EPI_FULL;
+}
 
 __device__ __forceinline__ float fast_silu(float v) { return __fdividef(v, 1.f + __expf(-v)); }
 
@@ -212,9 +230,18 @@ template <int kEpi>
 __device__ __forceinline__ float epi_elem(const EpiConsts& c, float acc, float bias, float res, float accum) {
   float v = acc + bias;
   if (kEpi == EPI_BIAS) return v;
-  if (kEpi == EPI_LRELU) return v >= 0.f ? v : v * c.act_slope;
+  if (kEpi == EPI_LRELU) return fmaxf(v, v * c.act_slope);  // 0 < slope <= 1
   if (kEpi == EPI_SILU) return fast_silu(v);
   if (kEpi == EPI_RES) return v + res;
+  if (kEpi == EPI_RB) {
+    v += fminf(res, res * c.inv_slope);                     // inv_slope >= 1
+    return fmaxf(v, v * c.act_slope);
+  }
+  if (kEpi == EPI_RB_ACC) {
+    v += fminf(res, res * c.inv_slope);
+    v = (v + accum) * c.out_scale;
+    return fmaxf(v, v * c.act_slope);                       // slope 1 = no activation
+  }
   const float rt = res >= 0.f ? res : res * c.inv_slope;
   v = fmaf(rt, c.pre_w, v);
   v += accum;
@@ -232,10 +259,13 @@ struct EpiWarp {
   int quad, half, lane, rr0, cc;
   int mask_mode;
   bool has_res, has_acc;
+  int dbg;  // probe switches (EngineParams::dbg): bit0 skip global stores, bit1 skip TMEM loads, bit2 skip SMEM transpose
 };
 
-__device__ __forceinline__ EpiWarp make_epi_warp(const Epilogue& e, uint32_t stage_base, int ew, int warp, int lane) {
+__device__ __forceinline__ EpiWarp make_epi_warp(const Epilogue& e, uint32_t stage_base, int ew, int warp, int lane,
+                                                 int dbg = 0) {
   EpiWarp w;
+  w.dbg = dbg;
   w.quad = warp & 3;  // TMEM lane quadrant this warp may access
   w.half = ew >> 2;   // which of the two warps of the quadrant
   w.lane = lane;
@@ -276,12 +306,93 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
     const int c0 = (u - sub * nchunks) << 5;
     const int qw = q0 + sub * 128 + quad * 32;  // first row of this warp's 32-row slab
     uint32_t r[32];
-    tmem_ld16(tmem_acc + sub * n_tile + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-    if (c0 + 16 < n_tile) tmem_ld16(tmem_acc + sub * n_tile + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+    if (!(ew_.dbg & 2)) {
+      tmem_ld16(tmem_acc + sub * n_tile + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+      if (c0 + 16 < n_tile) tmem_ld16(tmem_acc + sub * n_tile + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = 0x3f800000u + j + lane;
+    }
     // While the TMEM read is in flight: bias / residual / accumulate loads of this unit (the output may alias
     // them in place, so every load is issued before the first store).  Thread (rr0, cc) owns rows rr0 + 4i,
     // columns n .. n+3; all row predicates reduce to "4i + rr0 < bound".
     const int n = n0 + c0 + cc * 4;
+    constexpr bool kHasRes = kEpi == EPI_FULL || kEpi == EPI_FULL_SILU || kEpi == EPI_RES || kEpi == EPI_RB || kEpi == EPI_RB_ACC;
+    constexpr bool kHasAcc = kEpi == EPI_FULL || kEpi == EPI_FULL_SILU || kEpi == EPI_RB_ACC;
+    // ---- fast path: the whole 32 x 32 unit is inside the output and survives the mask (warp-uniform test): no
+    // predicates, row pointers stepped by warp-uniform strides.  The epilogue is instruction-issue-bound (32K outputs
+    // per 256-column tile on 8 warps), so this path is kept to ~6 instructions per output.
+    {
+      int rows_valid_u = 32;
+      if (mask_mode == M2S_MASK_LEN) rows_valid_u = len_rows - (qw + p.d_row_offset);
+      const bool fast = mask_mode != M2S_MASK_PITCH && c0 + 32 <= n_tile && n0 + c0 + 32 <= p.n &&
+                        p.l_out - qw >= 32 && rows_valid_u >= 32 && !ew_.dbg;
+      if (fast) {
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+        const size_t row0 = d_base + qw + rr0;
+        float4 res4[8], acc4[8];
+        if (kHasRes) {
+          const float4* rp = reinterpret_cast<const float4*>(e.res + row0 * e.res_ld + n);
+          if (has_res) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) res4[i] = rp[static_cast<size_t>(i) * e.res_ld];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) res4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        if (kHasAcc) {
+          const float4* ap = reinterpret_cast<const float4*>(e.accum + row0 * e.accum_ld + n);
+          if (has_acc) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc4[i] = ap[static_cast<size_t>(i) * e.accum_ld];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + lane * 128 + ((j ^ (lane & 7)) << 4)),
+                       "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                       : "memory");
+        __syncwarp();
+        float4 o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + rr0;
+          float4 a4;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w)
+                       : "r"(stage + rr * 128 + ((cc ^ (rr & 7)) << 4)));
+          const float4 r4 = kHasRes ? res4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 c4 = kHasAcc ? acc4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+          o[i].x = epi_elem<kEpi>(ec, a4.x, bias4.x, r4.x, c4.x);
+          o[i].y = epi_elem<kEpi>(ec, a4.y, bias4.y, r4.y, c4.y);
+          o[i].z = epi_elem<kEpi>(ec, a4.z, bias4.z, r4.z, c4.z);
+          o[i].w = epi_elem<kEpi>(ec, a4.w, bias4.w, r4.w, c4.w);
+        }
+        if (p.d) {
+          float4* dp = reinterpret_cast<float4*>(p.d + row0 * p.d_ld + n);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dp[static_cast<size_t>(i) * p.d_ld] = o[i];
+        }
+        if (p.d16) {  // fp16 copy: the tensor-core operand of the next conv (saturating conversion, never inf)
+          uint2* hp = reinterpret_cast<uint2*>(static_cast<__half*>(p.d16) + row0 * p.d_ld + n);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint2 pk;
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(o[i].y), "f"(o[i].x));
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(o[i].w), "f"(o[i].z));
+            hp[static_cast<size_t>(i) * p.d_ld] = pk;
+          }
+        }
+        __syncwarp();
+        continue;
+      }
+    }
     const bool col_ok = (c0 + cc * 4 < n_tile) && n < p.n;
     const int rows_ok = col_ok ? min(32, p.l_out - qw) : 0;                 // rows that exist
     int rows_valid = 32;                                                    // rows that survive the mask
@@ -298,7 +409,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
       res4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (kEpi == EPI_FULL || kEpi == EPI_FULL_SILU || kEpi == EPI_RES) {
+    if (kHasRes) {
       if (has_res) {
         const float* rptr = e.res + row0 * e.res_ld + n;
         const size_t r_step = static_cast<size_t>(4) * e.res_ld;
@@ -307,7 +418,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
           if (i * 4 + rr0 < rows_ok) res4[i] = *reinterpret_cast<const float4*>(rptr + i * r_step);
       }
     }
-    if (kEpi == EPI_FULL || kEpi == EPI_FULL_SILU) {
+    if (kHasAcc) {
       if (has_acc) {
         const float* aptr = e.accum + row0 * e.accum_ld + n;
         const size_t a_step = static_cast<size_t>(4) * e.accum_ld;
@@ -324,12 +435,14 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
       mj = drow - mi * e.pitch;
     }
     tmem_ld_wait();
+    if (!(ew_.dbg & 4)) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + lane * 128 + ((j ^ (lane & 7)) << 4)),
-                   "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
-                   : "memory");
-    __syncwarp();
+      for (int j = 0; j < 8; ++j)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + lane * 128 + ((j ^ (lane & 7)) << 4)),
+                     "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                     : "memory");
+      __syncwarp();
+    }
     // all 8 rows' (32 independent) element chains are computed unconditionally so the scheduler can interleave
     // them; only the stores are predicated
     float4 o[8];
@@ -337,9 +450,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
     for (int i = 0; i < 8; ++i) {
       const int rr = i * 4 + rr0;
       float4 a4;
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                   : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w)
-                   : "r"(stage + rr * 128 + ((cc ^ (rr & 7)) << 4)));
+      if (!(ew_.dbg & 4)) {
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w)
+                     : "r"(stage + rr * 128 + ((cc ^ (rr & 7)) << 4)));
+      } else {
+        a4 = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 8]), __uint_as_float(r[i + 16]), __uint_as_float(r[i + 24]));
+      }
       o[i].x = epi_elem<kEpi>(ec, a4.x, bias4.x, res4[i].x, acc4[i].x);
       o[i].y = epi_elem<kEpi>(ec, a4.y, bias4.y, res4[i].y, acc4[i].y);
       o[i].z = epi_elem<kEpi>(ec, a4.z, bias4.z, res4[i].z, acc4[i].z);
@@ -358,20 +475,18 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
       for (int i = 0; i < 8; ++i)
         if (i * 4 + rr0 >= rows_valid) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (p.d) {
+    if (p.d && !(ew_.dbg & 1)) {
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         if (i * 4 + rr0 < rows_ok) *reinterpret_cast<float4*>(dptr + i * d_step) = o[i];
     }
-    if (p.d16) {  // fp16 copy of the tile: the tensor-core operand of the next conv (saturating, never inf)
+    if (p.d16 && !(ew_.dbg & 1)) {  // fp16 copy of the tile: the tensor-core operand of the next conv (saturating, never inf)
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         if (i * 4 + rr0 < rows_ok) {
-          const __half2 lo = __floats2half2_rn(fminf(fmaxf(o[i].x, -65504.f), 65504.f), fminf(fmaxf(o[i].y, -65504.f), 65504.f));
-          const __half2 hi = __floats2half2_rn(fminf(fmaxf(o[i].z, -65504.f), 65504.f), fminf(fmaxf(o[i].w, -65504.f), 65504.f));
           uint2 pk;
-          pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-          pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(o[i].y), "f"(o[i].x));
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(o[i].w), "f"(o[i].z));
           *reinterpret_cast<uint2*>(hptr + i * d_step) = pk;
         }
     }

@@ -110,7 +110,8 @@ using namespace m2s;
 
 struct m2s_generator {
   m2s_generator_config cfg;
-  bool tf32 = true;
+  bool tf32 = true;   // tensor-core build (tf32 or fp16 operands); false = CUDA-core fp32 build
+  bool fp16 = false;  // M2S_PREC_FP16: layers with c_in % 8 == 0 run kind::f16 on fp16 copies of the activations
   int hop = 1;
   Layer pre;
   std::vector<Layer> ups;
@@ -127,7 +128,7 @@ namespace {
 
 // Conv1d weight (C_out, C_in, k) -> engine layout [tap][n][c]
 int make_conv1d_layer(const TensorMap& m, const std::string& prefix, int c_out, int c_in, int k, bool causal,
-                      int dilation, bool tf32, Layer* L) {
+                      int dilation, int mode, Layer* L) {
   std::vector<float> w;
   std::vector<int64_t> shape;
   M2S_TRY(folded_weight(m, prefix, &w, &shape));
@@ -141,7 +142,7 @@ int make_conv1d_layer(const TensorMap& m, const std::string& prefix, int c_out, 
         e[(static_cast<size_t>(j) * c_out + o) * c_in + c] = w[(static_cast<size_t>(o) * c_in + c) * k + j];
   L->taps = k;
   for (int j = 0; j < k; ++j) L->shift[j] = causal ? -(k - 1 - j) * dilation : j * dilation;
-  M2S_TRY(pack_weights(e.data(), k, c_out, c_in, tf32, &L->w));
+  M2S_TRY(pack_weights(e.data(), k, c_out, c_in, mode, &L->w));
   std::vector<float> b;
   M2S_TRY(get_bias(m, prefix, c_out, &b));
   return upload(b, &L->bias);
@@ -149,7 +150,7 @@ int make_conv1d_layer(const TensorMap& m, const std::string& prefix, int c_out, 
 
 // ConvTranspose1d weight (C_in, C_out, k), stride u, padding p -> polyphase GEMM:
 // row q, col r*C_out+co = sum_s sum_ci x[q - s, ci] * W[ci, co, s*u + r + p]
-int make_convT_layer(const TensorMap& m, const std::string& prefix, int c_in, int c_out, int k, int u, bool tf32,
+int make_convT_layer(const TensorMap& m, const std::string& prefix, int c_in, int c_out, int k, int u, int mode,
                      Layer* L) {
   std::vector<float> w;
   std::vector<int64_t> shape;
@@ -182,7 +183,7 @@ int make_convT_layer(const TensorMap& m, const std::string& prefix, int c_in, in
   }
   L->taps = taps;
   for (int t = 0; t < taps; ++t) L->shift[t] = -(s_lo + t);
-  M2S_TRY(pack_weights(e.data(), taps, n, c_in, tf32, &L->w));
+  M2S_TRY(pack_weights(e.data(), taps, n, c_in, mode, &L->w));
   std::vector<float> b, be(n);
   M2S_TRY(get_bias(m, prefix, c_out, &b));
   for (int r = 0; r < u; ++r)
@@ -200,10 +201,12 @@ int run_conv(const m2s_generator* g, const ConvProblem& p, const Layer& L, cudaS
   return g->tf32 ? conv_tcgen05(p, L.w, st) : conv_simt(p, L.w.plain, st);
 }
 
-ConvProblem base_problem(const float* a, int a_rows, int c_in, int batch, long long batch_rows_a, float* d,
+// `a` is read as fp16 rows when the layer's weights are packed for kind::f16 (L.w.half), as fp32 rows otherwise.
+ConvProblem base_problem(const void* a, int a_rows, int c_in, int batch, long long batch_rows_a, float* d,
                          int d_ld, long long batch_rows_d, int l_out, const Layer& L) {
   ConvProblem p{};
-  p.a = a; p.a_batch_rows = batch_rows_a; p.a_rows = a_rows; p.a_ld = c_in; p.c_in = c_in;
+  p.a = static_cast<const float*>(a); p.a_half = L.w.half != 0;
+  p.a_batch_rows = batch_rows_a; p.a_rows = a_rows; p.a_ld = c_in; p.c_in = c_in;
   p.batch = batch; p.l_out = l_out; p.taps = L.taps;
   for (int j = 0; j < L.taps; ++j) p.shift[j] = L.shift[j];
   p.n = L.w.n; p.d = d; p.d_batch_rows = batch_rows_d; p.d_ld = d_ld; p.d_row_offset = 0;
@@ -226,10 +229,17 @@ extern "C" int m2s_generator_create(const m2s_generator_config* cfg, const m2s_t
   auto* g = new m2s_generator();
   g->cfg = *cfg;
   g->tf32 = cfg->precision != M2S_PREC_FP32;
+  g->fp16 = cfg->precision == M2S_PREC_FP16;
+  // operand format per layer: fp16 needs 16-byte aligned rows of halves (c_in % 8 == 0); conv_pre reads the fp32 mel
+  auto mode_for = [&](int c_in) {
+    if (!g->tf32) return static_cast<int>(PACK_FP32);
+    return static_cast<int>((g->fp16 && c_in % 8 == 0) ? PACK_FP16 : PACK_TF32);
+  };
   int st = M2S_OK;
   auto bail = [&](int s) { m2s_generator_destroy(g); return s; };
   const int c0 = cfg->upsample_initial_channel;
-  if ((st = make_conv1d_layer(m, "conv_pre", c0, cfg->num_mels, 7, false, 1, g->tf32, &g->pre)) != M2S_OK)
+  if ((st = make_conv1d_layer(m, "conv_pre", c0, cfg->num_mels, 7, false, 1, g->tf32 ? PACK_TF32 : PACK_FP32,
+                              &g->pre)) != M2S_OK)
     return bail(st);
   g->hop = 1;
   int ch = c0;
@@ -237,7 +247,7 @@ extern "C" int m2s_generator_create(const m2s_generator_config* cfg, const m2s_t
     const int cout = c0 >> (i + 1);
     Layer L;
     if ((st = make_convT_layer(m, "ups." + std::to_string(i), ch, cout, cfg->upsample_kernel_sizes[i],
-                               cfg->upsample_rates[i], g->tf32, &L)) != M2S_OK)
+                               cfg->upsample_rates[i], mode_for(ch), &L)) != M2S_OK)
       return bail(st);
     g->ups.push_back(L);
     g->ups_cout.push_back(cout);
@@ -248,11 +258,11 @@ extern "C" int m2s_generator_create(const m2s_generator_config* cfg, const m2s_t
       for (int d = 0; d < 3; ++d) {
         Layer a, b;
         if ((st = make_conv1d_layer(m, p + ".convs1." + std::to_string(d), cout, cout, k, true,
-                                    cfg->resblock_dilations[j][d], g->tf32, &a)) != M2S_OK)
+                                    cfg->resblock_dilations[j][d], mode_for(cout), &a)) != M2S_OK)
           return bail(st);
         g->c1.push_back(a);
-        if ((st = make_conv1d_layer(m, p + ".convs2." + std::to_string(d), cout, cout, k, true, 1, g->tf32, &b)) !=
-            M2S_OK)
+        if ((st = make_conv1d_layer(m, p + ".convs2." + std::to_string(d), cout, cout, k, true, 1, mode_for(cout),
+                                    &b)) != M2S_OK)
           return bail(st);
         g->c2.push_back(b);
       }
@@ -312,7 +322,8 @@ GenBuffers plan_buffers(const m2s_generator* g, int batch, int frames) {
   b.mel_floats = al(b.mel_floats);
   b.p_floats = al(p);
   b.q_floats = al(q);
-  b.total_bytes = (b.mel_floats + b.p_floats + 4 * b.q_floats) * sizeof(float) + 256;
+  // P, Q, R, T, S (fp32-sized; P and T hold fp16 data when their consumer is an fp16 layer) + fp16 copies of Q and R
+  b.total_bytes = (b.mel_floats + b.p_floats + 5 * b.q_floats) * sizeof(float) + 256;
   return b;
 }
 }  // namespace
@@ -338,8 +349,14 @@ extern "C" int m2s_generator_forward(m2s_generator* g, const float* mel, int32_t
   float* R = Q + bufs.q_floats;
   float* T = R + bufs.q_floats;
   float* S = T + bufs.q_floats;
+  float* Q16 = S + bufs.q_floats;            // fp16 copies (tensor-core operands) of Q and R, half a q buffer each
+  float* R16 = Q16 + bufs.q_floats / 2;
   const m2s_generator_config& cfg = g->cfg;
   const int mask = lengths ? M2S_MASK_LEN : M2S_MASK_NONE;
+  // fp16 build: every tensor that is only ever a tensor-core operand (P, T) is stored as fp16; tensors that are also
+  // a residual / MRF source (Q, R) are stored twice -- fp32 for the residual chain (no rounding accumulates along it),
+  // fp16 for the operand -- and S stays fp32.  An fp32 output goes to `d`, an fp16 output to `d16`.
+  auto set_out = [](ConvProblem* p, float* buf32, void* buf16) { p->d = buf32; p->d16 = buf16; };
 
   // (B, mels, T) -> channels-last, zero past lengths (conv_pre look-ahead must see zeros)
   M2S_TRY(bct_to_btc(mel, M0, batch, cfg.num_mels, frames, lengths, false, st));
@@ -348,6 +365,7 @@ extern "C" int m2s_generator_forward(m2s_generator* g, const float* mel, int32_t
   int ch = cfg.upsample_initial_channel;
   {  // conv_pre -> P = mask(lrelu(conv+b, .1))  (only consumer: ups[0])
     ConvProblem p = base_problem(M0, L, cfg.num_mels, batch, L, P, ch, L, L, g->pre);
+    if (g->ups[0].w.half) set_out(&p, nullptr, P);
     p.epi.act = M2S_ACT_LRELU; p.epi.act_slope = 0.1f;
     p.epi.mask_mode = mask; p.epi.lens = lengths; p.epi.len_scale = 1;
     M2S_TRY(run_conv(g, p, g->pre, st));
@@ -356,30 +374,37 @@ extern "C" int m2s_generator_forward(m2s_generator* g, const float* mel, int32_t
   for (int i = 0; i < cfg.num_upsamples; ++i) {
     const int u = cfg.upsample_rates[i];
     const int cout = g->ups_cout[i];
+    const bool hs = g->c1[i * cfg.num_kernels * 3].w.half != 0;  // this stage's ResBlock convs take fp16 operands
     {  // ups: rows = L, N = u*cout; D viewed as (B, L, u*cout) == (B, L*u, cout)
       ConvProblem p = base_problem(P, L, ch, batch, L, Q, u * cout, L, L, g->ups[i]);
+      if (hs) p.d16 = Q16;
       p.epi.act = M2S_ACT_LRELU; p.epi.act_slope = 0.1f;
       M2S_TRY(run_conv(g, p, g->ups[i], st));
     }
     L *= u; scale *= u; ch = cout;
     const bool last_stage = (i + 1 == cfg.num_upsamples);
+    const bool next_half = !last_stage && g->ups[i + 1].w.half != 0;  // who reads this stage's output P
     for (int j = 0; j < cfg.num_kernels; ++j) {
       const float* state = Q;
+      const void* state_op = hs ? static_cast<const void*>(Q16) : static_cast<const void*>(Q);
       for (int d = 0; d < 3; ++d) {
         const Layer& l1 = g->c1[(i * cfg.num_kernels + j) * 3 + d];
         const Layer& l2 = g->c2[(i * cfg.num_kernels + j) * 3 + d];
-        ConvProblem p1 = base_problem(state, L, ch, batch, L, T, ch, L, L, l1);
+        ConvProblem p1 = base_problem(state_op, L, ch, batch, L, T, ch, L, L, l1);
+        if (hs) set_out(&p1, nullptr, T);
         p1.epi.act = M2S_ACT_LRELU; p1.epi.act_slope = 0.1f;
         M2S_TRY(run_conv(g, p1, l1, st));
         ConvProblem p2 = base_problem(T, L, ch, batch, L, R, ch, L, L, l2);
         p2.epi.res = state; p2.epi.res_ld = ch; p2.epi.res_inv_slope = 10.f;  // 1 / LRELU_SLOPE
         if (d < 2) {
           p2.epi.act = M2S_ACT_LRELU; p2.epi.act_slope = 0.1f;
+          if (hs) p2.d16 = R16;
         } else if (j + 1 < cfg.num_kernels) {
           p2.d = S;
           if (j > 0) { p2.epi.accum = S; p2.epi.accum_ld = ch; }
         } else {
-          p2.d = P;
+          if (next_half) set_out(&p2, nullptr, P);
+          else p2.d = P;
           if (j > 0) { p2.epi.accum = S; p2.epi.accum_ld = ch; }
           p2.epi.out_scale = 1.f / static_cast<float>(cfg.num_kernels);
           p2.epi.act = M2S_ACT_LRELU; p2.epi.act_slope = last_stage ? 0.01f : 0.1f;
@@ -387,6 +412,7 @@ extern "C" int m2s_generator_forward(m2s_generator* g, const float* mel, int32_t
         }
         M2S_TRY(run_conv(g, p2, l2, st));
         state = R;
+        state_op = hs ? static_cast<const void*>(R16) : static_cast<const void*>(R);
       }
     }
   }

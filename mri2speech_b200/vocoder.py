@@ -127,7 +127,7 @@ class Generator(nn.Module):
                 raise _lib.M2SError("ResBlock1 needs exactly 3 dilations per kernel size")
             for m, d in enumerate(ds):
                 cfg.resblock_dilations[j][m] = int(d)
-        cfg.precision = {"tf32": _lib.PREC_TF32, "fp32": _lib.PREC_FP32}[self.precision]
+        cfg.precision = _lib.PRECISIONS[self.precision]
         return cfg
 
     def refresh(self):

@@ -56,7 +56,7 @@ def test_bilstm_long_sequence_t600():
     assert (got - ref).abs().max().item() < 1e-3
 
 
-@pytest.mark.parametrize("precision,rel_tol", [("fp32", 2e-4), ("tf32", 5e-3)])
+@pytest.mark.parametrize("precision,rel_tol", [("fp32", 2e-4), ("tf32", 5e-3), ("fp16", 5e-3)])
 @pytest.mark.parametrize("randomize_bn", [False, True])
 def test_encoder_features(precision, rel_tol, randomize_bn):
     from mri2speech_b200 import synth
@@ -72,7 +72,7 @@ def test_encoder_features(precision, rel_tol, randomize_bn):
     assert rel < rel_tol
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "fp16"])
 def test_forward_ragged_vs_oracle(precision):
     from mri2speech_b200 import synth
     from oracle.acoustic import acoustic_forward
@@ -88,10 +88,11 @@ def test_forward_ragged_vs_oracle(precision):
     assert err / ref.abs().max().item() < (1e-3 if precision == "fp32" else 2e-2)
 
 
-def test_golden_acoustic_fixture():
+@pytest.mark.parametrize("precision", ["tf32", "fp16"])
+def test_golden_acoustic_fixture(precision):
     from mri2speech_b200 import synth
     z = np.load(os.path.join(GOLDEN, "acoustic_oracle_seed1234_clip0_t6.npz"))
-    m = _model("tf32")
+    m = _model(precision)
     clip = synth.synthetic_clip(0, 6)
     with torch.no_grad():
         mel = m(clip.unsqueeze(0).unsqueeze(2).cuda()).cpu().numpy()

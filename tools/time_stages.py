@@ -29,10 +29,11 @@ def timed(fn, n=3):
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     T = int(sys.argv[2]) if len(sys.argv) > 2 else 150
+    prec = sys.argv[3] if len(sys.argv) > 3 else "tf32"
     h = json.load(open(os.path.join(os.path.dirname(__file__), "..", "config_custom.json")))
     torch.manual_seed(1234)
-    ac = build_acoustic_model().cuda().eval()
-    gen = Generator(h).cuda().eval()
+    ac = build_acoustic_model(precision=prec).cuda().eval()
+    gen = Generator(h, precision=prec).cuda().eval()
     frames = torch.rand(B * T, 256, 256, device="cuda")
     feats = torch.randn(B, T, 208, device="cuda") * 0.1
     mel = synth.synthetic_mels(B, T).cuda()
@@ -44,7 +45,7 @@ def main():
     t_rnn = timed(lambda: ac.rnn_head(feats))
     t_voc = timed(lambda: gen(mel))
     audio_s = B * T * 420 / 11413
-    print(json.dumps({"B": B, "T": T, "audio_s": audio_s, "encoder_ms": t_enc, "encoder_engine_ms": sum(ms),
+    print(json.dumps({"precision": prec, "B": B, "T": T, "audio_s": audio_s, "encoder_ms": t_enc, "encoder_engine_ms": sum(ms),
                       "encoder_engine_launches": len(ms), "encoder_engine_tflops": sum(fl) / (sum(ms) * 1e-3) / 1e12,
                       "rnn_head_ms": t_rnn, "vocoder_ms": t_voc,
                       "e2e_audio_s_per_s": audio_s / ((t_enc + t_rnn + t_voc) * 1e-3),

@@ -8,19 +8,23 @@ import torch
 from mri2speech_b200 import _lib
 
 
-def run(B, L, C, k, d, res=False, tiles=40, knobs=None, N=None, act=None, shifts=None):
+def run(B, L, C, k, d, res=False, tiles=40, knobs=None, N=None, act=None, shifts=None, half=False, outs="32"):
     for kk, v in (knobs or {}).items():
         _lib.set_knob(kk, v)
     N = N or C
     act = _lib.ACT_LRELU if act is None else act
     a = torch.randn(B, L, C, device="cuda")
+    if half:
+        a = a.half()
     w = torch.randn(k, N, C, device="cuda") / (C * k) ** 0.5
     bias = torch.randn(N, device="cuda")
     r = torch.randn(B, L, N, device="cuda") if res else None
     shifts = shifts or [-(k - 1 - j) * d for j in range(k)]
     out = torch.empty(B, L, N, device="cuda")
     buf = torch.zeros(tiles * 9, dtype=torch.int64, device="cuda")
-    kw = dict(bias=bias, res=r, res_inv_slope=10.0 if res else 1.0, act=act, act_slope=0.1, out=out)
+    out16 = torch.empty(B, L, N, device="cuda", dtype=torch.float16) if outs in ("16", "both") else None
+    kw = dict(bias=bias, res=r, res_inv_slope=10.0 if res else 1.0, act=act, act_slope=0.1, out=out, out16=out16,
+              want_d32=outs in ("32", "both"))
     _lib.conv_fwd(a, w, shifts, L, **kw)
     _lib.check(_lib.lib().m2s_debug_trace(buf.data_ptr(), tiles))
     _lib.conv_fwd(a, w, shifts, L, **kw)
@@ -31,7 +35,7 @@ def run(B, L, C, k, d, res=False, tiles=40, knobs=None, N=None, act=None, shifts
     t = t[:valid]
     tiles = valid
     t0 = int(t[0, 0])
-    print(f"--- B={B} L={L} C={C} N={N} k={k} d={d} res={res} act={act} knobs={knobs}: CTA0 ran {tiles} tiles")
+    print(f"--- B={B} L={L} C={C} N={N} k={k} d={d} res={res} act={act} half={half} out={outs} knobs={knobs}: CTA0 ran {tiles} tiles")
     for i in range(min(tiles, 4)):
         print(f"{i:4d} | " + " ".join(f"{int(v) - t0:8d}" for v in t[i, 0:3]) + " | " +
               " ".join(f"{int(v) - t0:8d}" for v in t[i, 3:6]) + " | " + " ".join(f"{int(v) - t0:8d}" for v in t[i, 6:9]))
@@ -44,6 +48,16 @@ def run(B, L, C, k, d, res=False, tiles=40, knobs=None, N=None, act=None, shifts
           f"mma wait acc {f(t[s0:, 4] - t[s0:, 3]):.0f}; producer a_empty wait {f(t[s0:, 1] - t[s0:, 0]):.0f}; "
           f"producer issue {f(t[s0:, 2] - t[s0:, 1]):.0f}; total {int(t[tiles-1, 8]) - t0} cycles")
 
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "vocoder16":
+    # narrow vocoder layers with fp16 operands on the single-CTA kernel: where do the cycles of a tile go?
+    for dbg in (0, 1, 8, 9):
+        run(32, 107520, 32, 11, 1, half=True, outs="16", knobs={"pair": 0, "dbg": dbg})
+    for dbg in (0, 9):
+        run(32, 107520, 32, 11, 1, half=True, outs="both", res=True, knobs={"pair": 0, "dbg": dbg})
+        run(32, 53760, 64, 3, 1, half=True, outs="16", knobs={"pair": 0, "dbg": dbg})
+        run(32, 17920, 128, 3, 1, half=True, outs="16", knobs={"pair": 0, "dbg": dbg})
+    sys.exit(0)
 
 if __name__ == "__main__":
     S = _lib.ACT_SILU
