@@ -10,6 +10,9 @@ only collective being the final gather of the waveforms to rank 0, inside the ti
 
 Rank 0 prints ONE JSON line.  `value` = whole-job audio-s/s with inputs resident in HBM; `e2e` = the same
 metric through the public API (Generator.forward) with HOST buffers, H2D + D2H inside the timed region.
+The default build is precision="fp16" (tcgen05 kind::f16 operands -- the same 10-bit mantissa as tf32 -- fp32
+accumulate, fp32 residual streams; measured waveform SNR identical to the tf32 build); the tf32 build is timed in
+the same run (`tf32_build`), and at N=1 a bounded end-to-end rtMRI -> wav sample goes into `pipeline`.
 `--impl reference` times the CPU oracle port of the reference's Generator (the reference itself is Python
 and cannot travel to the GPU box) on all host cores, on a bounded sample of the same workload.
 """
@@ -127,7 +130,7 @@ def tf32_matmul_peak(device):
     return best
 
 
-def cpu_reference_rate(batch, frames, repeats, threads=None):
+def cpu_reference_rate(batch, frames, repeats, threads=None, min_seconds=0.0):
     """The CPU arm: oracle port of models.Generator.forward (oracle/vocoder.py), fp32, all host cores."""
     from oracle.vocoder import generator_forward
     from mri2speech_b200.vocoder import Generator
@@ -140,7 +143,7 @@ def cpu_reference_rate(batch, frames, repeats, threads=None):
     with torch.no_grad():
         generator_forward(sd, load_h(), mel[:1, :, :32])  # warm-up
         times = []
-        for _ in range(repeats):
+        while len(times) < repeats or sum(times) < min_seconds:
             t0 = time.perf_counter()
             generator_forward(sd, load_h(), mel)
             times.append(time.perf_counter() - t0)
@@ -160,18 +163,61 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "audio_seconds_per_second", "value": rate, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args),
+        "config": dict(workload_config(args), precision="fp32 on the host CPU (oracle port of models.Generator.forward)"),
         "cpu_baseline": {"value": rate, "unit": "audio-s/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
+def pipeline_sample(device, precision, n_clips=8):
+    """Bounded end-to-end sample (BASELINE.json configs[2] shape, 8 instead of 64 clips): ragged uint8 clips of
+    150-600 frames in pinned host memory -> H2D -> fused ingest -> encoder -> BiLSTM -> mel glue -> Generator -> D2H
+    of the waveforms, through pipeline.MriToSpeech.infer; CUDA events around the whole call."""
+    from mri2speech_b200 import synth
+    from mri2speech_b200.acoustic import build_acoustic_model
+    from mri2speech_b200.pipeline import MriToSpeech
+    from mri2speech_b200.vocoder import Generator
+    torch.manual_seed(1234)
+    ac = build_acoustic_model(precision=precision)
+    gen = Generator(load_h(), precision=precision)
+    mean, std = synth.synthetic_scaler()
+    pipe = MriToSpeech(ac, gen, mean, std, device)
+    lens = synth.synthetic_lengths(64)[:n_clips]
+    g = torch.Generator().manual_seed(1)
+    clips = [torch.randint(0, 256, (ln, 256, 256), generator=g, dtype=torch.uint8).pin_memory() for ln in lens]
+    frames = sum(lens)
+
+    def run():
+        out = pipe.infer(clips)
+        return [o["audio"].to("cpu", non_blocking=True) for o in out]
+
+    run()
+    torch.cuda.synchronize()
+    best = None
+    for _ in range(2):
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        wavs = run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    assert all(w.numel() == ln * HOP for w, ln in zip(wavs, lens))
+    audio_s = frames * HOP / SR
+    return {"workload": f"rtMRI->wav, {n_clips} ragged uint8 clips ({frames} frames, {audio_s:.1f} s audio), host buffers",
+            "ms": best, "value": audio_s / (best * 1e-3), "unit": "audio-s/s", "us_per_frame": best * 1e3 / frames,
+            "h2d_bytes": frames * 256 * 256, "d2h_bytes": frames * HOP * 4, "precision": precision}
+
+
 def workload_config(args):
     return {
         "workload": "BASELINE.json configs[1]: HiFi-GAN Generator only, batch 32 x 64-bin mel, 256 frames, "
                     "hop 420, 11413 Hz (per GPU)",
-        "batch_per_gpu": args.batch, "frames": args.frames, "precision": "tf32 (tcgen05 kind::tf32, fp32 accumulate)",
+        "batch_per_gpu": args.batch, "frames": args.frames,
+        "precision": ("fp16 operands (tcgen05 kind::f16; 10-bit mantissa like tf32), fp32 accumulate, fp32 residual / MRF "
+                      "streams" if getattr(args, "precision", "fp16") == "fp16" else
+                      "tf32 (tcgen05 kind::tf32, fp32 accumulate)"),
         "l2": "activations per stage (84-440 MB) exceed the 126 MB L2; no explicit flush",
         "sharding": "utterances per rank, final gather of waveforms to rank 0 inside the step (N>1)",
     }
@@ -186,7 +232,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--frames", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default=os.environ.get("M2S_BENCH_PRECISION", "tf32"), choices=["tf32", "fp16"])
+    ap.add_argument("--precision", default=os.environ.get("M2S_BENCH_PRECISION", "fp16"), choices=["tf32", "fp16"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the tf32-build and pipeline side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -291,6 +338,28 @@ def main():
         e2e_ms = float(tt.item())
     e2e_value = audio_s_per_step / (e2e_ms / args.steps * 1e-3)
 
+    # ---- side measurements (rank 0, N=1): the tf32 build on the same workload; a bounded rtMRI -> wav sample ----
+    tf32_build = pipeline_info = None
+    if world == 1 and not args.no_extras:
+        if args.precision != "tf32":
+            torch.manual_seed(1234)
+            gen32 = Generator(load_h(), precision="tf32").to(device).eval()
+            with torch.no_grad():
+                for _ in range(3):
+                    gen32(mel)
+                torch.cuda.synchronize()
+                k = max(3, min(args.steps, 5))
+                ea, eb = torch.cuda.Event(True), torch.cuda.Event(True)
+                ea.record()
+                for _ in range(k):
+                    gen32(mel)
+                eb.record()
+                torch.cuda.synchronize()
+            ms32 = ea.elapsed_time(eb) / k
+            tf32_build = {"ms_per_step": ms32, "value": audio_s_per_step / (ms32 * 1e-3), "unit": "audio-s/s", "steps": k}
+            del gen32
+        pipeline_info = pipeline_sample(device, args.precision)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -312,10 +381,11 @@ def main():
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
     roofline = {
-        "kernel": "conv_engine_kernel (tcgen05 kind::tf32 implicit-GEMM conv, all 77 GEMM-shaped layers)",
+        "kernel": f"conv_engine_kernel / conv_engine_pair_kernel (tcgen05 kind::{'f16' if args.precision == 'fp16' else 'tf32'} "
+                  "implicit-GEMM conv, all 77 GEMM-shaped layers)",
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "traffic": traffic,
-        "peak_source": f"{peak_src}: dense bf16 cuBLAS, sustained; kind::tf32 issues at half the bf16 rate",
+        "peak_source": f"{peak_src}: dense bf16 cuBLAS, sustained (kind::f16 issues at the bf16 rate, kind::tf32 at half)",
         "tf32_cublas_tflops_measured_here": tf32_peak, "frac_of_tf32_cublas": achieved / tf32_peak if tf32_peak else None,
         "launches_per_step": per_step_launches, "engine_ms_per_step": engine_ms_per_step,
         "engine_share_of_step": engine_ms_per_step / ms_per_step,
@@ -329,20 +399,20 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        rate, times, threads = cpu_reference_rate(1, T, 3)
+        rate, times, threads = cpu_reference_rate(1, T, 3, min_seconds=10.0)
         cpu = {"value": rate, "unit": "audio-s/s", "cores": threads, "kind": "port",
-               "sample": f"1 of {B} segments x {T} frames (B=1 as the reference CLI runs it), median of 3 passes "
-                         f"({sum(times):.1f} s CPU wall)"}
+               "sample": f"1 of {B} segments x {T} frames (B=1 as the reference CLI runs it), median of {len(times)} "
+                         f"passes ({sum(times):.1f} s CPU wall)"}
 
     line = {
         "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": workload_config(args), "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": mel_host.numel() * 4 * world,
                 "d2h_bytes_per_step": out_host.numel() * 4 * world, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(gen.launches_per_forward()) * args.steps,
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "cpu_baseline": cpu, "tf32_build": tf32_build, "pipeline": pipeline_info,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
