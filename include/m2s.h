@@ -117,6 +117,11 @@ typedef struct {
 } m2s_conv_args;
 
 int m2s_conv_fwd(const m2s_conv_args* args, int impl, m2s_stream_t stream);
+/* Fused ResBlock1 pair (reference models.py:36-48: xt = c1(lrelu(x)); xt = c2(lrelu(xt)); x = xt + x) in one kernel:
+ * conv1 (args1: a = fp16 x, w, causal shifts, bias, leaky-ReLU) feeds conv2 (args2: w, shifts -(k-1)..0, bias, fused
+ * epilogue and outputs; args2->a is ignored) through an fp16 tile that stays in shared memory.  fp16 operands only,
+ * c_in == n in {32, 64, 128}.  Exposed for parity tests of the kernel itself. */
+int m2s_resblock_pair_fwd(const m2s_conv_args* args1, const m2s_conv_args* args2, m2s_stream_t stream);
 
 /* ------------------------------------------------------------------------- */
 /* HiFi-GAN Generator (reference models.py:88-131, config_custom.json)        */

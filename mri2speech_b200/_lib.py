@@ -64,7 +64,7 @@ class AcousticConfig(C.Structure):
 
 
 EXPORTS = (
-    "m2s_version", "m2s_last_error_string", "m2s_device_check", "m2s_conv_fwd",
+    "m2s_version", "m2s_last_error_string", "m2s_device_check", "m2s_conv_fwd", "m2s_resblock_pair_fwd",
     "m2s_generator_create", "m2s_generator_destroy", "m2s_generator_workspace_bytes", "m2s_generator_forward",
     "m2s_generator_launches",
     "m2s_acoustic_create", "m2s_acoustic_destroy", "m2s_acoustic_workspace_bytes", "m2s_acoustic_forward",
@@ -90,6 +90,7 @@ def lib() -> C.CDLL:
     L.m2s_last_error_string.restype = C.c_char_p
     L.m2s_device_check.argtypes = [C.c_int]
     L.m2s_conv_fwd.argtypes = [C.POINTER(ConvArgs), C.c_int, C.c_void_p]
+    L.m2s_resblock_pair_fwd.argtypes = [C.POINTER(ConvArgs), C.POINTER(ConvArgs), C.c_void_p]
     L.m2s_debug_set_knob.argtypes = [C.c_char_p, C.c_int]
     L.m2s_debug_trace.argtypes = [C.c_void_p, C.c_int32]
     L.m2s_debug_profile.argtypes = [C.c_int]
@@ -186,7 +187,7 @@ def conv_fwd(a: torch.Tensor, w: torch.Tensor, shifts: Sequence[int], l_out: int
              out_scale: float = 1.0, act: int = ACT_NONE, act_slope: float = 0.0,
              lens=None, len_scale: int = 1, pitch_mask=None, d_row_offset: int = 0,
              d_rows: Optional[int] = None, out: Optional[torch.Tensor] = None,
-             out16: Optional[torch.Tensor] = None, want_d32: bool = True) -> torch.Tensor:
+             out16: Optional[torch.Tensor] = None, want_d32: bool = True, _return_args: bool = False):
     """Test helper around m2s_conv_fwd.  a: (B, L_in, C) cuda fp32 (tf32 operands) or fp16 (kind::f16 operands);
     w: (taps, N, C) cuda fp32.  ``out16``: optional fp16 second output (same shape as the fp32 one)."""
     require_device(a)
@@ -214,7 +215,24 @@ def conv_fwd(a: torch.Tensor, w: torch.Tensor, shifts: Sequence[int], l_out: int
     elif pitch_mask is not None:
         args.mask_mode = MASK_PITCH
         args.pitch, args.i_lo, args.i_hi, args.j_lo, args.j_hi = [int(v) for v in pitch_mask]
+    if _return_args:
+        return args, d
     check(lib().m2s_conv_fwd(C.byref(args), impl, current_stream()))
+    return d
+
+
+def resblock_pair_fwd(x16: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, dilation: int, w2: torch.Tensor,
+                      b2: torch.Tensor, *, slope: float = 0.1, **epilogue2):
+    """Test helper around m2s_resblock_pair_fwd: conv2(lrelu(conv1(x) + b1)) with conv2's fused epilogue
+    (``epilogue2``: the keyword arguments of conv_fwd -- res, accum, out_scale, act, lens, out16, want_d32 ...)."""
+    B, L, Cch = x16.shape
+    k1, k2 = w1.shape[0], w2.shape[0]
+    a1, _ = conv_fwd(x16, w1, [-(k1 - 1 - j) * dilation for j in range(k1)], L, bias=b1, act=ACT_LRELU,
+                     act_slope=slope, _return_args=True)
+    dummy = torch.empty(B, 1, w2.shape[2], device=x16.device, dtype=torch.float16)
+    a2, d = conv_fwd(dummy, w2, [-(k2 - 1 - j) for j in range(k2)], L, bias=b2, a_rows=L, _return_args=True, **epilogue2)
+    a2.a_batch_rows = L
+    check(lib().m2s_resblock_pair_fwd(C.byref(a1), C.byref(a2), current_stream()))
     return d
 
 

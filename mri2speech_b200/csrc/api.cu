@@ -84,6 +84,34 @@ extern "C" int m2s_conv_fwd(const m2s_conv_args* args, int impl, m2s_stream_t st
   return s;
 }
 
+// Test entry of the fused ResBlock pair kernel: a1 describes conv1 (a = fp16 x, w, shifts, bias, act), a2 conv2
+// (w, shifts, bias, epilogue, outputs; its `a` is ignored).  Weights are packed on the fly.
+extern "C" int m2s_resblock_pair_fwd(const m2s_conv_args* a1, const m2s_conv_args* a2, m2s_stream_t stream) {
+  if (!a1 || !a2 || !a1->a || !a1->w || !a2->w || (!a2->d && !a2->d16)) return fail(M2S_ERR_BAD_ARG, "null argument");
+  M2S_TRY(m2s_device_check(-1));
+  ConvProblem p1 = problem_from_args(*a1), p2 = problem_from_args(*a2);
+  p2.a_half = 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  PackedWeights w1, w2;
+  {
+    std::vector<float> hw(static_cast<size_t>(p1.taps) * p1.n * p1.c_in);
+    M2S_CUDA_OK(cudaMemcpy(hw.data(), a1->w, hw.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    M2S_TRY(pack_weights(hw.data(), p1.taps, p1.n, p1.c_in, PACK_FP16, &w1));
+  }
+  {
+    std::vector<float> hw(static_cast<size_t>(p2.taps) * p2.n * p2.c_in);
+    M2S_CUDA_OK(cudaMemcpy(hw.data(), a2->w, hw.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    int s2 = pack_weights(hw.data(), p2.taps, p2.n, p2.c_in, PACK_FP16, &w2);
+    if (s2 != M2S_OK) { free_weights(&w1); return s2; }
+  }
+  int s = resblock_pair_fused(p1, w1, p2, w2, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  free_weights(&w1);
+  free_weights(&w2);
+  if (s == M2S_OK && e != cudaSuccess) return fail(M2S_ERR_CUDA, "fused pair kernel failed: %s", cudaGetErrorString(e));
+  return s;
+}
+
 extern "C" int m2s_mel_glue(const float* pred_norm, const float* mean, const float* std, int32_t batch, int32_t frames,
                             int32_t n_mels, const int32_t* lengths, float* mel_db, float* mel_log, float* voc_in,
                             m2s_stream_t stream) {

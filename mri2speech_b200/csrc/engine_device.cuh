@@ -287,9 +287,11 @@ __device__ __forceinline__ EpiWarp make_epi_warp(const Epilogue& e, uint32_t sta
 // TMEM -> registers (row per thread) -> SMEM transpose (XOR-swizzled, conflict-free) -> coalesced global traffic:
 // 8 lanes cover one 128-byte row segment, a warp instruction covers 4 rows.  `tmem_acc` already carries this warp's
 // lane-quadrant offset.
+// `q_end` (exclusive) bounds the rows this tile may write (the fused pair kernel keeps only part of a tile).
 template <int kEpi>
 __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWarp& ew_, uint32_t tmem_acc, int b, int q0,
-                                              int n0, int msub, int n_tile) {
+                                              int n0, int msub, int n_tile, int q_end = 0x7fffffff) {
+  const int row_end = min(p.l_out, q_end);
   const Epilogue& e = p.epi;
   const EpiConsts& ec = ew_.ec;
   const uint32_t stage = ew_.stage;
@@ -326,7 +328,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
       int rows_valid_u = 32;
       if (mask_mode == M2S_MASK_LEN) rows_valid_u = len_rows - (qw + p.d_row_offset);
       const bool fast = mask_mode != M2S_MASK_PITCH && c0 + 32 <= n_tile && n0 + c0 + 32 <= p.n &&
-                        p.l_out - qw >= 32 && rows_valid_u >= 32 && !ew_.dbg;
+                        row_end - qw >= 32 && rows_valid_u >= 32 && !ew_.dbg;
       if (fast) {
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
@@ -394,7 +396,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
       }
     }
     const bool col_ok = (c0 + cc * 4 < n_tile) && n < p.n;
-    const int rows_ok = col_ok ? min(32, p.l_out - qw) : 0;                 // rows that exist
+    const int rows_ok = col_ok ? min(32, row_end - qw) : 0;                 // rows that exist
     int rows_valid = 32;                                                    // rows that survive the mask
     if (mask_mode == M2S_MASK_LEN) rows_valid = len_rows - (qw + p.d_row_offset);
     float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -17,6 +17,7 @@
 //            pair 2: j=0: S = x; j=1: S += x; j=2: P = mask(lrelu((S + x)/3, slope_next))
 #include "m2s_common.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -112,6 +113,7 @@ struct m2s_generator {
   m2s_generator_config cfg;
   bool tf32 = true;   // tensor-core build (tf32 or fp16 operands); false = CUDA-core fp32 build
   bool fp16 = false;  // M2S_PREC_FP16: layers with c_in % 8 == 0 run kind::f16 on fp16 copies of the activations
+  bool fuse_pairs = true;  // fp16 build: fused ResBlock pair kernel where it applies (M2S_FUSE_PAIRS=0 disables)
   int hop = 1;
   Layer pre;
   std::vector<Layer> ups;
@@ -230,6 +232,7 @@ extern "C" int m2s_generator_create(const m2s_generator_config* cfg, const m2s_t
   g->cfg = *cfg;
   g->tf32 = cfg->precision != M2S_PREC_FP32;
   g->fp16 = cfg->precision == M2S_PREC_FP16;
+  if (const char* f = std::getenv("M2S_FUSE_PAIRS")) g->fuse_pairs = std::atoi(f) != 0;
   // operand format per layer: fp16 needs 16-byte aligned rows of halves (c_in % 8 == 0); conv_pre reads the fp32 mel
   auto mode_for = [&](int c_in) {
     if (!g->tf32) return static_cast<int>(PACK_FP32);
@@ -285,6 +288,10 @@ extern "C" int m2s_generator_create(const m2s_generator_config* cfg, const m2s_t
     g->post_bias = b[0];
   }
   g->launches = 2 + cfg->num_upsamples * (1 + cfg->num_kernels * 6) + 1;
+  if (g->fp16 && g->fuse_pairs) {  // stages whose ResBlock pairs run fused: one launch per pair instead of two
+    for (int i = 0; i < cfg->num_upsamples; ++i)
+      if (g->ups_cout[i] <= 128 && g->ups_cout[i] % 32 == 0) g->launches -= cfg->num_kernels * 3;
+  }
   *out = g;
   return M2S_OK;
 }
@@ -393,7 +400,6 @@ extern "C" int m2s_generator_forward(m2s_generator* g, const float* mel, int32_t
         ConvProblem p1 = base_problem(state_op, L, ch, batch, L, T, ch, L, L, l1);
         if (hs) set_out(&p1, nullptr, T);
         p1.epi.act = M2S_ACT_LRELU; p1.epi.act_slope = 0.1f;
-        M2S_TRY(run_conv(g, p1, l1, st));
         ConvProblem p2 = base_problem(T, L, ch, batch, L, R, ch, L, L, l2);
         p2.epi.res = state; p2.epi.res_ld = ch; p2.epi.res_inv_slope = 10.f;  // 1 / LRELU_SLOPE
         if (d < 2) {
@@ -410,7 +416,13 @@ extern "C" int m2s_generator_forward(m2s_generator* g, const float* mel, int32_t
           p2.epi.act = M2S_ACT_LRELU; p2.epi.act_slope = last_stage ? 0.01f : 0.1f;
           p2.epi.mask_mode = mask; p2.epi.lens = lengths; p2.epi.len_scale = scale;
         }
-        M2S_TRY(run_conv(g, p2, l2, st));
+        // fp16 build, C <= 128: conv1 -> leaky-ReLU -> conv2 in ONE kernel, the intermediate stays in SMEM
+        if (hs && g->fuse_pairs && resblock_pair_supported(p1, l1.w, p2, l2.w)) {
+          M2S_TRY(resblock_pair_fused(p1, l1.w, p2, l2.w, st));
+        } else {
+          M2S_TRY(run_conv(g, p1, l1, st));
+          M2S_TRY(run_conv(g, p2, l2, st));
+        }
         state = R;
         state_op = hs ? static_cast<const void*>(R16) : static_cast<const void*>(R);
       }

@@ -146,6 +146,11 @@ void free_weights(PackedWeights* w);
 
 int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stream);
 int conv_tcgen05_pair(const ConvProblem& p, const PackedWeights& w, cudaStream_t stream);
+// Fused ResBlock pair (conv1 -> leaky-ReLU -> conv2 -> epilogue) with the intermediate kept in SMEM (fp16 build).
+bool resblock_pair_supported(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& p2,
+                             const PackedWeights& w2);
+int resblock_pair_fused(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& p2, const PackedWeights& w2,
+                        cudaStream_t stream);
 int profile_before(cudaStream_t stream);
 int profile_after(cudaStream_t stream, double flops);
 int conv_simt(const ConvProblem& p, const float* w_plain, cudaStream_t stream);
