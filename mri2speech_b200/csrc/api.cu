@@ -57,6 +57,7 @@ extern "C" int m2s_debug_set_knob(const char* name, int value) {
   else if (!std::strcmp(name, "n_tile_max")) k.n_tile_max = value;
   else if (!std::strcmp(name, "pair")) k.pair = value;
   else if (!std::strcmp(name, "pair_min_n")) k.pair_min_n = value;
+  else if (!std::strcmp(name, "fuse_max_n")) k.fuse_max_n = value;
   else return fail(M2S_ERR_BAD_ARG, "unknown knob %s", name);
   return M2S_OK;
 }

@@ -263,6 +263,7 @@ EngineKnobs& engine_knobs() {
     x.n_tile_max = env_int("M2S_ENGINE_NTILE_MAX", 128);
     x.pair = env_int("M2S_ENGINE_PAIR", 1);
     x.pair_min_n = env_int("M2S_ENGINE_PAIR_MIN_N", 32);
+    x.fuse_max_n = env_int("M2S_FUSE_MAX_N", 64);
     return x;
   }();
   return k;

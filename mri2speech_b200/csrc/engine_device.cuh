@@ -361,7 +361,11 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
                        "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
                        : "memory");
         __syncwarp();
-        float4 o[8];
+        // each row is stored as soon as it is computed (nothing but the prefetched operands stays live: the kernel
+        // runs at the 168-register cap of a 10-warp CTA)
+        float4* dp = reinterpret_cast<float4*>(p.d + row0 * p.d_ld + n);
+        uint2* hp = reinterpret_cast<uint2*>(static_cast<__half*>(p.d16) + row0 * p.d_ld + n);
+        const bool st32 = p.d != nullptr, st16 = p.d16 != nullptr;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + rr0;
@@ -371,23 +375,16 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
                        : "r"(stage + rr * 128 + ((cc ^ (rr & 7)) << 4)));
           const float4 r4 = kHasRes ? res4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
           const float4 c4 = kHasAcc ? acc4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-          o[i].x = epi_elem<kEpi>(ec, a4.x, bias4.x, r4.x, c4.x);
-          o[i].y = epi_elem<kEpi>(ec, a4.y, bias4.y, r4.y, c4.y);
-          o[i].z = epi_elem<kEpi>(ec, a4.z, bias4.z, r4.z, c4.z);
-          o[i].w = epi_elem<kEpi>(ec, a4.w, bias4.w, r4.w, c4.w);
-        }
-        if (p.d) {
-          float4* dp = reinterpret_cast<float4*>(p.d + row0 * p.d_ld + n);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) dp[static_cast<size_t>(i) * p.d_ld] = o[i];
-        }
-        if (p.d16) {  // fp16 copy: the tensor-core operand of the next conv (saturating conversion, never inf)
-          uint2* hp = reinterpret_cast<uint2*>(static_cast<__half*>(p.d16) + row0 * p.d_ld + n);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          float4 o;
+          o.x = epi_elem<kEpi>(ec, a4.x, bias4.x, r4.x, c4.x);
+          o.y = epi_elem<kEpi>(ec, a4.y, bias4.y, r4.y, c4.y);
+          o.z = epi_elem<kEpi>(ec, a4.z, bias4.z, r4.z, c4.z);
+          o.w = epi_elem<kEpi>(ec, a4.w, bias4.w, r4.w, c4.w);
+          if (st32) dp[static_cast<size_t>(i) * p.d_ld] = o;
+          if (st16) {  // fp16 copy: the tensor-core operand of the next conv (saturating conversion, never inf)
             uint2 pk;
-            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(o[i].y), "f"(o[i].x));
-            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(o[i].w), "f"(o[i].z));
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(o.y), "f"(o.x));
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(o.w), "f"(o.z));
             hp[static_cast<size_t>(i) * p.d_ld] = pk;
           }
         }

@@ -290,7 +290,7 @@ extern "C" int m2s_generator_create(const m2s_generator_config* cfg, const m2s_t
   g->launches = 2 + cfg->num_upsamples * (1 + cfg->num_kernels * 6) + 1;
   if (g->fp16 && g->fuse_pairs) {  // stages whose ResBlock pairs run fused: one launch per pair instead of two
     for (int i = 0; i < cfg->num_upsamples; ++i)
-      if (g->ups_cout[i] <= 128 && g->ups_cout[i] % 32 == 0) g->launches -= cfg->num_kernels * 3;
+      if (g->ups_cout[i] <= engine_knobs().fuse_max_n && g->ups_cout[i] % 32 == 0) g->launches -= cfg->num_kernels * 3;
   }
   *out = g;
   return M2S_OK;

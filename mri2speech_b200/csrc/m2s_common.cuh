@@ -168,6 +168,8 @@ struct EngineKnobs {
   int pair = 1;              // CTA-pair (cta_group::2) kernel: 0 never, 1 heuristic, 2 whenever packed
   int pair_min_n = 32;       // narrowest layer whose weights are also packed for the CTA-pair kernel
   int n_tile_max = 128;      // N columns per tile once N exceeds it (weights are packed accordingly)
+  int fuse_max_n = 64;       // widest layer the fused ResBlock-pair kernel takes (N = 128 works but is slower than
+                             // two CTA-pair launches: one accumulator buffer each, no cta_group::2 weight split)
 };
 EngineKnobs& engine_knobs();
 

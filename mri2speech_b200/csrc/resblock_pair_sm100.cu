@@ -184,8 +184,8 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
               const uint64_t db = desc_hi | (((b_tile + t * prm.b_tap_bytes) & 0x3FFFF) >> 4);
               const uint64_t da = desc_hi | (((a_tile + rel_shift[tap0 + t] * row_bytes) & 0x3FFFF) >> 4);
               const uint32_t first = (cb | tap0 | t) ? 1u : 0u;
-              mma_f16_k4(tmem_acc, da, db, prm.idesc, first, ksteps);
-              if (msub > 1) mma_f16_k4(tmem_acc + n, da + ((128 * row_bytes) >> 4), db, prm.idesc, first, ksteps);
+              for (int sub = 0; sub < msub; ++sub)
+                mma_f16_k4(tmem_acc + sub * n, da + sub * ((128 * row_bytes) >> 4), db, prm.idesc, first, ksteps);
             }
             tc_commit(b_empty(sb));
             const bool last_group = tap0 + cnt >= taps;
@@ -332,7 +332,9 @@ EncodeTiledFn encode_fn3() {
 bool resblock_pair_supported(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& p2,
                              const PackedWeights& w2) {
   if (!p1.a_half || !w1.half || !w2.half || w1.half != w2.half) return false;
-  if (p1.n != p2.n || p2.c_in != p1.n || p1.n > 128 || p1.n % 32 || w1.n_tiles != 1 || w2.n_tiles != 1) return false;
+  if (p1.n != p2.n || p2.c_in != p1.n || p1.n > engine_knobs().fuse_max_n || p1.n % 32 || w1.n_tiles != 1 ||
+      w2.n_tiles != 1)
+    return false;
   if (w1.n_tile != p1.n || w2.n_tile != p1.n) return false;
   if (p1.batch != p2.batch || p1.l_out != p2.l_out || p2.d_row_offset != 0) return false;
   if (p2.epi.mask_mode == M2S_MASK_PITCH) return false;
@@ -370,8 +372,10 @@ int resblock_pair_fused(const ConvProblem& p1, const PackedWeights& w1, const Co
   prm.desc_hi = make_desc_hi(w1.row_bytes);
   prm.cblocks1 = w1.cblocks;
   prm.cblocks2 = w2.cblocks;
-  prm.msub = 2;
-  prm.m1 = 256;
+  // 128-row sub-tiles per tile: 4 (M1 = 512) when all four accumulator buffers still fit the 512 TMEM columns
+  prm.msub = (16 * prm.n <= kTmemCols) ? 4 : 2;
+  if (engine_knobs().msub == 1 || engine_knobs().msub == 2) prm.msub = 2;
+  prm.m1 = 128 * prm.msub;
   prm.halo2 = p2.taps - 1;
   prm.m2 = prm.m1 - prm.halo2;
   int smin = 0;
@@ -381,7 +385,7 @@ int resblock_pair_fused(const ConvProblem& p1, const PackedWeights& w1, const Co
   prm.x_row0 = -prm.halo2 + smin;
   prm.tiles_per_batch = (p2.l_out + prm.m2 - 1) / prm.m2;
   prm.total_tiles = p2.batch * prm.tiles_per_batch;
-  prm.nbuf = (8 * prm.n <= kTmemCols) ? 2 : 1;
+  prm.nbuf = (4 * prm.msub * prm.n <= kTmemCols) ? 2 : 1;
   prm.dbg = engine_knobs().dbg;
 
   const int a_rows_needed = prm.m1 - smin;

@@ -47,6 +47,7 @@ def _inputs(B, L, C, k, seed=3):
 def test_fused_pair_matches_two_convs(case):
     from mri2speech_b200 import _lib
     B, L, C, k, d = case
+    _lib.set_knob("fuse_max_n", 128)  # N = 128 is supported (single-buffered) though the Generator does not use it
     x, w1, b1, w2, b2 = _inputs(B, L, C, k)
     ref = _reference(x, w1, b1, d, w2, b2, L)
     d16 = torch.zeros(B, L, C, device="cuda", dtype=torch.float16)
@@ -92,6 +93,7 @@ def test_fused_pair_plain_residual_fp32_out():
 
 def test_unsupported_pair_is_refused():
     from mri2speech_b200 import _lib
+    _lib.set_knob("fuse_max_n", 128)
     x, w1, b1, w2, b2 = _inputs(1, 300, 256, 3)          # N = 256 > 128
     with pytest.raises(_lib.M2SError):
         _lib.resblock_pair_fwd(x, w1, b1, 1, w2, b2)
