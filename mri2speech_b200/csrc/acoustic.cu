@@ -28,6 +28,8 @@ int enc_dwconv(const void* in, void* out, int half, float* sums, const float* w,
 int enc_se(const float* sums, float* scales, const float* w1, const float* b1, const float* w2, const float* b2, int n,
            int C, int rd, int hw, cudaStream_t st);
 int enc_se_scale(void* x, int half, const float* scales, int n, int hw, int C, cudaStream_t st);
+int enc_se_apply(void* x, int half, const float* sums, const float* w1, const float* b1, const float* w2, const float* b2,
+                 int n, int C, int rd, int hw, cudaStream_t st);
 int enc_gap(const float* x, const int32_t* fmap, float* feats, int n, int hw, int C, int feat_ld, cudaStream_t st);
 int lstm_recurrence(const float* gin, const float* w_hh_fwd, const float* w_hh_bwd, const int32_t* lens, float* hcat,
                     unsigned int* counters, int batch, int frames, int max_len, int hidden,
@@ -320,8 +322,7 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
       const int o = b.in_padded ? 1 : 0;
       M2S_TRY(enc_dwconv(B.e, B.e2, h, B.sums, b.dw_w, b.dw_b, n, b.mid, hin, win, pitch_in, o, o, rows_in, b.stride, st));
       const int hw = hout * wout;
-      M2S_TRY(enc_se(B.sums, B.scales, b.se_w1, b.se_b1, b.se_w2, b.se_b2, n, b.mid, b.rd, hw, st));
-      M2S_TRY(enc_se_scale(B.e2, h, B.scales, n, hw, b.mid, st));
+      M2S_TRY(enc_se_apply(B.e2, h, B.sums, b.se_w1, b.se_b1, b.se_w2, b.se_b2, n, b.mid, b.rd, hw, st));
       const int rows_out = n * hw;
       ConvProblem p = gemm_problem(B.e2, rows_out, rows_out, b.mid, 1, rows_out, y.f32, rows_out, b.cout, 0, b.pwl);
       set_block_out(&p);
@@ -504,7 +505,7 @@ extern "C" int m2s_acoustic_create(const m2s_acoustic_config* cfg, const m2s_ten
         m->e2_floats = std::max(m->e2_floats, static_cast<size_t>(ho) * wo * b.mid);
         m->x_floats = std::max(m->x_floats, static_cast<size_t>(ho) * wo * b.cout);
         m->max_mid = std::max(m->max_mid, b.mid);
-        launches += 5;
+        launches += 4;
       }
       m->blocks.push_back(b);
       padded = b.out_padded;

@@ -13,6 +13,7 @@
 // memory-bound kernels; the arithmetic stays fp32).
 #include "m2s_common.cuh"
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 namespace m2s {
 
@@ -296,6 +297,68 @@ __global__ void __launch_bounds__(1024) se_kernel(const float* __restrict__ sums
   }
 }
 
+// Squeeze-excite MLP and excite scale in ONE pass over the tensor: every block recomputes the (tiny) MLP of its frame
+// -- scale[c] = sigmoid(W2 silu(W1 mean + b1) + b2), 2 * C * rd MACs -- into SMEM and then scales its share of the
+// frame's pixels in place.  grid = (frames, splits); 1024 threads: phase 1 = one warp per reduced unit (float4 over
+// channels), phase 2 = one thread per channel (coalesced over W2^T), phase 3 = the streaming multiply.
+template <typename T>
+__global__ void __launch_bounds__(1024) se_apply_kernel(T* __restrict__ x, const float* __restrict__ sums,
+                                                        const float* __restrict__ w1 /*[rd][C]*/, const float* __restrict__ b1,
+                                                        const float* __restrict__ w2t /*[rd][C]*/, const float* __restrict__ b2,
+                                                        int C, int rd, int hw, float inv_hw) {
+  extern __shared__ float sm[];  // mean[C] + scale[C] + r[rd]
+  float* mean = sm;
+  float* scale = sm + C;
+  float* r = sm + 2 * C;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = sums[static_cast<size_t>(n) * C + c] * inv_hw;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int c4n = C >> 2;
+  for (int j = warp; j < rd; j += nwarps) {
+    const float4* wr = reinterpret_cast<const float4*>(w1 + static_cast<size_t>(j) * C);
+    float a = 0.f;
+    for (int k = lane; k < c4n; k += 32) {
+      const float4 wv = __ldg(wr + k);
+      const float4 mv = reinterpret_cast<const float4*>(mean)[k];
+      a = fmaf(wv.x, mv.x, a); a = fmaf(wv.y, mv.y, a); a = fmaf(wv.z, mv.z, a); a = fmaf(wv.w, mv.w, a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) {
+      a += b1[j];
+      r[j] = a / (1.f + expf(-a));
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a0 = b2[c], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int j = 0;
+    for (; j + 4 <= rd; j += 4) {
+      a0 = fmaf(__ldg(w2t + static_cast<size_t>(j) * C + c), r[j], a0);
+      a1 = fmaf(__ldg(w2t + static_cast<size_t>(j + 1) * C + c), r[j + 1], a1);
+      a2 = fmaf(__ldg(w2t + static_cast<size_t>(j + 2) * C + c), r[j + 2], a2);
+      a3 = fmaf(__ldg(w2t + static_cast<size_t>(j + 3) * C + c), r[j + 3], a3);
+    }
+    for (; j < rd; ++j) a0 = fmaf(__ldg(w2t + static_cast<size_t>(j) * C + c), r[j], a0);
+    const float a = (a0 + a1) + (a2 + a3);
+    scale[c] = 1.f / (1.f + expf(-a));
+  }
+  __syncthreads();
+  // this block's pixels of frame n
+  const int p0 = static_cast<int>((static_cast<long long>(hw) * blockIdx.y) / gridDim.y);
+  const int p1 = static_cast<int>((static_cast<long long>(hw) * (blockIdx.y + 1)) / gridDim.y);
+  T* xf = x + (static_cast<size_t>(n) * hw + p0) * C;
+  const int total4 = (p1 - p0) * c4n;
+  for (int k = threadIdx.x; k < total4; k += blockDim.x) {
+    const int c4 = k % c4n;
+    float4 v = load4(xf + 4 * static_cast<size_t>(k));
+    const float4 sc = reinterpret_cast<const float4*>(scale)[c4];
+    v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
+    store4(xf + 4 * static_cast<size_t>(k), v);
+  }
+}
+
 // x[n][p][c] *= scale[n][c]
 template <typename T>
 __global__ void se_scale_kernel(T* __restrict__ x, const float* __restrict__ scales, int hw, int c4n, size_t total4) {
@@ -400,8 +463,15 @@ int dwconv_launch(const T* in, T* out, float* sums, const float* w, const float*
 }
 }  // namespace
 
+bool dwconv_tma_supported(int half, int C, int H, int W);
+int dwconv_tma(const void* in, void* out, int half, float* sums, const float* w, const float* bias, int n, int C, int H,
+               int W, int pitch_in, int rows_in, int oy, int ox, cudaStream_t st);
+
 int enc_dwconv(const void* in, void* out, int half, float* sums, const float* w, const float* bias, int n, int C, int Hin,
                int Win, int pitch_in, int oy, int ox, int rows_in, int stride, cudaStream_t st) {
+  static const bool use_tma = !(std::getenv("M2S_DWCONV_TMA") && std::atoi(std::getenv("M2S_DWCONV_TMA")) == 0);
+  if (stride == 1 && use_tma && dwconv_tma_supported(half, C, Hin, Win))
+    return dwconv_tma(in, out, half, sums, w, bias, n, C, Hin, Win, pitch_in, rows_in, oy, ox, st);
   if (half)
     return dwconv_launch(static_cast<const __half*>(in), static_cast<__half*>(out), sums, w, bias, n, C, Hin, Win,
                          pitch_in, oy, ox, rows_in, stride, st);
@@ -412,6 +482,23 @@ int enc_dwconv(const void* in, void* out, int half, float* sums, const float* w,
 int enc_se(const float* sums, float* scales, const float* w1, const float* b1, const float* w2, const float* b2, int n,
            int C, int rd, int hw, cudaStream_t st) {
   se_kernel<<<n, 1024, (C + rd) * sizeof(float), st>>>(sums, scales, w1, b1, w2, b2, C, rd, 1.f / hw);
+  M2S_CUDA_OK(cudaGetLastError());
+  return M2S_OK;
+}
+
+// SE MLP + excite scale fused (replaces enc_se + enc_se_scale).
+int enc_se_apply(void* x, int half, const float* sums, const float* w1, const float* b1, const float* w2, const float* b2,
+                 int n, int C, int rd, int hw, cudaStream_t st) {
+  const size_t bytes = static_cast<size_t>(hw) * C * (half ? 2 : 4);
+  int splits = static_cast<int>((bytes + 192 * 1024 - 1) / (192 * 1024));  // ~<= 192 KB of the tensor per block
+  if (splits < 1) splits = 1;
+  if (splits > hw) splits = hw;
+  dim3 grid(n, splits);
+  const size_t sm = (2 * static_cast<size_t>(C) + rd) * sizeof(float);
+  if (half)
+    se_apply_kernel<<<grid, 1024, sm, st>>>(static_cast<__half*>(x), sums, w1, b1, w2, b2, C, rd, hw, 1.f / hw);
+  else
+    se_apply_kernel<<<grid, 1024, sm, st>>>(static_cast<float*>(x), sums, w1, b1, w2, b2, C, rd, hw, 1.f / hw);
   M2S_CUDA_OK(cudaGetLastError());
   return M2S_OK;
 }

@@ -8,8 +8,9 @@ import torch
 from mri2speech_b200.acoustic import build_acoustic_model
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+prec = sys.argv[2] if len(sys.argv) > 2 else "tf32"
 torch.manual_seed(1234)
-ac = build_acoustic_model().cuda().eval()
+ac = build_acoustic_model(precision=prec).cuda().eval()
 frames = torch.rand(n, 256, 256, device="cuda")
 for _ in range(3):
     f = ac.encode_frames(frames)
