@@ -260,14 +260,12 @@ struct EpiWarp {
   int mask_mode;
   bool has_res, has_acc;
   int dbg;  // probe switches (EngineParams::dbg): bit0 skip global stores, bit1 skip TMEM loads, bit2 skip SMEM transpose
-  bool direct;  // row-per-thread epilogue: TMEM -> registers -> global, no SMEM transpose (EngineParams::dbg bit 6)
 };
 
 __device__ __forceinline__ EpiWarp make_epi_warp(const Epilogue& e, uint32_t stage_base, int ew, int warp, int lane,
                                                  int dbg = 0) {
   EpiWarp w;
-  w.dbg = dbg & 63;
-  w.direct = (dbg & 64) != 0;
+  w.dbg = dbg;
   w.quad = warp & 3;  // TMEM lane quadrant this warp may access
   w.half = ew >> 2;   // which of the two warps of the quadrant
   w.lane = lane;
@@ -324,56 +322,15 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
     constexpr bool kHasRes = kEpi == EPI_FULL || kEpi == EPI_FULL_SILU || kEpi == EPI_RES || kEpi == EPI_RB || kEpi == EPI_RB_ACC;
     constexpr bool kHasAcc = kEpi == EPI_FULL || kEpi == EPI_FULL_SILU || kEpi == EPI_RB_ACC;
     // ---- fast path: the whole 32 x 32 unit is inside the output and survives the mask (warp-uniform test): no
-    // predicates, row pointers stepped by warp-uniform strides.  The epilogue is instruction-issue-bound (32K outputs
-    // per 256-column tile on 8 warps), so this path is kept to ~6 instructions per output.
+    // predicates, row pointers stepped by warp-uniform strides.  ~8 instructions per output instead of 20-37 on the
+    // general path.  Measured alternatives that lost: a row-per-thread epilogue straight from the TMEM registers to
+    // global memory without the SMEM transpose (1.4-2x slower: uncoalesced 16-byte accesses); prefetching the residual
+    // one unit / one tile ahead in registers or with cp.async.bulk.prefetch.L2 (slower at the 168-register cap).
     {
       int rows_valid_u = 32;
       if (mask_mode == M2S_MASK_LEN) rows_valid_u = len_rows - (qw + p.d_row_offset);
       const bool fast = mask_mode != M2S_MASK_PITCH && c0 + 32 <= n_tile && n0 + c0 + 32 <= p.n &&
                         row_end - qw >= 32 && rows_valid_u >= 32 && !ew_.dbg;
-      if (fast && ew_.direct) {
-        // Row-per-thread variant: thread `lane` owns row qw + lane and the unit's 32 columns straight out of TMEM.
-        // No SMEM round trip (the MMA's operand fetch and the transpose compete for the same 128 B/clk of SMEM);
-        // global accesses are 16 bytes per lane at row stride -- twice the L2 transactions of the coalesced path,
-        // the partial sectors merge in L2.
-        const size_t row = d_base + qw + lane;
-        const int nn = n0 + c0;
-        float4 res4[8], acc4[8];
-        if (kHasRes && has_res) {
-          const float4* rp = reinterpret_cast<const float4*>(e.res + row * e.res_ld + nn);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) res4[j] = rp[j];
-        }
-        if (kHasAcc && has_acc) {
-          const float4* ap = reinterpret_cast<const float4*>(e.accum + row * e.accum_ld + nn);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc4[j] = ap[j];
-        }
-        tmem_ld_wait();
-        float4* dp = reinterpret_cast<float4*>(p.d + row * p.d_ld + nn);
-        uint2* hp = reinterpret_cast<uint2*>(static_cast<__half*>(p.d16) + row * p.d_ld + nn);
-        const bool st32 = p.d != nullptr, st16 = p.d16 != nullptr;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (e.bias) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + nn) + j);
-          const float4 r4 = (kHasRes && has_res) ? res4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 c4 = (kHasAcc && has_acc) ? acc4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-          float4 o;
-          o.x = epi_elem<kEpi>(ec, __uint_as_float(r[4 * j]), b4.x, r4.x, c4.x);
-          o.y = epi_elem<kEpi>(ec, __uint_as_float(r[4 * j + 1]), b4.y, r4.y, c4.y);
-          o.z = epi_elem<kEpi>(ec, __uint_as_float(r[4 * j + 2]), b4.z, r4.z, c4.z);
-          o.w = epi_elem<kEpi>(ec, __uint_as_float(r[4 * j + 3]), b4.w, r4.w, c4.w);
-          if (st32) dp[j] = o;
-          if (st16) {
-            uint2 pk;
-            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(o.y), "f"(o.x));
-            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(o.w), "f"(o.z));
-            hp[j] = pk;
-          }
-        }
-        continue;
-      }
       if (fast) {
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
