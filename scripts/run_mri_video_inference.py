@@ -65,6 +65,33 @@ def load_video_frames(video_path, target_size=(256, 256), max_frames=None) -> to
     return torch.from_numpy(np.asarray(frames, dtype=np.float32))
 
 
+def load_video_frames_u8(video_path, target_size=(256, 256), max_frames=None) -> torch.Tensor:
+    """Decoded frames as raw uint8 gray (T,H,W): the gray conversion and the bilinear resize of _preprocess_frame
+    (:35-40 of the reference, both uint8 -> uint8 in OpenCV) stay on the host; the float cast, z-score and min-max
+    (:41-53) run on the device, fused into the encoder's stem load (m2s_acoustic_forward_u8) -- 4x fewer bytes over
+    PCIe / HBM than float32 frames."""
+    import cv2
+    cap = cv2.VideoCapture(str(video_path))
+    if not cap.isOpened():
+        raise ValueError(f"Unable to open video: {video_path}")
+    total = int(cap.get(cv2.CAP_PROP_FRAME_COUNT))
+    if max_frames is not None:
+        total = min(total, max_frames)
+    frames = []
+    while len(frames) < total:
+        ok, frame = cap.read()
+        if not ok:
+            break
+        gray = cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY) if frame.ndim == 3 else frame
+        if gray.shape[::-1] != tuple(target_size):
+            gray = cv2.resize(gray, tuple(target_size), interpolation=cv2.INTER_LINEAR)
+        frames.append(gray)
+    cap.release()
+    if not frames:
+        raise ValueError("No frames could be read from video")
+    return torch.from_numpy(np.asarray(frames, dtype=np.uint8))
+
+
 load_scaler = pipeline.load_scaler
 
 
@@ -180,6 +207,10 @@ def parse_args(argv=None):
     p.add_argument("--n-mels", type=int, default=64)
     p.add_argument("--rnn-hidden", type=int, default=640)
     p.add_argument("--dropout", type=float, default=0.5)
+    # in-memory articulator masking (replaces the mask_rtmri_video.py re-encode + second run of this CLI)
+    p.add_argument("--mask-type", choices=["lip", "tongue"], default=None, help="Apply a preset articulator mask")
+    p.add_argument("--mask-alpha", type=float, default=0.1, help="Residual intensity inside the mask (0-1)")
+    p.add_argument("--mask-blur-kernel", type=int, default=11, help="Gaussian blur kernel size for soft edges")
     return p.parse_args(argv)
 
 
@@ -195,13 +226,21 @@ def run(args, frames: torch.Tensor = None):
         raise RuntimeError("this build runs on sm_100 CUDA devices only (there is no CPU fallback)")
     device = torch.device("cuda")
     print(f"[INFO] Using device: {device}")
-    if frames is None:
-        frames = load_video_frames(video_path, target_size=(256, 256), max_frames=args.max_frames)
+    if frames is None:  # raw uint8 frames: normalisation happens on the device (fused ingest)
+        frames = load_video_frames_u8(video_path, target_size=(256, 256), max_frames=args.max_frames)
+    if args.mask_type:
+        if frames.dtype != torch.uint8:
+            raise ValueError("--mask-type applies to raw uint8 frames (the mask is applied before normalisation)")
+        from mri2speech_b200 import masking
+        mask = torch.from_numpy(masking.preset_mask(args.mask_type, args.mask_alpha, tuple(frames.shape[-2:]),
+                                                    args.mask_blur_kernel))
+    else:
+        mask = None
     frames_tensor = frames_to_tensor(frames, use_channel=True).to(device)
 
     mri_model = build_mri_model(args, device)
     with torch.no_grad():
-        pred_norm = mri_model(frames_tensor).squeeze(0)
+        pred_norm = (mri_model(frames_tensor, mask=mask) if mask is not None else mri_model(frames_tensor)).squeeze(0)
     print(f"[INFO] Predicted normalized mel shape: {tuple(pred_norm.shape)}")
     mel_db, mel_log, voc_in = pipeline.mel_glue(pred_norm, torch.from_numpy(mean), torch.from_numpy(std))
     mel_denorm_np = mel_db.cpu().numpy().astype(np.float32)

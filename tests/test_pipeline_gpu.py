@@ -95,3 +95,69 @@ def test_cli_run_with_synthetic_checkpoints(tmp_path):
         cli.load_scaler(bad)
     with pytest.raises(ValueError):
         cli.frames_to_tensor(torch.zeros(2, 2))
+
+
+def test_cli_uint8_ingest_and_mask(tmp_path):
+    """The CLI on raw uint8 frames (device-side normalisation) equals the float path on frames normalised by the
+    oracle's restatement of _preprocess_frame; --mask-type applies the articulator mask in memory."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import run_mri_video_inference as cli
+    from mri2speech_b200 import synth
+    from oracle import ingest
+    ac, gen = _models()
+    torch.save({"model_state_dict": ac.state_dict()}, tmp_path / "mri.pt")
+    torch.save({"generator": gen.state_dict()}, tmp_path / "g_00000001")
+    synth.write_scaler_json(tmp_path / "scaler.json")
+    base = ["--video", str(tmp_path / "clip9.mp4"), "--mri-checkpoint", str(tmp_path / "mri.pt"),
+            "--scaler-json", str(tmp_path / "scaler.json"), "--hifigan-config", os.path.join(ROOT, "config_custom.json"),
+            "--hifigan-checkpoint", str(tmp_path / "g_00000001"), "--mri-code-dir", os.path.join(ROOT, "mri2speech_code")]
+    u8 = synth.synthetic_clip_u8(9, 5)
+    a_u8, mel_u8, _ = cli.run(cli.parse_args(base + ["--output-dir", str(tmp_path / "o1")]), frames=u8)
+    f32 = torch.from_numpy(ingest.preprocess_clip(u8.numpy()))
+    a_f, mel_f, _ = cli.run(cli.parse_args(base + ["--output-dir", str(tmp_path / "o2")]), frames=f32)
+    assert np.abs(mel_u8 - mel_f).max() < 5e-3                     # dB scale (std 8-15 per normalised unit)
+    assert a_u8.shape == a_f.shape == (5 * 420,)
+    a_m, mel_m, _ = cli.run(cli.parse_args(base + ["--output-dir", str(tmp_path / "o3"), "--mask-type", "tongue",
+                                                   "--mask-alpha", "0.0"]), frames=u8)
+    assert np.abs(mel_m - mel_u8).max() > 1e-3                     # the mask changes the prediction
+    with pytest.raises(ValueError):
+        cli.run(cli.parse_args(base + ["--output-dir", str(tmp_path / "o4"), "--mask-type", "lip"]), frames=f32)
+
+
+def test_alternate_vocoder_clis(tmp_path):
+    """mel_to_audio_synthesis.py (ragged batch over .npy mels, bin padding) and inference_e2e.py (int16 wavs) against
+    direct Generator calls."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import inference_e2e
+    import mel_to_audio_synthesis as m2a
+    from scipy.io import wavfile
+    _, gen = _models()
+    torch.save({"generator": gen.state_dict()}, tmp_path / "g_00000002")
+    import shutil
+    shutil.copy(os.path.join(ROOT, "config_custom.json"), tmp_path / "config.json")
+    mels = tmp_path / "mels"
+    mels.mkdir()
+    g = torch.Generator().manual_seed(3)
+    m_a = torch.randn(64, 9, generator=g) * 2 - 5
+    m_b = torch.randn(60, 5, generator=g) * 2 - 5                 # 60 bins: zero-padded to 64 (:76-87)
+    np.save(mels / "a_mel.npy", m_a.numpy())
+    np.save(mels / "b.npy", m_b.numpy())
+    res = m2a.main(["--input", str(mels), "--checkpoint_file", str(tmp_path / "g_00000002"),
+                    "--config", os.path.join(ROOT, "config_custom.json"), "--output_dir", str(tmp_path / "syn")])
+    assert sorted(n for n, _ in res) == ["a", "b"]
+    gen = gen.cuda().eval()
+    with torch.no_grad():
+        ref_a = gen(m_a.cuda())[0, 0].cpu().numpy()
+        ref_b = gen(torch.nn.functional.pad(m_b, (0, 0, 0, 4)).cuda())[0, 0].cpu().numpy()
+    sr, wa = wavfile.read(tmp_path / "syn" / "a_from_mel.wav")
+    _, wb = wavfile.read(tmp_path / "syn" / "b_from_mel.wav")
+    assert sr == 11413 and wa.shape == (9 * 420,) and wb.shape == (5 * 420,)
+    assert np.abs(wa - ref_a).max() < 2e-4 and np.abs(wb - ref_b).max() < 2e-4      # ragged batch == own B=1 run
+    assert (tmp_path / "syn" / "overall_synthesis_stats.json").exists()
+    outs = inference_e2e.main(["--input_mels_dir", str(mels), "--output_dir", str(tmp_path / "e2e"),
+                               "--checkpoint_file", str(tmp_path / "g_00000002")])
+    assert len(outs) == 2
+    sr, ia = wavfile.read(tmp_path / "e2e" / "a_mel_generated_e2e.wav")
+    assert sr == 11413 and ia.dtype == np.int16 and np.abs(ia.astype(np.float32) / 32768.0 - ref_a).max() < 1e-3
