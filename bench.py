@@ -254,6 +254,8 @@ def main():
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=device)
 
     from mri2speech_b200 import _lib, synth
