@@ -22,7 +22,16 @@ namespace m2s {
 namespace {
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ float fsilu2(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+// float activations (tf32 / fp32 builds): exact-ish SiLU; fp16 activations: one-MUFU form h + h*tanh(h), h = v/2
+// (tanh.approx.f32, relative error 2^-11 = the rounding of the fp16 store that follows)
+template <typename T>
+__device__ __forceinline__ float fsilu2(float v) {
+  if (sizeof(T) == 4) return __fdividef(v, 1.f + __expf(-v));
+  const float h = 0.5f * v;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 lds4(const __half* p) {
@@ -189,7 +198,7 @@ __global__ void __launch_bounds__(256) dwconv_tma_kernel(const __grid_constant__
         T* op = out + (static_cast<size_t>(f0 + fs) * hw + y * W + x0) * prm.C + c;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          o[k].x = fsilu2(o[k].x); o[k].y = fsilu2(o[k].y); o[k].z = fsilu2(o[k].z); o[k].w = fsilu2(o[k].w);
+          o[k].x = fsilu2<T>(o[k].x); o[k].y = fsilu2<T>(o[k].y); o[k].z = fsilu2<T>(o[k].z); o[k].w = fsilu2<T>(o[k].w);
           if (c_ok && f_ok) stg4(op + static_cast<size_t>(k) * prm.C, o[k]);
           fsum.x += o[k].x; fsum.y += o[k].y; fsum.z += o[k].z; fsum.w += o[k].w;
         }

@@ -59,6 +59,17 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "vocoder16":
         run(32, 17920, 128, 3, 1, half=True, outs="16", knobs={"pair": 0, "dbg": dbg})
     sys.exit(0)
 
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "encoder16":
+    # encoder IR-stage GEMMs with fp16 operands on the single-CTA kernel
+    S = _lib.ACT_SILU
+    for dbg in (0, 1, 9):
+        run(1, 65536, 120, 1, 0, N=720, act=S, shifts=[0], half=True, outs="16", knobs={"pair": 0, "dbg": dbg})   # stage 4 expand
+    for dbg in (0, 9):
+        run(1, 65536, 720, 1, 0, N=120, act=_lib.ACT_NONE, shifts=[0], half=True, outs="both", res=True,
+            knobs={"pair": 0, "dbg": dbg})                                                                       # stage 4 project
+        run(1, 16384, 208, 1, 0, N=1248, act=S, shifts=[0], half=True, outs="16", knobs={"pair": 0, "dbg": dbg})  # stage 5 expand
+    sys.exit(0)
+
 if __name__ == "__main__":
     S = _lib.ACT_SILU
     for dbg in (0, 1, 2, 4, 7, 16, 23):
