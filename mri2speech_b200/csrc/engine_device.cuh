@@ -312,17 +312,28 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
   int len_rows = 0x7fffffff;
   if (mask_mode == M2S_MASK_LEN) len_rows = __ldg(e.lens + b) * e.len_scale;
   const size_t d_base = static_cast<size_t>(b) * p.d_batch_rows + p.d_row_offset;
+  // The accumulator registers of unit u+2 are requested from TMEM as soon as unit u's have been parked in the SMEM
+  // staging buffer: the TMEM read of the next unit overlaps the arithmetic / global traffic of the current one.
+  uint32_t r[32];
+  auto issue_tmem_ld = [&](int uu) {
+    const int sub_ = uu / nchunks;
+    const int c0_ = (uu - sub_ * nchunks) << 5;
+    tmem_ld16(tmem_acc + sub_ * n_tile + c0_, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+    if (c0_ + 16 < n_tile) tmem_ld16(tmem_acc + sub_ * n_tile + c0_ + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+  };
+  const bool pipelined = ew_.dbg == 0;
+  if (pipelined && half < units) issue_tmem_ld(half);
   for (int u = half; u < units; u += 2) {
     const int sub = u / nchunks;
     const int c0 = (u - sub * nchunks) << 5;
     const int qw = q0 + sub * 128 + quad * 32;  // first row of this warp's 32-row slab
-    uint32_t r[32];
-    if (!(ew_.dbg & 2)) {
-      tmem_ld16(tmem_acc + sub * n_tile + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-      if (c0 + 16 < n_tile) tmem_ld16(tmem_acc + sub * n_tile + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
-    } else {
+    if (!pipelined) {
+      if (!(ew_.dbg & 2)) {
+        issue_tmem_ld(u);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) r[j] = 0x3f800000u + j + lane;
+        for (int j = 0; j < 32; ++j) r[j] = 0x3f800000u + j + lane;
+      }
     }
     // While the TMEM read is in flight: bias / residual / accumulate loads of this unit (the output may alias
     // them in place, so every load is issued before the first store).  Thread (rr0, cc) owns rows rr0 + 4i,
@@ -372,18 +383,22 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
                        "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
                        : "memory");
         __syncwarp();
-        // each row is stored as soon as it is computed (nothing but the prefetched operands stays live: the kernel
-        // runs at the 168-register cap of a 10-warp CTA)
+        if (u + 2 < units) issue_tmem_ld(u + 2);   // (fast path implies pipelined)
+        // each row is stored as soon as it is computed (the kernel runs at the 168-register cap of a 10-warp CTA)
         float4* dp = reinterpret_cast<float4*>(p.d + row0 * p.d_ld + n);
         uint2* hp = reinterpret_cast<uint2*>(static_cast<__half*>(p.d16) + row0 * p.d_ld + n);
         const bool st32 = p.d != nullptr, st16 = p.d16 != nullptr;
+        float4 a8[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + rr0;
-          float4 a4;
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w)
+                       : "=f"(a8[i].x), "=f"(a8[i].y), "=f"(a8[i].z), "=f"(a8[i].w)
                        : "r"(stage + rr * 128 + ((cc ^ (rr & 7)) << 4)));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 a4 = a8[i];
           const float4 r4 = kHasRes ? res4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
           const float4 c4 = kHasAcc ? acc4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
           float4 o;
@@ -453,6 +468,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
                      : "memory");
       __syncwarp();
     }
+    if (pipelined && u + 2 < units) issue_tmem_ld(u + 2);
     // all 8 rows' (32 independent) element chains are computed unconditionally so the scheduler can interleave
     // them; only the stores are predicated
     float4 o[8];
