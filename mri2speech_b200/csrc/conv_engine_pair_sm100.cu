@@ -134,6 +134,7 @@ conv_engine_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
   }
   cluster_sync_all();  // barrier inits of both CTAs visible before any remote signal / TMA
+  const uint32_t bias_smem = stage_bias(p, stage_base);
   if (warp == 1) tmem_alloc2(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
@@ -231,7 +232,7 @@ conv_engine_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   } else {
     // ===================== epilogue warps (each CTA drains its own 128 TMEM lanes) =====================
     const int ew = warp - 2;
-    const EpiWarp epw = make_epi_warp(p.epi, stage_base, ew, warp, lane, prm.dbg);
+    const EpiWarp epw = make_epi_warp(p.epi, stage_base, ew, warp, lane, prm.dbg, bias_smem);
     int acc = 0;
     uint32_t pacc = 0;
     for (int tile = pair; tile < prm.total_tiles; tile += npairs) {
@@ -332,7 +333,7 @@ int conv_tcgen05_pair(const ConvProblem& p, const PackedWeights& w, cudaStream_t
   while (prm.tg > 1 && ((prm.tg * prm.b_tap_bytes) & 1023u)) --prm.tg;
   prm.b_stage_bytes = static_cast<uint32_t>(prm.tg) * prm.b_tap_bytes;
   if (prm.b_stage_bytes & 1023u) return fail(M2S_ERR_UNSUPPORTED, "pair mode: weight stage not 1 KB aligned");
-  const uint32_t bar_bytes = 1024 + kEpiWarps * 4096;
+  const uint32_t bar_bytes = 1024 + kEpiSmemBytes;
   int na = 2, nb = 2;
   auto total = [&](int a, int b) { return a * prm.a_stage_bytes + b * prm.b_stage_bytes + bar_bytes + 1024u; };
   if (total(na, nb) > kSmemBudget + 24 * 1024) return fail(M2S_ERR_UNSUPPORTED, "pair mode: tile does not fit SMEM");

@@ -66,6 +66,7 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     fence_barrier_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
   }
+  const uint32_t bias_smem = stage_bias(p, stage_base);
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
@@ -197,7 +198,7 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     // TMEM -> registers (row per thread) -> SMEM transpose (XOR-swizzled, conflict-free) -> coalesced global
     // traffic: 8 lanes cover one 128-byte row segment, a warp instruction covers 4 rows.
     const int ew = warp - 2;  // 0..7
-    const EpiWarp epw = make_epi_warp(p.epi, stage_base, ew, warp, lane, prm.dbg);
+    const EpiWarp epw = make_epi_warp(p.epi, stage_base, ew, warp, lane, prm.dbg, bias_smem);
     int acc = 0;
     uint32_t pacc = 0;
     int it = 0;
@@ -210,7 +211,10 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       tc_fence_after();
       if (ew == 0 && lane == 0) trace_stamp(prm, it, 7);
       const uint32_t tmem_acc = tmem_base + acc * prm.acc_stride + (static_cast<uint32_t>(epw.quad * 32) << 16);
-      epilogue_tile<kEpi>(p, epw, tmem_acc, b, mt * prm.m_tile, nt * n_tile, msub, n_tile);
+      unsigned long long* us = nullptr;
+      if (prm.trace && blockIdx.x == 0 && it < prm.trace_tiles && ew == 0 && lane == 0)
+        us = prm.trace + prm.trace_tiles * 9 + it * 8;
+      epilogue_tile<kEpi>(p, epw, tmem_acc, b, mt * prm.m_tile, nt * n_tile, msub, n_tile, 0x7fffffff, us);
       tc_fence_before();
       __syncwarp();
       if (ew == 0 && lane == 0) trace_stamp(prm, it, 8);
@@ -519,7 +523,7 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
   prm.b_stage_bytes = static_cast<uint32_t>(tg) * prm.b_tap_bytes;
   const uint32_t b_stage_alloc = (prm.b_stage_bytes + 1023u) & ~1023u;
   // stage counts inside the budget: at least 2 A + 2 B
-  const uint32_t bar_bytes = 1024 + kEpiWarps * 4096;  // barriers + epilogue staging
+  const uint32_t bar_bytes = 1024 + kEpiSmemBytes;  // barriers + epilogue staging
   int na = 2, nb = 2;
   auto total = [&](int a, int b) { return a * prm.a_stage_bytes + b * b_stage_alloc + bar_bytes + 1024u; };
   if (total(na, nb) > kSmemBudget + 24 * 1024)

@@ -16,6 +16,22 @@ constexpr int kTmemCols = 512;
 constexpr int kMaxStagesA = 4;
 constexpr int kMaxStagesB = 8;
 constexpr uint32_t kSmemBudget = 200 * 1024;  // > 114 KB forces 1 CTA / SM (TMEM is allocated whole)
+// The bias vector is staged in SMEM once per kernel when it has at most this many entries (everything but the
+// LSTM input projection): a per-unit __ldg of the bias sat on the epilogue's critical path with ~500 cycles of
+// exposed latency per 32 x 32 unit (measured with the intra-unit stamps of tools/trace_engine.py micro).
+constexpr int kBiasSmemFloats = 1280;
+constexpr uint32_t kEpiSmemBytes = kEpiWarps * 4096 + kBiasSmemFloats * 4;  // transpose staging + staged bias
+
+// all threads of the CTA, before the first __syncthreads
+__device__ __forceinline__ uint32_t stage_bias(const ConvProblem& p, uint32_t stage_base) {
+  if (p.n > kBiasSmemFloats) return 0u;
+  const uint32_t base = stage_base + kEpiWarps * 4096u;
+  for (int i = threadIdx.x; i < p.n; i += blockDim.x) {
+    const float v = p.epi.bias ? __ldg(p.epi.bias + i) : 0.f;
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + 4u * i), "f"(v) : "memory");
+  }
+  return base;
+}
 
 struct EngineParams {
   ConvProblem p;
@@ -265,6 +281,7 @@ __device__ __forceinline__ float epi_elem(const EpiConsts& c, float acc, float b
 struct EpiWarp {
   EpiConsts ec;
   uint32_t stage;  // this warp's 4 KB transpose staging (shared::cta address)
+  uint32_t bias_smem;  // staged bias vector (shared::cta address), 0 = read the bias from global memory
   int quad, half, lane, rr0, cc;
   int mask_mode;
   bool has_res, has_acc;
@@ -272,8 +289,9 @@ struct EpiWarp {
 };
 
 __device__ __forceinline__ EpiWarp make_epi_warp(const Epilogue& e, uint32_t stage_base, int ew, int warp, int lane,
-                                                 int dbg = 0) {
+                                                 int dbg = 0, uint32_t bias_smem = 0u) {
   EpiWarp w;
+  w.bias_smem = bias_smem;
   w.dbg = dbg;
   w.quad = warp & 3;  // TMEM lane quadrant this warp may access
   w.half = ew >> 2;   // which of the two warps of the quadrant
@@ -299,7 +317,11 @@ __device__ __forceinline__ EpiWarp make_epi_warp(const Epilogue& e, uint32_t sta
 // `q_end` (exclusive) bounds the rows this tile may write (the fused pair kernel keeps only part of a tile).
 template <int kEpi>
 __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWarp& ew_, uint32_t tmem_acc, int b, int q0,
-                                              int n0, int msub, int n_tile, int q_end = 0x7fffffff) {
+                                              int n0, int msub, int n_tile, int q_end = 0x7fffffff,
+                                              unsigned long long* ustamp = nullptr) {
+  // `ustamp` (debug, one lane of one warp): clock64 stamps inside the FIRST fast-path unit of the tile --
+  // [0] unit start, [1] accumulators arrived from TMEM, [2] parked in the staging buffer, [3] first row computed,
+  // [4] all rows computed and stores issued
   const int row_end = min(p.l_out, q_end);
   const Epilogue& e = p.epi;
   const EpiConsts& ec = ew_.ec;
@@ -353,7 +375,11 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
                         row_end - qw >= 32 && rows_valid_u >= 32 && !ew_.dbg;
       if (fast) {
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+        if (ew_.bias_smem)
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(bias4.x), "=f"(bias4.y), "=f"(bias4.z), "=f"(bias4.w)
+                       : "r"(ew_.bias_smem + 4u * n));
+        else if (e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
         const size_t row0 = d_base + qw + rr0;
         float4 res4[8], acc4[8];
         if (kHasRes) {
@@ -376,13 +402,17 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
             for (int i = 0; i < 8; ++i) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
+        const bool stamp = ustamp != nullptr && u == half;
+        if (stamp) ustamp[0] = clock64();
         tmem_ld_wait();
+        if (stamp) ustamp[1] = clock64();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + lane * 128 + ((j ^ (lane & 7)) << 4)),
                        "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
                        : "memory");
         __syncwarp();
+        if (stamp) ustamp[2] = clock64();
         if (u + 2 < units) issue_tmem_ld(u + 2);   // (fast path implies pipelined)
         // each row is stored as soon as it is computed (the kernel runs at the 168-register cap of a 10-warp CTA)
         float4* dp = reinterpret_cast<float4*>(p.d + row0 * p.d_ld + n);
@@ -413,7 +443,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
             asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(o.w), "f"(o.z));
             hp[static_cast<size_t>(i) * p.d_ld] = pk;
           }
+          if (stamp && i == 0) ustamp[3] = clock64();
         }
+        if (stamp) ustamp[4] = clock64();
         __syncwarp();
         continue;
       }

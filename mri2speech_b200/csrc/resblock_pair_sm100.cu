@@ -97,6 +97,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   }
   for (int i = threadIdx.x; i < prm.n; i += blockDim.x)
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias1_smem + 4u * i), "f"(__ldg(prm.bias1 + i)) : "memory");
+  const uint32_t bias_smem = stage_bias(p, stage_base);
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
@@ -223,7 +224,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   } else {
     // ===================== epilogue warps =====================
     const int ew = warp - 2;
-    const EpiWarp epw = make_epi_warp(p.epi, stage_base, ew, warp, lane, prm.dbg);
+    const EpiWarp epw = make_epi_warp(p.epi, stage_base, ew, warp, lane, prm.dbg, bias_smem);
     const int quad = epw.quad, half = epw.half;
     const int nchunks = (n + 31) >> 5;
     const int kb_shift = prm.kblock == 64 ? 6 : 5;
@@ -396,7 +397,7 @@ int resblock_pair_fused(const ConvProblem& p1, const PackedWeights& w1, const Co
   prm.t_buf_bytes = prm.cblocks2 * prm.t_kb_bytes;
   prm.b_tap_bytes = static_cast<uint32_t>(prm.n * prm.row_bytes);
   // SMEM plan: A stages, T buffers, weight stages (tap groups), staging
-  const uint32_t fixed = 1024u + kEpiWarps * 4096u + 1024u;
+  const uint32_t fixed = 1024u + kEpiSmemBytes + 1024u;
   const uint32_t budget = 225u * 1024u;
   int na = 2;
   uint32_t used = fixed + na * prm.a_stage_bytes + prm.nbuf * prm.t_buf_bytes;

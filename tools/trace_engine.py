@@ -21,7 +21,7 @@ def run(B, L, C, k, d, res=False, tiles=40, knobs=None, N=None, act=None, shifts
     r = torch.randn(B, L, N, device="cuda") if res else None
     shifts = shifts or [-(k - 1 - j) * d for j in range(k)]
     out = torch.empty(B, L, N, device="cuda")
-    buf = torch.zeros(tiles * 9, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(tiles * 17, dtype=torch.int64, device="cuda")
     out16 = torch.empty(B, L, N, device="cuda", dtype=torch.float16) if outs in ("16", "both") else None
     kw = dict(bias=bias, res=r, res_inv_slope=10.0 if res else 1.0, act=act, act_slope=0.1, out=out, out16=out16,
               want_d32=outs in ("32", "both"))
@@ -30,7 +30,8 @@ def run(B, L, C, k, d, res=False, tiles=40, knobs=None, N=None, act=None, shifts
     _lib.conv_fwd(a, w, shifts, L, **kw)
     torch.cuda.synchronize()
     _lib.check(_lib.lib().m2s_debug_trace(None, 0))
-    t = buf.cpu().view(tiles, 9)
+    micro = buf.cpu()[tiles * 9:].view(tiles, 8)
+    t = buf.cpu()[:tiles * 9].view(tiles, 9)
     valid = int((t[:, 8] > 0).sum())
     t = t[:valid]
     tiles = valid
@@ -47,6 +48,11 @@ def run(B, L, C, k, d, res=False, tiles=40, knobs=None, N=None, act=None, shifts
           f"epilogue wait {f(t[s0:, 7] - t[s0:, 6]):.0f}; mma issue {f(t[s0:, 5] - t[s0:, 4]):.0f}; "
           f"mma wait acc {f(t[s0:, 4] - t[s0:, 3]):.0f}; producer a_empty wait {f(t[s0:, 1] - t[s0:, 0]):.0f}; "
           f"producer issue {f(t[s0:, 2] - t[s0:, 1]):.0f}; total {int(t[tiles-1, 8]) - t0} cycles")
+    m = micro[s0:tiles]
+    if int((m[:, 4] > 0).sum()) > 0:
+        m = m[m[:, 4] > 0]
+        print(f"   first unit of the tile (warp 2): TMEM wait {f(m[:, 1] - m[:, 0]):.0f}; park in staging {f(m[:, 2] - m[:, 1]):.0f}; "
+              f"first row done {f(m[:, 3] - m[:, 2]):.0f}; rows 1-7 + stores {f(m[:, 4] - m[:, 3]):.0f}; unit total {f(m[:, 4] - m[:, 0]):.0f}")
 
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "vocoder16":
@@ -57,6 +63,14 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "vocoder16":
         run(32, 107520, 32, 11, 1, half=True, outs="both", res=True, knobs={"pair": 0, "dbg": dbg})
         run(32, 53760, 64, 3, 1, half=True, outs="16", knobs={"pair": 0, "dbg": dbg})
         run(32, 17920, 128, 3, 1, half=True, outs="16", knobs={"pair": 0, "dbg": dbg})
+    sys.exit(0)
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "micro":
+    S = _lib.ACT_SILU
+    run(1, 65536, 120, 1, 0, N=720, act=S, shifts=[0], half=True, outs="16", knobs={"pair": 0})        # SiLU, fp16 out
+    run(32, 17920, 128, 3, 1, half=True, outs="16", knobs={"pair": 0})                                  # lrelu, fp16 out
+    run(32, 17920, 128, 3, 1, half=True, outs="both", res=True, knobs={"pair": 0})                      # RB, both outs
+    run(32, 53760, 64, 3, 1, half=True, outs="both", res=True, knobs={"pair": 0})
     sys.exit(0)
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "encoder16":
