@@ -19,6 +19,17 @@ namespace m2s {
 
 namespace {
 
+// SiLU.  float activations (tf32 / fp32 builds): exp + divide.  fp16 activations (fp16 build): the one-MUFU form
+// h + h * tanh(h), h = v / 2 (tanh.approx.f32, relative error 2^-11 = the rounding of the fp16 store that follows);
+// the two-MUFU form makes these memory-bound kernels MUFU-bound (16 MUFU lanes per SM per clock).
+template <typename T>
+__device__ __forceinline__ float silu_t(float v) {
+  if (sizeof(T) == 4) return __fdividef(v, 1.f + __expf(-v));
+  const float h = 0.5f * v;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 __device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); }
 
 // 4 consecutive channels <-> float4
@@ -129,7 +140,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const void* __restrict__ fram
           for (int c = 0; c < 8; ++c) v[c] = fmaf(px, sw[(dy * 3 + dx) * 32 + cg + c], v[c]);
         }
 #pragma unroll
-      for (int c = 0; c < 8; ++c) v[c] = silu(v[c]);
+      for (int c = 0; c < 8; ++c) v[c] = sizeof(T) == 4 ? silu(v[c]) : silu_t<T>(v[c]);
     }
     T* o = orow + static_cast<size_t>(j) * 32 + cg;
     store4(o, make_float4(v[0], v[1], v[2], v[3]));
@@ -177,8 +188,6 @@ __global__ void im2col_s2_kernel(const float* __restrict__ in, float* __restrict
   }
 }
 
-__device__ __forceinline__ float fsilu(float v) { return __fdividef(v, 1.f + __expf(-v)); }
-
 // Depthwise 3x3 + bias (folded BN) + SiLU, with the SE squeeze (per-frame channel sums) fused.
 // Input pixel (y, x) is row (y + oy) * pitch_in + (x + ox) of the frame.  TF "same" padding: stride 1 pads 1/1,
 // stride 2 pads 0/1 -- both are served by ONE zero-bordered SMEM slab ((Hin+2) x (Win+2) pixels x 32 channels),
@@ -190,7 +199,8 @@ __global__ void __launch_bounds__(256, 3) dwconv_kernel(const T* __restrict__ in
                                                         const float* __restrict__ bias, int C, int Hin, int Win,
                                                         int pitch_in, int oy, int ox, int rows_in, int wo_shift,
                                                         int n_frames) {
-  extern __shared__ float4 slab[];  // [kF][(Hin+2)*(Win+2)][8 quads]
+  extern __shared__ __align__(16) unsigned char slab_raw[];  // [kF][(Hin+2)*(Win+2)][32 channels] of T
+  T* slab = reinterpret_cast<T*>(slab_raw);
   __shared__ float4 red[32][8];
   const int Ho = Hin / kStride, Wo = Win / kStride, Wp = Win + 2;
   const int hw = Ho * Wo, spix = (Hin + 2) * Wp;
@@ -207,8 +217,8 @@ __global__ void __launch_bounds__(256, 3) dwconv_kernel(const T* __restrict__ in
     for (int pix = pl; pix < spix; pix += 32) {
       const int yp = pix / Wp, xp = pix - yp * Wp;
       const bool inside = f_ok && c_ok && yp >= 1 && yp <= Hin && xp >= 1 && xp <= Win;
-      slab[(f * spix + pix) * 8 + cq] =
-          inside ? load4(src + (static_cast<size_t>(yp - 1 + oy) * pitch_in + (xp - 1 + ox)) * C + c) : z4;
+      store4(slab + (f * spix + pix) * 32 + cq * 4,
+             inside ? load4(src + (static_cast<size_t>(yp - 1 + oy) * pitch_in + (xp - 1 + ox)) * C + c) : z4);
     }
   }
   float4 wv[9], b4 = z4;
@@ -225,17 +235,17 @@ __global__ void __launch_bounds__(256, 3) dwconv_kernel(const T* __restrict__ in
     for (int p = pl; p < hw; p += 32) {
       const int y = wo_shift >= 0 ? (p >> wo_shift) : p / Wo;
       const int x = p - y * Wo;
-      const float4* base = slab + (f * spix + (y * kStride + kOff) * Wp + x * kStride + kOff) * 8 + cq;
+      const T* base = slab + (f * spix + (y * kStride + kOff) * Wp + x * kStride + kOff) * 32 + cq * 4;
       float4 v = b4;
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
-          const float4 a = base[(dy * Wp + dx) * 8];
+          const float4 a = load4(base + (dy * Wp + dx) * 32);
           const float4 ww = wv[dy * 3 + dx];
           v.x = fmaf(a.x, ww.x, v.x); v.y = fmaf(a.y, ww.y, v.y); v.z = fmaf(a.z, ww.z, v.z); v.w = fmaf(a.w, ww.w, v.w);
         }
-      v.x = fsilu(v.x); v.y = fsilu(v.y); v.z = fsilu(v.z); v.w = fsilu(v.w);
+      v.x = silu_t<T>(v.x); v.y = silu_t<T>(v.y); v.z = silu_t<T>(v.z); v.w = silu_t<T>(v.w);
       if (c_ok) store4(out + (static_cast<size_t>(f0 + f) * hw + p) * C + c, v);
       acc_sum.x += v.x; acc_sum.y += v.y; acc_sum.z += v.z; acc_sum.w += v.w;
     }
@@ -438,7 +448,7 @@ namespace {
 template <typename T>
 int dwconv_launch(const T* in, T* out, float* sums, const float* w, const float* bias, int n, int C, int Hin, int Win,
                   int pitch_in, int oy, int ox, int rows_in, int stride, cudaStream_t st) {
-  const size_t slab = static_cast<size_t>(Hin + 2) * (Win + 2) * 32 * sizeof(float);
+  const size_t slab = static_cast<size_t>(Hin + 2) * (Win + 2) * 32 * sizeof(T);
   if (slab > 200 * 1024) return fail(M2S_ERR_UNSUPPORTED, "depthwise input %dx%d too large for the SMEM slab", Hin, Win);
   if (stride != 1 && stride != 2) return fail(M2S_ERR_UNSUPPORTED, "depthwise stride %d", stride);
   // small images: several frames per block (amortises weight loads / block launch; more pixels per thread)
