@@ -365,9 +365,11 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
     constexpr bool kHasAcc = kEpi == EPI_FULL || kEpi == EPI_FULL_SILU || kEpi == EPI_RB_ACC;
     // ---- fast path: the whole 32 x 32 unit is inside the output and survives the mask (warp-uniform test): no
     // predicates, row pointers stepped by warp-uniform strides.  ~8 instructions per output instead of 20-37 on the
-    // general path.  Measured alternatives that lost: a row-per-thread epilogue straight from the TMEM registers to
-    // global memory without the SMEM transpose (1.4-2x slower: uncoalesced 16-byte accesses); prefetching the residual
-    // one unit / one tile ahead in registers or with cp.async.bulk.prefetch.L2 (slower at the 168-register cap).
+    // general path.  Measured alternatives that lost or tied (profiles/README.md): a row-per-thread epilogue straight from
+    // the TMEM registers to global memory (1.4-2x slower: uncoalesced 16-byte accesses); a fragment-layout epilogue
+    // (tcgen05.ld.16x256b + one lane-pair shuffle per column group, no SMEM transpose at all: correct, but no faster --
+    // the unit time is set by global-memory latency, not by the transpose); prefetching the residual one unit / one tile
+    // ahead in registers or with cp.async.bulk.prefetch.L2 (slower at the 168-register cap).
     {
       int rows_valid_u = 32;
       if (mask_mode == M2S_MASK_LEN) rows_valid_u = len_rows - (qw + p.d_row_offset);
