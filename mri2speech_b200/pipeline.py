@@ -135,26 +135,31 @@ def gather_waveforms(local: Sequence[torch.Tensor], local_ids: Sequence[int], ds
     dev = local[0].device if len(local) else torch.device("cpu")
     if dist.get_backend() == "nccl" and dev.type != "cuda":
         dev = torch.device("cuda", torch.cuda.current_device())
+    # (id, length) pairs: built on the host, one transfer, one all_gather of a max-sized table
     n_local = torch.tensor([len(local)], dtype=torch.int64, device=dev)
     counts = [torch.zeros_like(n_local) for _ in range(world)]
     dist.all_gather(counts, n_local)
-    max_n = max(int(c.item()) for c in counts)
-    meta = torch.full((max(max_n, 1), 2), -1, dtype=torch.int64, device=dev)
+    counts_host = torch.stack(counts).cpu().view(-1).tolist()
+    max_n = max(max(counts_host), 1)
+    meta_host = torch.full((max_n, 2), -1, dtype=torch.int64)
     for k, (cid, w) in enumerate(zip(local_ids, local)):
-        meta[k, 0], meta[k, 1] = int(cid), int(w.numel())
+        meta_host[k, 0], meta_host[k, 1] = int(cid), int(w.numel())
+    meta = meta_host.to(dev)
     metas = [torch.zeros_like(meta) for _ in range(world)]
     dist.all_gather(metas, meta)
-    max_len = max(int(m[:, 1].max().item()) for m in metas)
-    buf = torch.zeros(max(max_n, 1), max(max_len, 1), dtype=torch.float32, device=dev)
+    metas_host = torch.stack(metas).cpu()
+    max_len = max(int(metas_host[:, :, 1].max().item()), 1)
+    buf = torch.zeros(max_n, max_len, dtype=torch.float32, device=dev)
     for k, w in enumerate(local):
         buf[k, : w.numel()] = w.reshape(-1).to(dev)
-    bufs = [torch.zeros_like(buf) for _ in range(world)] if rank == dst else None
+    bufs = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
     dist.gather(buf, bufs, dst=dst)
     if rank != dst:
         return None
     out = {}
     for r in range(world):
-        for k in range(int(counts[r].item())):
-            cid, n = int(metas[r][k, 0].item()), int(metas[r][k, 1].item())
+        table = metas_host[r].tolist()
+        for k in range(counts_host[r]):
+            cid, n = table[k]
             out[cid] = bufs[r][k, :n]
     return out

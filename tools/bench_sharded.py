@@ -63,7 +63,9 @@ def main():
         points = [torch.from_numpy(masking.preset_mask(mt, a)) for mt in ("lip", "tongue") for a in alphas if a < 1.0]
         points.append(None)
 
-    pipe.infer([make(150)])  # warm-up (plans, workspaces)
+    warm = pipe.infer([make(150)])  # warm-up (plans, workspaces)
+    if world > 1:  # NCCL sets up its point-to-point channels on the first gather: keep that out of the timed region
+        gather_waveforms([warm[0]["audio"]], [rank], dst=0)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
