@@ -262,51 +262,6 @@ __global__ void __launch_bounds__(256, 3) dwconv_kernel(const T* __restrict__ in
   }
 }
 
-// Squeeze-excite MLP: scale[n][c] = sigmoid(W2 silu(W1 mean + b1) + b2).  One 1024-thread block per frame:
-// phase 1 = one warp per reduced unit (float4 over channels), phase 2 = one thread per channel (coalesced over W2^T).
-__global__ void __launch_bounds__(1024) se_kernel(const float* __restrict__ sums, float* __restrict__ scales,
-                                                  const float* __restrict__ w1 /*[rd][C]*/, const float* __restrict__ b1,
-                                                  const float* __restrict__ w2t /*[rd][C]*/, const float* __restrict__ b2,
-                                                  int C, int rd, float inv_hw) {
-  extern __shared__ float sm[];  // mean[C] + r[rd]
-  float* mean = sm;
-  float* r = sm + C;
-  const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = sums[static_cast<size_t>(n) * C + c] * inv_hw;
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int c4n = C >> 2;
-  for (int j = warp; j < rd; j += nwarps) {
-    const float4* wr = reinterpret_cast<const float4*>(w1 + static_cast<size_t>(j) * C);
-    float a = 0.f;
-    for (int k = lane; k < c4n; k += 32) {
-      const float4 wv = __ldg(wr + k);
-      const float4 mv = reinterpret_cast<const float4*>(mean)[k];
-      a = fmaf(wv.x, mv.x, a); a = fmaf(wv.y, mv.y, a); a = fmaf(wv.z, mv.z, a); a = fmaf(wv.w, mv.w, a);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) {
-      a += b1[j];
-      r[j] = a / (1.f + expf(-a));
-    }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a0 = b2[c], a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int j = 0;
-    for (; j + 4 <= rd; j += 4) {
-      a0 = fmaf(__ldg(w2t + static_cast<size_t>(j) * C + c), r[j], a0);
-      a1 = fmaf(__ldg(w2t + static_cast<size_t>(j + 1) * C + c), r[j + 1], a1);
-      a2 = fmaf(__ldg(w2t + static_cast<size_t>(j + 2) * C + c), r[j + 2], a2);
-      a3 = fmaf(__ldg(w2t + static_cast<size_t>(j + 3) * C + c), r[j + 3], a3);
-    }
-    for (; j < rd; ++j) a0 = fmaf(__ldg(w2t + static_cast<size_t>(j) * C + c), r[j], a0);
-    const float a = (a0 + a1) + (a2 + a3);
-    scales[static_cast<size_t>(n) * C + c] = 1.f / (1.f + expf(-a));
-  }
-}
-
 // Squeeze-excite MLP and excite scale in ONE pass over the tensor: every block recomputes the (tiny) MLP of its frame
 // -- scale[c] = sigmoid(W2 silu(W1 mean + b1) + b2), 2 * C * rd MACs -- into SMEM and then scales its share of the
 // frame's pixels in place.  grid = (frames, splits); 1024 threads: phase 1 = one warp per reduced unit (float4 over
@@ -366,20 +321,6 @@ __global__ void __launch_bounds__(1024) se_apply_kernel(T* __restrict__ x, const
     const float4 sc = reinterpret_cast<const float4*>(scale)[c4];
     v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
     store4(xf + 4 * static_cast<size_t>(k), v);
-  }
-}
-
-// x[n][p][c] *= scale[n][c]
-template <typename T>
-__global__ void se_scale_kernel(T* __restrict__ x, const float* __restrict__ scales, int hw, int c4n, size_t total4) {
-  for (size_t k = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < total4;
-       k += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c4 = k % c4n;
-    const size_t n = k / (static_cast<size_t>(c4n) * hw);
-    float4 v = load4(x + 4 * k);
-    const float4 s = reinterpret_cast<const float4*>(scales)[n * c4n + c4];
-    v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
-    store4(x + 4 * k, v);
   }
 }
 
@@ -489,14 +430,7 @@ int enc_dwconv(const void* in, void* out, int half, float* sums, const float* w,
                        oy, ox, rows_in, stride, st);
 }
 
-int enc_se(const float* sums, float* scales, const float* w1, const float* b1, const float* w2, const float* b2, int n,
-           int C, int rd, int hw, cudaStream_t st) {
-  se_kernel<<<n, 1024, (C + rd) * sizeof(float), st>>>(sums, scales, w1, b1, w2, b2, C, rd, 1.f / hw);
-  M2S_CUDA_OK(cudaGetLastError());
-  return M2S_OK;
-}
-
-// SE MLP + excite scale fused (replaces enc_se + enc_se_scale).
+// SE MLP + excite scale, one pass.
 int enc_se_apply(void* x, int half, const float* sums, const float* w1, const float* b1, const float* w2, const float* b2,
                  int n, int C, int rd, int hw, cudaStream_t st) {
   const size_t bytes = static_cast<size_t>(hw) * C * (half ? 2 : 4);
@@ -509,16 +443,6 @@ int enc_se_apply(void* x, int half, const float* sums, const float* w1, const fl
     se_apply_kernel<<<grid, 1024, sm, st>>>(static_cast<__half*>(x), sums, w1, b1, w2, b2, C, rd, hw, 1.f / hw);
   else
     se_apply_kernel<<<grid, 1024, sm, st>>>(static_cast<float*>(x), sums, w1, b1, w2, b2, C, rd, hw, 1.f / hw);
-  M2S_CUDA_OK(cudaGetLastError());
-  return M2S_OK;
-}
-
-int enc_se_scale(void* x, int half, const float* scales, int n, int hw, int C, cudaStream_t st) {
-  const size_t total4 = static_cast<size_t>(n) * hw * (C / 4);
-  unsigned blocks = static_cast<unsigned>((total4 + 255) / 256);
-  if (blocks > 148u * 16u) blocks = 148u * 16u;
-  if (half) se_scale_kernel<<<blocks, 256, 0, st>>>(static_cast<__half*>(x), scales, hw, C / 4, total4);
-  else se_scale_kernel<<<blocks, 256, 0, st>>>(static_cast<float*>(x), scales, hw, C / 4, total4);
   M2S_CUDA_OK(cudaGetLastError());
   return M2S_OK;
 }

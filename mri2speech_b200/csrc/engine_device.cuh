@@ -148,19 +148,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// SMEM matrix descriptor, K-major, SWIZZLE_128B: rows of 128 B, 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, int base_offset_mode) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);        // start address  [0,14)
-  d |= static_cast<uint64_t>(1) << 16;                       // LBO (unused for swizzled K-major) [16,30)
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;               // SBO = 1024 B   [32,46)
-  d |= static_cast<uint64_t>(1) << 46;                       // descriptor version (Blackwell) [46,48)
-  if (base_offset_mode) d |= static_cast<uint64_t>((saddr >> 7) & 7) << 49;  // base offset [49,52)
-  d |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B    [61,64)
-  return d;
-}
-
-// Same for rows of `row_bytes` (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B); 8-row groups are 8 * row_bytes apart.
+// SMEM matrix descriptor (without the start address), K-major, rows of `row_bytes` (128 -> SWIZZLE_128B, 64 ->
+// SWIZZLE_64B); 8-row groups are 8 * row_bytes apart.  base_offset stays 0: the hardware swizzles on absolute SMEM
+// address bits, so a start address advanced by whole rows needs no correction (profiles/probe_r01.log).
 inline uint64_t make_desc_hi(int row_bytes) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>(1) << 16;
