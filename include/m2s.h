@@ -154,6 +154,13 @@ size_t m2s_generator_workspace_bytes(const m2s_generator* g, int32_t batch, int3
 int m2s_generator_forward(m2s_generator* g, const float* mel, int32_t batch, int32_t frames,
                           const int32_t* lengths, float* audio, void* workspace, size_t workspace_bytes,
                           m2s_stream_t stream);
+/* Same forward, fed with conv_pre's operand directly: mel_btc = device (batch, frames, num_mels), channels-last, rows
+ * past lengths[b] zero -- exactly the mel_log output of m2s_mel_glue.  This is how the de-normalisation of
+ * scripts/run_mri_video_inference.py:160-163,232-239 is fused into the vocoder's conv_pre load: the glue kernel writes
+ * the tensor conv_pre's TMA reads, no (B, n_mels, T) tensor and no layout pass in between. */
+int m2s_generator_forward_btc(m2s_generator* g, const float* mel_btc, int32_t batch, int32_t frames,
+                              const int32_t* lengths, float* audio, void* workspace, size_t workspace_bytes,
+                              m2s_stream_t stream);
 /* Number of kernels one forward launches (for bench.py's gpu_launches). */
 int m2s_generator_launches(const m2s_generator* g);
 

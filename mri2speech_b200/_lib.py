@@ -66,6 +66,7 @@ class AcousticConfig(C.Structure):
 EXPORTS = (
     "m2s_version", "m2s_last_error_string", "m2s_device_check", "m2s_conv_fwd", "m2s_resblock_pair_fwd",
     "m2s_generator_create", "m2s_generator_destroy", "m2s_generator_workspace_bytes", "m2s_generator_forward",
+    "m2s_generator_forward_btc",
     "m2s_generator_launches",
     "m2s_acoustic_create", "m2s_acoustic_destroy", "m2s_acoustic_workspace_bytes", "m2s_acoustic_forward",
     "m2s_acoustic_forward_u8", "m2s_acoustic_encode", "m2s_acoustic_rnn_head", "m2s_acoustic_launches", "m2s_mel_glue",
@@ -104,6 +105,7 @@ def lib() -> C.CDLL:
     L.m2s_generator_workspace_bytes.restype = C.c_size_t
     L.m2s_generator_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_size_t, C.c_void_p]
+    L.m2s_generator_forward_btc.argtypes = L.m2s_generator_forward.argtypes
     L.m2s_generator_launches.argtypes = [C.c_void_p]
     missing = [name for name in EXPORTS if not hasattr(L, name)]
     if missing:

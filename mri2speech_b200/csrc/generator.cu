@@ -340,9 +340,12 @@ extern "C" size_t m2s_generator_workspace_bytes(const m2s_generator* g, int32_t 
   return plan_buffers(g, batch, frames).total_bytes;
 }
 
-extern "C" int m2s_generator_forward(m2s_generator* g, const float* mel, int32_t batch, int32_t frames,
-                                     const int32_t* lengths, float* audio, void* workspace, size_t workspace_bytes,
-                                     m2s_stream_t stream) {
+namespace {
+// mel_btc != 0: `mel` already is conv_pre's operand, channels-last (batch, frames, num_mels) with rows past lengths[b]
+// zeroed (what m2s_mel_glue writes as mel_log): no layout pass.
+int generator_forward_impl(m2s_generator* g, const float* mel, bool mel_btc, int32_t batch, int32_t frames,
+                           const int32_t* lengths, float* audio, void* workspace, size_t workspace_bytes,
+                           m2s_stream_t stream) {
   if (!g || !mel || !audio) return fail(M2S_ERR_BAD_ARG, "null argument");
   if (batch <= 0 || frames <= 0) return M2S_OK;
   const GenBuffers bufs = plan_buffers(g, batch, frames);
@@ -350,8 +353,8 @@ extern "C" int m2s_generator_forward(m2s_generator* g, const float* mel, int32_t
     return fail(M2S_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", bufs.total_bytes, workspace_bytes);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
-  float* M0 = base;
-  float* P = M0 + bufs.mel_floats;
+  const float* M0 = mel_btc ? mel : base;
+  float* P = base + bufs.mel_floats;
   float* Q = P + bufs.p_floats;
   float* R = Q + bufs.q_floats;
   float* T = R + bufs.q_floats;
@@ -366,7 +369,7 @@ extern "C" int m2s_generator_forward(m2s_generator* g, const float* mel, int32_t
   auto set_out = [](ConvProblem* p, float* buf32, void* buf16) { p->d = buf32; p->d16 = buf16; };
 
   // (B, mels, T) -> channels-last, zero past lengths (conv_pre look-ahead must see zeros)
-  M2S_TRY(bct_to_btc(mel, M0, batch, cfg.num_mels, frames, lengths, false, st));
+  if (!mel_btc) M2S_TRY(bct_to_btc(mel, base, batch, cfg.num_mels, frames, lengths, false, st));
 
   int L = frames;
   int ch = cfg.upsample_initial_channel;
@@ -431,4 +434,17 @@ extern "C" int m2s_generator_forward(m2s_generator* g, const float* mel, int32_t
   // conv_post + tanh: P holds mask(lrelu(x, .01)) as (B, L, ch)
   M2S_TRY(conv_post_tanh(P, g->post_w, g->post_bias, audio, batch, L, g->post_c, g->post_k, L, L, st));
   return M2S_OK;
+}
+}  // namespace
+
+extern "C" int m2s_generator_forward(m2s_generator* g, const float* mel, int32_t batch, int32_t frames,
+                                     const int32_t* lengths, float* audio, void* workspace, size_t workspace_bytes,
+                                     m2s_stream_t stream) {
+  return generator_forward_impl(g, mel, false, batch, frames, lengths, audio, workspace, workspace_bytes, stream);
+}
+
+extern "C" int m2s_generator_forward_btc(m2s_generator* g, const float* mel_btc, int32_t batch, int32_t frames,
+                                         const int32_t* lengths, float* audio, void* workspace,
+                                         size_t workspace_bytes, m2s_stream_t stream) {
+  return generator_forward_impl(g, mel_btc, true, batch, frames, lengths, audio, workspace, workspace_bytes, stream);
 }

@@ -34,8 +34,13 @@ def load_scaler(stats_path) -> Tuple[np.ndarray, np.ndarray]:
 
 
 def mel_glue(pred_norm: torch.Tensor, mean: torch.Tensor, std: torch.Tensor,
-             lengths: Optional[torch.Tensor] = None, want_db: bool = True, want_log: bool = True):
-    """(B,T,n) normalised mel (cuda) -> (mel_db (B,T,n), mel_log (B,T,n), vocoder input (B,n,T))."""
+             lengths: Optional[torch.Tensor] = None, want_db: bool = True, want_log: bool = True,
+             want_voc: bool = True):
+    """(B,T,n) normalised mel (cuda) -> (mel_db (B,T,n), mel_log (B,T,n), vocoder input (B,n,T)).
+
+    ``mel_log`` (B,T,n) is already the channels-last operand of the vocoder's conv_pre (rows past ``lengths`` zeroed):
+    ``Generator.forward(mel_log, channels_last=True)`` consumes it directly, in which case ``want_voc=False`` skips the
+    transposed (B,n,T) copy that only the reference-shaped call needs."""
     _lib.require_device(pred_norm)
     squeeze = pred_norm.dim() == 2
     if squeeze:
@@ -49,13 +54,13 @@ def mel_glue(pred_norm: torch.Tensor, mean: torch.Tensor, std: torch.Tensor,
         raise ValueError("Scaler mean/std length does not match n_mels")
     mel_db = torch.empty_like(pred_norm) if want_db else None
     mel_log = torch.empty_like(pred_norm) if want_log else None
-    voc_in = torch.empty(B, M, T, device=dev, dtype=torch.float32)
+    voc_in = torch.empty(B, M, T, device=dev, dtype=torch.float32) if want_voc else None
     if lengths is not None:
         lengths = lengths.to(dev, torch.int32).contiguous()
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().m2s_mel_glue(pred_norm.data_ptr(), mean.data_ptr(), std.data_ptr(), B, T, M,
                                            _lib.ptr(lengths), _lib.ptr(mel_db), _lib.ptr(mel_log),
-                                           voc_in.data_ptr(), _lib.current_stream()))
+                                           _lib.ptr(voc_in), _lib.current_stream()))
     if squeeze:
         return (None if mel_db is None else mel_db[0], None if mel_log is None else mel_log[0], voc_in)
     return mel_db, mel_log, voc_in
@@ -79,8 +84,9 @@ class MriToSpeech:
         optional (H,W) articulator ``mask``); lengths int32[B] (cpu or cuda) or None -> dict of padded tensors."""
         pred = self.acoustic(frames, lengths=lengths, mask=mask) if mask is not None else \
             self.acoustic(frames, lengths=lengths)
-        mel_db, mel_log, voc_in = mel_glue(pred, self.mean, self.std, lengths)
-        wav = self.generator(voc_in, lengths=lengths)
+        # the glue kernel writes conv_pre's operand (mel_log, channels-last) directly: no (B,n,T) tensor, no layout pass
+        mel_db, mel_log, _ = mel_glue(pred, self.mean, self.std, lengths, want_voc=False)
+        wav = self.generator(mel_log, lengths=lengths, channels_last=True)
         return {"mel_norm": pred, "mel_db": mel_db, "mel_log": mel_log, "audio": wav}
 
     @torch.no_grad()

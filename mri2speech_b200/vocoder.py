@@ -156,17 +156,23 @@ class Generator(nn.Module):
         return int(_lib.lib().m2s_generator_launches(self._handle)) if self._handle else 0
 
     # -- the drop-in call -----------------------------------------------------------------
-    def forward(self, x: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, lengths: Optional[torch.Tensor] = None,
+                channels_last: bool = False) -> torch.Tensor:
         """(B, num_mels, T) [or (num_mels, T)] float32 cuda -> (B, 1, T * prod(upsample_rates)).
 
         ``lengths`` (int32 cuda, optional extension): valid mel frames per utterance of a
         zero-padded batch; every utterance then equals its own B=1 result.
+        ``channels_last`` (extension): x is (B, T, num_mels) -- conv_pre's operand layout, e.g. the ``mel_log`` output
+        of ``pipeline.mel_glue`` (rows past ``lengths`` must be zero) -- and is consumed without a layout pass.
         """
         _lib.require_device(x)
         if x.dim() == 2:
             x = x.unsqueeze(0)
         x = x.contiguous().float()
-        B, M, T = x.shape
+        if channels_last:
+            B, T, M = x.shape
+        else:
+            B, M, T = x.shape
         with torch.cuda.device(x.device):
             if self._handle is None or self._handle_key != self._state_key():
                 self.refresh()
@@ -177,7 +183,8 @@ class Generator(nn.Module):
             out = torch.empty(B, 1, T * self.hop, dtype=torch.float32, device=x.device)
             if lengths is not None:
                 lengths = lengths.to(device=x.device, dtype=torch.int32).contiguous()
-            _lib.check(_lib.lib().m2s_generator_forward(
+            fwd = _lib.lib().m2s_generator_forward_btc if channels_last else _lib.lib().m2s_generator_forward
+            _lib.check(fwd(
                 self._handle, x.data_ptr(), B, T, _lib.ptr(lengths), out.data_ptr(),
                 self._workspace.data_ptr(), self._workspace.numel(), _lib.current_stream()))
         return out

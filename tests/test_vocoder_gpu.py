@@ -103,3 +103,18 @@ def test_cpu_tensor_is_refused():
     g = _generator("tf32")
     with pytest.raises(M2SError):
         g(torch.zeros(1, 64, 8))
+
+
+def test_channels_last_entry_equals_reference_layout():
+    """Generator.forward(mel_log, channels_last=True) -- conv_pre's operand written directly by the glue kernel -- equals
+    the reference-shaped (B, n_mels, T) call, ragged lengths included."""
+    g = _generator("fp16")
+    mel = torch.randn(3, 64, 17, generator=torch.Generator().manual_seed(11)).cuda() * 2 - 5
+    lens = torch.tensor([17, 9, 1], dtype=torch.int32).cuda()
+    btc = mel.transpose(1, 2).contiguous()
+    t = torch.arange(17, device="cuda").view(1, 17, 1)
+    btc = btc * (t < lens.view(3, 1, 1))                         # rows past the length are zero (mel_glue's contract)
+    with torch.no_grad():
+        a = g(mel, lengths=lens)
+        b = g(btc, lengths=lens, channels_last=True)
+    assert torch.equal(a, b)
