@@ -14,7 +14,7 @@ if str(PROJECT_ROOT) not in sys.path:
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from mri2speech_b200 import pipeline  # noqa: E402
+from mri2speech_b200 import io_formats, pipeline  # noqa: E402
 
 
 def load_scaler(scaler_path: Path):
@@ -74,7 +74,7 @@ def export_mels(args: argparse.Namespace) -> None:
             continue
         todo.append((mri_path, out_path))
 
-    with torch.no_grad():
+    with torch.no_grad(), io_formats.AsyncWriter() as writer:
         pending = []
 
         def flush():
@@ -89,13 +89,14 @@ def export_mels(args: argparse.Namespace) -> None:
             lt = torch.tensor(lens, dtype=torch.int32)
             pred = model(batch, lengths=lt)
             _, mel_log, _ = pipeline.mel_glue(pred, mean, std, lt, want_db=False)
-            for b, (_, out_path) in enumerate(pending):
-                np.save(out_path, mel_log[b, : lens[b]].transpose(0, 1).contiguous().cpu().numpy().astype(np.float32))
+            for b, (_, out_path) in enumerate(pending):  # (64, T) log-mel; D2H + np.save overlap the next batch
+                writer.submit(mel_log[b, : lens[b]].transpose(0, 1).contiguous(),
+                              lambda a, p=out_path: np.save(p, a.astype(np.float32)))
             pending.clear()
 
         frames_in_batch = 0
         for mri_path, out_path in todo:
-            clip = np.load(mri_path).astype(np.float32)
+            clip = io_formats.load_processed_clip(mri_path.parent).astype(np.float32)
             if pending and (frames_in_batch + clip.shape[0] > args.batch_frames
                             or clip.shape[-2:] != pending[0][0].shape[-2:]):
                 flush()

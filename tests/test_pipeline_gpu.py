@@ -161,3 +161,38 @@ def test_alternate_vocoder_clis(tmp_path):
     assert len(outs) == 2
     sr, ia = wavfile.read(tmp_path / "e2e" / "a_mel_generated_e2e.wav")
     assert sr == 11413 and ia.dtype == np.int16 and np.abs(ia.astype(np.float32) / 32768.0 - ref_a).max() < 1e-3
+
+
+def test_export_predicted_mels_cli(tmp_path):
+    """scripts/export_predicted_mels.py: samples/<ID>/mri.npy -> <ID>.npy of shape (64, T) log-mel, ragged batches equal
+    each clip's own B=1 result; --cpu and a missing samples directory are refused (SystemExit, like the reference)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import export_predicted_mels as cli
+    from mri2speech_b200 import pipeline, synth
+    ac, _ = _models()
+    torch.save({"model_state_dict": ac.state_dict()}, tmp_path / "mri.pt")
+    synth.write_scaler_json(tmp_path / "scaler.json")
+    proc = tmp_path / "processed"
+    clips = {"s01": synth.synthetic_clip(1, 5), "s02": synth.synthetic_clip(2, 3)}
+    for name, clip in clips.items():
+        (proc / "samples" / name).mkdir(parents=True)
+        arr = clip.numpy() if name == "s01" else clip.numpy()[:, None]           # (T,H,W) and (T,1,H,W) both occur
+        np.save(proc / "samples" / name / "mri.npy", arr)
+    base = ["--processed_dir", str(proc), "--mri_checkpoint", str(tmp_path / "mri.pt"), "--scaler_json",
+            str(tmp_path / "scaler.json"), "--output_dir", str(tmp_path / "mels"),
+            "--mri_code_dir", os.path.join(ROOT, "mri2speech_code")]
+    cli.export_mels(cli.parse_args(base))
+    mean, std = pipeline.load_scaler(tmp_path / "scaler.json")
+    ac = ac.cuda().eval()
+    for name, clip in clips.items():
+        got = np.load(tmp_path / "mels" / f"{name}.npy")
+        assert got.shape == (64, clip.shape[0]) and got.dtype == np.float32
+        with torch.no_grad():
+            pred = ac(clip.unsqueeze(0).cuda())
+            _, mel_log, _ = pipeline.mel_glue(pred, torch.from_numpy(mean), torch.from_numpy(std))
+        assert np.abs(got - mel_log[0].t().cpu().numpy()).max() < 2e-3
+    with pytest.raises(SystemExit):
+        cli.export_mels(cli.parse_args(base + ["--cpu", "--overwrite"]))
+    with pytest.raises(SystemExit):
+        cli.export_mels(cli.parse_args(["--processed_dir", str(tmp_path / "nope")] + base[2:]))
