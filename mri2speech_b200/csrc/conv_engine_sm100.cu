@@ -166,12 +166,13 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 const uint64_t db = desc_hi | (((b_tile + t * prm.b_tap_bytes) & 0x3FFFF) >> 4);
                 const uint32_t first = (cb | tap0 | t) ? 1u : 0u;
                 const uint64_t da0 = desc_hi | (((a_tile + row_shift * row_bytes) & 0x3FFFF) >> 4);
+                const uint32_t sub_step = (128 * row_bytes) >> 4;   // next 128-row sub-tile of the A stage
                 if (prm.half) {
-                  mma_f16_k4(tmem_acc, da0, db, prm.idesc, first, ksteps);
-                  if (msub > 1) mma_f16_k4(tmem_acc + n_tile, da0 + ((128 * row_bytes) >> 4), db, prm.idesc, first, ksteps);
+                  for (int sub = 0; sub < msub; ++sub)
+                    mma_f16_k4(tmem_acc + sub * n_tile, da0 + sub * sub_step, db, prm.idesc, first, ksteps);
                 } else {
-                  mma_tf32_k4(tmem_acc, da0, db, prm.idesc, first, ksteps);
-                  if (msub > 1) mma_tf32_k4(tmem_acc + n_tile, da0 + ((128 * row_bytes) >> 4), db, prm.idesc, first, ksteps);
+                  for (int sub = 0; sub < msub; ++sub)
+                    mma_tf32_k4(tmem_acc + sub * n_tile, da0 + sub * sub_step, db, prm.idesc, first, ksteps);
                 }
               }
             }
@@ -494,11 +495,20 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
 
   // M sub-tiles per CTA: 2 halves the weight traffic per output row; use it when there is enough work.
   int msub = knobs.msub;
-  if (msub != 1 && msub != 2) {
-    const long long tiles1 = static_cast<long long>(p.batch) * ((p.l_out + 127) / 128) * w.n_tiles;
-    // two M sub-tiles halve the weight traffic per output row; keep TWO accumulator buffers so that the
-    // epilogue of tile i overlaps the MMAs of tile i+1
-    msub = (tiles1 >= 2LL * sm_count() && 4 * w.n_tile <= kTmemCols) ? 2 : 1;
+  if (msub != 1 && msub != 2 && msub != 4 && msub != 8) {
+    // More 128-row sub-tiles per tile = less weight traffic and less halo re-load per output row, fewer barrier round
+    // trips per output.  Narrow layers (N <= 32) get up to 8 sub-tiles (1024 rows): the 3x3 convs of the encoder's first
+    // stages carry a halo of two image rows (262 rows at 128 x 128), which doubled the A traffic of a 256-row tile.
+    // Keep TWO accumulator buffers (the epilogue of tile i overlaps the MMAs of tile i+1), enough tiles to fill the
+    // machine twice, and two A stages within the SMEM budget.
+    msub = 1;
+    for (int cand = 2; cand <= 8; cand *= 2) {
+      const long long tiles = static_cast<long long>(p.batch) * ((p.l_out + 128 * cand - 1) / (128 * cand)) * w.n_tiles;
+      const size_t a_stage = static_cast<size_t>(128 * cand + halo + 16) * w.row_bytes;
+      if (2 * cand * w.n_tile <= kTmemCols && tiles >= 2LL * sm_count() && 2 * a_stage <= 150 * 1024 &&
+          (cand <= 2 || (halo >= 64 && w.n_tile <= 64)))
+        msub = cand;
+    }
   }
   if (msub * w.n_tile > kTmemCols) msub = 1;
   prm.msub = msub;
