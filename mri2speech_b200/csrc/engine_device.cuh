@@ -353,8 +353,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
     const int n = n0 + c0 + cc * 4;
     constexpr bool kHasRes = kEpi == EPI_FULL || kEpi == EPI_FULL_SILU || kEpi == EPI_RES || kEpi == EPI_RB || kEpi == EPI_RB_ACC;
     constexpr bool kHasAcc = kEpi == EPI_FULL || kEpi == EPI_FULL_SILU || kEpi == EPI_RB_ACC;
-    // ---- fast path: the whole 32 x 32 unit is inside the output and survives the mask (warp-uniform test): no
-    // predicates, row pointers stepped by warp-uniform strides.  ~8 instructions per output instead of 20-37 on the
+    // ---- fast path: all 32 rows of the unit are inside the output and survive the length mask (warp-uniform test): no
+    // row predicates, row pointers stepped by warp-uniform strides; a lane whose 4 columns fall outside a narrow / ragged
+    // N tile simply sits out (one predicate per thread); the image-border mask is evaluated per row (8 per thread).  ~8 instructions per output instead of 20-37 on the
     // general path.  Measured alternatives that lost or tied (profiles/README.md): a row-per-thread epilogue straight from
     // the TMEM registers to global memory (1.4-2x slower: uncoalesced 16-byte accesses); a fragment-layout epilogue
     // (tcgen05.ld.16x256b + one lane-pair shuffle per column group, no SMEM transpose at all: correct, but no faster --
@@ -363,11 +364,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
     {
       int rows_valid_u = 32;
       if (mask_mode == M2S_MASK_LEN) rows_valid_u = len_rows - (qw + p.d_row_offset);
-      const bool fast = mask_mode != M2S_MASK_PITCH && c0 + 32 <= n_tile && n0 + c0 + 32 <= p.n &&
-                        row_end - qw >= 32 && rows_valid_u >= 32 && !ew_.dbg;
+      const bool fast = row_end - qw >= 32 && rows_valid_u >= 32 && !ew_.dbg;
       if (fast) {
+        const bool lane_ok = (c0 + cc * 4 < n_tile) && n < p.n;
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ew_.bias_smem)
+        if (!lane_ok) {
+        } else if (ew_.bias_smem)
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                        : "=f"(bias4.x), "=f"(bias4.y), "=f"(bias4.z), "=f"(bias4.w)
                        : "r"(ew_.bias_smem + 4u * n));
@@ -376,7 +378,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
         float4 res4[8], acc4[8];
         if (kHasRes) {
           const float4* rp = reinterpret_cast<const float4*>(e.res + row0 * e.res_ld + n);
-          if (has_res) {
+          if (has_res && lane_ok) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) res4[i] = rp[static_cast<size_t>(i) * e.res_ld];
           } else {
@@ -386,7 +388,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
         }
         if (kHasAcc) {
           const float4* ap = reinterpret_cast<const float4*>(e.accum + row0 * e.accum_ld + n);
-          if (has_acc) {
+          if (has_acc && lane_ok) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc4[i] = ap[static_cast<size_t>(i) * e.accum_ld];
           } else {
@@ -409,7 +411,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
         // each row is stored as soon as it is computed (the kernel runs at the 168-register cap of a 10-warp CTA)
         float4* dp = reinterpret_cast<float4*>(p.d + row0 * p.d_ld + n);
         uint2* hp = reinterpret_cast<uint2*>(static_cast<__half*>(p.d16) + row0 * p.d_ld + n);
-        const bool st32 = p.d != nullptr, st16 = p.d16 != nullptr;
+        const bool st32 = p.d != nullptr && lane_ok, st16 = p.d16 != nullptr && lane_ok;
         float4 a8[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -417,6 +419,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                        : "=f"(a8[i].x), "=f"(a8[i].y), "=f"(a8[i].z), "=f"(a8[i].w)
                        : "r"(stage + rr * 128 + ((cc ^ (rr & 7)) << 4)));
+        }
+        // image-border mask: (mi, mj) = divmod(row, pitch) once, then stepped by 4 rows
+        int mi = 0, mj = 0;
+        if (mask_mode == M2S_MASK_PITCH) {
+          const int drow = qw + rr0 + p.d_row_offset;
+          mi = drow / e.pitch;
+          mj = drow - mi * e.pitch;
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -428,6 +437,11 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
           o.y = epi_elem<kEpi>(ec, a4.y, bias4.y, r4.y, c4.y);
           o.z = epi_elem<kEpi>(ec, a4.z, bias4.z, r4.z, c4.z);
           o.w = epi_elem<kEpi>(ec, a4.w, bias4.w, r4.w, c4.w);
+          if (mask_mode == M2S_MASK_PITCH) {
+            if (!(mi >= e.i_lo && mi < e.i_hi && mj >= e.j_lo && mj < e.j_hi)) o = make_float4(0.f, 0.f, 0.f, 0.f);
+            mj += 4;
+            if (mj >= e.pitch) { mj -= e.pitch; ++mi; }
+          }
           if (st32) dp[static_cast<size_t>(i) * p.d_ld] = o;
           if (st16) {  // fp16 copy: the tensor-core operand of the next conv (saturating conversion, never inf)
             uint2 pk;
