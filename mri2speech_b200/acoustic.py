@@ -211,6 +211,12 @@ class OTNLikeCNNBiLSTM(nn.Module):
             self._workspace = None
             self._workspace = torch.empty(need, dtype=torch.uint8, device=x.device)
 
+    def reserve(self, batch: int, frames: int, height: int = 256, width: int = 256) -> None:
+        """Size the workspace for (batch, frames) up front (see Generator.reserve)."""
+        dev = next(self.parameters()).device
+        with torch.cuda.device(dev):
+            self._prepare(torch.empty(0, device=dev), batch, frames, (height, width))
+
     def launches_per_forward(self) -> int:
         return int(_lib.lib().m2s_acoustic_launches(self._handle)) if self._handle else 0
 

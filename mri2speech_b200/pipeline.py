@@ -77,6 +77,17 @@ class MriToSpeech:
         self.std = torch.as_tensor(np.asarray(std, np.float32)).to(self.device)
         self.hop = generator.hop
 
+    def reserve(self, max_batch_frames: int = 4096, max_clip_frames: int = 600, height: int = 256, width: int = 256):
+        """Pre-size both models' workspaces for the largest padded micro-batch ``infer`` can build, so that no
+        allocation (and no implicit device synchronisation) happens once inference has started."""
+        nb = max(1, max_batch_frames // max(max_clip_frames, 1))
+        frames = max(max_clip_frames, max_batch_frames // nb)
+        self.acoustic.reserve(nb, frames, height, width)
+        self.generator.reserve(nb, frames)
+        # micro-batches of many short clips have the same padded frame count but a larger batch dimension
+        self.acoustic.reserve(max_batch_frames // 64 + 1, 64, height, width)
+        self.generator.reserve(max_batch_frames // 64 + 1, 64)
+
     @torch.no_grad()
     def infer_padded(self, frames: torch.Tensor, lengths: Optional[torch.Tensor],
                      mask: Optional[torch.Tensor] = None):

@@ -155,6 +155,18 @@ class Generator(nn.Module):
     def launches_per_forward(self) -> int:
         return int(_lib.lib().m2s_generator_launches(self._handle)) if self._handle else 0
 
+    def reserve(self, batch: int, frames: int) -> None:
+        """Size the workspace for (batch, frames) up front: a growing workspace is re-allocated (a synchronising
+        cudaFree + cudaMalloc) the first time each larger ragged batch arrives."""
+        dev = next(self.parameters()).device
+        with torch.cuda.device(dev):
+            if self._handle is None or self._handle_key != self._state_key():
+                self.refresh()
+            need = int(_lib.lib().m2s_generator_workspace_bytes(self._handle, batch, frames))
+            if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
+                self._workspace = None
+                self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+
     # -- the drop-in call -----------------------------------------------------------------
     def forward(self, x: torch.Tensor, lengths: Optional[torch.Tensor] = None,
                 channels_last: bool = False) -> torch.Tensor:
