@@ -114,6 +114,15 @@ typedef struct {
    * weights are rounded to fp16; d16 = optional second output in fp16, indexed like d (d may then be NULL) */
   int32_t a_half;
   void* d16;
+  /* split-fp16 residual stream (fp16 build of the vocoder): a tensor that is both a tensor-core operand and a
+   * residual source is stored as TWO fp16 planes, hi = fp16(v) (the operand, == d16) and lo = fp16((v - hi) * 2048),
+   * instead of an fp32 copy next to the fp16 operand copy: hi + lo / 2048 carries v to ~22 mantissa bits in 4 instead
+   * of 6 bytes (the scale keeps the remainder of small activations out of fp16's subnormal range).
+   * d16_lo: optional lo-plane output (needs d16; d is normally NULL then).  res_hi / res_lo: the residual read as
+   * float(hi) + float(lo) / 2048 (then res must be NULL); both indexed like res (res_ld elements per row). */
+  void* d16_lo;
+  const void* res_hi;
+  const void* res_lo;
 } m2s_conv_args;
 
 int m2s_conv_fwd(const m2s_conv_args* args, int impl, m2s_stream_t stream);

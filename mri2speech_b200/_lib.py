@@ -46,6 +46,7 @@ class ConvArgs(C.Structure):
         ("mask_mode", C.c_int32), ("lens", C.c_void_p), ("len_scale", C.c_int32),
         ("pitch", C.c_int32), ("i_lo", C.c_int32), ("i_hi", C.c_int32), ("j_lo", C.c_int32), ("j_hi", C.c_int32),
         ("a_half", C.c_int32), ("d16", C.c_void_p),
+        ("d16_lo", C.c_void_p), ("res_hi", C.c_void_p), ("res_lo", C.c_void_p),
     ]
 
 
@@ -189,9 +190,11 @@ def conv_fwd(a: torch.Tensor, w: torch.Tensor, shifts: Sequence[int], l_out: int
              out_scale: float = 1.0, act: int = ACT_NONE, act_slope: float = 0.0,
              lens=None, len_scale: int = 1, pitch_mask=None, d_row_offset: int = 0,
              d_rows: Optional[int] = None, out: Optional[torch.Tensor] = None,
-             out16: Optional[torch.Tensor] = None, want_d32: bool = True, _return_args: bool = False):
+             out16: Optional[torch.Tensor] = None, want_d32: bool = True, out16_lo: Optional[torch.Tensor] = None,
+             res_hi: Optional[torch.Tensor] = None, res_lo: Optional[torch.Tensor] = None, _return_args: bool = False):
     """Test helper around m2s_conv_fwd.  a: (B, L_in, C) cuda fp32 (tf32 operands) or fp16 (kind::f16 operands);
-    w: (taps, N, C) cuda fp32.  ``out16``: optional fp16 second output (same shape as the fp32 one)."""
+    w: (taps, N, C) cuda fp32.  ``out16``: optional fp16 second output (same shape as the fp32 one).
+    ``out16_lo`` / ``res_hi`` + ``res_lo``: the split-fp16 residual stream (include/m2s.h)."""
     require_device(a)
     B, L_in, Cin = a.shape
     taps, N, Cw = w.shape
@@ -201,6 +204,7 @@ def conv_fwd(a: torch.Tensor, w: torch.Tensor, shifts: Sequence[int], l_out: int
     args = ConvArgs()
     args.a_half = int(a.dtype == torch.float16)
     args.d16 = ptr(out16)
+    args.d16_lo = ptr(out16_lo); args.res_hi = ptr(res_hi); args.res_lo = ptr(res_lo)
     args.a = a.data_ptr(); args.a_batch_rows = L_in; args.a_rows = a_rows if a_rows is not None else L_in
     args.a_ld = Cin; args.c_in = Cin; args.batch = B; args.l_out = l_out; args.taps = taps
     for i, s in enumerate(shifts):

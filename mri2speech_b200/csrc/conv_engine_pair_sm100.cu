@@ -383,7 +383,8 @@ int conv_tcgen05_pair(const ConvProblem& p, const PackedWeights& w, cudaStream_t
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const EngineParams);
   static const KernelFn kernels[EPI_COUNT] = {conv_engine_pair_kernel<EPI_FULL>,  conv_engine_pair_kernel<EPI_FULL_SILU>, conv_engine_pair_kernel<EPI_BIAS>,
                                               conv_engine_pair_kernel<EPI_LRELU>, conv_engine_pair_kernel<EPI_SILU>,      conv_engine_pair_kernel<EPI_RES>,
-                                              conv_engine_pair_kernel<EPI_RB>,    conv_engine_pair_kernel<EPI_RB_ACC>};
+                                              conv_engine_pair_kernel<EPI_RB>,    conv_engine_pair_kernel<EPI_RB_ACC>,
+                                              conv_engine_pair_kernel<EPI_RB_S>,  conv_engine_pair_kernel<EPI_RB_ACC_S>};
   static bool attr_set = false;
   if (!attr_set) {
     for (KernelFn k : kernels) {

@@ -446,8 +446,15 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
     return fail(M2S_ERR_UNSUPPORTED, "fp16 operands need c_in/a_ld multiples of 8 (got %d/%d)", p.c_in, p.a_ld);
   if (!p.d && !p.d16) return fail(M2S_ERR_BAD_ARG, "no output pointer");
   if ((reinterpret_cast<uintptr_t>(p.a) & 15) || (reinterpret_cast<uintptr_t>(p.d) & 15) ||
-      (reinterpret_cast<uintptr_t>(p.d16) & 7))
+      (reinterpret_cast<uintptr_t>(p.d16) & 7) || (reinterpret_cast<uintptr_t>(p.d16_lo) & 7) ||
+      (reinterpret_cast<uintptr_t>(p.epi.res_hi) & 15) || (reinterpret_cast<uintptr_t>(p.epi.res_lo) & 15))
     return fail(M2S_ERR_BAD_ARG, "A and D must be 16-byte aligned");
+  if (p.d16_lo && !p.d16) return fail(M2S_ERR_BAD_ARG, "d16_lo (lo plane) needs d16 (hi plane)");
+  if (p.d16_lo && !lo_output_supported(choose_epilogue(p.epi)))
+    return fail(M2S_ERR_UNSUPPORTED, "d16_lo: only the bias + leaky-ReLU program and the split-residual programs write a lo plane");
+  if (choose_epilogue(p.epi) < 0 || (p.epi.res_hi && (p.n % 8 || p.epi.res_ld % 8)))
+    return fail(M2S_ERR_UNSUPPORTED, "split-fp16 residual: needs res_hi and res_lo, res == NULL, a pre-activation "
+                "residual with res_inv_slope >= 1, no activation or a leaky-ReLU with slope in (0, 1], n and res_ld multiples of 8");
   if (w.n != p.n || w.c_in != p.c_in || w.taps != p.taps)
     return fail(M2S_ERR_BAD_ARG, "packed weights do not match the problem");
   if (p.batch <= 0 || p.l_out <= 0) return M2S_OK;
@@ -460,7 +467,7 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
       const int kstep = w.half ? 16 : 8;
       const double mma_clk =
           static_cast<double>(p.taps) * ((p.c_in + kstep - 1) / kstep) * (4096.0 + 32.0 * w.n_tile) / 75.0;
-      const double out_bytes = (p.d ? 4.0 : 0.0) + (p.d16 ? 2.0 : 0.0) + (p.epi.res ? 4.0 : 0.0) + (p.epi.accum ? 4.0 : 0.0);
+      const double out_bytes = (p.d ? 4.0 : 0.0) + (p.d16 ? 2.0 : 0.0) + (p.d16_lo ? 2.0 : 0.0) + (p.epi.res || p.epi.res_hi ? 4.0 : 0.0) + (p.epi.accum ? 4.0 : 0.0);
       const double hbm_clk = 128.0 * (p.c_in * (w.half ? 2.0 : 4.0) + static_cast<double>(p.n) * out_bytes) / 23.0;
       use_pair = mma_clk > 1.5 * hbm_clk;
     }
@@ -583,7 +590,8 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
   using KernelFn = void (*)(const CUtensorMap, const EngineParams);
   static const KernelFn kernels[EPI_COUNT] = {conv_engine_kernel<EPI_FULL>,  conv_engine_kernel<EPI_FULL_SILU>, conv_engine_kernel<EPI_BIAS>,
                                               conv_engine_kernel<EPI_LRELU>, conv_engine_kernel<EPI_SILU>,      conv_engine_kernel<EPI_RES>,
-                                              conv_engine_kernel<EPI_RB>,    conv_engine_kernel<EPI_RB_ACC>};
+                                              conv_engine_kernel<EPI_RB>,    conv_engine_kernel<EPI_RB_ACC>,
+                                              conv_engine_kernel<EPI_RB_S>,  conv_engine_kernel<EPI_RB_ACC_S>};
   static bool attr_set = false;
   if (!attr_set) {
     for (KernelFn k : kernels)

@@ -212,13 +212,22 @@ struct EpiConsts {
 // epilogue is ALU-issue-bound (32K outputs per tile on 8 warps), so instructions per output are what matters.
 // EPI_RB / EPI_RB_ACC are the two ResBlock conv2 programs of the vocoder (residual stored post-leaky-ReLU and recovered
 // with min(y, y/slope); leaky-ReLU as max(v, slope*v), which also covers "no activation" with slope = 1).
+// EPI_RB_S / EPI_RB_ACC_S: the same two programs with the residual read from the split-fp16 planes (hi + lo).
 enum { EPI_FULL = 0, EPI_FULL_SILU = 1, EPI_BIAS = 2, EPI_LRELU = 3, EPI_SILU = 4, EPI_RES = 5, EPI_RB = 6, EPI_RB_ACC = 7,
-       EPI_COUNT = 8 };
+       EPI_RB_S = 8, EPI_RB_ACC_S = 9, EPI_COUNT = 10 };
 
 // Host-side choice of the epilogue program for a problem (shared by both kernels).
+// -1: a split-fp16 residual with an epilogue the two ResBlock programs do not cover (unsupported).
+inline int choose_epilogue(const Epilogue& e);
+// ... and the lo-plane output exists only in the programs that produce a split stream
+inline bool lo_output_supported(int epi) { return epi == EPI_LRELU || epi == EPI_RB_S || epi == EPI_RB_ACC_S; }
 inline int choose_epilogue(const Epilogue& e) {
   const bool lrelu_ok = (e.act == M2S_ACT_LRELU && e.act_slope > 0.f && e.act_slope <= 1.f);
   const bool plain = !e.accum && e.out_scale == 1.f;
+  if (e.res_hi) {
+    if (e.res || !e.res_lo || e.res_after_act || e.res_inv_slope < 1.f || !(lrelu_ok || e.act == M2S_ACT_NONE)) return -1;
+    return plain && lrelu_ok ? EPI_RB_S : EPI_RB_ACC_S;
+  }
   if (plain && !e.res) {
     if (e.act == M2S_ACT_SILU) return EPI_SILU;
     if (lrelu_ok) return EPI_LRELU;
@@ -241,8 +250,33 @@ __device__ __forceinline__ float fast_silu(float v) {
   return fmaf(h, t, h);
 }
 
-template <int kEpi>
+// Split-fp16 stream: hi = fp16(v), lo = fp16((v - hi) * 2^11).  The scale keeps lo in v's own exponent range: an
+// unscaled remainder of a small activation (|v| < 0.1) would land in fp16's subnormals and lose its mantissa.
+constexpr float kSplitScale = 2048.f, kSplitInvScale = 1.f / 2048.f;
+// value of 4 consecutive elements of the split-fp16 residual: bits = (hi[0:2], hi[2:4], lo[0:2], lo[2:4])
+__device__ __forceinline__ float4 split_decode(const float4& bits) {
+  const uint32_t h0 = __float_as_uint(bits.x), h1 = __float_as_uint(bits.y);
+  const uint32_t l0 = __float_as_uint(bits.z), l1 = __float_as_uint(bits.w);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h0));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&h1));
+  const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&l0));
+  const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&l1));
+  return make_float4(fmaf(c.x, kSplitInvScale, a.x), fmaf(c.y, kSplitInvScale, a.y), fmaf(d.x, kSplitInvScale, b.x),
+                     fmaf(d.y, kSplitInvScale, b.y));
+}
+// hi plane = fp16(v) (saturating), lo plane = fp16((v - hi) * 2^11)
+__device__ __forceinline__ void split_encode(const float4& o, uint2* hi, uint2* lo) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi->x) : "f"(o.y), "f"(o.x));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi->y) : "f"(o.w), "f"(o.z));
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hi->x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&hi->y));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo->x) : "f"((o.y - a.y) * kSplitScale), "f"((o.x - a.x) * kSplitScale));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo->y) : "f"((o.w - b.y) * kSplitScale), "f"((o.z - b.x) * kSplitScale));
+}
+
+template <int kEpiS>
 __device__ __forceinline__ float epi_elem(const EpiConsts& c, float acc, float bias, float res, float accum) {
+  constexpr int kEpi = kEpiS == EPI_RB_S ? EPI_RB : kEpiS == EPI_RB_ACC_S ? EPI_RB_ACC : kEpiS;
   float v = acc + bias;
   if (kEpi == EPI_BIAS) return v;
   if (kEpi == EPI_LRELU) return fmaxf(v, v * c.act_slope);  // 0 < slope <= 1
@@ -289,7 +323,7 @@ __device__ __forceinline__ EpiWarp make_epi_warp(const Epilogue& e, uint32_t sta
   w.rr0 = lane >> 3;
   w.cc = lane & 7;
   w.stage = stage_base + ew * 4096;
-  w.has_res = e.res != nullptr;
+  w.has_res = e.res != nullptr || e.res_hi != nullptr;
   w.has_acc = e.accum != nullptr;
   w.ec.inv_slope = e.res_inv_slope;
   w.ec.pre_w = (w.has_res && !e.res_after_act) ? 1.f : 0.f;
@@ -351,8 +385,14 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
     // them in place, so every load is issued before the first store).  Thread (rr0, cc) owns rows rr0 + 4i,
     // columns n .. n+3; all row predicates reduce to "4i + rr0 < bound".
     const int n = n0 + c0 + cc * 4;
-    constexpr bool kHasRes = kEpi == EPI_FULL || kEpi == EPI_FULL_SILU || kEpi == EPI_RES || kEpi == EPI_RB || kEpi == EPI_RB_ACC;
-    constexpr bool kHasAcc = kEpi == EPI_FULL || kEpi == EPI_FULL_SILU || kEpi == EPI_RB_ACC;
+    constexpr bool kSplit = kEpi == EPI_RB_S || kEpi == EPI_RB_ACC_S;  // residual = float(hi) + float(lo), fp16 planes
+    constexpr bool kHasRes = kEpi == EPI_FULL || kEpi == EPI_FULL_SILU || kEpi == EPI_RES || kEpi == EPI_RB || kEpi == EPI_RB_ACC || kSplit;
+    constexpr bool kHasAcc = kEpi == EPI_FULL || kEpi == EPI_FULL_SILU || kEpi == EPI_RB_ACC || kEpi == EPI_RB_ACC_S;
+    // programs that can write the lo plane (d16_lo): the producers of a split stream -- the transposed-conv epilogue
+    // (EPI_LRELU) and the split ResBlock programs.  Compile-time, like kCutFast below: the other programs run at the
+    // 168-register cap and every extra pointer / predicate spills in their hot loop.
+    constexpr bool kLoOut = kSplit || kEpi == EPI_LRELU;
+    constexpr bool kCutFast = !kHasAcc;  // units cut by q_end take the fast path with predicated stores
     // ---- fast path: all 32 rows of the unit are inside the output and survive the length mask (warp-uniform test): no
     // row predicates, row pointers stepped by warp-uniform strides; a lane whose 4 columns fall outside a narrow / ragged
     // N tile simply sits out (one predicate per thread); the image-border mask is evaluated per row (8 per thread).  ~8 instructions per output instead of 20-37 on the
@@ -364,7 +404,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
     {
       int rows_valid_u = 32;
       if (mask_mode == M2S_MASK_LEN) rows_valid_u = len_rows - (qw + p.d_row_offset);
-      const bool fast = row_end - qw >= 32 && rows_valid_u >= 32 && !ew_.dbg;
+      // `keep`: rows of the unit this tile may write.  A unit cut only by q_end (the fused pair kernel keeps M1 - (k-1)
+      // rows of a tile) still takes the fast path with predicated stores: its rows exist in memory, and the one warp
+      // that owns the cut unit of EVERY tile must not be slower than the other seven (it delayed the T-tile barrier of
+      // the next tile by 2-8 k cycles: tools/trace_pair.py).
+      const int keep = row_end - qw;
+      const bool fast = (kCutFast ? p.l_out : row_end) - qw >= 32 && rows_valid_u >= 32 && !ew_.dbg;
       if (fast) {
         const bool lane_ok = (c0 + cc * 4 < n_tile) && n < p.n;
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -377,8 +422,21 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
         const size_t row0 = d_base + qw + rr0;
         float4 res4[8], acc4[8];
         if (kHasRes) {
-          const float4* rp = reinterpret_cast<const float4*>(e.res + row0 * e.res_ld + n);
-          if (has_res && lane_ok) {
+          if (kSplit && lane_ok) {
+            // Lanes (cc even, cc + 1) own adjacent 4-column groups of the same rows: the even lane fetches 16 bytes
+            // (8 columns) of the hi plane, the odd lane 16 bytes of the lo plane, and they swap halves by shuffle when
+            // the row is used.  One 512-byte request per warp instruction like the fp32 residual: 8-byte loads (two
+            // 256-byte requests per row group) made the split stream SLOWER than fp32 -- the epilogue is bound by memory
+            // requests in flight, not by bytes (tools/pair_bench.py).  The hi plane is the tile conv1 just read: an L2 hit.
+            const __half* plane = static_cast<const __half*>((cc & 1) ? e.res_lo : e.res_hi);
+            const uint4* rp = reinterpret_cast<const uint4*>(plane + row0 * e.res_ld + (n & ~7));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint4 v = rp[static_cast<size_t>(i) * (e.res_ld >> 1)];
+              res4[i] = make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+            }
+          } else if (!kSplit && has_res && lane_ok) {
+            const float4* rp = reinterpret_cast<const float4*>(e.res + row0 * e.res_ld + n);
 #pragma unroll
             for (int i = 0; i < 8; ++i) res4[i] = rp[static_cast<size_t>(i) * e.res_ld];
           } else {
@@ -411,7 +469,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
         // each row is stored as soon as it is computed (the kernel runs at the 168-register cap of a 10-warp CTA)
         float4* dp = reinterpret_cast<float4*>(p.d + row0 * p.d_ld + n);
         uint2* hp = reinterpret_cast<uint2*>(static_cast<__half*>(p.d16) + row0 * p.d_ld + n);
+        uint2* lp = reinterpret_cast<uint2*>(static_cast<__half*>(p.d16_lo) + row0 * p.d_ld + n);
         const bool st32 = p.d != nullptr && lane_ok, st16 = p.d16 != nullptr && lane_ok;
+        const bool st_lo = kLoOut && p.d16_lo != nullptr;
         float4 a8[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -429,8 +489,16 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + rr0;
           const float4 a4 = a8[i];
-          const float4 r4 = kHasRes ? res4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 r4 = kHasRes ? res4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kSplit) {
+            // even lane holds hi[own 4 | neighbour's 4], odd lane lo[neighbour's 4 | own 4]: swap the neighbour's half
+            const bool odd = (cc & 1) != 0;
+            const float g0 = __shfl_xor_sync(0xffffffffu, odd ? r4.x : r4.z, 1);
+            const float g1 = __shfl_xor_sync(0xffffffffu, odd ? r4.y : r4.w, 1);
+            r4 = split_decode(odd ? make_float4(g0, g1, r4.z, r4.w) : make_float4(r4.x, r4.y, g0, g1));
+          }
           const float4 c4 = kHasAcc ? acc4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
           float4 o;
           o.x = epi_elem<kEpi>(ec, a4.x, bias4.x, r4.x, c4.x);
@@ -442,11 +510,17 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
             mj += 4;
             if (mj >= e.pitch) { mj -= e.pitch; ++mi; }
           }
-          if (st32) dp[static_cast<size_t>(i) * p.d_ld] = o;
-          if (st16) {  // fp16 copy: the tensor-core operand of the next conv (saturating conversion, never inf)
-            uint2 pk;
-            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(o.y), "f"(o.x));
-            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(o.w), "f"(o.z));
+          const bool row_ok = !kCutFast || rr < keep;   // always true unless q_end cuts this unit
+          if (st32 && row_ok) dp[static_cast<size_t>(i) * p.d_ld] = o;
+          if (st16 && row_ok) {  // fp16 copy: the tensor-core operand of the next conv (saturating conversion, never inf)
+            uint2 pk, pl;
+            if (st_lo) {  // + the lo plane: (hi, lo) together are the residual source of the next pair
+              split_encode(o, &pk, &pl);
+              lp[static_cast<size_t>(i) * p.d_ld] = pl;
+            } else {
+              asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(o.y), "f"(o.x));
+              asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(o.w), "f"(o.z));
+            }
             hp[static_cast<size_t>(i) * p.d_ld] = pk;
           }
           if (stamp && i == 0) ustamp[3] = clock64();
@@ -465,6 +539,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
     const size_t row0 = d_base + qw + rr0;
     float* dptr = p.d + row0 * p.d_ld + n;
     __half* hptr = static_cast<__half*>(p.d16) + row0 * p.d_ld + n;
+    __half* lptr = static_cast<__half*>(p.d16_lo) + row0 * p.d_ld + n;
     const size_t d_step = static_cast<size_t>(4) * p.d_ld;
     float4 res4[8], acc4[8];
 #pragma unroll
@@ -472,7 +547,19 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
       res4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (kHasRes) {
+    if (kSplit) {
+      const __half* rh = static_cast<const __half*>(e.res_hi) + row0 * e.res_ld + n;
+      const __half* rl = static_cast<const __half*>(e.res_lo) + row0 * e.res_ld + n;
+      const size_t r_step = static_cast<size_t>(4) * e.res_ld;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i * 4 + rr0 < rows_ok) {
+          const uint2 h = *reinterpret_cast<const uint2*>(rh + i * r_step), l = *reinterpret_cast<const uint2*>(rl + i * r_step);
+          res4[i] = make_float4(__uint_as_float(h.x), __uint_as_float(h.y), __uint_as_float(l.x), __uint_as_float(l.y));
+        }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) res4[i] = split_decode(res4[i]);   // zero bits decode to zero
+    } else if (kHasRes) {
       if (has_res) {
         const float* rptr = e.res + row0 * e.res_ld + n;
         const size_t r_step = static_cast<size_t>(4) * e.res_ld;
@@ -548,10 +635,10 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         if (i * 4 + rr0 < rows_ok) {
-          uint2 pk;
-          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(o[i].y), "f"(o[i].x));
-          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(o[i].w), "f"(o[i].z));
+          uint2 pk, pl;
+          split_encode(o[i], &pk, &pl);
           *reinterpret_cast<uint2*>(hptr + i * d_step) = pk;
+          if (kLoOut && p.d16_lo) *reinterpret_cast<uint2*>(lptr + i * d_step) = pl;
         }
     }
     __syncwarp();

@@ -16,6 +16,7 @@
 //   block j: c1: A=state -> T = lrelu(c1+b); c2: A=T, res=state -> R (pairs 0,1)
 //            pair 2: j=0: S = x; j=1: S += x; j=2: P = mask(lrelu((S + x)/3, slope_next))
 #include "m2s_common.cuh"
+#include <cuda_fp16.h>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -114,6 +115,10 @@ struct m2s_generator {
   bool tf32 = true;   // tensor-core build (tf32 or fp16 operands); false = CUDA-core fp32 build
   bool fp16 = false;  // M2S_PREC_FP16: layers with c_in % 8 == 0 run kind::f16 on fp16 copies of the activations
   bool fuse_pairs = true;  // fp16 build: fused ResBlock pair kernel where it applies (M2S_FUSE_PAIRS=0 disables)
+  bool split_res = false;  // fp16 build, opt-in (M2S_SPLIT_RES=1): residual stream stored as two fp16 planes (hi = the
+                           // operand, lo = fp16(v - hi)) instead of fp32 + an fp16 operand copy.  8 instead of 12 bytes
+                           // of DRAM traffic per element of a pair, bit-compatible results -- but measured SLOWER
+                           // (profiles/README.md): the epilogue is bound by memory requests in flight, not by bytes.
   int hop = 1;
   Layer pre;
   std::vector<Layer> ups;
@@ -233,6 +238,7 @@ extern "C" int m2s_generator_create(const m2s_generator_config* cfg, const m2s_t
   g->tf32 = cfg->precision != M2S_PREC_FP32;
   g->fp16 = cfg->precision == M2S_PREC_FP16;
   if (const char* f = std::getenv("M2S_FUSE_PAIRS")) g->fuse_pairs = std::atoi(f) != 0;
+  if (const char* f = std::getenv("M2S_SPLIT_RES")) g->split_res = g->fp16 && std::atoi(f) != 0;
   // operand format per layer: fp16 needs 16-byte aligned rows of halves (c_in % 8 == 0); conv_pre reads the fp32 mel
   auto mode_for = [&](int c_in) {
     if (!g->tf32) return static_cast<int>(PACK_FP32);
@@ -287,6 +293,8 @@ extern "C" int m2s_generator_create(const m2s_generator_config* cfg, const m2s_t
     if ((st = get_bias(m, "conv_post", 1, &b)) != M2S_OK) return bail(st);
     g->post_bias = b[0];
   }
+  for (const Layer& L : g->c1)  // the split stream needs fp16 operands in every stage
+    if (!L.w.half) g->split_res = false;
   g->launches = 2 + cfg->num_upsamples * (1 + cfg->num_kernels * 6) + 1;
   if (g->fp16 && g->fuse_pairs) {  // stages whose ResBlock pairs run fused: one launch per pair instead of two
     for (int i = 0; i < cfg->num_upsamples; ++i)
@@ -329,8 +337,11 @@ GenBuffers plan_buffers(const m2s_generator* g, int batch, int frames) {
   b.mel_floats = al(b.mel_floats);
   b.p_floats = al(p);
   b.q_floats = al(q);
-  // P, Q, R, T, S (fp32-sized; P and T hold fp16 data when their consumer is an fp16 layer) + fp16 copies of Q and R
-  b.total_bytes = (b.mel_floats + b.p_floats + 5 * b.q_floats) * sizeof(float) + 256;
+  // P, T, S (fp32-sized; P and T hold fp16 data when their consumer is an fp16 layer) and the stage input Q plus two
+  // ResBlock states Ra / Rb (ping-pong: a pair never writes the tensor it reads, the fused pair kernel re-reads a halo
+  // of its input).  Split-fp16 residual stream: each of Q, Ra, Rb is a (hi, lo) pair of fp16 planes = one fp32-sized
+  // slot; otherwise an fp32 tensor plus an fp16 operand copy = 1.5 slots.
+  b.total_bytes = (b.mel_floats + b.p_floats + (g->split_res ? 5 : 6) * b.q_floats + (g->split_res ? 0 : b.q_floats / 2)) * sizeof(float) + 256;
   return b;
 }
 }  // namespace
@@ -355,17 +366,33 @@ int generator_forward_impl(m2s_generator* g, const float* mel, bool mel_btc, int
   float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
   const float* M0 = mel_btc ? mel : base;
   float* P = base + bufs.mel_floats;
-  float* Q = P + bufs.p_floats;
-  float* R = Q + bufs.q_floats;
-  float* T = R + bufs.q_floats;
+  float* T = P + bufs.p_floats;
   float* S = T + bufs.q_floats;
-  float* Q16 = S + bufs.q_floats;            // fp16 copies (tensor-core operands) of Q and R, half a q buffer each
-  float* R16 = Q16 + bufs.q_floats / 2;
+  // stage input Q and the two ResBlock states: fp32 tensor + fp16 operand copy, or the (hi, lo) fp16 planes
+  struct Stream { float* f32; __half* hi; __half* lo; };
+  Stream Qs{}, Rs[2] = {};
+  {
+    float* cur = S + bufs.q_floats;
+    Stream* all[3] = {&Qs, &Rs[0], &Rs[1]};
+    for (Stream* x : all) {
+      if (g->split_res) {
+        x->hi = reinterpret_cast<__half*>(cur);
+        x->lo = reinterpret_cast<__half*>(cur + bufs.q_floats / 2);
+        cur += bufs.q_floats;
+      } else {
+        x->f32 = cur;
+        x->hi = reinterpret_cast<__half*>(cur + bufs.q_floats);
+        cur += bufs.q_floats + bufs.q_floats / 2;
+      }
+    }
+  }
   const m2s_generator_config& cfg = g->cfg;
   const int mask = lengths ? M2S_MASK_LEN : M2S_MASK_NONE;
   // fp16 build: every tensor that is only ever a tensor-core operand (P, T) is stored as fp16; tensors that are also
-  // a residual / MRF source (Q, R) are stored twice -- fp32 for the residual chain (no rounding accumulates along it),
-  // fp16 for the operand -- and S stays fp32.  An fp32 output goes to `d`, an fp16 output to `d16`.
+  // a residual / MRF source (Q, R) are stored as the fp16 operand plane `hi` plus EITHER an fp16 correction plane
+  // `lo` = fp16(v - hi) (split stream: hi + lo carries v to ~22 mantissa bits, so nothing accumulates along the residual
+  // chain, in 4 instead of 6 bytes per element) OR an fp32 copy; S stays fp32.  An fp32 output goes to `d`, an fp16
+  // output to `d16` (+ `d16_lo`).
   auto set_out = [](ConvProblem* p, float* buf32, void* buf16) { p->d = buf32; p->d16 = buf16; };
 
   // (B, mels, T) -> channels-last, zero past lengths (conv_pre look-ahead must see zeros)
@@ -386,8 +413,10 @@ int generator_forward_impl(m2s_generator* g, const float* mel, bool mel_btc, int
     const int cout = g->ups_cout[i];
     const bool hs = g->c1[i * cfg.num_kernels * 3].w.half != 0;  // this stage's ResBlock convs take fp16 operands
     {  // ups: rows = L, N = u*cout; D viewed as (B, L, u*cout) == (B, L*u, cout)
-      ConvProblem p = base_problem(P, L, ch, batch, L, Q, u * cout, L, L, g->ups[i]);
-      if (hs) p.d16 = Q16;
+      const bool split = hs && g->split_res;
+      ConvProblem p = base_problem(P, L, ch, batch, L, split ? nullptr : Qs.f32, u * cout, L, L, g->ups[i]);
+      if (hs) p.d16 = Qs.hi;
+      if (split) p.d16_lo = Qs.lo;
       p.epi.act = M2S_ACT_LRELU; p.epi.act_slope = 0.1f;
       M2S_TRY(run_conv(g, p, g->ups[i], st));
     }
@@ -395,19 +424,24 @@ int generator_forward_impl(m2s_generator* g, const float* mel, bool mel_btc, int
     const bool last_stage = (i + 1 == cfg.num_upsamples);
     const bool next_half = !last_stage && g->ups[i + 1].w.half != 0;  // who reads this stage's output P
     for (int j = 0; j < cfg.num_kernels; ++j) {
-      const float* state = Q;
-      const void* state_op = hs ? static_cast<const void*>(Q16) : static_cast<const void*>(Q);
+      const bool split = hs && g->split_res;
+      const Stream* state = &Qs;
       for (int d = 0; d < 3; ++d) {
+        const Stream& out = Rs[d & 1];
+        const void* state_op = hs ? static_cast<const void*>(state->hi) : static_cast<const void*>(state->f32);
         const Layer& l1 = g->c1[(i * cfg.num_kernels + j) * 3 + d];
         const Layer& l2 = g->c2[(i * cfg.num_kernels + j) * 3 + d];
         ConvProblem p1 = base_problem(state_op, L, ch, batch, L, T, ch, L, L, l1);
         if (hs) set_out(&p1, nullptr, T);
         p1.epi.act = M2S_ACT_LRELU; p1.epi.act_slope = 0.1f;
-        ConvProblem p2 = base_problem(T, L, ch, batch, L, R, ch, L, L, l2);
-        p2.epi.res = state; p2.epi.res_ld = ch; p2.epi.res_inv_slope = 10.f;  // 1 / LRELU_SLOPE
+        ConvProblem p2 = base_problem(T, L, ch, batch, L, split ? nullptr : out.f32, ch, L, L, l2);
+        if (split) { p2.epi.res_hi = state->hi; p2.epi.res_lo = state->lo; }
+        else p2.epi.res = state->f32;
+        p2.epi.res_ld = ch; p2.epi.res_inv_slope = 10.f;  // 1 / LRELU_SLOPE
         if (d < 2) {
           p2.epi.act = M2S_ACT_LRELU; p2.epi.act_slope = 0.1f;
-          if (hs) p2.d16 = R16;
+          if (hs) p2.d16 = out.hi;
+          if (split) p2.d16_lo = out.lo;
         } else if (j + 1 < cfg.num_kernels) {
           p2.d = S;
           if (j > 0) { p2.epi.accum = S; p2.epi.accum_ld = ch; }
@@ -426,8 +460,7 @@ int generator_forward_impl(m2s_generator* g, const float* mel, bool mel_btc, int
           M2S_TRY(run_conv(g, p1, l1, st));
           M2S_TRY(run_conv(g, p2, l2, st));
         }
-        state = R;
-        state_op = hs ? static_cast<const void*>(R16) : static_cast<const void*>(R);
+        state = &out;
       }
     }
   }

@@ -32,6 +32,8 @@ int fail(int status, const char* fmt, ...);
 struct Epilogue {
   const float* bias;
   const float* res;
+  const void* res_hi;  // split-fp16 residual (res == nullptr): value = float(hi) + float(lo), __half planes
+  const void* res_lo;
   const float* accum;
   const int32_t* lens;
   int res_ld;
@@ -60,6 +62,7 @@ struct ConvProblem {
   Epilogue epi;
   int a_half;          // A operand is fp16 (tcgen05 kind::f16); 0 = fp32 rounded to tf32 by TMA
   void* d16;           // optional second output, fp16, indexed like d (same d_ld in elements); null = none
+  void* d16_lo;        // optional lo plane of the split-fp16 pair (d16 = hi): fp16(v - float(fp16(v))); needs d16
 };
 
 inline ConvProblem problem_from_args(const m2s_conv_args& a) {
@@ -73,7 +76,7 @@ inline ConvProblem problem_from_args(const m2s_conv_args& a) {
   p.epi.act_slope = a.act_slope; p.epi.mask_mode = a.mask_mode;
   p.epi.lens = a.lens; p.epi.len_scale = a.len_scale; p.epi.pitch = a.pitch; p.epi.i_lo = a.i_lo;
   p.epi.i_hi = a.i_hi; p.epi.j_lo = a.j_lo; p.epi.j_hi = a.j_hi;
-  p.a_half = a.a_half; p.d16 = a.d16;
+  p.a_half = a.a_half; p.d16 = a.d16; p.d16_lo = a.d16_lo; p.epi.res_hi = a.res_hi; p.epi.res_lo = a.res_lo;
   return p;
 }
 

@@ -50,9 +50,17 @@ struct PairParams {
   int na, nb, tg1, tg2;
   int nbuf;                      // 1 or 2: buffers of acc1 / acc2 / T;  lookahead = nbuf - 1
   int dbg;
+  unsigned long long* trace;     // debug timeline of CTA 0 (tools/trace_pair.py): trace[iteration * 8 + slot], null = off
+  int trace_tiles;
 };
 
 constexpr int kMaxBuf = 2;
+
+// slots: 0 epilogue got acc1, 1 epilogue 1 done, 2 epilogue got acc2, 3 epilogue 2 done (epilogue warp 0);
+//        4 conv1 issued, 5 MMA warp got t_full, 6 conv2 issued; 7 producer issued the x tile
+__device__ __forceinline__ void pair_stamp(const PairParams& prm, int it, int slot) {
+  if (prm.trace && blockIdx.x == 0 && it < prm.trace_tiles) prm.trace[it * 8 + slot] = clock64();
+}
 
 template <int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -147,6 +155,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                           cb * prm.kblock, q0 + prm.x_row0 + bx * prm.a_box_rows, b);
           }
           __syncwarp();
+          if (lane == 0 && cb == 0) pair_stamp(prm, s, 7);
           if (++sa == prm.na) { sa = 0; pa ^= 1; }
           load_weights(prm.w1, cb, prm.taps1, prm.tg1);
         }
@@ -210,15 +219,18 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         mbar_wait(acc1_empty(buf), ((s / nbuf) & 1) ^ 1);
         tc_fence_after();
         conv(acc1_addr(buf), prm.cblocks1, prm.c_in, prm.taps1, prm.tg1, prm.rel_shift1, true, 0u, acc1_full(buf), 0u);
+        if (lane == 0) pair_stamp(prm, s, 4);
       }
       if (s >= la) {
         const int i = s - la;
         const int buf = i % nbuf;
         mbar_wait(t_full(buf), (i / nbuf) & 1);
+        if (lane == 0) pair_stamp(prm, i, 5);
         mbar_wait(acc2_empty(buf), ((i / nbuf) & 1) ^ 1);
         tc_fence_after();
         conv(acc2_addr(buf), prm.cblocks2, n, prm.taps2, prm.tg2, prm.rel_shift2, false, t_base + buf * prm.t_buf_bytes,
              acc2_full(buf), t_empty(buf));
+        if (lane == 0) pair_stamp(prm, i, 6);
       }
     }
   } else {
@@ -238,6 +250,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         mbar_wait(acc1_full(buf), (s / nbuf) & 1);
         mbar_wait(t_empty(buf), ((s / nbuf) & 1) ^ 1);
         tc_fence_after();
+        if (ew == 0 && lane == 0) pair_stamp(prm, s, 0);
         const uint32_t tacc = acc1_addr(buf) + (static_cast<uint32_t>(quad * 32) << 16);
         const uint32_t tt = t_base + buf * prm.t_buf_bytes;
         for (int u = half; u < msub * nchunks; u += 2) {
@@ -283,6 +296,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         if (lane == 0) {
           mbar_arrive(t_full(buf));
           mbar_arrive(acc1_empty(buf));
+          if (ew == 0) pair_stamp(prm, s, 1);
         }
       }
       if (s >= la) {
@@ -294,11 +308,13 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         const int buf = i % nbuf;
         mbar_wait(acc2_full(buf), (i / nbuf) & 1);
         tc_fence_after();
+        if (ew == 0 && lane == 0) pair_stamp(prm, i, 2);
         const uint32_t tacc = acc2_addr(buf) + (static_cast<uint32_t>(quad * 32) << 16);
         epilogue_tile<kEpi>(p, epw, tacc, b, q0, 0, msub, n, min(p.l_out, q0 + prm.m2));
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc2_empty(buf));
+        if (ew == 0 && lane == 0) pair_stamp(prm, i, 3);
       }
     }
   }
@@ -388,6 +404,8 @@ int resblock_pair_fused(const ConvProblem& p1, const PackedWeights& w1, const Co
   prm.total_tiles = p2.batch * prm.tiles_per_batch;
   prm.nbuf = (4 * prm.msub * prm.n <= kTmemCols) ? 2 : 1;
   prm.dbg = engine_knobs().dbg;
+  prm.trace = engine_knobs().trace;
+  prm.trace_tiles = engine_knobs().trace_tiles;
 
   const int a_rows_needed = prm.m1 - smin;
   prm.a_nbox = (a_rows_needed + 255) / 256;
@@ -443,7 +461,8 @@ int resblock_pair_fused(const ConvProblem& p1, const PackedWeights& w1, const Co
   static const KernelFn kernels[EPI_COUNT] = {resblock_pair_kernel<EPI_FULL>,  resblock_pair_kernel<EPI_FULL_SILU>,
                                               resblock_pair_kernel<EPI_BIAS>,  resblock_pair_kernel<EPI_LRELU>,
                                               resblock_pair_kernel<EPI_SILU>,  resblock_pair_kernel<EPI_RES>,
-                                              resblock_pair_kernel<EPI_RB>,    resblock_pair_kernel<EPI_RB_ACC>};
+                                              resblock_pair_kernel<EPI_RB>,    resblock_pair_kernel<EPI_RB_ACC>,
+                                              resblock_pair_kernel<EPI_RB_S>,  resblock_pair_kernel<EPI_RB_ACC_S>};
   static bool attr_set = false;
   if (!attr_set) {
     for (KernelFn k : kernels)
@@ -451,6 +470,9 @@ int resblock_pair_fused(const ConvProblem& p1, const PackedWeights& w1, const Co
     attr_set = true;
   }
   const int epi = choose_epilogue(p2.epi);
+  if (epi < 0 || (p2.d16_lo && (!p2.d16 || !lo_output_supported(epi))) || (p2.epi.res_hi && (p2.epi.res_ld % 8 || (reinterpret_cast<uintptr_t>(p2.epi.res_hi) & 15) ||
+                                                            (reinterpret_cast<uintptr_t>(p2.epi.res_lo) & 15))))
+    return fail(M2S_ERR_UNSUPPORTED, "fused pair: unsupported split-fp16 residual epilogue");
   int grid = engine_knobs().max_ctas > 0 ? engine_knobs().max_ctas : sm_count();
   if (grid > prm.total_tiles) grid = prm.total_tiles;
   M2S_TRY(profile_before(stream));

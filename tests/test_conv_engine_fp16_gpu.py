@@ -94,3 +94,58 @@ def test_operand_format_mismatch_is_refused():
     w = torch.zeros(1, 16, 12, device="cuda")
     with pytest.raises(_lib.M2SError):
         _lib.conv_fwd(a, w, [0], 128)
+
+
+def _split(v):
+    """(hi, lo) fp16 planes of an fp32 tensor: hi = fp16(v), lo = fp16((v - hi) * 2048)."""
+    hi = v.half()
+    lo = ((v - hi.float()) * 2048.0).half()
+    return hi, lo
+
+
+@pytest.mark.parametrize("case", [(3, 400, 64, 64, [-6, -3, 0], True), (2, 700, 32, 32, [-2, -1, 0], False),
+                                  (1, 30000, 128, 128, [-10, -5, 0], True), (2, 333, 256, 256, [-1, 0], False)])
+def test_split_fp16_residual_stream(case):
+    """Split-fp16 residual stream (include/m2s.h): residual read as float(hi) + float(lo), output written as the
+    (hi, lo) planes.  hi must be bit-identical to the plain fp16 output, hi + lo must carry the fp32 result to
+    ~2^-21 relative, and the residual read must agree with the fp32-residual program on the same values."""
+    from mri2speech_b200 import _lib
+    B, L, C, N, shifts, with_acc = case
+    a, w, bias = _inputs(B, L, C, N, len(shifts), seed=21)
+    g = torch.Generator().manual_seed(22)
+    res = torch.randn(B, L, N, generator=g).cuda()
+    res_hi, res_lo = _split(res)
+    res_q = res_hi.float() + res_lo.float() / 2048.0          # what the split stream carries
+    assert (res_q - res).abs().max().item() < 4e-6
+    acc = torch.randn(B, L, N, generator=g).cuda() if with_acc else None
+    lens = torch.tensor(([L, L // 3, 7] * B)[:B], dtype=torch.int32).cuda()
+    kw = dict(bias=bias, res_inv_slope=10.0, accum=acc, out_scale=1.0 / 3.0 if with_acc else 1.0,
+              act=_lib.ACT_LRELU, act_slope=0.1, lens=lens)
+    # fp32-residual program on the values the split stream carries: the reference for this test
+    ref16 = torch.zeros(B, L, N, device="cuda", dtype=torch.float16)
+    ref = _lib.conv_fwd(a, w, shifts, L, res=res_q, out16=ref16, **kw)
+    hi = torch.full((B, L, N), 5.0, device="cuda", dtype=torch.float16)
+    lo = torch.full((B, L, N), 5.0, device="cuda", dtype=torch.float16)
+    _lib.conv_fwd(a, w, shifts, L, res_hi=res_hi, res_lo=res_lo, out16=hi, out16_lo=lo, want_d32=False, **kw)
+    assert torch.equal(hi, ref16)
+    rec = hi.float() + lo.float() / 2048.0
+    scale = max(1.0, ref.abs().max().item())
+    assert (rec - ref).abs().max().item() < 2e-6 * scale
+    # rows past the length mask are zero in both planes
+    t = torch.arange(L, device="cuda").view(1, L, 1)
+    dead = (t >= lens.view(B, 1, 1)).expand(B, L, N)
+    if dead.any():
+        assert hi[dead].abs().max().item() == 0 and lo[dead].abs().max().item() == 0
+
+
+def test_split_fp16_residual_refuses_unsupported_epilogues():
+    from mri2speech_b200 import _lib
+    a, w, bias = _inputs(1, 200, 64, 64, 1, seed=2)
+    res_hi, res_lo = _split(torch.randn(1, 200, 64).cuda())
+    d16 = torch.zeros(1, 200, 64, device="cuda", dtype=torch.float16)
+    with pytest.raises(_lib.M2SError):   # SiLU is not one of the two ResBlock programs
+        _lib.conv_fwd(a, w, [0], 200, bias=bias, res_hi=res_hi, res_lo=res_lo, act=_lib.ACT_SILU, out16=d16)
+    with pytest.raises(_lib.M2SError):   # lo plane missing
+        _lib.conv_fwd(a, w, [0], 200, bias=bias, res_hi=res_hi, out16=d16)
+    with pytest.raises(_lib.M2SError):   # lo output without the hi output
+        _lib.conv_fwd(a, w, [0], 200, bias=bias, out16_lo=d16)

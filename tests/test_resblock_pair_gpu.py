@@ -97,3 +97,25 @@ def test_unsupported_pair_is_refused():
     x, w1, b1, w2, b2 = _inputs(1, 300, 256, 3)          # N = 256 > 128
     with pytest.raises(_lib.M2SError):
         _lib.resblock_pair_fwd(x, w1, b1, 1, w2, b2)
+
+
+@pytest.mark.parametrize("case", [(2, 3000, 64, 3, 1), (2, 5000, 32, 11, 5), (1, 2500, 64, 7, 3)])
+def test_fused_pair_split_fp16_stream(case):
+    """The fused pair on the split-fp16 residual stream: x arrives as (hi, lo) planes (hi is conv1's operand, hi + lo
+    the residual), the result leaves as (hi, lo) planes in DIFFERENT buffers (the kernel re-reads a halo of x)."""
+    from mri2speech_b200 import _lib
+    B, L, C, k, d = case
+    x, w1, b1, w2, b2 = _inputs(B, L, C, k, seed=13)
+    g = torch.Generator().manual_seed(14)
+    x_lo = (torch.randn(B, L, C, generator=g) * 0.4).half().cuda()      # any lo plane: the residual is hi + lo
+    res = x.float() + x_lo.float() / 2048.0
+    out_hi = torch.full((B, L, C), 9.0, device="cuda", dtype=torch.float16)
+    out_lo = torch.full((B, L, C), 9.0, device="cuda", dtype=torch.float16)
+    _lib.resblock_pair_fwd(x, w1, b1, d, w2, b2, res_hi=x, res_lo=x_lo, res_inv_slope=10.0, act=_lib.ACT_LRELU,
+                           act_slope=0.1, out16=out_hi, out16_lo=out_lo, want_d32=False)
+    ref = _lib.resblock_pair_fwd(x, w1, b1, d, w2, b2, res=res, res_inv_slope=10.0, act=_lib.ACT_LRELU, act_slope=0.1)
+    rec = out_hi.float() + out_lo.float() / 2048.0
+    assert (rec - ref).abs().max().item() < 2e-6 * max(1.0, ref.abs().max().item())
+    r = res.double().cpu()
+    v = _lrelu(_reference(x, w1, b1, d, w2, b2, L) + torch.where(r >= 0, r, r * 10.0), 0.1)
+    assert (rec.double().cpu() - v).abs().max().item() < 2e-3 * max(1.0, v.abs().max().item())
