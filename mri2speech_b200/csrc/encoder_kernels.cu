@@ -148,6 +148,95 @@ __global__ void __launch_bounds__(256) stem_kernel(const void* __restrict__ fram
   }
 }
 
+// The same layer, R output rows per block: the 2R + 1 input rows are staged once (4 pixels per load), each thread keeps
+// the 9 x 8 weights of ITS 8-channel group in registers (72 LDS per block instead of 72 per output pixel) and walks
+// R * Wo * 4 (pixel, channel group) items -- a whole number of 256-thread passes, where the one-row kernel above ran a
+// third pass for 8 border items.  Needs W % 4 == 0, (H / 2) % R == 0 and frames aligned for 4-pixel loads.
+template <bool kU8, typename T, int R>
+__global__ void __launch_bounds__(256) stem_rows_kernel(const void* __restrict__ frames_v, const int32_t* __restrict__ fmap,
+                                                        const float* __restrict__ mask, const float2* __restrict__ norm,
+                                                        T* __restrict__ out, const float* __restrict__ w /*[9][32]*/,
+                                                        const float* __restrict__ bias, int H, int W) {
+  const int Ho = H / 2, Wo = W / 2, pitch = Wo + 2, Wp = W + 1;
+  constexpr int kRowsIn = 2 * R + 1;
+  constexpr int kUnits = 32 * sizeof(T) / 16;   // 16-byte vectors per output pixel
+  const int n = blockIdx.y;
+  const int y0 = blockIdx.x * R;
+  const int tid = threadIdx.x;
+  T* obase = out + static_cast<size_t>(n) * (Ho + 2) * pitch * 32;
+  extern __shared__ float srow[];  // kRowsIn x (W + 1) input pixels (column W = the zero pad)
+  __shared__ float sw[9 * 32 + 32];
+  for (int k = tid; k < 9 * 32 + 32; k += 256) sw[k] = k < 288 ? w[k] : bias[k - 288];
+  const size_t foff = static_cast<size_t>(fmap ? fmap[n] : n) * H * W;
+  float2 nm = make_float2(0.f, 1.f);
+  if (kU8) nm = norm[n];
+  const int w4 = W >> 2;
+  for (int k = tid; k < kRowsIn * w4; k += 256) {
+    const int r = k / w4, x4 = (k - r * w4) << 2;
+    const int yy = 2 * y0 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (yy < H) {
+      const size_t idx = static_cast<size_t>(yy) * W + x4;
+      if (kU8) {
+        const uchar4 u = *reinterpret_cast<const uchar4*>(static_cast<const uint8_t*>(frames_v) + foff + idx);
+        float4 f = make_float4(u.x, u.y, u.z, u.w);
+        if (mask) {
+          const float4 m = *reinterpret_cast<const float4*>(mask + idx);
+          f = make_float4(masked_u8(u.x, m.x), masked_u8(u.y, m.y), masked_u8(u.z, m.z), masked_u8(u.w, m.w));
+        }
+        v = make_float4((f.x - nm.x) * nm.y, (f.y - nm.x) * nm.y, (f.z - nm.x) * nm.y, (f.w - nm.x) * nm.y);
+      } else {
+        v = *reinterpret_cast<const float4*>(static_cast<const float*>(frames_v) + foff + idx);
+      }
+    }
+    float* d = srow + r * Wp + x4;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  if (tid < kRowsIn) srow[tid * Wp + W] = 0.f;
+  __syncthreads();
+  const int cg = (tid & 3) * 8;   // 256 and Wo * 4 are multiples of 4: every item of this thread has this channel group
+  float wr[9][8], br[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) wr[t][c] = sw[t * 32 + cg + c];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) br[c] = sw[288 + cg + c];
+  const int per_row = Wo * 4;
+  for (int k = tid; k < R * per_row; k += 256) {
+    const int r = k / per_row, x = (k - r * per_row) >> 2;
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = br[c];
+    const float* px0 = srow + (2 * r) * Wp + 2 * x;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const float px = px0[dy * Wp + dx];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = fmaf(px, wr[dy * 3 + dx][c], v[c]);
+      }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = sizeof(T) == 4 ? silu(v[c]) : silu_t<T>(v[c]);
+    T* o = obase + (static_cast<size_t>(y0 + r + 1) * pitch + x + 1) * 32 + cg;
+    store4(o, make_float4(v[0], v[1], v[2], v[3]));
+    store4(o + 4, make_float4(v[4], v[5], v[6], v[7]));
+  }
+  // the zero border: columns 0 and Wo + 1 of these rows, plus padded row 0 / Ho + 1 from the first / last block
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = tid; k < R * 2 * kUnits; k += 256) {
+    const int r = k / (2 * kUnits), rem = k - r * 2 * kUnits;
+    const int col = rem < kUnits ? 0 : Wo + 1, uu = rem < kUnits ? rem : rem - kUnits;
+    reinterpret_cast<float4*>(obase + (static_cast<size_t>(y0 + r + 1) * pitch + col) * 32)[uu] = z4;
+  }
+  if (blockIdx.x == 0)
+    for (int k = tid; k < pitch * kUnits; k += 256) reinterpret_cast<float4*>(obase)[k] = z4;
+  if (blockIdx.x == gridDim.x - 1)
+    for (int k = tid; k < pitch * kUnits; k += 256)
+      reinterpret_cast<float4*>(obase + static_cast<size_t>(Ho + 1) * pitch * 32)[k] = z4;
+}
+
 // Zero the rows of a padded layout that the engine's masked epilogue never writes:
 // [0, head_rows) and [tail_start, rows_per_frame) of every frame.
 // (Type-agnostic: `ld4` = 16-byte vectors per row.)
@@ -338,16 +427,34 @@ __global__ void gap_kernel(const float* __restrict__ x, const int32_t* __restric
 }  // namespace
 
 // `half` selects the activation element type: 0 = float, 1 = __half (`out` / `in` are then __half buffers).
-int enc_stem(const float* frames, const int32_t* fmap, void* out, int half, const float* w, const float* bias, int n,
-             int H, int W, cudaStream_t st) {
-  dim3 grid(H / 2 + 2, n);
-  const size_t sm = 3 * (W + 1) * sizeof(float);
-  if (half)
-    stem_kernel<false, __half><<<grid, 256, sm, st>>>(frames, fmap, nullptr, nullptr, static_cast<__half*>(out), w, bias, H, W);
-  else
-    stem_kernel<false, float><<<grid, 256, sm, st>>>(frames, fmap, nullptr, nullptr, static_cast<float*>(out), w, bias, H, W);
+namespace {
+constexpr int kStemRows = 4;
+// the R-rows kernel when the geometry and the frame alignment allow 4-pixel loads, else the one-row kernel
+template <bool kU8, typename T>
+int launch_stem(const void* frames, const int32_t* fmap, const float* mask, const float2* norm, T* out, const float* w,
+                const float* bias, int n, int H, int W, cudaStream_t st) {
+  const size_t frame_bytes = static_cast<size_t>(H) * W * (kU8 ? 1 : 4);
+  const bool rows_ok = W % 4 == 0 && (H / 2) % kStemRows == 0 && H % 2 == 0 &&
+                       (reinterpret_cast<uintptr_t>(frames) % (kU8 ? 4 : 16)) == 0 && frame_bytes % 16 == 0 &&
+                       (!mask || reinterpret_cast<uintptr_t>(mask) % 16 == 0);
+  if (rows_ok) {
+    dim3 grid(H / 2 / kStemRows, n);
+    const size_t sm = (2 * kStemRows + 1) * (W + 1) * sizeof(float);
+    stem_rows_kernel<kU8, T, kStemRows><<<grid, 256, sm, st>>>(frames, fmap, mask, norm, out, w, bias, H, W);
+  } else {
+    dim3 grid(H / 2 + 2, n);
+    const size_t sm = 3 * (W + 1) * sizeof(float);
+    stem_kernel<kU8, T><<<grid, 256, sm, st>>>(frames, fmap, mask, norm, out, w, bias, H, W);
+  }
   M2S_CUDA_OK(cudaGetLastError());
   return M2S_OK;
+}
+}  // namespace
+
+int enc_stem(const float* frames, const int32_t* fmap, void* out, int half, const float* w, const float* bias, int n,
+             int H, int W, cudaStream_t st) {
+  if (half) return launch_stem<false, __half>(frames, fmap, nullptr, nullptr, static_cast<__half*>(out), w, bias, n, H, W, st);
+  return launch_stem<false, float>(frames, fmap, nullptr, nullptr, static_cast<float*>(out), w, bias, n, H, W, st);
 }
 
 // uint8 ingest: per-frame min-max (after the optional articulator mask) fused into the stem load.
@@ -355,14 +462,8 @@ int enc_stem_u8(const uint8_t* frames, const int32_t* fmap, const float* mask, f
                 const float* w, const float* bias, int n, int H, int W, cudaStream_t st) {
   frame_minmax_kernel<<<n, 256, 0, st>>>(frames, fmap, mask, norm, H * W);
   M2S_CUDA_OK(cudaGetLastError());
-  dim3 grid(H / 2 + 2, n);
-  const size_t sm = 3 * (W + 1) * sizeof(float);
-  if (half)
-    stem_kernel<true, __half><<<grid, 256, sm, st>>>(frames, fmap, mask, norm, static_cast<__half*>(out), w, bias, H, W);
-  else
-    stem_kernel<true, float><<<grid, 256, sm, st>>>(frames, fmap, mask, norm, static_cast<float*>(out), w, bias, H, W);
-  M2S_CUDA_OK(cudaGetLastError());
-  return M2S_OK;
+  if (half) return launch_stem<true, __half>(frames, fmap, mask, norm, static_cast<__half*>(out), w, bias, n, H, W, st);
+  return launch_stem<true, float>(frames, fmap, mask, norm, static_cast<float*>(out), w, bias, n, H, W, st);
 }
 
 // `ld` counts elements of `esize` bytes (rows are multiples of 16 bytes).

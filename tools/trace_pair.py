@@ -31,11 +31,13 @@ def main():
     b2 = torch.randn(C, generator=g).cuda()
     ohi = torch.zeros(B, L, C, device="cuda", dtype=torch.float16)
     olo = torch.zeros(B, L, C, device="cuda", dtype=torch.float16)
-    kw = dict(res_inv_slope=10.0, act=_lib.ACT_LRELU, act_slope=0.1, out16=ohi, out16_lo=olo, want_d32=False)
-    if mode == "fp32":
+    kw = dict(res_inv_slope=10.0, act=_lib.ACT_LRELU, act_slope=0.1, out16=ohi)
+    if mode == "fp32":      # fp32 residual -> fp32 + fp16 outputs (the default fp16 build)
         kw["res"] = x.float() + x_lo.float() / 2048.0
-    elif mode == "split":
-        kw["res_hi"], kw["res_lo"] = x, x_lo
+    elif mode == "split":   # (hi, lo) residual -> (hi, lo) outputs (M2S_SPLIT_RES=1)
+        kw.update(res_hi=x, res_lo=x_lo, out16_lo=olo, want_d32=False)
+    else:
+        kw["want_d32"] = False
     buf = torch.zeros(tiles * 8, dtype=torch.int64, device="cuda")
     _lib.resblock_pair_fwd(x, w1, b1, dil, w2, b2, **kw)
     _lib.check(_lib.lib().m2s_debug_trace(buf.data_ptr(), tiles))
