@@ -18,10 +18,10 @@
 // rel_shift[j] rows.  Weights are pre-packed on the host in the exact swizzled SMEM image and
 // streamed per (channel block, tap) with 1-D bulk copies.
 //
-// Warp roles (320 threads, 1 CTA / SM, persistent over tiles):
+// Warp roles (576 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0   : TMA producer (one lane)
 //   warp 1   : TMEM allocator + MMA issuer (one lane)
-//   warps 2-9: epilogue (two per TMEM lane quadrant): tcgen05.ld -> SMEM transpose -> bias / residual /
+//   warps 2-17: epilogue (four per TMEM lane quadrant, 32 x 16 units): tcgen05.ld -> SMEM transpose -> bias / residual /
 //              MRF accumulate / scale / activation / mask -> coalesced global stores
 #include "engine_device.cuh"
 #include <cstdlib>
@@ -36,7 +36,7 @@ using namespace engine;
 namespace {
 
 // ---- the kernel ----------------------------------------------------------------
-// 320 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue (two warps per
+// 576 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-17 = epilogue (four warps per
 // TMEM lane quadrant; a pair splits the (sub-tile, 32-column chunk) units of a tile).
 template <int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -53,7 +53,7 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   auto acc_full = [&](int s) { return bar_base + 8u * (2 * kMaxStagesA + 2 * kMaxStagesB + s); };
   auto acc_empty = [&](int s) { return bar_base + 8u * (2 * kMaxStagesA + 2 * kMaxStagesB + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStagesA + 2 * kMaxStagesB + 4);
-  const uint32_t stage_base = bar_base + 1024u;  // 8 epilogue warps x 4 KB transpose staging
+  const uint32_t stage_base = bar_base + 1024u;  // 16 epilogue warps x 2 KB transpose staging
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;

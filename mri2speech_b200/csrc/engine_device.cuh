@@ -8,8 +8,11 @@
 namespace m2s {
 namespace engine {
 
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kEpiWarps = 16;                 // four per TMEM lane quadrant
+constexpr int kEpiGroups = kEpiWarps / 4;     // epilogue warps per quadrant: a warp takes every kEpiGroups-th unit
+constexpr int kEpiUnitCols = 16;              // an epilogue unit is 32 rows x 16 columns
+constexpr uint32_t kEpiStageBytes = 32 * kEpiUnitCols * 4;   // transpose staging per warp
+constexpr int kThreads = 64 + 32 * kEpiWarps; // 18 warps: 112 registers per thread
 constexpr int kKBlock = 32;     // tf32 elements per 128-byte swizzle row (fp16: EngineParams::kblock = 64 or 32)
 constexpr int kRowBytes = 128;  // tf32 / wide fp16 rows; narrow fp16 layers (c_in <= 32) use 64-byte rows (SWIZZLE_64B)
 constexpr int kTmemCols = 512;
@@ -20,12 +23,12 @@ constexpr uint32_t kSmemBudget = 200 * 1024;  // > 114 KB forces 1 CTA / SM (TME
 // LSTM input projection): a per-unit __ldg of the bias sat on the epilogue's critical path with ~500 cycles of
 // exposed latency per 32 x 32 unit (measured with the intra-unit stamps of tools/trace_engine.py micro).
 constexpr int kBiasSmemFloats = 1280;
-constexpr uint32_t kEpiSmemBytes = kEpiWarps * 4096 + kBiasSmemFloats * 4;  // transpose staging + staged bias
+constexpr uint32_t kEpiSmemBytes = kEpiWarps * kEpiStageBytes + kBiasSmemFloats * 4;  // transpose staging + staged bias
 
 // all threads of the CTA, before the first __syncthreads
 __device__ __forceinline__ uint32_t stage_bias(const ConvProblem& p, uint32_t stage_base) {
   if (p.n > kBiasSmemFloats) return 0u;
-  const uint32_t base = stage_base + kEpiWarps * 4096u;
+  const uint32_t base = stage_base + kEpiWarps * kEpiStageBytes;
   for (int i = threadIdx.x; i < p.n; i += blockDim.x) {
     const float v = p.epi.bias ? __ldg(p.epi.bias + i) : 0.f;
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + 4u * i), "f"(v) : "memory");
@@ -209,7 +212,7 @@ struct EpiConsts {
 };
 
 // Epilogue programs (compile-time): the common cases drop every unused instruction -- with 256-column-wide tiles the
-// epilogue is ALU-issue-bound (32K outputs per tile on 8 warps), so instructions per output are what matters.
+// epilogue is ALU-issue-bound (32K outputs per tile), so instructions per output are what matters.
 // EPI_RB / EPI_RB_ACC are the two ResBlock conv2 programs of the vocoder (residual stored post-leaky-ReLU and recovered
 // with min(y, y/slope); leaky-ReLU as max(v, slope*v), which also covers "no activation" with slope = 1).
 // EPI_RB_S / EPI_RB_ACC_S: the same two programs with the residual read from the split-fp16 planes (hi + lo).
@@ -302,11 +305,18 @@ __device__ __forceinline__ float epi_elem(const EpiConsts& c, float acc, float b
 
 
 // Per-warp epilogue state that does not change across tiles.
+//
+// Geometry: 16 epilogue warps, four per TMEM lane quadrant.  A warp works on units of 32 rows x 16 columns: thread
+// (rr0 = lane / 4, cc = lane % 4) owns rows rr0 + 8 i (i = 0..3) and columns 4 cc .. 4 cc + 3 of the unit.  Half-width
+// units halve the registers a thread needs (16 accumulators in flight, 4 float4 of residual / accumulate / transposed
+// data instead of 8), which is what lets 18 warps fit the register file (112 registers each): the epilogue is a
+// latency chain (TMEM -> SMEM transpose -> global load -> FMA -> global store) and with two warps per scheduler
+// half of its time was dependency stalls (tools/trace_pair.py, profiles/README.md).
 struct EpiWarp {
   EpiConsts ec;
-  uint32_t stage;  // this warp's 4 KB transpose staging (shared::cta address)
+  uint32_t stage;  // this warp's 2 KB transpose staging (shared::cta address)
   uint32_t bias_smem;  // staged bias vector (shared::cta address), 0 = read the bias from global memory
-  int quad, half, lane, rr0, cc;
+  int quad, grp, lane, rr0, cc;
   int mask_mode;
   bool has_res, has_acc;
   int dbg;  // probe switches (EngineParams::dbg): bit0 skip global stores, bit1 skip TMEM loads, bit2 skip SMEM transpose
@@ -318,11 +328,11 @@ __device__ __forceinline__ EpiWarp make_epi_warp(const Epilogue& e, uint32_t sta
   w.bias_smem = bias_smem;
   w.dbg = dbg;
   w.quad = warp & 3;  // TMEM lane quadrant this warp may access
-  w.half = ew >> 2;   // which of the two warps of the quadrant
+  w.grp = ew >> 2;    // which of the kEpiGroups warps of the quadrant
   w.lane = lane;
-  w.rr0 = lane >> 3;
-  w.cc = lane & 7;
-  w.stage = stage_base + ew * 4096;
+  w.rr0 = lane >> 2;
+  w.cc = lane & 3;
+  w.stage = stage_base + ew * kEpiStageBytes;
   w.has_res = e.res != nullptr || e.res_hi != nullptr;
   w.has_acc = e.accum != nullptr;
   w.ec.inv_slope = e.res_inv_slope;
@@ -334,10 +344,16 @@ __device__ __forceinline__ EpiWarp make_epi_warp(const Epilogue& e, uint32_t sta
   return w;
 }
 
+// transpose staging: row r of the unit (16 floats = 64 bytes) lives at stage + 64 r, its 16-byte chunk c at
+// chunk (c ^ ((r >> 1) & 3)): conflict-free for the row-per-lane writes and for the 4-lanes-per-row reads
+__device__ __forceinline__ uint32_t epi_stage_addr(uint32_t stage, int row, int chunk) {
+  return stage + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
+}
+
 // Epilogue of one accumulator tile for one warp: rows [q0, q0 + 128*msub) of batch item b, columns [n0, n0+n_tile).
 // TMEM -> registers (row per thread) -> SMEM transpose (XOR-swizzled, conflict-free) -> coalesced global traffic:
-// 8 lanes cover one 128-byte row segment, a warp instruction covers 4 rows.  `tmem_acc` already carries this warp's
-// lane-quadrant offset.
+// 4 lanes cover one 64-byte row segment, a warp instruction covers 8 rows (512 bytes per request).  `tmem_acc` already
+// carries this warp's lane-quadrant offset.
 // `q_end` (exclusive) bounds the rows this tile may write (the fused pair kernel keeps only part of a tile).
 template <int kEpi>
 __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWarp& ew_, uint32_t tmem_acc, int b, int q0,
@@ -346,70 +362,65 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
   // `ustamp` (debug, one lane of one warp): clock64 stamps inside the FIRST fast-path unit of the tile --
   // [0] unit start, [1] accumulators arrived from TMEM, [2] parked in the staging buffer, [3] first row computed,
   // [4] all rows computed and stores issued
+  constexpr int kR = 4;   // rows per thread: rr0 + 8 i
   const int row_end = min(p.l_out, q_end);
   const Epilogue& e = p.epi;
   const EpiConsts& ec = ew_.ec;
   const uint32_t stage = ew_.stage;
-  const int quad = ew_.quad, half = ew_.half, lane = ew_.lane, rr0 = ew_.rr0, cc = ew_.cc;
+  const int quad = ew_.quad, grp = ew_.grp, lane = ew_.lane, rr0 = ew_.rr0, cc = ew_.cc;
   const int mask_mode = ew_.mask_mode;
   const bool has_res = ew_.has_res, has_acc = ew_.has_acc;
-  const int nchunks = (n_tile + 31) >> 5;
+  const int nchunks = (n_tile + kEpiUnitCols - 1) / kEpiUnitCols;
   const int units = msub * nchunks;
   int len_rows = 0x7fffffff;
   if (mask_mode == M2S_MASK_LEN) len_rows = __ldg(e.lens + b) * e.len_scale;
   const size_t d_base = static_cast<size_t>(b) * p.d_batch_rows + p.d_row_offset;
-  // The accumulator registers of unit u+2 are requested from TMEM as soon as unit u's have been parked in the SMEM
-  // staging buffer: the TMEM read of the next unit overlaps the arithmetic / global traffic of the current one.
-  uint32_t r[32];
+  // The accumulator registers of the warp's next unit are requested from TMEM as soon as the current unit's have been
+  // parked in the SMEM staging buffer: the TMEM read overlaps the arithmetic / global traffic of the current one.
+  uint32_t r[16];
   auto issue_tmem_ld = [&](int uu) {
     const int sub_ = uu / nchunks;
-    const int c0_ = (uu - sub_ * nchunks) << 5;
-    tmem_ld16(tmem_acc + sub_ * n_tile + c0_, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-    if (c0_ + 16 < n_tile) tmem_ld16(tmem_acc + sub_ * n_tile + c0_ + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+    const int c0_ = (uu - sub_ * nchunks) * kEpiUnitCols;
+    tmem_ld16(tmem_acc + sub_ * n_tile + c0_, r);
   };
   const bool pipelined = ew_.dbg == 0;
-  if (pipelined && half < units) issue_tmem_ld(half);
-  for (int u = half; u < units; u += 2) {
+  if (pipelined && grp < units) issue_tmem_ld(grp);
+  for (int u = grp; u < units; u += kEpiGroups) {
     const int sub = u / nchunks;
-    const int c0 = (u - sub * nchunks) << 5;
+    const int c0 = (u - sub * nchunks) * kEpiUnitCols;
     const int qw = q0 + sub * 128 + quad * 32;  // first row of this warp's 32-row slab
     if (!pipelined) {
       if (!(ew_.dbg & 2)) {
         issue_tmem_ld(u);
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0x3f800000u + j + lane;
+        for (int j = 0; j < 16; ++j) r[j] = 0x3f800000u + j + lane;
       }
     }
     // While the TMEM read is in flight: bias / residual / accumulate loads of this unit (the output may alias
-    // them in place, so every load is issued before the first store).  Thread (rr0, cc) owns rows rr0 + 4i,
-    // columns n .. n+3; all row predicates reduce to "4i + rr0 < bound".
+    // them in place, so every load is issued before the first store).  Thread (rr0, cc) owns rows rr0 + 8i,
+    // columns n .. n+3; all row predicates reduce to "8i + rr0 < bound".
     const int n = n0 + c0 + cc * 4;
     constexpr bool kSplit = kEpi == EPI_RB_S || kEpi == EPI_RB_ACC_S;  // residual = float(hi) + float(lo), fp16 planes
     constexpr bool kHasRes = kEpi == EPI_FULL || kEpi == EPI_FULL_SILU || kEpi == EPI_RES || kEpi == EPI_RB || kEpi == EPI_RB_ACC || kSplit;
     constexpr bool kHasAcc = kEpi == EPI_FULL || kEpi == EPI_FULL_SILU || kEpi == EPI_RB_ACC || kEpi == EPI_RB_ACC_S;
     // programs that can write the lo plane (d16_lo): the producers of a split stream -- the transposed-conv epilogue
-    // (EPI_LRELU) and the split ResBlock programs.  Compile-time, like kCutFast below: the other programs run at the
-    // 168-register cap and every extra pointer / predicate spills in their hot loop.
+    // (EPI_LRELU) and the split ResBlock programs (compile-time: the hot loop carries no pointer it does not use)
     constexpr bool kLoOut = kSplit || kEpi == EPI_LRELU;
-    constexpr bool kCutFast = !kHasAcc;  // units cut by q_end take the fast path with predicated stores
-    // ---- fast path: all 32 rows of the unit are inside the output and survive the length mask (warp-uniform test): no
-    // row predicates, row pointers stepped by warp-uniform strides; a lane whose 4 columns fall outside a narrow / ragged
-    // N tile simply sits out (one predicate per thread); the image-border mask is evaluated per row (8 per thread).  ~8 instructions per output instead of 20-37 on the
-    // general path.  Measured alternatives that lost or tied (profiles/README.md): a row-per-thread epilogue straight from
-    // the TMEM registers to global memory (1.4-2x slower: uncoalesced 16-byte accesses); a fragment-layout epilogue
-    // (tcgen05.ld.16x256b + one lane-pair shuffle per column group, no SMEM transpose at all: correct, but no faster --
-    // the unit time is set by global-memory latency, not by the transpose); prefetching the residual one unit / one tile
-    // ahead in registers or with cp.async.bulk.prefetch.L2 (slower at the 168-register cap).
+    // ---- fast path: all 32 rows of the unit exist and survive the length mask (warp-uniform test): no row predicates on
+    // the loads, row pointers stepped by warp-uniform strides; a lane whose 4 columns fall outside a narrow / ragged N tile
+    // simply sits out (one predicate per thread); the image-border mask is evaluated per row.  A unit cut only by q_end
+    // (the fused pair kernel keeps M1 - (k-1) rows of a tile) takes this path too, with predicated stores: its rows exist
+    // in memory, and the warp that owns the cut unit of EVERY tile must not be slower than the others (it delayed the
+    // T-tile barrier of the next tile by 2-8 k cycles: tools/trace_pair.py).
+    // Measured alternatives that lost or tied (profiles/README.md): a row-per-thread epilogue straight from the TMEM
+    // registers to global memory; a fragment-layout epilogue (tcgen05.ld.16x256b + lane-pair shuffles, no SMEM transpose);
+    // prefetching the residual one unit / one tile ahead in registers or with cp.async.bulk.prefetch.L2.
     {
       int rows_valid_u = 32;
       if (mask_mode == M2S_MASK_LEN) rows_valid_u = len_rows - (qw + p.d_row_offset);
-      // `keep`: rows of the unit this tile may write.  A unit cut only by q_end (the fused pair kernel keeps M1 - (k-1)
-      // rows of a tile) still takes the fast path with predicated stores: its rows exist in memory, and the one warp
-      // that owns the cut unit of EVERY tile must not be slower than the other seven (it delayed the T-tile barrier of
-      // the next tile by 2-8 k cycles: tools/trace_pair.py).
       const int keep = row_end - qw;
-      const bool fast = (kCutFast ? p.l_out : row_end) - qw >= 32 && rows_valid_u >= 32 && !ew_.dbg;
+      const bool fast = p.l_out - qw >= 32 && rows_valid_u >= 32 && !ew_.dbg;
       if (fast) {
         const bool lane_ok = (c0 + cc * 4 < n_tile) && n < p.n;
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -420,67 +431,65 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
                        : "r"(ew_.bias_smem + 4u * n));
         else if (e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
         const size_t row0 = d_base + qw + rr0;
-        float4 res4[8], acc4[8];
+        float4 res4[kR], acc4[kR];
         if (kHasRes) {
           if (kSplit && lane_ok) {
             // Lanes (cc even, cc + 1) own adjacent 4-column groups of the same rows: the even lane fetches 16 bytes
             // (8 columns) of the hi plane, the odd lane 16 bytes of the lo plane, and they swap halves by shuffle when
-            // the row is used.  One 512-byte request per warp instruction like the fp32 residual: 8-byte loads (two
-            // 256-byte requests per row group) made the split stream SLOWER than fp32 -- the epilogue is bound by memory
-            // requests in flight, not by bytes (tools/pair_bench.py).  The hi plane is the tile conv1 just read: an L2 hit.
+            // the row is used: 8-byte loads (twice the requests for the same bytes) made the split stream much SLOWER
+            // than fp32 (tools/pair_bench.py).  The hi plane is the tile conv1 just read: an L2 hit.
             const __half* plane = static_cast<const __half*>((cc & 1) ? e.res_lo : e.res_hi);
             const uint4* rp = reinterpret_cast<const uint4*>(plane + row0 * e.res_ld + (n & ~7));
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const uint4 v = rp[static_cast<size_t>(i) * (e.res_ld >> 1)];
+            for (int i = 0; i < kR; ++i) {
+              const uint4 v = rp[static_cast<size_t>(i) * e.res_ld];
               res4[i] = make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
             }
           } else if (!kSplit && has_res && lane_ok) {
             const float4* rp = reinterpret_cast<const float4*>(e.res + row0 * e.res_ld + n);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) res4[i] = rp[static_cast<size_t>(i) * e.res_ld];
+            for (int i = 0; i < kR; ++i) res4[i] = rp[static_cast<size_t>(i) * 2 * e.res_ld];
           } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) res4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < kR; ++i) res4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         if (kHasAcc) {
           const float4* ap = reinterpret_cast<const float4*>(e.accum + row0 * e.accum_ld + n);
           if (has_acc && lane_ok) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc4[i] = ap[static_cast<size_t>(i) * e.accum_ld];
+            for (int i = 0; i < kR; ++i) acc4[i] = ap[static_cast<size_t>(i) * 2 * e.accum_ld];
           } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < kR; ++i) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-        const bool stamp = ustamp != nullptr && u == half;
+        const bool stamp = ustamp != nullptr && u == grp;
         if (stamp) ustamp[0] = clock64();
         tmem_ld_wait();
         if (stamp) ustamp[1] = clock64();
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + lane * 128 + ((j ^ (lane & 7)) << 4)),
+        for (int j = 0; j < 4; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(epi_stage_addr(stage, lane, j)),
                        "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
                        : "memory");
         __syncwarp();
         if (stamp) ustamp[2] = clock64();
-        if (u + 2 < units) issue_tmem_ld(u + 2);   // (fast path implies pipelined)
-        // each row is stored as soon as it is computed (the kernel runs at the 168-register cap of a 10-warp CTA)
+        if (u + kEpiGroups < units) issue_tmem_ld(u + kEpiGroups);   // (fast path implies pipelined)
         float4* dp = reinterpret_cast<float4*>(p.d + row0 * p.d_ld + n);
         uint2* hp = reinterpret_cast<uint2*>(static_cast<__half*>(p.d16) + row0 * p.d_ld + n);
         uint2* lp = reinterpret_cast<uint2*>(static_cast<__half*>(p.d16_lo) + row0 * p.d_ld + n);
         const bool st32 = p.d != nullptr && lane_ok, st16 = p.d16 != nullptr && lane_ok;
         const bool st_lo = kLoOut && p.d16_lo != nullptr;
-        float4 a8[8];
+        float4 a8[kR];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + rr0;
+        for (int i = 0; i < kR; ++i) {
+          const int rr = i * 8 + rr0;
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                        : "=f"(a8[i].x), "=f"(a8[i].y), "=f"(a8[i].z), "=f"(a8[i].w)
-                       : "r"(stage + rr * 128 + ((cc ^ (rr & 7)) << 4)));
+                       : "r"(epi_stage_addr(stage, rr, cc)));
         }
-        // image-border mask: (mi, mj) = divmod(row, pitch) once, then stepped by 4 rows
+        // image-border mask: (mi, mj) = divmod(row, pitch) once, then stepped by 8 rows
         int mi = 0, mj = 0;
         if (mask_mode == M2S_MASK_PITCH) {
           const int drow = qw + rr0 + p.d_row_offset;
@@ -488,8 +497,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
           mj = drow - mi * e.pitch;
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + rr0;
+        for (int i = 0; i < kR; ++i) {
+          const int rr = i * 8 + rr0;
           const float4 a4 = a8[i];
           float4 r4 = kHasRes ? res4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
           if (kSplit) {
@@ -507,21 +516,21 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
           o.w = epi_elem<kEpi>(ec, a4.w, bias4.w, r4.w, c4.w);
           if (mask_mode == M2S_MASK_PITCH) {
             if (!(mi >= e.i_lo && mi < e.i_hi && mj >= e.j_lo && mj < e.j_hi)) o = make_float4(0.f, 0.f, 0.f, 0.f);
-            mj += 4;
-            if (mj >= e.pitch) { mj -= e.pitch; ++mi; }
+            mj += 8;
+            while (mj >= e.pitch) { mj -= e.pitch; ++mi; }
           }
-          const bool row_ok = !kCutFast || rr < keep;   // always true unless q_end cuts this unit
-          if (st32 && row_ok) dp[static_cast<size_t>(i) * p.d_ld] = o;
+          const bool row_ok = rr < keep;   // always true unless q_end cuts this unit
+          if (st32 && row_ok) dp[static_cast<size_t>(i) * 2 * p.d_ld] = o;
           if (st16 && row_ok) {  // fp16 copy: the tensor-core operand of the next conv (saturating conversion, never inf)
             uint2 pk, pl;
             if (st_lo) {  // + the lo plane: (hi, lo) together are the residual source of the next pair
               split_encode(o, &pk, &pl);
-              lp[static_cast<size_t>(i) * p.d_ld] = pl;
+              lp[static_cast<size_t>(i) * 2 * p.d_ld] = pl;
             } else {
               asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(o.y), "f"(o.x));
               asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(o.w), "f"(o.z));
             }
-            hp[static_cast<size_t>(i) * p.d_ld] = pk;
+            hp[static_cast<size_t>(i) * 2 * p.d_ld] = pk;
           }
           if (stamp && i == 0) ustamp[3] = clock64();
         }
@@ -530,6 +539,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
         continue;
       }
     }
+    // ---- general path: rows that do not exist or are masked (tile / utterance ends), probe switches ----
     const bool col_ok = (c0 + cc * 4 < n_tile) && n < p.n;
     const int rows_ok = col_ok ? min(32, row_end - qw) : 0;                 // rows that exist
     int rows_valid = 32;                                                    // rows that survive the mask
@@ -540,44 +550,44 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
     float* dptr = p.d + row0 * p.d_ld + n;
     __half* hptr = static_cast<__half*>(p.d16) + row0 * p.d_ld + n;
     __half* lptr = static_cast<__half*>(p.d16_lo) + row0 * p.d_ld + n;
-    const size_t d_step = static_cast<size_t>(4) * p.d_ld;
-    float4 res4[8], acc4[8];
+    const size_t d_step = static_cast<size_t>(8) * p.d_ld;
+    float4 res4[kR], acc4[kR];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < kR; ++i) {
       res4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (kSplit) {
       const __half* rh = static_cast<const __half*>(e.res_hi) + row0 * e.res_ld + n;
       const __half* rl = static_cast<const __half*>(e.res_lo) + row0 * e.res_ld + n;
-      const size_t r_step = static_cast<size_t>(4) * e.res_ld;
+      const size_t r_step = static_cast<size_t>(8) * e.res_ld;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i * 4 + rr0 < rows_ok) {
+      for (int i = 0; i < kR; ++i)
+        if (i * 8 + rr0 < rows_ok) {
           const uint2 h = *reinterpret_cast<const uint2*>(rh + i * r_step), l = *reinterpret_cast<const uint2*>(rl + i * r_step);
           res4[i] = make_float4(__uint_as_float(h.x), __uint_as_float(h.y), __uint_as_float(l.x), __uint_as_float(l.y));
         }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) res4[i] = split_decode(res4[i]);   // zero bits decode to zero
+      for (int i = 0; i < kR; ++i) res4[i] = split_decode(res4[i]);   // zero bits decode to zero
     } else if (kHasRes) {
       if (has_res) {
         const float* rptr = e.res + row0 * e.res_ld + n;
-        const size_t r_step = static_cast<size_t>(4) * e.res_ld;
+        const size_t r_step = static_cast<size_t>(8) * e.res_ld;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (i * 4 + rr0 < rows_ok) res4[i] = *reinterpret_cast<const float4*>(rptr + i * r_step);
+        for (int i = 0; i < kR; ++i)
+          if (i * 8 + rr0 < rows_ok) res4[i] = *reinterpret_cast<const float4*>(rptr + i * r_step);
       }
     }
     if (kHasAcc) {
       if (has_acc) {
         const float* aptr = e.accum + row0 * e.accum_ld + n;
-        const size_t a_step = static_cast<size_t>(4) * e.accum_ld;
+        const size_t a_step = static_cast<size_t>(8) * e.accum_ld;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (i * 4 + rr0 < rows_ok) acc4[i] = *reinterpret_cast<const float4*>(aptr + i * a_step);
+        for (int i = 0; i < kR; ++i)
+          if (i * 8 + rr0 < rows_ok) acc4[i] = *reinterpret_cast<const float4*>(aptr + i * a_step);
       }
     }
-    // image-border mask: (i, j) = divmod(row, pitch) once, then stepped by 4 rows
+    // image-border mask: (i, j) = divmod(row, pitch) once, then stepped by 8 rows
     int mi = 0, mj = 0;
     if (mask_mode == M2S_MASK_PITCH) {
       const int drow = qw + rr0 + p.d_row_offset;
@@ -587,26 +597,24 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
     tmem_ld_wait();
     if (!(ew_.dbg & 4)) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + lane * 128 + ((j ^ (lane & 7)) << 4)),
+      for (int j = 0; j < 4; ++j)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(epi_stage_addr(stage, lane, j)),
                      "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
                      : "memory");
       __syncwarp();
     }
-    if (pipelined && u + 2 < units) issue_tmem_ld(u + 2);
-    // all 8 rows' (32 independent) element chains are computed unconditionally so the scheduler can interleave
-    // them; only the stores are predicated
-    float4 o[8];
+    if (pipelined && u + kEpiGroups < units) issue_tmem_ld(u + kEpiGroups);
+    float4 o[kR];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rr = i * 4 + rr0;
+    for (int i = 0; i < kR; ++i) {
+      const int rr = i * 8 + rr0;
       float4 a4;
       if (!(ew_.dbg & 4)) {
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                      : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w)
-                     : "r"(stage + rr * 128 + ((cc ^ (rr & 7)) << 4)));
+                     : "r"(epi_stage_addr(stage, rr, cc)));
       } else {
-        a4 = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 8]), __uint_as_float(r[i + 16]), __uint_as_float(r[i + 24]));
+        a4 = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 4]), __uint_as_float(r[i + 8]), __uint_as_float(r[i + 12]));
       }
       o[i].x = epi_elem<kEpi>(ec, a4.x, bias4.x, res4[i].x, acc4[i].x);
       o[i].y = epi_elem<kEpi>(ec, a4.y, bias4.y, res4[i].y, acc4[i].y);
@@ -615,26 +623,26 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
     }
     if (mask_mode == M2S_MASK_PITCH) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < kR; ++i) {
         const bool valid = mi >= e.i_lo && mi < e.i_hi && mj >= e.j_lo && mj < e.j_hi;
         if (!valid) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        mj += 4;
-        if (mj >= e.pitch) { mj -= e.pitch; ++mi; }
+        mj += 8;
+        while (mj >= e.pitch) { mj -= e.pitch; ++mi; }
       }
     } else if (mask_mode == M2S_MASK_LEN) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i * 4 + rr0 >= rows_valid) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < kR; ++i)
+        if (i * 8 + rr0 >= rows_valid) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (p.d && !(ew_.dbg & 1)) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i * 4 + rr0 < rows_ok) *reinterpret_cast<float4*>(dptr + i * d_step) = o[i];
+      for (int i = 0; i < kR; ++i)
+        if (i * 8 + rr0 < rows_ok) *reinterpret_cast<float4*>(dptr + i * d_step) = o[i];
     }
     if (p.d16 && !(ew_.dbg & 1)) {  // fp16 copy of the tile: the tensor-core operand of the next conv (saturating, never inf)
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i * 4 + rr0 < rows_ok) {
+      for (int i = 0; i < kR; ++i)
+        if (i * 8 + rr0 < rows_ok) {
           uint2 pk, pl;
           split_encode(o[i], &pk, &pl);
           *reinterpret_cast<uint2*>(hptr + i * d_step) = pk;

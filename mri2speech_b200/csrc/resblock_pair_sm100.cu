@@ -16,7 +16,7 @@
 // against 16 B for two launches; the MMAs of conv1 of tile i+1 overlap both epilogues of tile i (accumulators and the
 // T tile are double-buffered whenever 8 * N <= 512 TMEM columns).
 //
-// Warp roles (320 threads, 1 CTA / SM, persistent): warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogues.
+// Warp roles (576 threads, 1 CTA / SM, persistent): warp 0 TMA producer, warp 1 MMA issuer, warps 2-17 epilogues.
 // Operands are fp16 only (the fp16 build); N = C_out <= 128 (one N tile), weights in the single-CTA packed layout.
 #include "engine_device.cuh"
 #include <mutex>
@@ -84,7 +84,7 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   auto t_empty = [&](int s) { return x_base + 8u * (10 + s); };
   const uint32_t tmem_slot = x_base + 8u * 12;
   const uint32_t bias1_smem = bar_base + 512u;            // n floats (<= 128)
-  const uint32_t stage_base = bar_base + 1024u;           // 8 epilogue warps x 4 KB transpose staging
+  const uint32_t stage_base = bar_base + 1024u;           // 16 epilogue warps x 2 KB transpose staging
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -237,8 +237,8 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     // ===================== epilogue warps =====================
     const int ew = warp - 2;
     const EpiWarp epw = make_epi_warp(p.epi, stage_base, ew, warp, lane, prm.dbg, bias_smem);
-    const int quad = epw.quad, half = epw.half;
-    const int nchunks = (n + 31) >> 5;
+    const int quad = epw.quad, grp = epw.grp;
+    const int nchunks = (n + kEpiUnitCols - 1) / kEpiUnitCols;
     const int kb_shift = prm.kblock == 64 ? 6 : 5;
     for (int s = 0; s < my_tiles + la; ++s) {
       if (s < my_tiles) {
@@ -253,18 +253,17 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         if (ew == 0 && lane == 0) pair_stamp(prm, s, 0);
         const uint32_t tacc = acc1_addr(buf) + (static_cast<uint32_t>(quad * 32) << 16);
         const uint32_t tt = t_base + buf * prm.t_buf_bytes;
-        for (int u = half; u < msub * nchunks; u += 2) {
+        for (int u = grp; u < msub * nchunks; u += kEpiGroups) {
           const int sub = u / nchunks;
-          const int c0 = (u - sub * nchunks) << 5;
+          const int c0 = (u - sub * nchunks) * kEpiUnitCols;
           const int row = sub * 128 + quad * 32 + lane;   // row of the T tile; time = q0 - halo2 + row
-          uint32_t r[32];
-          tmem_ld16(tacc + sub * n + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-          tmem_ld16(tacc + sub * n + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+          uint32_t r[16];
+          tmem_ld16(tacc + sub * n + c0, r);
           const bool zero_row = q0 - prm.halo2 + row < 0;
           tmem_ld_wait();
-          uint32_t pk[16];
+          uint32_t pk[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 4; ++j) {
             float4 b4;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w)
@@ -277,14 +276,14 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
             asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk[2 * j]) : "f"(v1), "f"(v0));
             asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk[2 * j + 1]) : "f"(v3), "f"(v2));
           }
-          // 32 halves = 64 bytes = four 16-byte chunks of this row inside K block kb
+          // 16 halves = 32 bytes = two 16-byte chunks of this row inside K block kb
           const int kb = c0 >> kb_shift;
           const int chunk0 = ((c0 & (prm.kblock - 1)) * 2) >> 4;
           const uint32_t swz = row_bytes == 128 ? (row & 7) : ((row >> 1) & 3);
           const uint32_t rbase = tt + kb * prm.t_kb_bytes + row * row_bytes;
           if (c0 < n) {
 #pragma unroll
-            for (int m = 0; m < 4; ++m)
+            for (int m = 0; m < 2; ++m)
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + (((chunk0 + m) ^ swz) << 4)),
                            "r"(pk[4 * m]), "r"(pk[4 * m + 1]), "r"(pk[4 * m + 2]), "r"(pk[4 * m + 3])
                            : "memory");
