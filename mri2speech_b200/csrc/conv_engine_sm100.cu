@@ -197,8 +197,8 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   } else {
     // ===================== epilogue warps =====================
     // TMEM -> registers (row per thread) -> SMEM transpose (XOR-swizzled, conflict-free) -> coalesced global
-    // traffic: 8 lanes cover one 128-byte row segment, a warp instruction covers 4 rows.
-    const int ew = warp - 2;  // 0..7
+    // traffic: 4 lanes cover one 64-byte row segment, a warp instruction covers 8 rows.
+    const int ew = warp - 2;  // 0..15
     const EpiWarp epw = make_epi_warp(p.epi, stage_base, ew, warp, lane, prm.dbg, bias_smem);
     int acc = 0;
     uint32_t pacc = 0;
@@ -212,10 +212,7 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       tc_fence_after();
       if (ew == 0 && lane == 0) trace_stamp(prm, it, 7);
       const uint32_t tmem_acc = tmem_base + acc * prm.acc_stride + (static_cast<uint32_t>(epw.quad * 32) << 16);
-      unsigned long long* us = nullptr;
-      if (prm.trace && blockIdx.x == 0 && it < prm.trace_tiles && ew == 0 && lane == 0)
-        us = prm.trace + prm.trace_tiles * 9 + it * 8;
-      epilogue_tile<kEpi>(p, epw, tmem_acc, b, mt * prm.m_tile, nt * n_tile, msub, n_tile, 0x7fffffff, us);
+      epilogue_tile<kEpi>(p, epw, tmem_acc, b, mt * prm.m_tile, nt * n_tile, msub, n_tile);
       tc_fence_before();
       __syncwarp();
       if (ew == 0 && lane == 0) trace_stamp(prm, it, 8);

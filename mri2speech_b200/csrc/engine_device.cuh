@@ -21,7 +21,7 @@ constexpr int kMaxStagesB = 8;
 constexpr uint32_t kSmemBudget = 200 * 1024;  // > 114 KB forces 1 CTA / SM (TMEM is allocated whole)
 // The bias vector is staged in SMEM once per kernel when it has at most this many entries (everything but the
 // LSTM input projection): a per-unit __ldg of the bias sat on the epilogue's critical path with ~500 cycles of
-// exposed latency per 32 x 32 unit (measured with the intra-unit stamps of tools/trace_engine.py micro).
+// exposed latency per 32 x 32 unit (measured with intra-unit clock stamps, profiles/README.md).
 constexpr int kBiasSmemFloats = 1280;
 constexpr uint32_t kEpiSmemBytes = kEpiWarps * kEpiStageBytes + kBiasSmemFloats * 4;  // transpose staging + staged bias
 
@@ -344,6 +344,9 @@ __device__ __forceinline__ EpiWarp make_epi_warp(const Epilogue& e, uint32_t sta
   return w;
 }
 
+// row-loop variants: 0 = no image-border mask, 1 = image-border mask, 2 = decided at run time per row (one loop copy)
+template <int kV> struct PitchTag { static constexpr int value = kV; };
+
 // transpose staging: row r of the unit (16 floats = 64 bytes) lives at stage + 64 r, its 16-byte chunk c at
 // chunk (c ^ ((r >> 1) & 3)): conflict-free for the row-per-lane writes and for the 4-lanes-per-row reads
 __device__ __forceinline__ uint32_t epi_stage_addr(uint32_t stage, int row, int chunk) {
@@ -357,11 +360,7 @@ __device__ __forceinline__ uint32_t epi_stage_addr(uint32_t stage, int row, int 
 // `q_end` (exclusive) bounds the rows this tile may write (the fused pair kernel keeps only part of a tile).
 template <int kEpi>
 __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWarp& ew_, uint32_t tmem_acc, int b, int q0,
-                                              int n0, int msub, int n_tile, int q_end = 0x7fffffff,
-                                              unsigned long long* ustamp = nullptr) {
-  // `ustamp` (debug, one lane of one warp): clock64 stamps inside the FIRST fast-path unit of the tile --
-  // [0] unit start, [1] accumulators arrived from TMEM, [2] parked in the staging buffer, [3] first row computed,
-  // [4] all rows computed and stores issued
+                                              int n0, int msub, int n_tile, int q_end = 0x7fffffff) {
   constexpr int kR = 4;   // rows per thread: rr0 + 8 i
   const int row_end = min(p.l_out, q_end);
   const Epilogue& e = p.epi;
@@ -371,27 +370,30 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
   const int mask_mode = ew_.mask_mode;
   const bool has_res = ew_.has_res, has_acc = ew_.has_acc;
   const int nchunks = (n_tile + kEpiUnitCols - 1) / kEpiUnitCols;
-  const int units = msub * nchunks;
   int len_rows = 0x7fffffff;
   if (mask_mode == M2S_MASK_LEN) len_rows = __ldg(e.lens + b) * e.len_scale;
   const size_t d_base = static_cast<size_t>(b) * p.d_batch_rows + p.d_row_offset;
   // The accumulator registers of the warp's next unit are requested from TMEM as soon as the current unit's have been
   // parked in the SMEM staging buffer: the TMEM read overlaps the arithmetic / global traffic of the current one.
   uint32_t r[16];
-  auto issue_tmem_ld = [&](int uu) {
-    const int sub_ = uu / nchunks;
-    const int c0_ = (uu - sub_ * nchunks) * kEpiUnitCols;
-    tmem_ld16(tmem_acc + sub_ * n_tile + c0_, r);
-  };
+  auto issue_tmem_ld = [&](int sub_, int ci_) { tmem_ld16(tmem_acc + sub_ * n_tile + ci_ * kEpiUnitCols, r); };
   const bool pipelined = ew_.dbg == 0;
-  if (pipelined && grp < units) issue_tmem_ld(grp);
-  for (int u = grp; u < units; u += kEpiGroups) {
-    const int sub = u / nchunks;
-    const int c0 = (u - sub * nchunks) * kEpiUnitCols;
+  // this warp's units: (sub-tile, 16-column chunk) pairs in row-major order, every kEpiGroups-th one, stepped without
+  // divisions (the epilogue is half issue-bound: profiles/README.md)
+  int sub = 0, ci = grp;
+  while (ci >= nchunks) { ci -= nchunks; ++sub; }
+  if (pipelined && sub < msub) issue_tmem_ld(sub, ci);
+  const bool pitch_mask = mask_mode == M2S_MASK_PITCH;
+  for (int sub_n, ci_n; sub < msub; sub = sub_n, ci = ci_n) {
+    sub_n = sub;
+    ci_n = ci + kEpiGroups;
+    while (ci_n >= nchunks) { ci_n -= nchunks; ++sub_n; }
+    const bool has_next = sub_n < msub;
+    const int c0 = ci * kEpiUnitCols;
     const int qw = q0 + sub * 128 + quad * 32;  // first row of this warp's 32-row slab
     if (!pipelined) {
       if (!(ew_.dbg & 2)) {
-        issue_tmem_ld(u);
+        issue_tmem_ld(sub, ci);
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) r[j] = 0x3f800000u + j + lane;
@@ -464,18 +466,17 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
             for (int i = 0; i < kR; ++i) acc4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-        const bool stamp = ustamp != nullptr && u == grp;
-        if (stamp) ustamp[0] = clock64();
         tmem_ld_wait();
-        if (stamp) ustamp[1] = clock64();
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(epi_stage_addr(stage, lane, j)),
                        "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
                        : "memory");
         __syncwarp();
-        if (stamp) ustamp[2] = clock64();
-        if (u + kEpiGroups < units) issue_tmem_ld(u + kEpiGroups);   // (fast path implies pipelined)
+        // (fast path implies pipelined)  Programs with an accumulate stream hold 16 more registers (acc4) through the
+        // row loop: they request the next unit's accumulators after it instead -- 36 bytes of spills in that loop cost
+        // 10 % of the launch, the exposed TMEM read a few dozen cycles per unit.
+        if (!kHasAcc && has_next) issue_tmem_ld(sub_n, ci_n);
         float4* dp = reinterpret_cast<float4*>(p.d + row0 * p.d_ld + n);
         uint2* hp = reinterpret_cast<uint2*>(static_cast<__half*>(p.d16) + row0 * p.d_ld + n);
         uint2* lp = reinterpret_cast<uint2*>(static_cast<__half*>(p.d16_lo) + row0 * p.d_ld + n);
@@ -489,52 +490,59 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
                        : "=f"(a8[i].x), "=f"(a8[i].y), "=f"(a8[i].z), "=f"(a8[i].w)
                        : "r"(epi_stage_addr(stage, rr, cc)));
         }
-        // image-border mask: (mi, mj) = divmod(row, pitch) once, then stepped by 8 rows
-        int mi = 0, mj = 0;
-        if (mask_mode == M2S_MASK_PITCH) {
-          const int drow = qw + rr0 + p.d_row_offset;
-          mi = drow / e.pitch;
-          mj = drow - mi * e.pitch;
-        }
+        // one row loop per mask kind (compile-time inside: the image-border test costs a divmod and a compare chain per row)
+        auto rows = [&](auto pitch_tag) {
+          constexpr int kPitchMode = decltype(pitch_tag)::value;
+          const bool kPitch = kPitchMode == 2 ? pitch_mask : kPitchMode == 1;
+          int mi = 0, mj = 0;
+          if (kPitch) {
+            const int drow = qw + rr0 + p.d_row_offset;
+            mi = drow / e.pitch;
+            mj = drow - mi * e.pitch;
+          }
 #pragma unroll
-        for (int i = 0; i < kR; ++i) {
-          const int rr = i * 8 + rr0;
-          const float4 a4 = a8[i];
-          float4 r4 = kHasRes ? res4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-          if (kSplit) {
-            // even lane holds hi[own 4 | neighbour's 4], odd lane lo[neighbour's 4 | own 4]: swap the neighbour's half
-            const bool odd = (cc & 1) != 0;
-            const float g0 = __shfl_xor_sync(0xffffffffu, odd ? r4.x : r4.z, 1);
-            const float g1 = __shfl_xor_sync(0xffffffffu, odd ? r4.y : r4.w, 1);
-            r4 = split_decode(odd ? make_float4(g0, g1, r4.z, r4.w) : make_float4(r4.x, r4.y, g0, g1));
-          }
-          const float4 c4 = kHasAcc ? acc4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-          float4 o;
-          o.x = epi_elem<kEpi>(ec, a4.x, bias4.x, r4.x, c4.x);
-          o.y = epi_elem<kEpi>(ec, a4.y, bias4.y, r4.y, c4.y);
-          o.z = epi_elem<kEpi>(ec, a4.z, bias4.z, r4.z, c4.z);
-          o.w = epi_elem<kEpi>(ec, a4.w, bias4.w, r4.w, c4.w);
-          if (mask_mode == M2S_MASK_PITCH) {
-            if (!(mi >= e.i_lo && mi < e.i_hi && mj >= e.j_lo && mj < e.j_hi)) o = make_float4(0.f, 0.f, 0.f, 0.f);
-            mj += 8;
-            while (mj >= e.pitch) { mj -= e.pitch; ++mi; }
-          }
-          const bool row_ok = rr < keep;   // always true unless q_end cuts this unit
-          if (st32 && row_ok) dp[static_cast<size_t>(i) * 2 * p.d_ld] = o;
-          if (st16 && row_ok) {  // fp16 copy: the tensor-core operand of the next conv (saturating conversion, never inf)
-            uint2 pk, pl;
-            if (st_lo) {  // + the lo plane: (hi, lo) together are the residual source of the next pair
-              split_encode(o, &pk, &pl);
-              lp[static_cast<size_t>(i) * 2 * p.d_ld] = pl;
-            } else {
-              asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(o.y), "f"(o.x));
-              asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(o.w), "f"(o.z));
+          for (int i = 0; i < kR; ++i) {
+            const int rr = i * 8 + rr0;
+            const float4 a4 = a8[i];
+            float4 r4 = kHasRes ? res4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kSplit) {
+              // even lane holds hi[own 4 | neighbour's 4], odd lane lo[neighbour's 4 | own 4]: swap the neighbour's half
+              const bool odd = (cc & 1) != 0;
+              const float g0 = __shfl_xor_sync(0xffffffffu, odd ? r4.x : r4.z, 1);
+              const float g1 = __shfl_xor_sync(0xffffffffu, odd ? r4.y : r4.w, 1);
+              r4 = split_decode(odd ? make_float4(g0, g1, r4.z, r4.w) : make_float4(r4.x, r4.y, g0, g1));
             }
-            hp[static_cast<size_t>(i) * 2 * p.d_ld] = pk;
+            const float4 c4 = kHasAcc ? acc4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 o;
+            o.x = epi_elem<kEpi>(ec, a4.x, bias4.x, r4.x, c4.x);
+            o.y = epi_elem<kEpi>(ec, a4.y, bias4.y, r4.y, c4.y);
+            o.z = epi_elem<kEpi>(ec, a4.z, bias4.z, r4.z, c4.z);
+            o.w = epi_elem<kEpi>(ec, a4.w, bias4.w, r4.w, c4.w);
+            if (kPitch) {
+              if (!(mi >= e.i_lo && mi < e.i_hi && mj >= e.j_lo && mj < e.j_hi)) o = make_float4(0.f, 0.f, 0.f, 0.f);
+              mj += 8;
+              while (mj >= e.pitch) { mj -= e.pitch; ++mi; }
+            }
+            const bool row_ok = rr < keep;   // always true unless q_end cuts this unit
+            if (st32 && row_ok) dp[static_cast<size_t>(i) * 2 * p.d_ld] = o;
+            if (st16 && row_ok) {  // fp16 copy: the tensor-core operand of the next conv (saturating conversion, never inf)
+              uint2 pk, pl;
+              if (st_lo) {  // + the lo plane: (hi, lo) together are the residual source of the next pair
+                split_encode(o, &pk, &pl);
+                lp[static_cast<size_t>(i) * 2 * p.d_ld] = pl;
+              } else {
+                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(o.y), "f"(o.x));
+                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(o.w), "f"(o.z));
+              }
+              hp[static_cast<size_t>(i) * 2 * p.d_ld] = pk;
+            }
           }
-          if (stamp && i == 0) ustamp[3] = clock64();
-        }
-        if (stamp) ustamp[4] = clock64();
+        };
+        // (programs with an accumulate stream are at the register cap: ONE copy of the loop, or ptxas spills in it)
+        if (kHasAcc) rows(PitchTag<2>{});
+        else if (pitch_mask) rows(PitchTag<1>{});
+        else rows(PitchTag<0>{});
+        if (kHasAcc && has_next) issue_tmem_ld(sub_n, ci_n);
         __syncwarp();
         continue;
       }
@@ -603,7 +611,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
                      : "memory");
       __syncwarp();
     }
-    if (pipelined && u + kEpiGroups < units) issue_tmem_ld(u + kEpiGroups);
+    if (pipelined && has_next) issue_tmem_ld(sub_n, ci_n);
     float4 o[kR];
 #pragma unroll
     for (int i = 0; i < kR; ++i) {

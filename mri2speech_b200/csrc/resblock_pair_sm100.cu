@@ -253,9 +253,10 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
         if (ew == 0 && lane == 0) pair_stamp(prm, s, 0);
         const uint32_t tacc = acc1_addr(buf) + (static_cast<uint32_t>(quad * 32) << 16);
         const uint32_t tt = t_base + buf * prm.t_buf_bytes;
-        for (int u = grp; u < msub * nchunks; u += kEpiGroups) {
-          const int sub = u / nchunks;
-          const int c0 = (u - sub * nchunks) * kEpiUnitCols;
+        int sub = 0, ci = grp;   // this warp's (sub-tile, 16-column chunk) units, stepped without divisions
+        while (ci >= nchunks) { ci -= nchunks; ++sub; }
+        for (; sub < msub; ) {
+          const int c0 = ci * kEpiUnitCols;
           const int row = sub * 128 + quad * 32 + lane;   // row of the T tile; time = q0 - halo2 + row
           uint32_t r[16];
           tmem_ld16(tacc + sub * n + c0, r);
@@ -288,6 +289,8 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
                            "r"(pk[4 * m]), "r"(pk[4 * m + 1]), "r"(pk[4 * m + 2]), "r"(pk[4 * m + 3])
                            : "memory");
           }
+          ci += kEpiGroups;
+          while (ci >= nchunks) { ci -= nchunks; ++sub; }
         }
         fence_proxy_async();   // generic-proxy writes of T -> visible to the tensor core's async-proxy reads
         tc_fence_before();

@@ -48,7 +48,7 @@ def run(B, L, C, k, d, res=False, tiles=40, knobs=None, N=None, act=None, shifts
           f"epilogue wait {f(t[s0:, 7] - t[s0:, 6]):.0f}; mma issue {f(t[s0:, 5] - t[s0:, 4]):.0f}; "
           f"mma wait acc {f(t[s0:, 4] - t[s0:, 3]):.0f}; producer a_empty wait {f(t[s0:, 1] - t[s0:, 0]):.0f}; "
           f"producer issue {f(t[s0:, 2] - t[s0:, 1]):.0f}; total {int(t[tiles-1, 8]) - t0} cycles")
-    m = micro[s0:tiles]
+    m = micro[s0:tiles]   # intra-unit stamps: only written by builds before the 16-warp epilogue (kept for old logs)
     if int((m[:, 4] > 0).sum()) > 0:
         m = m[m[:, 4] > 0]
         print(f"   first unit of the tile (warp 2): TMEM wait {f(m[:, 1] - m[:, 0]):.0f}; park in staging {f(m[:, 2] - m[:, 1]):.0f}; "
