@@ -147,12 +147,15 @@ typedef struct {
   int32_t resblock_kernel_sizes[M2S_MAX_RBK];
   int32_t resblock_dilations[M2S_MAX_RBK][3];
   int32_t precision;                /* M2S_PREC_*                      */
+  int32_t resblock;                 /* h.resblock: 0 or 1 = ResBlock1 (3 pairs of convs1 / convs2, 3 dilations),
+                                     * 2 = ResBlock2 (models.py:58-85: 2 convs, resblock_dilations[j][0..1])      */
 } m2s_generator_config;
 
 typedef struct m2s_generator m2s_generator;
 
 /* Tensors: the Generator state_dict (233 entries for config_custom.json), either
- * weight_g/weight_v pairs or plain .weight (weight-norm removed). */
+ * weight_g/weight_v pairs or plain .weight (weight-norm removed).  ResBlock2 configs name their convs
+ * resblocks.N.convs.M instead of resblocks.N.convs1.M / convs2.M. */
 int m2s_generator_create(const m2s_generator_config* cfg, const m2s_tensor* tensors, int32_t n_tensors,
                          m2s_generator** out);
 void m2s_generator_destroy(m2s_generator* g);

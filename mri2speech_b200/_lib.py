@@ -56,6 +56,7 @@ class GeneratorConfig(C.Structure):
         ("upsample_rates", C.c_int32 * M2S_MAX_UPS), ("upsample_kernel_sizes", C.c_int32 * M2S_MAX_UPS),
         ("num_kernels", C.c_int32), ("resblock_kernel_sizes", C.c_int32 * M2S_MAX_RBK),
         ("resblock_dilations", (C.c_int32 * 3) * M2S_MAX_RBK), ("precision", C.c_int32),
+        ("resblock", C.c_int32),
     ]
 
 

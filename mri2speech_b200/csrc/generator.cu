@@ -119,6 +119,7 @@ struct m2s_generator {
                            // operand, lo = fp16(v - hi)) instead of fp32 + an fp16 operand copy.  8 instead of 12 bytes
                            // of DRAM traffic per element of a pair, bit-compatible results -- but measured SLOWER
                            // (profiles/README.md): the epilogue is bound by memory requests in flight, not by bytes.
+  bool rb2 = false;        // cfg.resblock == 2: ResBlock2 branches (c1 holds their 2 convs each, c2 stays empty)
   int hop = 1;
   Layer pre;
   std::vector<Layer> ups;
@@ -237,6 +238,8 @@ extern "C" int m2s_generator_create(const m2s_generator_config* cfg, const m2s_t
   g->cfg = *cfg;
   g->tf32 = cfg->precision != M2S_PREC_FP32;
   g->fp16 = cfg->precision == M2S_PREC_FP16;
+  g->rb2 = cfg->resblock == 2;
+  if (cfg->resblock < 0 || cfg->resblock > 2) { delete g; return fail(M2S_ERR_BAD_ARG, "resblock must be 1 or 2"); }
   if (const char* f = std::getenv("M2S_FUSE_PAIRS")) g->fuse_pairs = std::atoi(f) != 0;
   if (const char* f = std::getenv("M2S_SPLIT_RES")) g->split_res = g->fp16 && std::atoi(f) != 0;
   // operand format per layer: fp16 needs 16-byte aligned rows of halves (c_in % 8 == 0); conv_pre reads the fp32 mel
@@ -264,6 +267,16 @@ extern "C" int m2s_generator_create(const m2s_generator_config* cfg, const m2s_t
     for (int j = 0; j < cfg->num_kernels; ++j) {
       const std::string p = "resblocks." + std::to_string(i * cfg->num_kernels + j);
       const int k = cfg->resblock_kernel_sizes[j];
+      if (g->rb2) {  // models.py:58-80: convs.0 / convs.1, causal like ResBlock1 (utils.py:34-35 + the keep-first-L trim)
+        for (int d = 0; d < 2; ++d) {
+          Layer a;
+          if ((st = make_conv1d_layer(m, p + ".convs." + std::to_string(d), cout, cout, k, true,
+                                      cfg->resblock_dilations[j][d], mode_for(cout), &a)) != M2S_OK)
+            return bail(st);
+          g->c1.push_back(a);
+        }
+        continue;
+      }
       for (int d = 0; d < 3; ++d) {
         Layer a, b;
         if ((st = make_conv1d_layer(m, p + ".convs1." + std::to_string(d), cout, cout, k, true,
@@ -295,8 +308,8 @@ extern "C" int m2s_generator_create(const m2s_generator_config* cfg, const m2s_t
   }
   for (const Layer& L : g->c1)  // the split stream needs fp16 operands in every stage
     if (!L.w.half) g->split_res = false;
-  g->launches = 2 + cfg->num_upsamples * (1 + cfg->num_kernels * 6) + 1;
-  if (g->fp16 && g->fuse_pairs) {  // stages whose ResBlock pairs run fused: one launch per pair instead of two
+  g->launches = 2 + cfg->num_upsamples * (1 + cfg->num_kernels * (g->rb2 ? 2 : 6)) + 1;
+  if (g->fp16 && g->fuse_pairs && !g->rb2) {  // stages whose ResBlock pairs run fused: one launch per pair instead of two
     for (int i = 0; i < cfg->num_upsamples; ++i)
       if (g->ups_cout[i] <= engine_knobs().fuse_max_n && g->ups_cout[i] % 32 == 0) g->launches -= cfg->num_kernels * 3;
   }
@@ -411,7 +424,8 @@ int generator_forward_impl(m2s_generator* g, const float* mel, bool mel_btc, int
   for (int i = 0; i < cfg.num_upsamples; ++i) {
     const int u = cfg.upsample_rates[i];
     const int cout = g->ups_cout[i];
-    const bool hs = g->c1[i * cfg.num_kernels * 3].w.half != 0;  // this stage's ResBlock convs take fp16 operands
+    const int per_block = g->rb2 ? 2 : 3;   // convs (ResBlock2) / conv pairs (ResBlock1) per branch
+    const bool hs = g->c1[i * cfg.num_kernels * per_block].w.half != 0;  // this stage's ResBlock convs take fp16 operands
     {  // ups: rows = L, N = u*cout; D viewed as (B, L, u*cout) == (B, L*u, cout)
       const bool split = hs && g->split_res;
       ConvProblem p = base_problem(P, L, ch, batch, L, split ? nullptr : Qs.f32, u * cout, L, L, g->ups[i]);
@@ -426,6 +440,42 @@ int generator_forward_impl(m2s_generator* g, const float* mel, bool mel_btc, int
     for (int j = 0; j < cfg.num_kernels; ++j) {
       const bool split = hs && g->split_res;
       const Stream* state = &Qs;
+      // the epilogue of a branch's LAST conv: MRF bookkeeping -- S = x | S += x | P = mask(lrelu((S + x) / nk, slope_next))
+      auto finish_branch = [&](ConvProblem* pl) {
+        if (j + 1 < cfg.num_kernels) {
+          pl->d = S; pl->d16 = nullptr; pl->d16_lo = nullptr;
+          if (j > 0) { pl->epi.accum = S; pl->epi.accum_ld = ch; }
+        } else {
+          if (next_half) set_out(pl, nullptr, P);
+          else { pl->d = P; pl->d16 = nullptr; }
+          pl->d16_lo = nullptr;
+          if (j > 0) { pl->epi.accum = S; pl->epi.accum_ld = ch; }
+          pl->epi.out_scale = 1.f / static_cast<float>(cfg.num_kernels);
+          pl->epi.act = M2S_ACT_LRELU; pl->epi.act_slope = last_stage ? 0.01f : 0.1f;
+          pl->epi.mask_mode = mask; pl->epi.lens = lengths; pl->epi.len_scale = scale;
+        }
+      };
+      if (g->rb2) {  // ResBlock2: x = x + c_d(lrelu(x)) for the two dilations -- one launch per conv, residual fused
+        for (int d = 0; d < 2; ++d) {
+          const Stream& out = Rs[d & 1];
+          const Layer& l = g->c1[(i * cfg.num_kernels + j) * 2 + d];
+          const void* state_op = hs ? static_cast<const void*>(state->hi) : static_cast<const void*>(state->f32);
+          ConvProblem pc = base_problem(state_op, L, ch, batch, L, split ? nullptr : out.f32, ch, L, L, l);
+          if (split) { pc.epi.res_hi = state->hi; pc.epi.res_lo = state->lo; }
+          else pc.epi.res = state->f32;
+          pc.epi.res_ld = ch; pc.epi.res_inv_slope = 10.f;
+          if (d == 0) {
+            pc.epi.act = M2S_ACT_LRELU; pc.epi.act_slope = 0.1f;
+            if (hs) pc.d16 = out.hi;
+            if (split) pc.d16_lo = out.lo;
+          } else {
+            finish_branch(&pc);
+          }
+          M2S_TRY(run_conv(g, pc, l, st));
+          state = &out;
+        }
+        continue;
+      }
       for (int d = 0; d < 3; ++d) {
         const Stream& out = Rs[d & 1];
         const void* state_op = hs ? static_cast<const void*>(state->hi) : static_cast<const void*>(state->f32);
@@ -442,16 +492,8 @@ int generator_forward_impl(m2s_generator* g, const float* mel, bool mel_btc, int
           p2.epi.act = M2S_ACT_LRELU; p2.epi.act_slope = 0.1f;
           if (hs) p2.d16 = out.hi;
           if (split) p2.d16_lo = out.lo;
-        } else if (j + 1 < cfg.num_kernels) {
-          p2.d = S;
-          if (j > 0) { p2.epi.accum = S; p2.epi.accum_ld = ch; }
         } else {
-          if (next_half) set_out(&p2, nullptr, P);
-          else p2.d = P;
-          if (j > 0) { p2.epi.accum = S; p2.epi.accum_ld = ch; }
-          p2.epi.out_scale = 1.f / static_cast<float>(cfg.num_kernels);
-          p2.epi.act = M2S_ACT_LRELU; p2.epi.act_slope = last_stage ? 0.01f : 0.1f;
-          p2.epi.mask_mode = mask; p2.epi.lens = lengths; p2.epi.len_scale = scale;
+          finish_branch(&p2);
         }
         // fp16 build, C <= 128: conv1 -> leaky-ReLU -> conv2 in ONE kernel, the intermediate stays in SMEM
         if (hs && g->fuse_pairs && resblock_pair_supported(p1, l1.w, p2, l2.w)) {

@@ -70,12 +70,31 @@ class ResBlock1(nn.Module):
             remove_weight_norm(layer)
 
 
+class ResBlock2(nn.Module):
+    """Parameter holder for the light multi-receptive-field branch of configs with ``"resblock": "2"`` (reference
+    models.py:58-85): two causal dilated convs, each x = x + c(lrelu(x))."""
+
+    def __init__(self, h, channels, kernel_size=3, dilation=(1, 3)):
+        super().__init__()
+        self.h = h
+        self.convs = nn.ModuleList([
+            _wn(Conv1d(channels, channels, kernel_size, 1, dilation=dilation[m], padding=get_padding(kernel_size, dilation[m])))
+            for m in range(2)])
+        self.convs.apply(init_weights)
+
+    def forward(self, x):
+        raise _lib.M2SError("ResBlock2 is fused into Generator.forward on the sm_100a path; call the Generator")
+
+    def remove_weight_norm(self):
+        for layer in self.convs:
+            remove_weight_norm(layer)
+
+
 class Generator(nn.Module):
     def __init__(self, h, precision: str = "tf32"):
         super().__init__()
         self.h = h
-        if str(_cfg(h, "resblock")) != "1":
-            raise _lib.M2SError("only resblock == '1' (config_custom.json:2) is implemented on the sm_100a path")
+        self.resblock_type = 1 if str(_cfg(h, "resblock")) == "1" else 2   # models.py:95
         rates = list(_cfg(h, "upsample_rates"))
         ksizes = list(_cfg(h, "upsample_kernel_sizes"))
         rb_k = list(_cfg(h, "resblock_kernel_sizes"))
@@ -92,7 +111,7 @@ class Generator(nn.Module):
         for i in range(len(self.ups)):
             ch = c0 // (2 ** (i + 1))
             for k, d in zip(rb_k, rb_d):
-                self.resblocks.append(ResBlock1(h, ch, k, d))
+                self.resblocks.append(ResBlock1(h, ch, k, d) if self.resblock_type == 1 else ResBlock2(h, ch, k, d))
         self.conv_post = _wn(Conv1d(ch, 1, 7, 1, padding=0))
         self.ups.apply(init_weights)
         self.conv_post.apply(init_weights)
@@ -123,11 +142,13 @@ class Generator(nn.Module):
         cfg.num_kernels = self.num_kernels
         for j, (k, ds) in enumerate(zip(_cfg(h, "resblock_kernel_sizes"), _cfg(h, "resblock_dilation_sizes"))):
             cfg.resblock_kernel_sizes[j] = int(k)
-            if len(ds) != 3:
-                raise _lib.M2SError("ResBlock1 needs exactly 3 dilations per kernel size")
-            for m, d in enumerate(ds):
+            need = 3 if self.resblock_type == 1 else 2
+            if (len(ds) != 3) if self.resblock_type == 1 else (len(ds) < 2):
+                raise _lib.M2SError(f"ResBlock{self.resblock_type} needs {need} dilations per kernel size")
+            for m, d in enumerate(list(ds)[:need]):
                 cfg.resblock_dilations[j][m] = int(d)
         cfg.precision = _lib.PRECISIONS[self.precision]
+        cfg.resblock = self.resblock_type
         return cfg
 
     def refresh(self):

@@ -42,6 +42,16 @@ def vocoder_goldens():
     # cross-check the restatement while we are here
     y = generator_forward(g_ref.state_dict(), h, mel)
     assert (y - wav).abs().max().item() < 1e-6
+    # config with "resblock": "2" (models.py:58-80, :95): same seed, ResBlock2 branches with dilations (1, 3)
+    g2, h2 = ref_import.reference_generator(1234, resblock="2", resblock_dilation_sizes=[[1, 3], [1, 3], [1, 3]])
+    lens = [24, 13]
+    with torch.no_grad():
+        wav2 = g2(mel)
+        solo = g2(mel[1:2, :, :13])[0, 0]
+    np.savez_compressed(os.path.join(GOLDEN, "vocoder_ref_seed1234_resblock2.npz"),
+                        mel=mel.numpy(), wav=wav2.numpy(), lens=np.asarray(lens, np.int32), wav1_ragged=solo.numpy())
+    y2 = generator_forward(g2.state_dict(), h2, mel)
+    assert (y2 - wav2).abs().max().item() < 1e-6
     print("vocoder goldens written")
 
 

@@ -51,13 +51,14 @@ def import_reference_models():
     return ref_models
 
 
-def reference_generator(seed: int = 1234):
+def reference_generator(seed: int = 1234, **overrides):
     """Reference Generator with its own default random init under ``seed``
-    (= config_custom.json:9)."""
+    (= config_custom.json:9); ``overrides`` replace config entries (e.g. resblock="2")."""
     import warnings
     import torch
     ref_models = import_reference_models()
     h = load_config()
+    h.update(overrides)
     torch.manual_seed(seed)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")

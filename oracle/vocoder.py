@@ -59,6 +59,7 @@ def generator_forward(sd: dict, h, mel: torch.Tensor, lengths=None, dtype=torch.
     rb_k = list(h["resblock_kernel_sizes"])
     rb_d = [list(d) for d in h["resblock_dilation_sizes"]]
     nk = len(rb_k)
+    rb2 = str(h["resblock"]) != "1"   # models.py:95: ResBlock1 if h.resblock == '1' else ResBlock2
     if mel.dim() == 2:
         mel = mel.unsqueeze(0)
     x = mel.to(dtype)
@@ -83,12 +84,20 @@ def generator_forward(sd: dict, h, mel: torch.Tensor, lengths=None, dtype=torch.
         for j in range(nk):
             r = x
             p = f"resblocks.{i * nk + j}"
-            for m, d in enumerate(rb_d[j]):
-                t = causal_conv1d(F.leaky_relu(r, LRELU_SLOPE),
-                                  fold_weight_norm(sd, f"{p}.convs1.{m}", dtype), get(f"{p}.convs1.{m}.bias"), d)
-                t = causal_conv1d(F.leaky_relu(t, LRELU_SLOPE),
-                                  fold_weight_norm(sd, f"{p}.convs2.{m}", dtype), get(f"{p}.convs2.{m}.bias"), 1)
-                r = r + t
+            if rb2:
+                # ResBlock2 (models.py:58-80): two units x = x + c(lrelu(x)) with dilation[0], dilation[1]; the conv pads
+                # (k-1)*d on both sides (utils.py:34-35) and :74-78 keeps the first L outputs -> causal, like ResBlock1
+                for m in range(2):
+                    t = causal_conv1d(F.leaky_relu(r, LRELU_SLOPE),
+                                      fold_weight_norm(sd, f"{p}.convs.{m}", dtype), get(f"{p}.convs.{m}.bias"), rb_d[j][m])
+                    r = r + t
+            else:
+                for m, d in enumerate(rb_d[j]):
+                    t = causal_conv1d(F.leaky_relu(r, LRELU_SLOPE),
+                                      fold_weight_norm(sd, f"{p}.convs1.{m}", dtype), get(f"{p}.convs1.{m}.bias"), d)
+                    t = causal_conv1d(F.leaky_relu(t, LRELU_SLOPE),
+                                      fold_weight_norm(sd, f"{p}.convs2.{m}", dtype), get(f"{p}.convs2.{m}.bias"), 1)
+                    r = r + t
             xs = r if xs is None else xs + r
         x = xs / nk
     x = mask(F.leaky_relu(x, 0.01), scale)

@@ -33,7 +33,7 @@ def test_ctypes_struct_sizes_match_header_layout():
     assert _lib.ConvArgs.shift.offset == 40 and _lib.ConvArgs.shift.size == 64
     assert _lib.ConvArgs.w.offset == 104
     assert C.sizeof(_lib.Tensor) == 8 + 8 + 8 + 32
-    assert C.sizeof(_lib.GeneratorConfig) == 4 * (3 + 8 + 8 + 1 + 8 + 24 + 1)
+    assert C.sizeof(_lib.GeneratorConfig) == 4 * (3 + 8 + 8 + 1 + 8 + 24 + 1 + 1)   # ... precision, resblock
 
 
 def test_cpu_tensors_are_refused_loudly():

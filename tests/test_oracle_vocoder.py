@@ -73,3 +73,30 @@ def test_against_live_reference_when_present():
     assert (generator_forward(sd, h, mel) - y_ref).abs().max().item() < 1e-6
     # float64 restatement == reference to fp32 rounding
     assert (generator_forward(sd, h, mel, dtype=torch.float64).float() - y_ref).abs().max().item() < 1e-6
+
+
+def _config_rb2():
+    h = load_config()
+    h["resblock"] = "2"
+    h["resblock_dilation_sizes"] = [[1, 3], [1, 3], [1, 3]]
+    return h
+
+
+def test_resblock2_oracle_matches_reference_golden():
+    """Configs with "resblock": "2" (reference models.py:58-85, :95).  The golden comes from the reference's own
+    Generator under seed 1234; the product's Generator must re-create the same tensors from the same seed (names
+    resblocks.N.convs.M.*), and the oracle's ResBlock2 branch must reproduce the waveform, ragged clip included."""
+    from mri2speech_b200.vocoder import Generator
+    from oracle.vocoder import generator_forward
+    h = _config_rb2()
+    torch.manual_seed(1234)
+    sd = Generator(h).state_dict()
+    assert "resblocks.0.convs.1.weight_v" in sd and "resblocks.0.convs1.0.weight_v" not in sd
+    assert sd["resblocks.11.convs.1.weight_v"].shape == (32, 32, 11)
+    z = np.load(os.path.join(GOLDEN, "vocoder_ref_seed1234_resblock2.npz"))
+    mel = torch.from_numpy(z["mel"])
+    wav = generator_forward(sd, h, mel)
+    assert np.abs(wav.numpy() - z["wav"]).max() < 1e-6
+    rag = generator_forward(sd, h, mel, lengths=z["lens"].tolist())
+    n = z["wav1_ragged"].shape[0]
+    assert np.abs(rag[1, 0, :n].numpy() - z["wav1_ragged"]).max() < 1e-6

@@ -151,3 +151,27 @@ def test_split_fp16_residual_stream_build(monkeypatch):
     with torch.no_grad():
         wav = g3(torch.from_numpy(z["mel"]).cuda()).cpu().numpy()
     assert _snr(z["wav"], wav) >= 40.0 and _snr(z["wav"], wav, True) >= 40.0
+
+
+@pytest.mark.parametrize("precision,min_snr,min_snr_ac", [("fp32", 90.0, 70.0), ("tf32", 40.0, 40.0),
+                                                          ("fp16", 40.0, 40.0)])
+def test_resblock2_config_against_reference_golden(precision, min_snr, min_snr_ac):
+    """"resblock": "2" configs (reference models.py:58-85): one engine launch per conv with the residual fused; golden
+    from the reference's own Generator (tests/golden/vocoder_ref_seed1234_resblock2.npz), full and ragged batch."""
+    from mri2speech_b200.vocoder import Generator
+    h = load_config()
+    h["resblock"] = "2"
+    h["resblock_dilation_sizes"] = [[1, 3], [1, 3], [1, 3]]
+    torch.manual_seed(1234)
+    g = Generator(h, precision=precision).cuda().eval()
+    z = np.load(os.path.join(GOLDEN, "vocoder_ref_seed1234_resblock2.npz"))
+    mel = torch.from_numpy(z["mel"]).cuda()
+    with torch.no_grad():
+        wav = g(mel).cpu().numpy()
+        rag = g(mel, lengths=torch.from_numpy(z["lens"]).cuda()).cpu().numpy()
+    snr, snr_ac = _snr(z["wav"], wav), _snr(z["wav"], wav, True)
+    print(f"[resblock2 {precision}] SNR {snr:.1f} dB, mean-removed {snr_ac:.1f} dB")
+    assert snr >= min_snr and snr_ac >= min_snr_ac
+    n = z["wav1_ragged"].shape[0]
+    assert _snr(z["wav1_ragged"], rag[1, 0, :n], True) >= min_snr_ac
+    assert g.launches_per_forward() == 2 + 4 * (1 + 3 * 2) + 1
