@@ -219,6 +219,11 @@ struct EpiConsts {
 enum { EPI_FULL = 0, EPI_FULL_SILU = 1, EPI_BIAS = 2, EPI_LRELU = 3, EPI_SILU = 4, EPI_RES = 5, EPI_RB = 6, EPI_RB_ACC = 7,
        EPI_RB_S = 8, EPI_RB_ACC_S = 9, EPI_COUNT = 10 };
 
+// Host side, every launcher, after copying the problem into its kernel parameters: derived epilogue constants.
+inline void finalize_epilogue(Epilogue* e) {
+  e->pitch_magic = (e->mask_mode == M2S_MASK_PITCH && e->pitch > 0) ? 0xFFFFFFFFu / static_cast<unsigned>(e->pitch) + 1u : 0u;
+}
+
 // Host-side choice of the epilogue program for a problem (shared by both kernels).
 // -1: a split-fp16 residual with an epilogue the two ResBlock programs do not cover (unsupported).
 inline int choose_epilogue(const Epilogue& e);
@@ -246,8 +251,9 @@ inline int choose_epilogue(const Epilogue& e) {
 // same size as the operand rounding of the next GEMM).  The exp + reciprocal form costs two quarter-rate MUFU ops per
 // output and made every SiLU epilogue MUFU-bound (measured: 2000 cycles per 32 x 32 unit per warp, stores or MMAs
 // switched off made no difference).
-__device__ __forceinline__ float fast_silu(float v) {
-  const float h = 0.5f * v;
+// `hm` = 0.5, or 0 for an output the image-border mask zeroes (the mask then costs nothing: silu(0) = 0).
+__device__ __forceinline__ float fast_silu(float v, float hm = 0.5f) {
+  const float h = hm * v;
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
   return fmaf(h, t, h);
@@ -278,12 +284,13 @@ __device__ __forceinline__ void split_encode(const float4& o, uint2* hi, uint2* 
 }
 
 template <int kEpiS>
-__device__ __forceinline__ float epi_elem(const EpiConsts& c, float acc, float bias, float res, float accum) {
+__device__ __forceinline__ float epi_elem(const EpiConsts& c, float acc, float bias, float res, float accum,
+                                          float hm = 0.5f) {
   constexpr int kEpi = kEpiS == EPI_RB_S ? EPI_RB : kEpiS == EPI_RB_ACC_S ? EPI_RB_ACC : kEpiS;
   float v = acc + bias;
   if (kEpi == EPI_BIAS) return v;
   if (kEpi == EPI_LRELU) return fmaxf(v, v * c.act_slope);  // 0 < slope <= 1
-  if (kEpi == EPI_SILU) return fast_silu(v);
+  if (kEpi == EPI_SILU) return fast_silu(v, hm);
   if (kEpi == EPI_RES) return v + res;
   if (kEpi == EPI_RB) {
     v += fminf(res, res * c.inv_slope);                     // inv_slope >= 1
@@ -384,6 +391,11 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
   while (ci >= nchunks) { ci -= nchunks; ++sub; }
   if (pipelined && sub < msub) issue_tmem_ld(sub, ci);
   const bool pitch_mask = mask_mode == M2S_MASK_PITCH;
+  // image-border mask as one multiplier (1 or 0) per row of this thread, recomputed only when the 32-row slab changes
+  // (the units of a slab share their rows): the per-row divmod + compare chain + selects were a third of the
+  // instructions of the encoder's 3x3 convs, which are issue-bound in the epilogue (62 % issue-active, profiles/README.md)
+  float rm[kR] = {1.f, 1.f, 1.f, 1.f};
+  int rm_sub = -1;   // (dead code in the accumulate programs)
   for (int sub_n, ci_n; sub < msub; sub = sub_n, ci = ci_n) {
     sub_n = sub;
     ci_n = ci + kEpiGroups;
@@ -490,12 +502,26 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
                        : "=f"(a8[i].x), "=f"(a8[i].y), "=f"(a8[i].z), "=f"(a8[i].w)
                        : "r"(epi_stage_addr(stage, rr, cc)));
         }
-        // one row loop per mask kind (compile-time inside: the image-border test costs a divmod and a compare chain per row)
+        // (programs with an accumulate stream are at the register cap and never run on images in this path: they keep
+        // the plain per-row test below)
+        if (!kHasAcc && pitch_mask && sub != rm_sub) {   // (warp-uniform)
+          rm_sub = sub;
+          const int drow = qw + rr0 + p.d_row_offset;
+          int mi = static_cast<int>(__umulhi(static_cast<unsigned>(drow), e.pitch_magic));
+          int mj = drow - mi * e.pitch;
+#pragma unroll
+          for (int i = 0; i < kR; ++i) {
+            rm[i] = (mi >= e.i_lo && mi < e.i_hi && mj >= e.j_lo && mj < e.j_hi) ? 1.f : 0.f;
+            mj += 8;
+            while (mj >= e.pitch) { mj -= e.pitch; ++mi; }
+          }
+        }
+        // one row loop per mask kind (compile-time inside)
         auto rows = [&](auto pitch_tag) {
           constexpr int kPitchMode = decltype(pitch_tag)::value;
           const bool kPitch = kPitchMode == 2 ? pitch_mask : kPitchMode == 1;
           int mi = 0, mj = 0;
-          if (kPitch) {
+          if (kHasAcc && kPitch) {
             const int drow = qw + rr0 + p.d_row_offset;
             mi = drow / e.pitch;
             mj = drow - mi * e.pitch;
@@ -514,11 +540,14 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
             }
             const float4 c4 = kHasAcc ? acc4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
             float4 o;
-            o.x = epi_elem<kEpi>(ec, a4.x, bias4.x, r4.x, c4.x);
-            o.y = epi_elem<kEpi>(ec, a4.y, bias4.y, r4.y, c4.y);
-            o.z = epi_elem<kEpi>(ec, a4.z, bias4.z, r4.z, c4.z);
-            o.w = epi_elem<kEpi>(ec, a4.w, bias4.w, r4.w, c4.w);
-            if (kPitch) {
+            // plain SiLU program: the mask rides on the 0.5 of h = v / 2; every other program multiplies its result
+            const float hm = (kEpi == EPI_SILU && kPitch) ? 0.5f * rm[i] : 0.5f;
+            o.x = epi_elem<kEpi>(ec, a4.x, bias4.x, r4.x, c4.x, hm);
+            o.y = epi_elem<kEpi>(ec, a4.y, bias4.y, r4.y, c4.y, hm);
+            o.z = epi_elem<kEpi>(ec, a4.z, bias4.z, r4.z, c4.z, hm);
+            o.w = epi_elem<kEpi>(ec, a4.w, bias4.w, r4.w, c4.w, hm);
+            if (!kHasAcc && kEpi != EPI_SILU && kPitch) { o.x *= rm[i]; o.y *= rm[i]; o.z *= rm[i]; o.w *= rm[i]; }
+            if (kHasAcc && kPitch) {
               if (!(mi >= e.i_lo && mi < e.i_hi && mj >= e.j_lo && mj < e.j_hi)) o = make_float4(0.f, 0.f, 0.f, 0.f);
               mj += 8;
               while (mj >= e.pitch) { mj -= e.pitch; ++mi; }

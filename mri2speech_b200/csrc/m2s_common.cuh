@@ -46,6 +46,8 @@ struct Epilogue {
   int mask_mode;
   int len_scale;
   int pitch, i_lo, i_hi, j_lo, j_hi;
+  unsigned pitch_magic;  // floor(2^32 / pitch) + 1: row / pitch == __umulhi(row, pitch_magic) for row * pitch < 2^32
+                         // (filled in by the launchers: finalize_epilogue)
 };
 
 struct ConvProblem {
