@@ -25,7 +25,7 @@ int enc_zero_rows(void* buf, int esize, int n, int rows_per_frame, int ld, int h
 int enc_im2col_s2(const void* in, void* col, int esize, int n, int Hin, int Win, int C, cudaStream_t st);
 int enc_dwconv(const void* in, void* out, int half, float* sums, const float* w, const float* bias, int n, int C, int Hin,
                int Win, int pitch_in, int oy, int ox, int rows_in, int stride, cudaStream_t st);
-int enc_se_apply(void* x, int half, const float* sums, const float* w1, const float* b1, const float* w2, const float* b2,
+int enc_se_apply(void* x, int half, float* sums, const float* w1, const float* b1, const float* w2, const float* b2,
                  int n, int C, int rd, int hw, cudaStream_t st);
 int enc_gap(const float* x, const int32_t* fmap, float* feats, int n, int hw, int C, int feat_ld, cudaStream_t st);
 int lstm_recurrence(const float* gin, const float* w_hh_fwd, const float* w_hh_bwd, const int32_t* lens, float* hcat,
@@ -503,7 +503,7 @@ extern "C" int m2s_acoustic_create(const m2s_acoustic_config* cfg, const m2s_ten
         m->e2_floats = std::max(m->e2_floats, static_cast<size_t>(ho) * wo * b.mid);
         m->x_floats = std::max(m->x_floats, static_cast<size_t>(ho) * wo * b.cout);
         m->max_mid = std::max(m->max_mid, b.mid);
-        launches += 4;
+        launches += 5;  // expand, depthwise, SE MLP, SE scale, project
       }
       m->blocks.push_back(b);
       padded = b.out_padded;

@@ -351,54 +351,90 @@ __global__ void __launch_bounds__(256, 3) dwconv_kernel(const T* __restrict__ in
   }
 }
 
-// Squeeze-excite MLP and excite scale in ONE pass over the tensor: every block recomputes the (tiny) MLP of its frame
-// -- scale[c] = sigmoid(W2 silu(W1 mean + b1) + b2), 2 * C * rd MACs -- into SMEM and then scales its share of the
-// frame's pixels in place.  grid = (frames, splits); 1024 threads: phase 1 = one warp per reduced unit (float4 over
-// channels), phase 2 = one thread per channel (coalesced over W2^T), phase 3 = the streaming multiply.
-template <typename T>
-__global__ void __launch_bounds__(1024) se_apply_kernel(T* __restrict__ x, const float* __restrict__ sums,
-                                                        const float* __restrict__ w1 /*[rd][C]*/, const float* __restrict__ b1,
-                                                        const float* __restrict__ w2t /*[rd][C]*/, const float* __restrict__ b2,
-                                                        int C, int rd, int hw, float inv_hw) {
-  extern __shared__ float sm[];  // mean[C] + scale[C] + r[rd]
+// Squeeze-excite in two kernels.
+//  (1) se_mlp_kernel: scale[n][c] = sigmoid(W2 silu(W1 mean_n + b1) + b2) for KF frames per block, written over the
+//      squeeze sums.  The MLP weights (2 * rd * C floats: 520 KB at C = 1248) are read ONCE per KF frames; the earlier
+//      fused kernel re-read them in every block of every frame, which cost more L2 traffic than the tensor it scaled.
+//  (2) se_scale_kernel: the streaming multiply, in place; grid = (frames, splits).
+template <int KF>
+__global__ void __launch_bounds__(1024) se_mlp_kernel(float* __restrict__ sums /* in: sums, out: scales */,
+                                                     const float* __restrict__ w1 /*[rd][C]*/, const float* __restrict__ b1,
+                                                     const float* __restrict__ w2t /*[rd][C]*/, const float* __restrict__ b2,
+                                                     int C, int rd, float inv_hw, int n_frames) {
+  extern __shared__ float sm[];  // mean[KF][C] + r[KF][rd]
   float* mean = sm;
-  float* scale = sm + C;
-  float* r = sm + 2 * C;
-  const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = sums[static_cast<size_t>(n) * C + c] * inv_hw;
+  float* r = sm + KF * C;
+  const int n0 = blockIdx.x * KF;
+  for (int i = threadIdx.x; i < KF * C; i += blockDim.x) {
+    const int f = i / C;
+    mean[i] = n0 + f < n_frames ? sums[static_cast<size_t>(n0) * C + i] * inv_hw : 0.f;
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int c4n = C >> 2;
   for (int j = warp; j < rd; j += nwarps) {
     const float4* wr = reinterpret_cast<const float4*>(w1 + static_cast<size_t>(j) * C);
-    float a = 0.f;
+    float a[KF];
+#pragma unroll
+    for (int f = 0; f < KF; ++f) a[f] = 0.f;
+#pragma unroll 2
     for (int k = lane; k < c4n; k += 32) {
       const float4 wv = __ldg(wr + k);
-      const float4 mv = reinterpret_cast<const float4*>(mean)[k];
-      a = fmaf(wv.x, mv.x, a); a = fmaf(wv.y, mv.y, a); a = fmaf(wv.z, mv.z, a); a = fmaf(wv.w, mv.w, a);
+#pragma unroll
+      for (int f = 0; f < KF; ++f) {
+        const float4 mv = reinterpret_cast<const float4*>(mean + f * C)[k];
+        a[f] = fmaf(wv.x, mv.x, a[f]); a[f] = fmaf(wv.y, mv.y, a[f]); a[f] = fmaf(wv.z, mv.z, a[f]); a[f] = fmaf(wv.w, mv.w, a[f]);
+      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    for (int f = 0; f < KF; ++f) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a[f] += __shfl_xor_sync(0xffffffffu, a[f], o);
+    }
     if (lane == 0) {
-      a += b1[j];
-      r[j] = a / (1.f + expf(-a));
+      const float bj = b1[j];
+#pragma unroll
+      for (int f = 0; f < KF; ++f) {
+        const float v = a[f] + bj;
+        r[f * rd + j] = v / (1.f + expf(-v));
+      }
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a0 = b2[c], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    float a[KF];
+    const float bc = b2[c];
+#pragma unroll
+    for (int f = 0; f < KF; ++f) a[f] = bc;
     int j = 0;
-    for (; j + 4 <= rd; j += 4) {
-      a0 = fmaf(__ldg(w2t + static_cast<size_t>(j) * C + c), r[j], a0);
-      a1 = fmaf(__ldg(w2t + static_cast<size_t>(j + 1) * C + c), r[j + 1], a1);
-      a2 = fmaf(__ldg(w2t + static_cast<size_t>(j + 2) * C + c), r[j + 2], a2);
-      a3 = fmaf(__ldg(w2t + static_cast<size_t>(j + 3) * C + c), r[j + 3], a3);
+    for (; j + 8 <= rd; j += 8) {   // eight independent weight loads in flight (the loop is L2-latency bound otherwise)
+      float w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) w[u] = __ldg(w2t + static_cast<size_t>(j + u) * C + c);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+#pragma unroll
+        for (int f = 0; f < KF; ++f) a[f] = fmaf(w[u], r[f * rd + j + u], a[f]);
+      }
     }
-    for (; j < rd; ++j) a0 = fmaf(__ldg(w2t + static_cast<size_t>(j) * C + c), r[j], a0);
-    const float a = (a0 + a1) + (a2 + a3);
-    scale[c] = 1.f / (1.f + expf(-a));
+    for (; j < rd; ++j) {
+      const float w = __ldg(w2t + static_cast<size_t>(j) * C + c);
+#pragma unroll
+      for (int f = 0; f < KF; ++f) a[f] = fmaf(w, r[f * rd + j], a[f]);
+    }
+#pragma unroll
+    for (int f = 0; f < KF; ++f)
+      if (n0 + f < n_frames) sums[static_cast<size_t>(n0 + f) * C + c] = 1.f / (1.f + expf(-a[f]));
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) se_scale_kernel(T* __restrict__ x, const float* __restrict__ scales, int C, int hw) {
+  extern __shared__ float scale[];  // [C]
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) scale[c] = scales[static_cast<size_t>(n) * C + c];
   __syncthreads();
+  const int c4n = C >> 2;
   // this block's pixels of frame n
   const int p0 = static_cast<int>((static_cast<long long>(hw) * blockIdx.y) / gridDim.y);
   const int p1 = static_cast<int>((static_cast<long long>(hw) * (blockIdx.y + 1)) / gridDim.y);
@@ -532,18 +568,28 @@ int enc_dwconv(const void* in, void* out, int half, float* sums, const float* w,
 }
 
 // SE MLP + excite scale, one pass.
-int enc_se_apply(void* x, int half, const float* sums, const float* w1, const float* b1, const float* w2, const float* b2,
+int enc_se_apply(void* x, int half, float* sums, const float* w1, const float* b1, const float* w2, const float* b2,
                  int n, int C, int rd, int hw, cudaStream_t st) {
+  constexpr int kF = 8;  // frames per MLP block
+  const size_t sm_mlp = (static_cast<size_t>(kF) * C + static_cast<size_t>(kF) * rd) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    M2S_CUDA_OK(cudaFuncSetAttribute(se_mlp_kernel<kF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  if (sm_mlp > 100 * 1024) return fail(M2S_ERR_UNSUPPORTED, "squeeze-excite: %d channels exceed the MLP kernel's SMEM", C);
+  se_mlp_kernel<kF><<<(n + kF - 1) / kF, 1024, sm_mlp, st>>>(sums, w1, b1, w2, b2, C, rd, 1.f / hw, n);
+  M2S_CUDA_OK(cudaGetLastError());
   const size_t bytes = static_cast<size_t>(hw) * C * (half ? 2 : 4);
   int splits = static_cast<int>((bytes + 192 * 1024 - 1) / (192 * 1024));  // ~<= 192 KB of the tensor per block
   if (splits < 1) splits = 1;
   if (splits > hw) splits = hw;
   dim3 grid(n, splits);
-  const size_t sm = (2 * static_cast<size_t>(C) + rd) * sizeof(float);
+  const size_t sm = static_cast<size_t>(C) * sizeof(float);
   if (half)
-    se_apply_kernel<<<grid, 1024, sm, st>>>(static_cast<__half*>(x), sums, w1, b1, w2, b2, C, rd, hw, 1.f / hw);
+    se_scale_kernel<<<grid, 1024, sm, st>>>(static_cast<__half*>(x), sums, C, hw);
   else
-    se_apply_kernel<<<grid, 1024, sm, st>>>(static_cast<float*>(x), sums, w1, b1, w2, b2, C, rd, hw, 1.f / hw);
+    se_scale_kernel<<<grid, 1024, sm, st>>>(static_cast<float*>(x), sums, C, hw);
   M2S_CUDA_OK(cudaGetLastError());
   return M2S_OK;
 }
