@@ -567,7 +567,7 @@ int enc_dwconv(const void* in, void* out, int half, float* sums, const float* w,
                        oy, ox, rows_in, stride, st);
 }
 
-// SE MLP + excite scale, one pass.
+// Squeeze-excite: batched MLP (scales written over the squeeze sums), then the streaming in-place multiply.
 int enc_se_apply(void* x, int half, float* sums, const float* w1, const float* b1, const float* w2, const float* b2,
                  int n, int C, int rd, int hw, cudaStream_t st) {
   constexpr int kF = 8;  // frames per MLP block
