@@ -7,9 +7,8 @@ import argparse
 import sys
 from pathlib import Path
 
-PROJECT_ROOT = Path(__file__).resolve().parents[1]
-if str(PROJECT_ROOT) not in sys.path:
-    sys.path.insert(0, str(PROJECT_ROOT))
+REPO = Path(__file__).resolve().parent.parent
+sys.path[:0] = [p for p in (str(REPO),) if p not in sys.path]
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -18,28 +17,43 @@ from mri2speech_b200 import io_formats, pipeline  # noqa: E402
 
 
 def load_scaler(scaler_path: Path):
-    mean, std = pipeline.load_scaler(scaler_path)
-    return torch.from_numpy(mean), torch.from_numpy(std)
+    """(mean, std) of scaler.json as float32 tensors."""
+    return tuple(torch.from_numpy(v) for v in pipeline.load_scaler(scaler_path))
 
 
 def build_model(checkpoint_path: Path, n_mels: int, device: torch.device):
+    """The acoustic model with the checkpoint's weights (plain state_dict or {"model_state_dict": ...}), eval mode."""
     from mri_acoustic_model import build_acoustic_model
     model = build_acoustic_model(n_mels=n_mels, cnn_pretrained=False, rnn_hidden=640, dropout=0.5,
-                                 use_checkpoint=False, ckpt_segments=2, use_reentrant=False).to(device)
-    checkpoint = torch.load(checkpoint_path, map_location=device)
-    state_dict = checkpoint.get("model_state_dict", checkpoint)
-    missing, unexpected = model.load_state_dict(state_dict, strict=False)
-    if missing:
-        print(f"[WARN] missing keys when loading MRI model: {missing}")
-    if unexpected:
-        print(f"[WARN] unexpected keys when loading MRI model: {unexpected}")
-    model.eval()
-    return model
+                                 use_checkpoint=False, ckpt_segments=2, use_reentrant=False)
+    payload = torch.load(checkpoint_path, map_location=device)
+    report = model.to(device).load_state_dict(payload.get("model_state_dict", payload), strict=False)
+    for kind, keys in (("missing", report.missing_keys), ("unexpected", report.unexpected_keys)):
+        if keys:
+            print(f"[WARN] {kind} keys when loading MRI model: {keys}")
+    return model.eval()
+
+
+def _work_list(samples_dir: Path, output_dir: Path, overwrite: bool):
+    """(samples/<stem>/mri.npy, <output_dir>/<stem>.npy) pairs still to do, in name order."""
+    clips = sorted((d for d in samples_dir.iterdir() if d.is_dir()), key=lambda d: d.name)
+    if not clips:
+        raise SystemExit(f"No sample folders found under {samples_dir}")
+    todo = []
+    for clip_dir in clips:
+        target = output_dir / f"{clip_dir.name}.npy"
+        if target.exists() and not overwrite:
+            continue
+        source = clip_dir / "mri.npy"
+        if source.is_file():
+            todo.append((source, target))
+        else:
+            print(f"[WARN] MRI file missing for {clip_dir.name}, skipping")
+    return todo
 
 
 def export_mels(args: argparse.Namespace) -> None:
-    processed_dir = Path(args.processed_dir).resolve()
-    samples_dir = processed_dir / "samples"
+    samples_dir = Path(args.processed_dir).resolve() / "samples"
     if not samples_dir.is_dir():
         raise SystemExit(f"samples directory not found: {samples_dir}")
     output_dir = Path(args.output_dir).resolve()
@@ -47,7 +61,6 @@ def export_mels(args: argparse.Namespace) -> None:
     mean, std = load_scaler(Path(args.scaler_json).resolve())
     if mean.numel() != std.numel():
         raise SystemExit("Scaler mean/std length mismatch")
-    n_mels = mean.numel()
     if args.cpu:
         raise SystemExit("--cpu: this build has no CPU fallback (sm_100 CUDA device required)")
     if not torch.cuda.is_available():
@@ -55,24 +68,11 @@ def export_mels(args: argparse.Namespace) -> None:
     device = torch.device("cuda")
     print(f"[INFO] Using device: {device}")
 
-    code_dir = Path(args.mri_code_dir).resolve() if args.mri_code_dir else PROJECT_ROOT / "mri2speech_code"
+    code_dir = Path(args.mri_code_dir).resolve() if args.mri_code_dir else REPO / "mri2speech_code"
     if code_dir.is_dir() and str(code_dir) not in sys.path:
         sys.path.insert(0, str(code_dir))
-    model = build_model(Path(args.mri_checkpoint).resolve(), n_mels, device)
-
-    sample_dirs = sorted([p for p in samples_dir.iterdir() if p.is_dir()], key=lambda p: p.name)
-    if not sample_dirs:
-        raise SystemExit(f"No sample folders found under {samples_dir}")
-    todo = []
-    for sample_path in sample_dirs:
-        out_path = output_dir / f"{sample_path.name}.npy"
-        if out_path.exists() and not args.overwrite:
-            continue
-        mri_path = sample_path / "mri.npy"
-        if not mri_path.is_file():
-            print(f"[WARN] MRI file missing for {sample_path.name}, skipping")
-            continue
-        todo.append((mri_path, out_path))
+    model = build_model(Path(args.mri_checkpoint).resolve(), mean.numel(), device)
+    todo = _work_list(samples_dir, output_dir, args.overwrite)
 
     with torch.no_grad(), io_formats.AsyncWriter() as writer:
         pending = []
