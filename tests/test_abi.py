@@ -78,3 +78,38 @@ def test_acoustic_load_state_dict_reports_missing_and_unexpected():
     missing, unexpected = m.load_state_dict(sd, strict=False)
     assert missing == ["head.bias"] and unexpected == ["extra.key"]
     assert hasattr(m.cnn, "backbone") and hasattr(m.cnn, "gap") and hasattr(m.rnn, "lstm") and hasattr(m.rnn, "dropout")
+
+
+def test_ctypes_structs_match_the_header_as_the_c_compiler_sees_it(tmp_path):
+    """Compile include/m2s.h with gcc (plain C: the header is the boundary a maintainer binds against) and compare
+    sizeof / offsetof of every struct that crosses the boundary with the ctypes mirrors in mri2speech_b200/_lib.py."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from mri2speech_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    checks = {
+        "m2s_conv_args": (_lib.ConvArgs, ["a", "shift", "w", "n", "d", "d_row_offset", "bias", "res", "res_inv_slope",
+                                          "accum", "out_scale", "act_slope", "lens", "len_scale", "pitch", "j_hi",
+                                          "a_half", "d16", "d16_lo", "res_hi", "res_lo"]),
+        "m2s_generator_config": (_lib.GeneratorConfig, ["num_mels", "num_upsamples", "upsample_rates", "num_kernels",
+                                                        "resblock_dilations", "precision", "resblock"]),
+        "m2s_tensor": (_lib.Tensor, ["name", "data", "ndim", "shape"]),
+        "m2s_acoustic_config": (_lib.AcousticConfig, ["n_mels", "rnn_hidden", "height", "width", "precision"]),
+    }
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "m2s.h"', 'int main(void) {']
+    for struct, (_, fields) in checks.items():
+        lines.append(f'  printf("{struct} %zu\\n", sizeof({struct}));')
+        for f in fields:
+            lines.append(f'  printf("{struct}.{f} %zu\\n", offsetof({struct}, {f}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi_probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi_probe"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    seen = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for struct, (mirror, fields) in checks.items():
+        assert int(seen[struct]) == C.sizeof(mirror), struct
+        for f in fields:
+            assert int(seen[f"{struct}.{f}"]) == getattr(mirror, f).offset, f"{struct}.{f}"
