@@ -56,3 +56,31 @@ def test_sweep_alphas():
     assert len(a) == 11 and a[0] == 0.0 and a[-1] == 1.0 and abs(a[3] - 0.3) < 1e-12
     with pytest.raises(KeyError):
         masking.preset_mask("jaw", 0.5)
+
+
+def test_cli_frame_helpers_match_reference_preprocessing(gold):
+    """scripts/run_mri_video_inference.py keeps the reference's helper names (_preprocess_frame, frames_to_tensor);
+    its normalisation must reproduce the reference's own _preprocess_frame output (the golden), constant frames and
+    already-sized gray frames included."""
+    import sys
+    import torch
+    sys.path.insert(0, os.path.normpath(os.path.join(GOLDEN, "..", "..", "scripts")))
+    import run_mri_video_inference as cli
+    frames = gold["clip_u8"]
+    ref = gold["norm"]            # the reference's own _preprocess_frame, frame by frame (oracle/gen_golden.py)
+    try:
+        import cv2  # noqa: F401  (_preprocess_frame converts / resizes with OpenCV before normalising)
+        helpers = (cli._normalise, cli._preprocess_frame)
+    except ImportError:
+        helpers = (cli._normalise,)
+    for i in range(frames.shape[0]):
+        for fn in helpers:
+            got = fn(frames[i])
+            assert got.dtype == np.float32 and np.array_equal(got, ref[i])
+    flat = np.full((256, 256), 37, np.uint8)
+    assert np.array_equal(cli._normalise(flat), np.zeros((256, 256), np.float32))
+    t = cli.frames_to_tensor(torch.from_numpy(frames[:3]))
+    assert tuple(t.shape) == (1, 3, 1, 256, 256)
+    assert tuple(cli.frames_to_tensor(torch.from_numpy(frames[:3]), use_channel=False).shape) == (1, 3, 256, 256)
+    with pytest.raises(ValueError):
+        cli.frames_to_tensor(torch.zeros(4, 4))
