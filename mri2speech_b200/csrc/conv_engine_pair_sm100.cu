@@ -294,7 +294,7 @@ int conv_tcgen05_pair(const ConvProblem& p, const PackedWeights& w, cudaStream_t
   const EngineKnobs& knobs = engine_knobs();
   EngineParams prm{};
   prm.p = p;
-  finalize_epilogue(&prm.p.epi);
+  finalize_epilogue(&prm.p.epi, static_cast<long long>(p.l_out) + p.d_row_offset);
   prm.wpacked = w.dev_pair;
   prm.n_tile = w.n_tile_pair;
   prm.n_tiles = w.n_tiles_pair;

@@ -477,7 +477,7 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
 
   EngineParams prm{};
   prm.p = p;
-  finalize_epilogue(&prm.p.epi);
+  finalize_epilogue(&prm.p.epi, static_cast<long long>(p.l_out) + p.d_row_offset);
   prm.wpacked = w.dev;
   prm.n_tile = w.n_tile;
   prm.n_tiles = w.n_tiles;

@@ -220,8 +220,12 @@ enum { EPI_FULL = 0, EPI_FULL_SILU = 1, EPI_BIAS = 2, EPI_LRELU = 3, EPI_SILU = 
        EPI_RB_S = 8, EPI_RB_ACC_S = 9, EPI_COUNT = 10 };
 
 // Host side, every launcher, after copying the problem into its kernel parameters: derived epilogue constants.
-inline void finalize_epilogue(Epilogue* e) {
-  e->pitch_magic = (e->mask_mode == M2S_MASK_PITCH && e->pitch > 0) ? 0xFFFFFFFFu / static_cast<unsigned>(e->pitch) + 1u : 0u;
+// `rows` = largest row index the mask is evaluated for (l_out + d_row_offset): the magic number is exact while
+// rows * pitch < 2^32; beyond that pitch_magic stays 0 and the kernels divide.
+inline void finalize_epilogue(Epilogue* e, long long rows = 0) {
+  const bool on = e->mask_mode == M2S_MASK_PITCH && e->pitch > 0;
+  const bool exact = on && (rows + 64) * static_cast<long long>(e->pitch) < (1ll << 32);
+  e->pitch_magic = exact ? 0xFFFFFFFFu / static_cast<unsigned>(e->pitch) + 1u : 0u;
 }
 
 // Host-side choice of the epilogue program for a problem (shared by both kernels).
@@ -507,7 +511,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
         if (!kHasAcc && pitch_mask && sub != rm_sub) {   // (warp-uniform)
           rm_sub = sub;
           const int drow = qw + rr0 + p.d_row_offset;
-          int mi = static_cast<int>(__umulhi(static_cast<unsigned>(drow), e.pitch_magic));
+          int mi = e.pitch_magic ? static_cast<int>(__umulhi(static_cast<unsigned>(drow), e.pitch_magic)) : drow / e.pitch;
           int mj = drow - mi * e.pitch;
 #pragma unroll
           for (int i = 0; i < kR; ++i) {

@@ -377,7 +377,7 @@ int resblock_pair_fused(const ConvProblem& p1, const PackedWeights& w1, const Co
   if (!enc) return fail(M2S_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   PairParams prm{};
   prm.p2 = p2;
-  finalize_epilogue(&prm.p2.epi);
+  finalize_epilogue(&prm.p2.epi, static_cast<long long>(p2.l_out) + p2.d_row_offset);
   prm.bias1 = p1.epi.bias;
   prm.slope1 = p1.epi.act == M2S_ACT_LRELU ? p1.epi.act_slope : 1.f;
   prm.w1 = w1.dev;
