@@ -23,8 +23,9 @@ def load(path):
 
 
 def short(name):
-    for key in ("conv_engine_pair_kernel", "conv_engine_kernel", "resblock_pair_kernel", "dwconv_kernel", "se_scale_kernel",
-                "se_kernel", "im2col_s2_kernel", "stem_kernel", "gap_kernel", "zero_rows_kernel", "conv_post_kernel",
+    for key in ("conv_engine_pair_kernel", "conv_engine_kernel", "resblock_pair_kernel", "dwconv_tma_kernel",
+                "dwconv_kernel", "se_scale_kernel", "se_mlp_kernel", "se_apply_kernel", "im2col_s2_kernel",
+                "stem_rows_kernel", "stem_kernel", "gap_kernel", "zero_rows_kernel", "conv_post_kernel",
                 "bct_to_btc_kernel", "frame_minmax_kernel", "lstm_recurrence_kernel"):
         if key in name:
             return key
