@@ -40,7 +40,12 @@ STEM_CH = 32
 FEAT_CH = 208
 
 
-def _bn(sd, p, x, act):
+def _bn(sd, p, x, act, calibrate=False):
+    if calibrate:
+        # scaled-init variant (oracle/scaled_init.py): running statistics := the statistics of THIS batch, as training
+        # would have left them, so that every layer's activations are O(1) (in place: sd aliases the module's buffers)
+        sd[p + ".running_mean"].copy_(x.mean((0, 2, 3)))
+        sd[p + ".running_var"].copy_(x.var((0, 2, 3), unbiased=False).clamp_min(1e-6))
     y = F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"],
                      sd[p + ".weight"], sd[p + ".bias"], training=False, eps=BN_EPS)
     return F.silu(y) if act else y
@@ -56,15 +61,16 @@ def _conv_same(x, w, stride, groups=1):
     return F.conv2d(x, w, None, stride=stride, groups=groups)
 
 
-def encoder_forward(sd: dict, frames: torch.Tensor, prefix: str = "cnn.backbone.") -> torch.Tensor:
-    """(N,1,H,W) or (N,H,W) float32 -> (N,208) features (global-average-pooled last stage)."""
+def encoder_forward(sd: dict, frames: torch.Tensor, prefix: str = "cnn.backbone.", calibrate: bool = False) -> torch.Tensor:
+    """(N,1,H,W) or (N,H,W) float32 -> (N,208) features (global-average-pooled last stage).
+    ``calibrate``: overwrite every BatchNorm's running statistics with this batch's (see ``_bn``)."""
     sd = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
     x = frames
     if x.dim() == 3:
         x = x.unsqueeze(1)
     if x.size(1) == 1:
         x = x.repeat(1, 3, 1, 1)
-    x = _bn(sd, "bn1", _conv_same(x, sd["conv_stem.weight"], 2), True)
+    x = _bn(sd, "bn1", _conv_same(x, sd["conv_stem.weight"], 2), True, calibrate)
     cin = STEM_CH
     for s, (kind, reps, stride, _exp, cout, _se) in enumerate(STAGES):
         for b in range(reps):
@@ -73,19 +79,19 @@ def encoder_forward(sd: dict, frames: torch.Tensor, prefix: str = "cnn.backbone.
             skip = (st == 1 and cin == cout)
             inp = x
             if kind == "cn":
-                x = _bn(sd, p + ".bn1", _conv_same(x, sd[p + ".conv.weight"], st), True)
+                x = _bn(sd, p + ".bn1", _conv_same(x, sd[p + ".conv.weight"], st), True, calibrate)
             elif kind == "er":
-                x = _bn(sd, p + ".bn1", _conv_same(x, sd[p + ".conv_exp.weight"], st), True)
-                x = _bn(sd, p + ".bn2", F.conv2d(x, sd[p + ".conv_pwl.weight"]), False)
+                x = _bn(sd, p + ".bn1", _conv_same(x, sd[p + ".conv_exp.weight"], st), True, calibrate)
+                x = _bn(sd, p + ".bn2", F.conv2d(x, sd[p + ".conv_pwl.weight"]), False, calibrate)
             else:
-                x = _bn(sd, p + ".bn1", F.conv2d(x, sd[p + ".conv_pw.weight"]), True)
+                x = _bn(sd, p + ".bn1", F.conv2d(x, sd[p + ".conv_pw.weight"]), True, calibrate)
                 x = _bn(sd, p + ".bn2",
-                        _conv_same(x, sd[p + ".conv_dw.weight"], st, groups=x.shape[1]), True)
+                        _conv_same(x, sd[p + ".conv_dw.weight"], st, groups=x.shape[1]), True, calibrate)
                 se = x.mean((2, 3), keepdim=True)
                 se = F.silu(F.conv2d(se, sd[p + ".se.conv_reduce.weight"], sd[p + ".se.conv_reduce.bias"]))
                 se = F.conv2d(se, sd[p + ".se.conv_expand.weight"], sd[p + ".se.conv_expand.bias"])
                 x = x * torch.sigmoid(se)
-                x = _bn(sd, p + ".bn3", F.conv2d(x, sd[p + ".conv_pwl.weight"]), False)
+                x = _bn(sd, p + ".bn3", F.conv2d(x, sd[p + ".conv_pwl.weight"]), False, calibrate)
             if skip:
                 x = x + inp
             cin = cout

@@ -25,7 +25,7 @@ def _model(precision):
     return m.cuda().eval()
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("tf32", 3e-4)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("tf32", 3e-4), ("fp16", 3e-4)])
 def test_u8_ingest_equals_reference_preprocessing(gold, precision, tol):
     """forward(uint8 frames) == forward(frames normalised by the reference's _preprocess_frame)."""
     m = _model(precision)
@@ -38,7 +38,7 @@ def test_u8_ingest_equals_reference_preprocessing(gold, precision, tol):
     assert (a - b).abs().max().item() < tol
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("tf32", 3e-4)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("tf32", 3e-4), ("fp16", 3e-4)])
 def test_masked_ingest_equals_reference_masking(gold, precision, tol):
     """forward(uint8, mask) == forward(reference-normalised frames of the reference-masked clip)."""
     m = _model(precision)
@@ -53,7 +53,8 @@ def test_masked_ingest_equals_reference_masking(gold, precision, tol):
     assert (a - c).abs().max().item() > 10 * tol  # the mask does change the prediction
 
 
-def test_masked_ragged_batch_against_oracle():
+@pytest.mark.parametrize("precision", ["tf32", "fp16"])
+def test_masked_ragged_batch_against_oracle(precision):
     """Ragged uint8 batch with a mask through the pipeline == oracle (mask -> normalise -> model) per clip."""
     from mri2speech_b200 import masking, synth
     from mri2speech_b200.pipeline import MriToSpeech
@@ -62,8 +63,8 @@ def test_masked_ragged_batch_against_oracle():
     from oracle.acoustic import acoustic_forward
     from tests.util import load_config
     torch.manual_seed(1234)
-    gen = Generator(load_config())
-    ac = _model("tf32")
+    gen = Generator(load_config(), precision=precision)
+    ac = _model(precision)
     mean, std = synth.synthetic_scaler()
     clips = [synth.synthetic_clip_u8(3, 5), synth.synthetic_clip_u8(4, 3)]
     mask = masking.preset_mask("lip", 0.2)

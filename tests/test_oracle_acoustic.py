@@ -60,3 +60,48 @@ def test_mel_glue_closed_form():
     assert (mel_log - closed).abs().max().item() < 1e-4
     assert voc.shape == (64, 7) and mel_db.shape == (7, 64)
     assert mel_log.min().item() >= np.log(1e-5) - 1e-5
+
+
+def test_second_encoder_oracle_from_torchvision_blocks():
+    """oracle/acoustic.py (restatement of timm's topology) == oracle/acoustic_tv.py (torchvision's own FusedMBConv /
+    MBConv / SqueezeExcitation blocks + TF-same padding) on the same state_dict: default init and scaled init."""
+    from mri2speech_b200 import synth
+    from oracle.acoustic import encoder_forward
+    from oracle.acoustic_tv import encoder_forward_tv
+    from oracle.scaled_init import calibration_frames, scale_acoustic
+    clip = synth.synthetic_clip(2, 2)
+    m = _model()
+    for scaled in (False, True):
+        if scaled:
+            scale_acoustic(m, calibration_frames(4))
+        sd = m.state_dict()
+        with torch.no_grad():
+            a = encoder_forward(sd, clip.unsqueeze(1))
+        b = encoder_forward_tv(sd, clip.unsqueeze(1))
+        assert a.shape == b.shape == (2, 208)
+        assert (a - b).abs().max().item() <= 1e-5 * max(1.0, a.abs().max().item())
+        if scaled:
+            assert 0.2 < a.std().item() < 20.0          # the scaled init does put the features at O(1)
+
+
+def test_scaled_init_ranges():
+    """The scaled-init helpers do what the parity tests rely on: O(1) mel, a waveform that uses tanh's range."""
+    from mri2speech_b200 import synth
+    from mri2speech_b200.vocoder import Generator
+    from oracle.acoustic import acoustic_forward
+    from oracle.glue import mel_glue
+    from oracle.scaled_init import calibration_frames, scale_acoustic, scale_generator
+    from oracle.vocoder import generator_forward
+    from tests.util import load_config
+    m = _model()
+    scale_acoustic(m, calibration_frames(6))
+    clip = synth.synthetic_clip(1, 4)
+    mel = acoustic_forward(m.state_dict(), clip[None, :, None])
+    assert 0.3 < mel.std().item() < 5.0
+    h = load_config()
+    torch.manual_seed(1234)
+    g = Generator(h)
+    scale_generator(g, h, synth.synthetic_mels(1, 32, seed=5))
+    _, _, voc = mel_glue(mel[0], *synth.synthetic_scaler())
+    wav = generator_forward(g.state_dict(), h, voc.unsqueeze(0))
+    assert wav.std().item() > 0.1 and wav.abs().max().item() <= 1.0
