@@ -17,7 +17,8 @@
  *     inputs, outputs and the workspace (size from *_workspace_bytes);
  *   - every call returns M2S_OK (0) or a negative m2s_status; the message of the
  *     last failure on the calling thread is m2s_last_error_string();
- *   - calls on distinct streams / distinct handles are thread-safe;
+ *   - calls on distinct streams / distinct handles are thread-safe (one-time kernel attributes and the SM count are
+ *     kept per device under a mutex); the m2s_debug_* probes are process-global and single-threaded;
  *   - anything but an sm_100 device is refused (there is no CPU fallback).
  */
 #ifndef M2S_H_
@@ -47,7 +48,9 @@ enum {
   M2S_PREC_TF32 = 0, /* tcgen05 kind::tf32, fp32 accumulate in TMEM (default build) */
   M2S_PREC_FP32 = 1, /* CUDA-core fp32 FMA kernels (exact-fp32 build, slow)          */
   M2S_PREC_FP16 = 2  /* tcgen05 kind::f16: fp16 operands (10-bit mantissa, the same as tf32), fp32 accumulate,
-                        fp32 residual / MRF streams; layers whose c_in is not a multiple of 32 stay on tf32 */
+                        fp32 residual / MRF streams.  A layer runs kind::f16 iff its c_in is a multiple of 8
+                        (16-byte rows of halves); conv_pre (fp32 mel operand), the BiLSTM input projection
+                        and the mel head stay on tf32 */
 };
 
 const char* m2s_version(void);
@@ -195,7 +198,7 @@ void m2s_acoustic_destroy(m2s_acoustic* m);
 size_t m2s_acoustic_workspace_bytes(const m2s_acoustic* m, int32_t batch, int32_t frames);
 /* frames: device (batch, frames, height, width) float32 in [0,1];
  * lengths: device int32[batch] or NULL; lengths_host: the same values on the host
- * (needed to size the recurrence; NULL iff lengths is NULL);
+ * (they size the launches, so that nothing has to be read back; NULL iff lengths is NULL);
  * mel_norm: device (batch, frames, n_mels) normalised mel (rows past lengths[b] are zero). */
 int m2s_acoustic_forward(m2s_acoustic* m, const float* frames_dev, int32_t batch, int32_t frames,
                          const int32_t* lengths, const int32_t* lengths_host, float* mel_norm,
@@ -209,6 +212,16 @@ int m2s_acoustic_forward(m2s_acoustic* m, const float* frames_dev, int32_t batch
 int m2s_acoustic_forward_u8(m2s_acoustic* m, const uint8_t* frames_dev, const float* mask, int32_t batch,
                             int32_t frames, const int32_t* lengths, const int32_t* lengths_host,
                             float* mel_norm, void* workspace, size_t workspace_bytes, m2s_stream_t stream);
+/* Ragged batch WITHOUT padding on the input side: frames_dev holds only the valid frames, clip after clip --
+ * sum(lengths) frames of height x width, float32 in [0,1] (frames_are_u8 == 0) or raw uint8 (frames_are_u8 != 0, with
+ * the optional mask, as m2s_acoustic_forward_u8).  This is how a batch runner feeds clips of 150-600 frames without
+ * zero-filling and copying a padded (batch, max_frames) tensor (the reference runs one clip per call,
+ * scripts/run_mri_video_inference.py:218-243; it has no batched feeder to mirror).  lengths / lengths_host: int32[batch]
+ * on the device / on the host (same values; the host copy sizes the launches, so nothing synchronises).
+ * mel_norm: device (batch, max_frames, n_mels), rows past lengths[b] are zero.  Workspace as for (batch, max_frames). */
+int m2s_acoustic_forward_packed(m2s_acoustic* m, const void* frames_dev, int32_t frames_are_u8, const float* mask,
+                                int32_t batch, int32_t max_frames, const int32_t* lengths, const int32_t* lengths_host,
+                                float* mel_norm, void* workspace, size_t workspace_bytes, m2s_stream_t stream);
 /* Encoder only: (n_frames, height, width) -> (n_frames, 208) features. */
 int m2s_acoustic_encode(m2s_acoustic* m, const float* frames_dev, int32_t n_frames, float* feats,
                         void* workspace, size_t workspace_bytes, m2s_stream_t stream);

@@ -71,7 +71,7 @@ def synthesize(mel_files, h, generator, device, output_dir):
         for b, (path, base) in enumerate(names):
             wav = audio[b, 0, : lens[b] * hop]
             writer.submit(wav, lambda a, p=os.path.join(output_dir, f"{base}_from_mel.wav"):
-                          io_formats.write_wav_float32(p, a, h.sampling_rate))
+                          io_formats.write_wav_pcm16(p, a, h.sampling_rate))
             lo, hi = float(wav.min()), float(wav.max())
             stats = {"input_file": path, "mel_shape": [1, h.num_mels, lens[b]],
                      "mel_range": [float(mels[b].min()), float(mels[b].max())], "audio_shape": [lens[b] * hop],

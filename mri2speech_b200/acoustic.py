@@ -155,6 +155,11 @@ class OTNLikeCNNBiLSTM(nn.Module):
                  use_checkpoint: bool = False, ckpt_segments: int = 2, use_reentrant: bool = False,
                  precision: str = "tf32"):
         super().__init__()
+        if rnn_hidden != 640:
+            # the persistent recurrence kernel (csrc/lstm_sm100.cu) partitions exactly 640 hidden units over its CTAs
+            raise _lib.M2SError(f"rnn_hidden={rnn_hidden}: the sm_100a BiLSTM recurrence is specialised for the "
+                                "reference's hidden size 640 (mri_acoustic_model.py:148); other sizes are refused here "
+                                "rather than at the first forward")
         self.n_mels = n_mels
         self.use_checkpoint = use_checkpoint
         self.ckpt_segments = ckpt_segments
@@ -167,6 +172,7 @@ class OTNLikeCNNBiLSTM(nn.Module):
         self._handle: Optional[int] = None
         self._handle_key = None
         self._workspace: Optional[torch.Tensor] = None
+        self._graph_pins = 0   # live CUDA graphs holding this module's workspace / handle pointers (graphs.py)
 
     # -- libm2s plumbing -----------------------------------------------------------------
     def _state_key(self, hw):
@@ -174,6 +180,9 @@ class OTNLikeCNNBiLSTM(nn.Module):
         for p in list(self.parameters()) + list(self.buffers()):
             key.append((p.data_ptr(), p._version))
         return tuple(key)
+
+    def _current_key(self):
+        return self._state_key(self._handle_key[1] if self._handle_key else (256, 256))
 
     def refresh(self, height: int = 256, width: int = 256):
         self._release()
@@ -208,6 +217,9 @@ class OTNLikeCNNBiLSTM(nn.Module):
             self.refresh(*hw)
         need = int(_lib.lib().m2s_acoustic_workspace_bytes(self._handle, batch, frames))
         if self._workspace is None or self._workspace.numel() < need or self._workspace.device != x.device:
+            if self._graph_pins > 0 and self._workspace is not None:
+                raise _lib.M2SError("this model's workspace is referenced by a captured CUDA graph and would have to "
+                                    "grow: call reserve() for the largest shape before capturing, or release the graph")
             self._workspace = None
             self._workspace = torch.empty(need, dtype=torch.uint8, device=x.device)
 
@@ -258,6 +270,39 @@ class OTNLikeCNNBiLSTM(nn.Module):
                 _lib.check(_lib.lib().m2s_acoustic_forward(
                     self._handle, x.data_ptr(), B, T, _lib.ptr(lens_dev), lens_host_ptr, out.data_ptr(),
                     self._workspace.data_ptr(), self._workspace.numel(), _lib.current_stream()))
+        return out
+
+    def forward_packed(self, frames: torch.Tensor, lengths: torch.Tensor, max_frames: Optional[int] = None,
+                       mask: Optional[torch.Tensor] = None, lengths_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Ragged batch without input padding (extension; the reference runs one clip per call): ``frames``
+        (sum(lengths), H, W) cuda, float32 in [0,1] or raw uint8 -- clip after clip; ``lengths`` int32[B] on the HOST
+        (``lengths_dev``: the same values already on the device, optional).  Returns (B, max_frames, n_mels) with
+        rows past lengths[b] zero; every clip equals its own B=1 run."""
+        _lib.require_device(frames)
+        if frames.dim() != 3:
+            raise ValueError(f"expected packed frames (sum T, H, W), got {tuple(frames.shape)}")
+        raw = frames.dtype == torch.uint8
+        if mask is not None and not raw:
+            raise ValueError("mask applies to raw uint8 frames (it is applied before normalisation)")
+        frames = frames.contiguous() if raw else frames.contiguous().float()
+        lens_host = lengths.detach().to("cpu", torch.int32).contiguous()
+        B = int(lens_host.numel())
+        total, H, W = frames.shape
+        if int(lens_host.sum()) != total:
+            raise ValueError(f"sum(lengths)={int(lens_host.sum())} != packed frames {total}")
+        T = int(max_frames) if max_frames is not None else int(lens_host.max())
+        with torch.cuda.device(frames.device):
+            self._prepare(frames, B, T, (H, W))
+            out = torch.empty(B, T, self.n_mels, dtype=torch.float32, device=frames.device)
+            lens_dev = lengths_dev if lengths_dev is not None else lens_host.to(frames.device, non_blocking=True)
+            if mask is not None:
+                if tuple(mask.shape) != (H, W):
+                    raise ValueError(f"Mask shape {tuple(mask.shape)} != frame shape {(H, W)}")
+                mask = mask.to(frames.device, torch.float32).contiguous()
+            _lib.check(_lib.lib().m2s_acoustic_forward_packed(
+                self._handle, frames.data_ptr(), int(raw), _lib.ptr(mask), B, T, lens_dev.data_ptr(),
+                lens_host.data_ptr(), out.data_ptr(), self._workspace.data_ptr(), self._workspace.numel(),
+                _lib.current_stream()))
         return out
 
     def encode_frames(self, frames: torch.Tensor) -> torch.Tensor:

@@ -28,6 +28,7 @@ int enc_dwconv(const void* in, void* out, int half, float* sums, const float* w,
 int enc_se_apply(void* x, int half, float* sums, const float* w1, const float* b1, const float* w2, const float* b2,
                  int n, int C, int rd, int hw, cudaStream_t st);
 int enc_gap(const float* x, const int32_t* fmap, float* feats, int n, int hw, int C, int feat_ld, cudaStream_t st);
+int enc_build_fmap(const int32_t* lens, int batch, int frames, int32_t* fmap, cudaStream_t st);
 int lstm_recurrence(const float* gin, const float* w_hh_fwd, const float* w_hh_bwd, const int32_t* lens, float* hcat,
                     unsigned int* counters, int batch, int frames, int max_len, int hidden,
                     cudaStream_t stream);
@@ -232,9 +233,10 @@ struct Act {
   void* f16;
 };
 
-// encoder over `n` frames (compact list; fmap maps compact index -> source frame / feature row, or null)
-int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float* mask, const int32_t* fmap, int n,
-                 float* feats, int feat_ld, const EncBuffers& B, cudaStream_t st) {
+// encoder over `n` frames (compact list).  src_map: compact index -> source frame (null = the frames are already the
+// compact list); dst_map: compact index -> feature row (null = compact)
+int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float* mask, const int32_t* src_map,
+                 const int32_t* dst_map, int n, float* feats, int feat_ld, const EncBuffers& B, cudaStream_t st) {
   const int H = m->cfg.height, W = m->cfg.width;
   const bool h = m->fp16;
   const int esz = h ? 2 : 4;
@@ -248,9 +250,9 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
   {  // the stem's only consumer is block 0.0 (no skip): operand copy only in the fp16 build
     void* out = h ? x.f16 : static_cast<void*>(x.f32);
     if (u8)
-      M2S_TRY(enc_stem_u8(static_cast<const uint8_t*>(frames), fmap, mask, B.norm, out, h, m->stem_w, m->stem_b, n, H, W, st));
+      M2S_TRY(enc_stem_u8(static_cast<const uint8_t*>(frames), src_map, mask, B.norm, out, h, m->stem_w, m->stem_b, n, H, W, st));
     else
-      M2S_TRY(enc_stem(static_cast<const float*>(frames), fmap, out, h, m->stem_w, m->stem_b, n, H, W, st));
+      M2S_TRY(enc_stem(static_cast<const float*>(frames), src_map, out, h, m->stem_w, m->stem_b, n, H, W, st));
   }
   for (size_t bi = 0; bi < m->blocks.size(); ++bi) {
     const Block& b = m->blocks[bi];
@@ -331,11 +333,12 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
   }
   const Block& lastb = m->blocks.back();
   const int hw = (lastb.hin / lastb.stride) * (lastb.win / lastb.stride);
-  return enc_gap(x.f32, fmap, feats, n, hw, kFeat, feat_ld, st);
+  return enc_gap(x.f32, dst_map, feats, n, hw, kFeat, feat_ld, st);
 }
 
-int encode_all(const m2s_acoustic* m, const void* frames, bool u8, const float* mask, const int32_t* fmap_dev,
-               int n_frames, float* feats, float* enc_base, cudaStream_t st) {
+// src_map / dst_map: device tables over the compact frame list (see encode_chunk), either may be null
+int encode_all(const m2s_acoustic* m, const void* frames, bool u8, const float* mask, const int32_t* src_map,
+               const int32_t* dst_map, int n_frames, float* feats, float* enc_base, cudaStream_t st) {
   const int nc = n_frames < m->chunk ? n_frames : m->chunk;
   EncBuffers B{};
   float* p = enc_base;
@@ -354,13 +357,11 @@ int encode_all(const m2s_acoustic* m, const void* frames, bool u8, const float* 
   }
   for (int f0 = 0; f0 < n_frames; f0 += nc) {
     const int n = n_frames - f0 < nc ? n_frames - f0 : nc;
-    if (fmap_dev) {
-      M2S_TRY(encode_chunk(m, frames, u8, mask, fmap_dev + f0, n, feats, kFeat, B, st));
-    } else {
-      const size_t fsz = static_cast<size_t>(m->cfg.height) * m->cfg.width * (u8 ? 1 : 4);
-      M2S_TRY(encode_chunk(m, static_cast<const char*>(frames) + f0 * fsz, u8, mask, nullptr, n,
-                           feats + static_cast<size_t>(f0) * kFeat, kFeat, B, st));
-    }
+    const size_t fsz = static_cast<size_t>(m->cfg.height) * m->cfg.width * (u8 ? 1 : 4);
+    const void* src = src_map ? frames : static_cast<const void*>(static_cast<const char*>(frames) + f0 * fsz);
+    float* dst = dst_map ? feats : feats + static_cast<size_t>(f0) * kFeat;
+    M2S_TRY(encode_chunk(m, src, u8, mask, src_map ? src_map + f0 : nullptr, dst_map ? dst_map + f0 : nullptr, n, dst,
+                         kFeat, B, st));
   }
   return M2S_OK;
 }
@@ -596,7 +597,8 @@ extern "C" int m2s_acoustic_encode(m2s_acoustic* m, const float* frames_dev, int
   if (n_frames <= 0) return M2S_OK;
   WsPtrs w;
   M2S_TRY(carve(m, 1, n_frames, workspace, workspace_bytes, &w));
-  return encode_all(m, frames_dev, false, nullptr, nullptr, n_frames, feats, w.enc, reinterpret_cast<cudaStream_t>(stream));
+  return encode_all(m, frames_dev, false, nullptr, nullptr, nullptr, n_frames, feats, w.enc,
+                    reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int m2s_acoustic_rnn_head(m2s_acoustic* m, const float* feats, int32_t batch, int32_t frames,
@@ -613,34 +615,36 @@ extern "C" int m2s_acoustic_rnn_head(m2s_acoustic* m, const float* feats, int32_
 }
 
 namespace {
-int acoustic_forward_impl(m2s_acoustic* m, const void* frames_dev, bool u8, const float* mask, int32_t batch,
+// `packed`: frames_dev holds only the valid frames, clip after clip (sum of lengths frames); otherwise the padded
+// (batch, frames) layout.  Ragged batches encode the compact list of valid frames either way; the table that scatters
+// the features into the padded (batch, frames) layout of the recurrence is built on the device from `lengths`.
+int acoustic_forward_impl(m2s_acoustic* m, const void* frames_dev, bool u8, bool packed, const float* mask, int32_t batch,
                           int32_t frames, const int32_t* lengths, const int32_t* lengths_host, float* mel_norm,
                           void* workspace, size_t workspace_bytes, m2s_stream_t stream) {
   if (!m || !frames_dev || !mel_norm) return fail(M2S_ERR_BAD_ARG, "null argument");
   if ((lengths == nullptr) != (lengths_host == nullptr))
     return fail(M2S_ERR_BAD_ARG, "lengths and lengths_host must be given together");
+  if (packed && !lengths) return fail(M2S_ERR_BAD_ARG, "a packed batch needs lengths");
   if (batch <= 0 || frames <= 0) return M2S_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   WsPtrs w;
   M2S_TRY(carve(m, batch, frames, workspace, workspace_bytes, &w));
   const int total = batch * frames;
   if (lengths_host) {
-    // encode only the valid frames of a ragged batch: compact list of (b, t) source indices
-    std::vector<int32_t> fmap;
-    fmap.reserve(total);
+    long long valid = 0;
     for (int b = 0; b < batch; ++b) {
       if (lengths_host[b] < 0 || lengths_host[b] > frames)
         return fail(M2S_ERR_BAD_ARG, "lengths[%d]=%d out of range", b, lengths_host[b]);
-      for (int t = 0; t < lengths_host[b]; ++t) fmap.push_back(b * frames + t);
+      valid += lengths_host[b];
     }
     M2S_CUDA_OK(cudaMemsetAsync(w.feats, 0, static_cast<size_t>(total) * kFeat * sizeof(float), st));
-    if (!fmap.empty()) {
-      M2S_CUDA_OK(cudaMemcpyAsync(w.fmap, fmap.data(), fmap.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-      M2S_CUDA_OK(cudaStreamSynchronize(st));  // fmap is a stack-lifetime host buffer
-      M2S_TRY(encode_all(m, frames_dev, u8, mask, w.fmap, static_cast<int>(fmap.size()), w.feats, w.enc, st));
+    if (valid > 0) {
+      M2S_TRY(enc_build_fmap(lengths, batch, frames, w.fmap, st));
+      M2S_TRY(encode_all(m, frames_dev, u8, mask, packed ? nullptr : w.fmap, w.fmap, static_cast<int>(valid), w.feats,
+                         w.enc, st));
     }
   } else {
-    M2S_TRY(encode_all(m, frames_dev, u8, mask, nullptr, total, w.feats, w.enc, st));
+    M2S_TRY(encode_all(m, frames_dev, u8, mask, nullptr, nullptr, total, w.feats, w.enc, st));
   }
   return rnn_head(m, w.feats, batch, frames, lengths, lengths_host, mel_norm, w.gin, w.hcat, w.counters, st);
 }
@@ -649,13 +653,22 @@ int acoustic_forward_impl(m2s_acoustic* m, const void* frames_dev, bool u8, cons
 extern "C" int m2s_acoustic_forward(m2s_acoustic* m, const float* frames_dev, int32_t batch, int32_t frames,
                                     const int32_t* lengths, const int32_t* lengths_host, float* mel_norm,
                                     void* workspace, size_t workspace_bytes, m2s_stream_t stream) {
-  return acoustic_forward_impl(m, frames_dev, false, nullptr, batch, frames, lengths, lengths_host, mel_norm, workspace,
-                               workspace_bytes, stream);
+  return acoustic_forward_impl(m, frames_dev, false, false, nullptr, batch, frames, lengths, lengths_host, mel_norm,
+                               workspace, workspace_bytes, stream);
 }
 
 extern "C" int m2s_acoustic_forward_u8(m2s_acoustic* m, const uint8_t* frames_dev, const float* mask, int32_t batch,
                                        int32_t frames, const int32_t* lengths, const int32_t* lengths_host,
                                        float* mel_norm, void* workspace, size_t workspace_bytes, m2s_stream_t stream) {
-  return acoustic_forward_impl(m, frames_dev, true, mask, batch, frames, lengths, lengths_host, mel_norm, workspace,
+  return acoustic_forward_impl(m, frames_dev, true, false, mask, batch, frames, lengths, lengths_host, mel_norm, workspace,
                                workspace_bytes, stream);
+}
+
+extern "C" int m2s_acoustic_forward_packed(m2s_acoustic* m, const void* frames_dev, int32_t frames_are_u8, const float* mask,
+                                           int32_t batch, int32_t max_frames, const int32_t* lengths,
+                                           const int32_t* lengths_host, float* mel_norm, void* workspace,
+                                           size_t workspace_bytes, m2s_stream_t stream) {
+  if (mask && !frames_are_u8) return fail(M2S_ERR_BAD_ARG, "the articulator mask applies to raw uint8 frames");
+  return acoustic_forward_impl(m, frames_dev, frames_are_u8 != 0, true, mask, batch, max_frames, lengths, lengths_host,
+                               mel_norm, workspace, workspace_bytes, stream);
 }

@@ -386,13 +386,11 @@ int conv_tcgen05_pair(const ConvProblem& p, const PackedWeights& w, cudaStream_t
                                               conv_engine_pair_kernel<EPI_LRELU>, conv_engine_pair_kernel<EPI_SILU>,      conv_engine_pair_kernel<EPI_RES>,
                                               conv_engine_pair_kernel<EPI_RB>,    conv_engine_pair_kernel<EPI_RB_ACC>,
                                               conv_engine_pair_kernel<EPI_RB_S>,  conv_engine_pair_kernel<EPI_RB_ACC_S>};
-  static bool attr_set = false;
-  if (!attr_set) {
-    for (KernelFn k : kernels) {
-      M2S_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    }
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;
+  M2S_TRY(attr_once.run([&]() -> int {
+    for (KernelFn k : kernels) M2S_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    return M2S_OK;
+  }));
   const int epi = choose_epilogue(p.epi);
 
   int pairs = (knobs.max_ctas > 0 ? knobs.max_ctas : sm_count()) / 2;

@@ -273,7 +273,8 @@ EngineKnobs& engine_knobs() {
 
 // ---- optional per-launch timing (bench.py roofline leg) -----------------------------
 namespace {
-struct ProfileRing {
+struct ProfileRing {   // debug probe (m2s_debug_profile*): one ring per process, guarded for concurrent launchers
+  std::mutex mu;
   std::vector<cudaEvent_t> ev;
   std::vector<double> flops;
   int count = 0;
@@ -287,6 +288,7 @@ ProfileRing& ring() {
 
 int profile_enable(int on) {
   ProfileRing& r = ring();
+  std::lock_guard<std::mutex> g(r.mu);
   r.on = on != 0;
   r.count = 0;
   r.flops.clear();
@@ -296,6 +298,7 @@ int profile_enable(int on) {
 int profile_read(float* ms, double* flops, int cap, int* n_out) {
   ProfileRing& r = ring();
   M2S_CUDA_OK(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> g(r.mu);
   int n = r.count < cap ? r.count : cap;
   for (int i = 0; i < n; ++i) {
     float t = 0.f;
@@ -311,7 +314,8 @@ int profile_read(float* ms, double* flops, int cap, int* n_out) {
 
 int profile_before(cudaStream_t stream) {
   ProfileRing& pr = ring();
-  if (!pr.on) return M2S_OK;
+  if (!pr.on) return M2S_OK;   // (unsynchronised fast path: the probe is switched on / off between launches)
+  std::lock_guard<std::mutex> g(pr.mu);
   while (static_cast<int>(pr.ev.size()) < 2 * (pr.count + 1)) {
     cudaEvent_t e;
     M2S_CUDA_OK(cudaEventCreate(&e));
@@ -324,20 +328,26 @@ int profile_before(cudaStream_t stream) {
 int profile_after(cudaStream_t stream, double flops) {
   ProfileRing& pr = ring();
   if (!pr.on) return M2S_OK;
+  std::lock_guard<std::mutex> g(pr.mu);
   M2S_CUDA_OK(cudaEventRecord(pr.ev[2 * pr.count + 1], stream));
   pr.flops.push_back(flops);
   ++pr.count;
   return M2S_OK;
 }
 
-int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+int sm_count() {   // of the current device (cached per device)
+  static std::mutex mu;
+  static int n[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> g(mu);
+  if (dev < 0 || dev >= 64) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
   }
-  return n;
+  if (!n[dev]) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+  return n[dev];
 }
 
 void choose_n_tiling(int n, int* n_tile, int* n_tiles) {
@@ -398,6 +408,7 @@ int pack_weights(const float* host_w, int taps, int n, int c_in, int mode, Packe
         const int chunk = (off >> 4) ^ (w.row_bytes == 128 ? (r & 7) : ((r >> 1) & 3));
         put(&packed[blk + static_cast<size_t>(r) * w.row_bytes + chunk * 16 + (off & 15)], v);
       }
+  std::vector<uint8_t> pair_host;
   if (n >= engine_knobs().pair_min_n && n % 16 == 0 && engine_knobs().pair) {
     // CTA-pair layout: [nt][cb][half][tap][nh rows][row_bytes], unswizzled (TMA applies the swizzle)
     const int tiles = (n + 255) / 256;
@@ -413,13 +424,22 @@ int pack_weights(const float* host_w, int taps, int n, int c_in, int mode, Packe
           const size_t row = ((static_cast<size_t>(nt * w.cblocks + cb) * 2 + half) * taps + j) * nh + r;
           put(&pk[row * w.row_bytes + static_cast<size_t>(cc) * esize], plain[(static_cast<size_t>(j) * n + o) * c_in + c]);
         }
-    M2S_CUDA_OK(cudaMalloc(&w.dev_pair, pk.size()));
-    M2S_CUDA_OK(cudaMemcpy(w.dev_pair, pk.data(), pk.size(), cudaMemcpyHostToDevice));
+    pair_host.swap(pk);
   }
-  M2S_CUDA_OK(cudaMalloc(&w.dev, packed.size()));
-  M2S_CUDA_OK(cudaMalloc(&w.plain, plain.size() * sizeof(float)));
-  M2S_CUDA_OK(cudaMemcpy(w.dev, packed.data(), packed.size(), cudaMemcpyHostToDevice));
-  M2S_CUDA_OK(cudaMemcpy(w.plain, plain.data(), plain.size() * sizeof(float), cudaMemcpyHostToDevice));
+  // device copies: on any failure everything allocated so far is released
+  auto up = [&](float** dst, const void* src, size_t bytes) -> int {
+    M2S_CUDA_OK(cudaMalloc(dst, bytes));
+    M2S_CUDA_OK(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return M2S_OK;
+  };
+  int st = M2S_OK;
+  if (!pair_host.empty()) st = up(&w.dev_pair, pair_host.data(), pair_host.size());
+  if (st == M2S_OK) st = up(&w.dev, packed.data(), packed.size());
+  if (st == M2S_OK) st = up(&w.plain, plain.data(), plain.size() * sizeof(float));
+  if (st != M2S_OK) {
+    free_weights(&w);
+    return st;
+  }
   *out = w;
   return M2S_OK;
 }
@@ -590,12 +610,11 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
                                               conv_engine_kernel<EPI_LRELU>, conv_engine_kernel<EPI_SILU>,      conv_engine_kernel<EPI_RES>,
                                               conv_engine_kernel<EPI_RB>,    conv_engine_kernel<EPI_RB_ACC>,
                                               conv_engine_kernel<EPI_RB_S>,  conv_engine_kernel<EPI_RB_ACC_S>};
-  static bool attr_set = false;
-  if (!attr_set) {
-    for (KernelFn k : kernels)
-      M2S_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;
+  M2S_TRY(attr_once.run([&]() -> int {
+    for (KernelFn k : kernels) M2S_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    return M2S_OK;
+  }));
   const int epi = choose_epilogue(p.epi);
   int grid = knobs.max_ctas > 0 ? knobs.max_ctas : sm_count();
   if (grid > prm.total_tiles) grid = prm.total_tiles;

@@ -260,11 +260,11 @@ int launch(const T* in, T* out, float* sums, const float* w, const float* bias, 
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(M2S_ERR_CUDA, "depthwise tensor map failed (%d)", static_cast<int>(cr));
   const size_t smem = 2 * static_cast<size_t>(prm.stage_bytes) + 256;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;   // (one per instantiation T)
+  M2S_TRY(attr_once.run([&]() -> int {
     M2S_CUDA_OK(cudaFuncSetAttribute(dwconv_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
+    return M2S_OK;
+  }));
   int grid = 2 * sm_count();
   if (grid > prm.n_items) grid = prm.n_items;
   dwconv_tma_kernel<T><<<grid, 256, smem, st>>>(tmap, out, sums, w, bias, prm);

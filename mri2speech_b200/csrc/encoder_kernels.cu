@@ -533,13 +533,13 @@ int dwconv_launch(const T* in, T* out, float* sums, const float* w, const float*
   const int kf = (stride == 1 && slab * 4 <= 64 * 1024) ? 4 : 1;
   using Fn = void (*)(const T*, T*, float*, const float*, const float*, int, int, int, int, int, int, int, int, int);
   Fn fn = stride == 2 ? dwconv_kernel<2, 1, T> : (kf == 4 ? dwconv_kernel<1, 4, T> : dwconv_kernel<1, 1, T>);
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;   // (one per instantiation T)
+  M2S_TRY(attr_once.run([&]() -> int {
     M2S_CUDA_OK(cudaFuncSetAttribute(dwconv_kernel<1, 1, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     M2S_CUDA_OK(cudaFuncSetAttribute(dwconv_kernel<1, 4, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     M2S_CUDA_OK(cudaFuncSetAttribute(dwconv_kernel<2, 1, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
+    return M2S_OK;
+  }));
   const int wo = Win / stride;
   int wo_shift = -1;
   for (int k = 0; k < 16; ++k)
@@ -572,11 +572,11 @@ int enc_se_apply(void* x, int half, float* sums, const float* w1, const float* b
                  int n, int C, int rd, int hw, cudaStream_t st) {
   constexpr int kF = 8;  // frames per MLP block
   const size_t sm_mlp = (static_cast<size_t>(kF) * C + static_cast<size_t>(kF) * rd) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  M2S_TRY(attr_once.run([&]() -> int {
     M2S_CUDA_OK(cudaFuncSetAttribute(se_mlp_kernel<kF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr = true;
-  }
+    return M2S_OK;
+  }));
   if (sm_mlp > 100 * 1024) return fail(M2S_ERR_UNSUPPORTED, "squeeze-excite: %d channels exceed the MLP kernel's SMEM", C);
   se_mlp_kernel<kF><<<(n + kF - 1) / kF, 1024, sm_mlp, st>>>(sums, w1, b1, w2, b2, C, rd, 1.f / hw, n);
   M2S_CUDA_OK(cudaGetLastError());
@@ -590,6 +590,31 @@ int enc_se_apply(void* x, int half, float* sums, const float* w1, const float* b
     se_scale_kernel<<<grid, 1024, sm, st>>>(static_cast<__half*>(x), sums, C, hw);
   else
     se_scale_kernel<<<grid, 1024, sm, st>>>(static_cast<float*>(x), sums, C, hw);
+  M2S_CUDA_OK(cudaGetLastError());
+  return M2S_OK;
+}
+
+namespace {
+// fmap[off_b + t] = b * frames + t for t < lens[b], off_b = sum_{i<b} lens[i]: the compact list of the valid frames of a
+// ragged batch, built on the device (no host table, no synchronisation: the forward stays capturable)
+__global__ void __launch_bounds__(256) build_fmap_kernel(const int32_t* __restrict__ lens, int frames,
+                                                         int32_t* __restrict__ fmap) {
+  __shared__ int part[8];
+  const int b = blockIdx.x;
+  int s = 0;
+  for (int i = threadIdx.x; i < b; i += blockDim.x) s += lens[i];
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  int off = 0;
+  for (int w = 0; w < 8; ++w) off += part[w];
+  const int len = lens[b];
+  for (int t = threadIdx.x; t < len; t += blockDim.x) fmap[off + t] = b * frames + t;
+}
+}  // namespace
+
+int enc_build_fmap(const int32_t* lens, int batch, int frames, int32_t* fmap, cudaStream_t st) {
+  build_fmap_kernel<<<batch, 256, 0, st>>>(lens, frames, fmap);
   M2S_CUDA_OK(cudaGetLastError());
   return M2S_OK;
 }

@@ -168,11 +168,11 @@ int lstm_recurrence(const float* gin, const float* w_hh_fwd, const float* w_hh_b
   LstmParams prm{};
   prm.gin = gin; prm.w_hh[0] = w_hh_fwd; prm.w_hh[1] = w_hh_bwd; prm.lens = lens; prm.hcat = hcat;
   prm.counters = counters; prm.batch = batch; prm.frames = frames; prm.max_len = max_len;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  M2S_TRY(attr_once.run([&]() -> int {
     M2S_CUDA_OK(cudaFuncSetAttribute(lstm_recurrence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr = true;
-  }
+    return M2S_OK;
+  }));
   M2S_CUDA_OK(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), stream));
   void* args[] = {&prm};
   M2S_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_recurrence_kernel), dim3(2 * kParts),

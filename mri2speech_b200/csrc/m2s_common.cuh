@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
+#include <mutex>
 #include <string>
 #include "../../include/m2s.h"
 
@@ -26,6 +27,25 @@ int fail(int status, const char* fmt, ...);
     int _s = (expr);              \
     if (_s != M2S_OK) return _s;  \
   } while (0)
+
+// One-time setup that CUDA keeps PER DEVICE (cudaFuncSetAttribute: function attributes belong to the device's copy of
+// the kernel): run `f` once for each device a call site is reached on.  Thread-safe.
+class PerDeviceOnce {
+  std::mutex mu_;
+  uint64_t done_ = 0;
+
+ public:
+  template <class F>
+  int run(F&& f) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(mu_);
+    if (dev >= 0 && dev < 64 && ((done_ >> dev) & 1)) return M2S_OK;
+    const int s = f();
+    if (s == M2S_OK && dev >= 0 && dev < 64) done_ |= 1ull << dev;
+    return s;
+  }
+};
 
 // ---- the conv problem as the kernels see it ----------------------------------
 // D[b, q + d_row_offset, n] = epi(sum_j sum_c A[b, q + shift[j], c] * W[j][n][c])

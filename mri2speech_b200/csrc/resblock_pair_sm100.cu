@@ -466,12 +466,11 @@ int resblock_pair_fused(const ConvProblem& p1, const PackedWeights& w1, const Co
                                               resblock_pair_kernel<EPI_SILU>,  resblock_pair_kernel<EPI_RES>,
                                               resblock_pair_kernel<EPI_RB>,    resblock_pair_kernel<EPI_RB_ACC>,
                                               resblock_pair_kernel<EPI_RB_S>,  resblock_pair_kernel<EPI_RB_ACC_S>};
-  static bool attr_set = false;
-  if (!attr_set) {
-    for (KernelFn k : kernels)
-      M2S_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;
+  M2S_TRY(attr_once.run([&]() -> int {
+    for (KernelFn k : kernels) M2S_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    return M2S_OK;
+  }));
   const int epi = choose_epilogue(p2.epi);
   if (epi < 0 || (p2.d16_lo && (!p2.d16 || !lo_output_supported(epi))) || (p2.epi.res_hi && (p2.epi.res_ld % 8 || (reinterpret_cast<uintptr_t>(p2.epi.res_hi) & 15) ||
                                                             (reinterpret_cast<uintptr_t>(p2.epi.res_lo) & 15))))

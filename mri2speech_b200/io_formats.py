@@ -1,9 +1,10 @@
 """Output / interchange formats of the path and an asynchronous writer.
 
 Files the reference CLIs produce and consume, kept byte-compatible:
-  * ``<stem>_generated.wav`` / ``<stem>_from_mel.wav``: float32 PCM at h.sampling_rate
-    (scripts/run_mri_video_inference.py:166-170, mel_to_audio_synthesis.py:101-103: ``sf.write`` of a float32 array;
-    soundfile is optional here, scipy.io.wavfile writes the same IEEE-float WAV);
+  * ``<stem>_generated.wav`` / ``<stem>_from_mel.wav``: 16-bit PCM at h.sampling_rate
+    (scripts/run_mri_video_inference.py:166-170, mel_to_audio_synthesis.py:101-103: ``sf.write(path, float32_array, sr)``
+    -- soundfile's default subtype for WAV is PCM_16, libsndfile converts with round(x * 32767); the same file is
+    written here whether or not soundfile is installed: see ``write_wav_pcm16``);
   * ``<name>_generated_e2e.wav``: int16 PCM, ``(audio * 32768).astype(int16)`` (inference_e2e.py:52-57);
   * ``<stem>_mel.npy`` (T, n_mels) dB, ``<stem>_mel_log.npy`` (T, n_mels) log-power (run_mri_video_inference.py:171,248);
   * ``<stem>.npy`` (n_mels, T) log-power for HiFi-GAN fine-tuning (scripts/export_predicted_mels.py:98-99);
@@ -25,11 +26,27 @@ import torch
 MAX_WAV_VALUE = 32768.0  # meldataset.py:13 of the reference
 
 
-def write_wav_float32(path, audio: np.ndarray, sampling_rate: int) -> None:
+def write_wav_pcm16(path, audio: np.ndarray, sampling_rate: int) -> None:
+    """What the reference's ``sf.write(path, float32_audio, sr)`` leaves on disk: a PCM_16 WAV (soundfile's default
+    subtype for the WAV container), samples = round-to-nearest(x * 32767) as libsndfile converts normalised floats.
+    The subtype is explicit in BOTH branches, so the file format does not depend on which library is installed."""
     audio = np.asarray(audio, dtype=np.float32).reshape(-1)
     try:
         import soundfile as sf
-        sf.write(str(path), audio, int(sampling_rate))
+        sf.write(str(path), audio, int(sampling_rate), subtype="PCM_16")
+    except ImportError:
+        from scipy.io import wavfile
+        pcm = np.clip(np.rint(audio.astype(np.float64) * 32767.0), -32768, 32767).astype(np.int16)
+        wavfile.write(str(path), int(sampling_rate), pcm)
+
+
+def write_wav_float32(path, audio: np.ndarray, sampling_rate: int) -> None:
+    """IEEE-float WAV (format 3): NOT what the reference CLIs write -- a lossless option for callers that want the
+    generator's float32 samples on disk."""
+    audio = np.asarray(audio, dtype=np.float32).reshape(-1)
+    try:
+        import soundfile as sf
+        sf.write(str(path), audio, int(sampling_rate), subtype="FLOAT")
     except ImportError:
         from scipy.io import wavfile
         wavfile.write(str(path), int(sampling_rate), audio)
@@ -130,7 +147,7 @@ def save_clip_outputs(writer: AsyncWriter, result: dict, output_dir, stem: str, 
     out = Path(output_dir)
     out.mkdir(parents=True, exist_ok=True)
     wav, mel, mel_log = out / f"{stem}_generated.wav", out / f"{stem}_mel.npy", out / f"{stem}_mel_log.npy"
-    writer.submit(result["audio"], lambda a, p=wav: write_wav_float32(p, a, sampling_rate))
+    writer.submit(result["audio"], lambda a, p=wav: write_wav_pcm16(p, a, sampling_rate))
     writer.submit(result["mel_db"], lambda a, p=mel: np.save(p, a.astype(np.float32)))
     writer.submit(result["mel_log"], lambda a, p=mel_log: np.save(p, a.astype(np.float32)))
     return [wav, mel, mel_log]

@@ -78,7 +78,7 @@ class MriToSpeech:
         self.hop = generator.hop
 
     def reserve(self, max_batch_frames: int = 4096, max_clip_frames: int = 600, height: int = 256, width: int = 256):
-        """Pre-size both models' workspaces for the largest padded micro-batch ``infer`` can build, so that no
+        """Pre-size both models' workspaces for the largest micro-batch ``infer`` can build, so that no
         allocation (and no implicit device synchronisation) happens once inference has started."""
         nb = max(1, max_batch_frames // max(max_clip_frames, 1))
         frames = max(max_clip_frames, max_batch_frames // nb)
@@ -95,38 +95,108 @@ class MriToSpeech:
         optional (H,W) articulator ``mask``); lengths int32[B] (cpu or cuda) or None -> dict of padded tensors."""
         pred = self.acoustic(frames, lengths=lengths, mask=mask) if mask is not None else \
             self.acoustic(frames, lengths=lengths)
+        return self._vocode(pred, lengths)
+
+    def _vocode(self, pred: torch.Tensor, lengths: Optional[torch.Tensor]):
         # the glue kernel writes conv_pre's operand (mel_log, channels-last) directly: no (B,n,T) tensor, no layout pass
         mel_db, mel_log, _ = mel_glue(pred, self.mean, self.std, lengths, want_voc=False)
         wav = self.generator(mel_log, lengths=lengths, channels_last=True)
         return {"mel_norm": pred, "mel_db": mel_db, "mel_log": mel_log, "audio": wav}
 
+    @staticmethod
+    def plan_micro_batches(lengths: Sequence[int], max_batch_frames: int) -> List[List[int]]:
+        """Clip indices sorted by length (longest first) and cut into micro-batches of at most ``max_batch_frames``
+        PADDED frames (batch x longest clip: what the recurrence and the vocoder run on)."""
+        order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+        plan, i = [], 0
+        while i < len(order):
+            tmax = int(lengths[order[i]])
+            nb = max(1, min(len(order) - i, max_batch_frames // max(tmax, 1)))
+            plan.append(order[i:i + nb])
+            i += nb
+        return plan
+
     @torch.no_grad()
     def infer(self, clips: Sequence[torch.Tensor], max_batch_frames: int = 4096,
-              mask: Optional[torch.Tensor] = None) -> List[Dict[str, torch.Tensor]]:
+              mask: Optional[torch.Tensor] = None, audio_to_host: bool = False) -> List[Dict[str, torch.Tensor]]:
         """clips: list of (T_i,H,W) tensors (host or device), all float32 in [0,1] or all raw uint8 (4x fewer
         bytes over PCIe / HBM; normalised on the device).  Returns one dict per clip, in order.
 
-        Clips are sorted by length and packed into micro-batches of at most ``max_batch_frames`` padded
-        frames so that padding waste stays small; every clip equals its own B=1 run (ragged parity)."""
-        order = sorted(range(len(clips)), key=lambda i: -int(clips[i].shape[0]))
+        Clips are sorted by length and cut into micro-batches of at most ``max_batch_frames`` padded frames.  A
+        micro-batch is fed PACKED -- its clips' frames one after the other in a staging buffer, no zero-filled
+        (B, Tmax, H, W) tensor -- through ``m2s_acoustic_forward_packed``; the staging buffers are double-buffered
+        and filled on a copy stream, so the host-to-device copies of micro-batch k+1 overlap the kernels of k.
+        ``audio_to_host``: the waveforms are returned in pinned host memory (one device-to-host copy per micro-batch
+        on a third stream, overlapping the next micro-batch; the call returns once they have landed).
+        Every clip equals its own B=1 run (ragged parity)."""
+        if not len(clips):
+            return []
+        lens_all = [int(c.shape[0]) for c in clips]
+        plan = self.plan_micro_batches(lens_all, max_batch_frames)
+        H, W = clips[0].shape[-2:]
+        dtype = torch.uint8 if clips[0].dtype == torch.uint8 else torch.float32
+        dev = self.device
         results: List[Optional[Dict[str, torch.Tensor]]] = [None] * len(clips)
-        i = 0
-        while i < len(order):
-            tmax = int(clips[order[i]].shape[0])
-            nb = max(1, min(len(order) - i, max_batch_frames // max(tmax, 1)))
-            idx = order[i:i + nb]
-            lens = [int(clips[j].shape[0]) for j in idx]
-            H, W = clips[idx[0]].shape[-2:]
-            dtype = torch.uint8 if clips[idx[0]].dtype == torch.uint8 else torch.float32
-            batch = torch.zeros(nb, tmax, H, W, device=self.device, dtype=dtype)
-            for b, j in enumerate(idx):
-                batch[b, :lens[b]].copy_(clips[j], non_blocking=True)
-            out = self.infer_padded(batch, torch.tensor(lens, dtype=torch.int32), mask=mask)
-            for b, j in enumerate(idx):
-                n = lens[b]
-                results[j] = {"mel_norm": out["mel_norm"][b, :n], "mel_db": out["mel_db"][b, :n],
-                              "mel_log": out["mel_log"][b, :n], "audio": out["audio"][b, 0, :n * self.hop]}
-            i += nb
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            cap = max(sum(lens_all[j] for j in idx) for idx in plan)
+            nbuf = 2 if len(plan) > 1 else 1
+            key = (cap, H, W, dtype, nbuf)
+            if getattr(self, "_stage_key", None) is None or self._stage_key[1:4] != key[1:4] or \
+                    self._stage_key[0] < cap or self._stage_key[4] < nbuf:
+                self._stage = [torch.empty(cap, H, W, device=dev, dtype=dtype) for _ in range(nbuf)]
+                self._stage_key = key
+                self._copy_stream = torch.cuda.Stream(dev)
+                self._d2h_stream = torch.cuda.Stream(dev)
+            stage, copy_s, d2h_s = self._stage, self._copy_stream, self._d2h_stream
+            filled = [torch.cuda.Event() for _ in plan]
+            consumed: List[Optional[torch.cuda.Event]] = [None] * len(plan)
+            copy_s.wait_stream(main)     # the staging buffers may still be read by kernels of a previous call
+
+            def fill(k):
+                buf = stage[k % len(stage)]
+                with torch.cuda.stream(copy_s):
+                    if k >= len(stage) and consumed[k - len(stage)] is not None:
+                        copy_s.wait_event(consumed[k - len(stage)])
+                    off = 0
+                    for j in plan[k]:
+                        n = lens_all[j]
+                        buf[off:off + n].copy_(clips[j], non_blocking=True)
+                        off += n
+                    filled[k].record(copy_s)
+
+            host_done = []
+            fill(0)
+            for k, idx in enumerate(plan):
+                if k + 1 < len(plan):
+                    fill(k + 1)
+                lens = [lens_all[j] for j in idx]
+                total = sum(lens)
+                lens_t = torch.tensor(lens, dtype=torch.int32)
+                main.wait_event(filled[k])
+                pred = self.acoustic.forward_packed(stage[k % len(stage)][:total], lens_t, max_frames=max(lens), mask=mask)
+                consumed[k] = torch.cuda.Event()
+                consumed[k].record(main)
+                out = self._vocode(pred, lens_t)
+                audio = out["audio"]
+                if audio_to_host:
+                    ready = torch.cuda.Event()
+                    ready.record(main)
+                    host = torch.empty(audio.shape, dtype=audio.dtype, pin_memory=True)
+                    with torch.cuda.stream(d2h_s):
+                        d2h_s.wait_event(ready)
+                        host.copy_(audio, non_blocking=True)
+                        audio.record_stream(d2h_s)
+                        ev = torch.cuda.Event()
+                        ev.record(d2h_s)
+                    host_done.append(ev)
+                    audio = host
+                for b, j in enumerate(idx):
+                    n = lens[b]
+                    results[j] = {"mel_norm": out["mel_norm"][b, :n], "mel_db": out["mel_db"][b, :n],
+                                  "mel_log": out["mel_log"][b, :n], "audio": audio[b, 0, :n * self.hop]}
+            for ev in host_done:
+                ev.synchronize()
         return results  # type: ignore[return-value]
 
 

@@ -119,6 +119,7 @@ class Generator(nn.Module):
         self._handle: Optional[int] = None
         self._handle_key = None
         self._workspace: Optional[torch.Tensor] = None
+        self._graph_pins = 0   # live CUDA graphs holding this module's workspace / handle pointers (graphs.py)
         self.hop = 1
         for u in rates:
             self.hop *= int(u)
@@ -129,6 +130,18 @@ class Generator(nn.Module):
         for p in self.parameters():
             key.append((p.data_ptr(), p._version))
         return tuple(key)
+
+    def _current_key(self):
+        return self._state_key()
+
+    def _ensure_workspace(self, need: int, dev) -> None:
+        if self._workspace is not None and self._workspace.numel() >= need and self._workspace.device == dev:
+            return
+        if self._graph_pins > 0 and self._workspace is not None:
+            raise _lib.M2SError("this Generator's workspace is referenced by a captured CUDA graph and would have to "
+                                "grow: call reserve() for the largest shape before capturing, or release the graph")
+        self._workspace = None
+        self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
 
     def _config(self) -> _lib.GeneratorConfig:
         h = self.h
@@ -183,10 +196,7 @@ class Generator(nn.Module):
         with torch.cuda.device(dev):
             if self._handle is None or self._handle_key != self._state_key():
                 self.refresh()
-            need = int(_lib.lib().m2s_generator_workspace_bytes(self._handle, batch, frames))
-            if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
-                self._workspace = None
-                self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+            self._ensure_workspace(int(_lib.lib().m2s_generator_workspace_bytes(self._handle, batch, frames)), dev)
 
     # -- the drop-in call -----------------------------------------------------------------
     def forward(self, x: torch.Tensor, lengths: Optional[torch.Tensor] = None,
@@ -209,10 +219,7 @@ class Generator(nn.Module):
         with torch.cuda.device(x.device):
             if self._handle is None or self._handle_key != self._state_key():
                 self.refresh()
-            need = int(_lib.lib().m2s_generator_workspace_bytes(self._handle, B, T))
-            if self._workspace is None or self._workspace.numel() < need or self._workspace.device != x.device:
-                self._workspace = None
-                self._workspace = torch.empty(need, dtype=torch.uint8, device=x.device)
+            self._ensure_workspace(int(_lib.lib().m2s_generator_workspace_bytes(self._handle, B, T)), x.device)
             out = torch.empty(B, 1, T * self.hop, dtype=torch.float32, device=x.device)
             if lengths is not None:
                 lengths = lengths.to(device=x.device, dtype=torch.int32).contiguous()

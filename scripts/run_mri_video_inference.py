@@ -187,7 +187,7 @@ def save_outputs(audio: np.ndarray, mel: np.ndarray, output_dir, sampling_rate: 
     target = Path(output_dir)
     target.mkdir(parents=True, exist_ok=True)
     audio_path, mel_path = target / f"{stem}_generated.wav", target / f"{stem}_mel.npy"
-    io_formats.write_wav_float32(audio_path, audio, sampling_rate)
+    io_formats.write_wav_pcm16(audio_path, audio, sampling_rate)
     np.save(mel_path, mel)
     fig_path = _mel_figure(mel, target / f"{stem}_mel.png", f"Generated Mel Spectrogram - {stem}")
     return audio_path, mel_path, fig_path

@@ -39,3 +39,30 @@ def test_acoustic_graph_replay_matches_eager():
         ref, ref2 = ac(clip).clone(), ac(other).clone()
     assert torch.equal(graphed(clip).clone(), ref)
     assert torch.equal(graphed(other).clone(), ref2)
+
+
+def test_graph_survives_plan_changes_and_pins_the_workspace():
+    """a captured graph holds raw pointers into the module's workspace and the handle's packed weights.
+    A larger eager forward must not free the captured workspace; a parameter update (which rebuilds the handle) must
+    lead to a re-capture, never to a replay on freed memory."""
+    from mri2speech_b200._lib import M2SError
+    from mri2speech_b200.graphs import graph_generator
+    from mri2speech_b200.vocoder import Generator
+    torch.manual_seed(1234)
+    gen = Generator(load_config(), precision="fp16").cuda().eval()
+    mel = (torch.randn(1, 64, 40, generator=torch.Generator().manual_seed(5)) * 2 - 5).cuda()
+    graphed = graph_generator(gen, mel)
+    with torch.no_grad():
+        ref = gen(mel).clone()
+        with pytest.raises(M2SError):                      # would have to grow the workspace the graph points into
+            gen(torch.zeros(2, 64, 200, device="cuda"))
+    assert torch.equal(graphed(mel), ref)                  # ... and the graph is intact
+    with torch.no_grad():
+        gen.conv_pre.bias.add_(0.25)                       # plan change: the handle is rebuilt on the next forward
+        ref2 = gen(mel).clone()
+    assert not torch.equal(ref2, ref)
+    out2 = graphed(mel).clone()
+    assert graphed.captures == 2 and torch.equal(out2, ref2)
+    graphed.release()
+    with torch.no_grad():
+        assert gen(torch.zeros(2, 64, 200, device="cuda")).shape == (2, 1, 200 * 420)   # free to grow again

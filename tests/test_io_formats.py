@@ -8,8 +8,13 @@ from scipy.io import wavfile
 from mri2speech_b200 import io_formats
 
 
-def test_wav_float32_and_int16(tmp_path):
+def test_wav_flavours(tmp_path):
     audio = np.linspace(-0.999, 0.999, 2048).astype(np.float32)
+    # the reference CLIs' sf.write(path, float32, sr): PCM_16, round(x * 32767) -- whichever library writes it
+    io_formats.write_wav_pcm16(tmp_path / "p.wav", audio, 11413)
+    sr, p = wavfile.read(tmp_path / "p.wav")
+    assert sr == 11413 and p.dtype == np.int16
+    assert np.array_equal(p, np.rint(audio.astype(np.float64) * 32767.0).astype(np.int16))
     io_formats.write_wav_float32(tmp_path / "f.wav", audio, 11413)
     sr, a = wavfile.read(tmp_path / "f.wav")
     assert sr == 11413 and a.dtype == np.float32 and np.array_equal(a, audio)
@@ -53,7 +58,7 @@ def test_async_writer_writes_and_reports_errors(tmp_path):
         paths = io_formats.save_clip_outputs(w, res, tmp_path / "out", "clip3", 11413)
     assert [p.name for p in paths] == ["clip3_generated.wav", "clip3_mel.npy", "clip3_mel_log.npy"]
     sr, a = wavfile.read(paths[0])
-    assert sr == 11413 and a.shape == (840,)
+    assert sr == 11413 and a.shape == (840,) and a.dtype == np.int16     # the reference's <stem>_generated.wav format
     assert np.load(paths[1]).shape == (2, 64) and np.load(paths[2]).mean() == 1.0
 
     def boom(_):
