@@ -249,6 +249,13 @@ int m2s_debug_set_knob(const char* name, int value);
  * ms[i] = duration of launch i, flops[i] = 2*M*N*K it executed. */
 int m2s_debug_profile(int enable);
 int m2s_debug_profile_read(float* ms, double* flops, int32_t cap, int32_t* n);
+/* Per-launch timing covers every kernel of the path (not only the conv engine): tags[i] of the launches returned by the
+ * last m2s_debug_profile_read -- 1 encoder GEMM (tcgen05 engine), 2 encoder CUDA-core kernels (stem, depthwise, SE,
+ * pooling ...), 3 BiLSTM (input projection, recurrence, head), 4 vocoder GEMM (engine / fused pair), 5 vocoder CUDA-core
+ * kernels (mel glue, layout, conv_post). */
+int m2s_debug_profile_tags(int32_t* tags, int32_t cap, int32_t* n);
+/* Kernels launched by this library since the last reset (process-wide; bench.py's gpu_launches). */
+long long m2s_debug_launch_count(int reset);
 /* clock64 timeline of CTA 0 (producer / MMA / epilogue stamps, 9 per tile) into a device buffer; NULL = off. */
 int m2s_debug_trace(unsigned long long* buf, int32_t tiles);
 

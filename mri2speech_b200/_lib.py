@@ -99,6 +99,9 @@ def lib() -> C.CDLL:
     L.m2s_debug_profile.argtypes = [C.c_int]
     L.m2s_debug_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int32,
                                          C.POINTER(C.c_int32)]
+    L.m2s_debug_profile_tags.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]
+    L.m2s_debug_launch_count.argtypes = [C.c_int]
+    L.m2s_debug_launch_count.restype = C.c_longlong
     L.m2s_generator_create.argtypes = [C.POINTER(GeneratorConfig), C.POINTER(Tensor), C.c_int32,
                                        C.POINTER(C.c_void_p)]
     L.m2s_generator_destroy.argtypes = [C.c_void_p]
@@ -249,10 +252,23 @@ def profile(enable: bool) -> None:
     check(lib().m2s_debug_profile(int(enable)))
 
 
-def profile_read(cap: int = 65536):
-    """Per-launch (ms, executed flops) of the conv engine since the last read."""
+PROFILE_TAGS = {0: "other", 1: "encoder_gemm", 2: "encoder_simt", 3: "bilstm", 4: "vocoder_gemm", 5: "vocoder_simt"}
+
+
+def profile_read(cap: int = 262144, with_tags: bool = False):
+    """Per-launch (ms, executed flops[, tag]) of every bracketed launch since the last read."""
     ms = (C.c_float * cap)()
     fl = (C.c_double * cap)()
     n = C.c_int32(0)
     check(lib().m2s_debug_profile_read(ms, fl, cap, C.byref(n)))
-    return list(ms[: n.value]), list(fl[: n.value])
+    if not with_tags:
+        return list(ms[: n.value]), list(fl[: n.value])
+    tg = (C.c_int32 * cap)()
+    nt = C.c_int32(0)
+    check(lib().m2s_debug_profile_tags(tg, cap, C.byref(nt)))
+    return list(ms[: n.value]), list(fl[: n.value]), list(tg[: nt.value])
+
+
+def launch_count(reset: bool = False) -> int:
+    """Kernels launched by libm2s in this process since the last reset."""
+    return int(lib().m2s_debug_launch_count(int(reset)))

@@ -176,7 +176,8 @@ void free_block(Block* b) {
 
 size_t padded_rows(int h, int w) { return static_cast<size_t>(h + 2) * (w + 2); }
 
-int run_gemm(const m2s_acoustic* m, const ConvProblem& p, const GemmLayer& L, cudaStream_t st) {
+int run_gemm(const m2s_acoustic* m, const ConvProblem& p, const GemmLayer& L, cudaStream_t st, int tag = PROF_ENC_GEMM) {
+  profile_set_tag(tag);
   return m->tf32 ? conv_tcgen05(p, L.w, st) : conv_simt(p, L.w.plain, st);
 }
 
@@ -241,6 +242,14 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
   const bool h = m->fp16;
   const int esz = h ? 2 : 4;
   Act x{B.x0, B.x0h}, y{B.x1, B.x1h};
+  // CUDA-core launches of the encoder, bracketed for the launch accounting (kernels = launches inside the call)
+  auto simt = [&](int status_before, auto&& call, int kernels) -> int {
+    (void)status_before;
+    profile_set_tag(PROF_ENC_SIMT);
+    M2S_TRY(profile_before(st));
+    M2S_TRY(call());
+    return profile_after(st, 0.0, kernels);
+  };
   // operand view of an activation / of the scratch tensors e, e2, col (fp16 build: fp16 data in the same buffers)
   auto op = [&](const Act& a) { return h ? static_cast<const void*>(a.f16) : static_cast<const void*>(a.f32); };
   // a GEMM output that is only ever an operand (e, e2): fp16 in the fp16 build
@@ -250,9 +259,9 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
   {  // the stem's only consumer is block 0.0 (no skip): operand copy only in the fp16 build
     void* out = h ? x.f16 : static_cast<void*>(x.f32);
     if (u8)
-      M2S_TRY(enc_stem_u8(static_cast<const uint8_t*>(frames), src_map, mask, B.norm, out, h, m->stem_w, m->stem_b, n, H, W, st));
+      M2S_TRY(simt(0, [&] { return enc_stem_u8(static_cast<const uint8_t*>(frames), src_map, mask, B.norm, out, h, m->stem_w, m->stem_b, n, H, W, st); }, 2));
     else
-      M2S_TRY(enc_stem(static_cast<const float*>(frames), src_map, out, h, m->stem_w, m->stem_b, n, H, W, st));
+      M2S_TRY(simt(0, [&] { return enc_stem(static_cast<const float*>(frames), src_map, out, h, m->stem_w, m->stem_b, n, H, W, st); }, 1));
   }
   for (size_t bi = 0; bi < m->blocks.size(); ++bi) {
     const Block& b = m->blocks[bi];
@@ -266,8 +275,8 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
       p->d16 = out16 ? y.f16 : nullptr;
     };
     auto zero_border = [&](int rows, int ld, int head, int tail) -> int {
-      if (out32) M2S_TRY(enc_zero_rows(y.f32, 4, n, rows, ld, head, tail, st));
-      if (out16) M2S_TRY(enc_zero_rows(y.f16, 2, n, rows, ld, head, tail, st));
+      if (out32) M2S_TRY(simt(0, [&] { return enc_zero_rows(y.f32, 4, n, rows, ld, head, tail, st); }, 1));
+      if (out16) M2S_TRY(simt(0, [&] { return enc_zero_rows(y.f16, 2, n, rows, ld, head, tail, st); }, 1));
       return M2S_OK;
     };
     const int hin = b.hin, win = b.win;
@@ -288,7 +297,7 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
       const int rows_out = static_cast<int>(padded_rows(hout, wout));
       const int lq = hout * (wout + 2);  // rows in the (W+2)-pitch output space
       if (b.stride == 2) {
-        M2S_TRY(enc_im2col_s2(op(x), B.col, esz, n, hin, win, b.cin, st));
+        M2S_TRY(simt(0, [&] { return enc_im2col_s2(op(x), B.col, esz, n, hin, win, b.cin, st); }, 1));
         ConvProblem p = gemm_problem(B.col, lq, lq, 9 * b.cin, n, lq, B.e, lq, b.mid, 0, b.conv);
         set_operand_out(&p, B.e);
         p.epi.act = M2S_ACT_SILU;
@@ -320,9 +329,9 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
       }
       const int pitch_in = b.in_padded ? win + 2 : win;
       const int o = b.in_padded ? 1 : 0;
-      M2S_TRY(enc_dwconv(B.e, B.e2, h, B.sums, b.dw_w, b.dw_b, n, b.mid, hin, win, pitch_in, o, o, rows_in, b.stride, st));
+      M2S_TRY(simt(0, [&] { return enc_dwconv(B.e, B.e2, h, B.sums, b.dw_w, b.dw_b, n, b.mid, hin, win, pitch_in, o, o, rows_in, b.stride, st); }, 1));
       const int hw = hout * wout;
-      M2S_TRY(enc_se_apply(B.e2, h, B.sums, b.se_w1, b.se_b1, b.se_w2, b.se_b2, n, b.mid, b.rd, hw, st));
+      M2S_TRY(simt(0, [&] { return enc_se_apply(B.e2, h, B.sums, b.se_w1, b.se_b1, b.se_w2, b.se_b2, n, b.mid, b.rd, hw, st); }, 2));
       const int rows_out = n * hw;
       ConvProblem p = gemm_problem(B.e2, rows_out, rows_out, b.mid, 1, rows_out, y.f32, rows_out, b.cout, 0, b.pwl);
       set_block_out(&p);
@@ -333,7 +342,7 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
   }
   const Block& lastb = m->blocks.back();
   const int hw = (lastb.hin / lastb.stride) * (lastb.win / lastb.stride);
-  return enc_gap(x.f32, dst_map, feats, n, hw, kFeat, feat_ld, st);
+  return simt(0, [&] { return enc_gap(x.f32, dst_map, feats, n, hw, kFeat, feat_ld, st); }, 1);
 }
 
 // src_map / dst_map: device tables over the compact frame list (see encode_chunk), either may be null
@@ -381,14 +390,17 @@ int rnn_head(const m2s_acoustic* m, const float* feats, int batch, int frames, c
   }
   {  // input projection for every timestep and both directions: (rows, 208) x (208, 8H) + (b_ih + b_hh)
     ConvProblem p = gemm_problem(feats, rows, rows, kFeat, 1, rows, gin, rows, 8 * Hd, 0, m->inproj);
-    M2S_TRY(run_gemm(m, p, m->inproj, st));
+    M2S_TRY(run_gemm(m, p, m->inproj, st, PROF_RNN));
   }
   M2S_CUDA_OK(cudaMemsetAsync(hcat, 0, static_cast<size_t>(rows) * 2 * Hd * sizeof(float), st));
+  profile_set_tag(PROF_RNN);
+  M2S_TRY(profile_before(st));
   M2S_TRY(lstm_recurrence(gin, m->w_hh[0], m->w_hh[1], lens, hcat, counters, batch, frames, max_len, Hd, st));
+  M2S_TRY(profile_after(st, 2.0 * 2 * 4 * Hd * static_cast<double>(Hd) * batch * max_len));
   {  // head on [h_fwd | h_bwd] with the weight duplicated: y = W (h_fwd + h_bwd) + b ; rows past lens -> 0
     ConvProblem p = gemm_problem(hcat, frames, frames, 2 * Hd, batch, frames, mel_norm, frames, m->cfg.n_mels, 0, m->head);
     if (lens) { p.epi.mask_mode = M2S_MASK_LEN; p.epi.lens = lens; p.epi.len_scale = 1; }
-    M2S_TRY(run_gemm(m, p, m->head, st));
+    M2S_TRY(run_gemm(m, p, m->head, st, PROF_RNN));
   }
   return M2S_OK;
 }
@@ -639,7 +651,10 @@ int acoustic_forward_impl(m2s_acoustic* m, const void* frames_dev, bool u8, bool
     }
     M2S_CUDA_OK(cudaMemsetAsync(w.feats, 0, static_cast<size_t>(total) * kFeat * sizeof(float), st));
     if (valid > 0) {
+      profile_set_tag(PROF_ENC_SIMT);
+      M2S_TRY(profile_before(st));
       M2S_TRY(enc_build_fmap(lengths, batch, frames, w.fmap, st));
+      M2S_TRY(profile_after(st, 0.0));
       M2S_TRY(encode_all(m, frames_dev, u8, mask, packed ? nullptr : w.fmap, w.fmap, static_cast<int>(valid), w.feats,
                          w.enc, st));
     }

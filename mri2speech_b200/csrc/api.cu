@@ -130,6 +130,13 @@ extern "C" int m2s_debug_profile_read(float* ms, double* flops, int32_t cap, int
   return s;
 }
 
+extern "C" int m2s_debug_profile_tags(int32_t* tags, int32_t cap, int32_t* n) {
+  if (!tags || !n) return fail(M2S_ERR_BAD_ARG, "null argument");
+  *n = profile_read_tags(tags, cap);
+  return M2S_OK;
+}
+extern "C" long long m2s_debug_launch_count(int reset) { return launch_count(reset != 0); }
+
 // Debug timeline of CTA 0 of the conv engine: buf = device uint64[tiles * 9] (null disables).
 extern "C" int m2s_debug_trace(unsigned long long* buf, int32_t tiles) {
   EngineKnobs& k = engine_knobs();

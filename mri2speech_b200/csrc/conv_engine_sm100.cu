@@ -25,6 +25,7 @@
 //              MRF accumulate / scale / activation / mask -> coalesced global stores
 #include "engine_device.cuh"
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -277,9 +278,12 @@ struct ProfileRing {   // debug probe (m2s_debug_profile*): one ring per process
   std::mutex mu;
   std::vector<cudaEvent_t> ev;
   std::vector<double> flops;
+  std::vector<int32_t> tags, tags_read;
   int count = 0;
+  int tag = 0;
   bool on = false;
 };
+std::atomic<long long> g_launches{0};
 ProfileRing& ring() {
   static ProfileRing r;
   return r;
@@ -292,7 +296,21 @@ int profile_enable(int on) {
   r.on = on != 0;
   r.count = 0;
   r.flops.clear();
+  r.tags.clear();
   return M2S_OK;
+}
+
+void profile_set_tag(int tag) { ring().tag = tag; }
+
+long long launch_count(bool reset) { return reset ? g_launches.exchange(0) : g_launches.load(); }
+
+// tags of the launches returned by the last profile_read
+int profile_read_tags(int32_t* tags, int cap) {
+  ProfileRing& r = ring();
+  std::lock_guard<std::mutex> g(r.mu);
+  const int n = static_cast<int>(r.tags_read.size()) < cap ? static_cast<int>(r.tags_read.size()) : cap;
+  for (int i = 0; i < n; ++i) tags[i] = r.tags_read[i];
+  return n;
 }
 
 int profile_read(float* ms, double* flops, int cap, int* n_out) {
@@ -309,6 +327,8 @@ int profile_read(float* ms, double* flops, int cap, int* n_out) {
   *n_out = n;
   r.count = 0;
   r.flops.clear();
+  r.tags_read.swap(r.tags);
+  r.tags.clear();
   return M2S_OK;
 }
 
@@ -325,12 +345,14 @@ int profile_before(cudaStream_t stream) {
   return M2S_OK;
 }
 
-int profile_after(cudaStream_t stream, double flops) {
+int profile_after(cudaStream_t stream, double flops, int kernels) {
+  g_launches.fetch_add(kernels);
   ProfileRing& pr = ring();
   if (!pr.on) return M2S_OK;
   std::lock_guard<std::mutex> g(pr.mu);
   M2S_CUDA_OK(cudaEventRecord(pr.ev[2 * pr.count + 1], stream));
   pr.flops.push_back(flops);
+  pr.tags.push_back(pr.tag);
   ++pr.count;
   return M2S_OK;
 }

@@ -171,14 +171,17 @@ int conv_simt(const ConvProblem& p, const float* w_plain, cudaStream_t stream) {
   if (p.batch <= 0 || p.l_out <= 0) return M2S_OK;
   const int tiles_per_batch = (p.l_out + TM - 1) / TM;
   dim3 grid(p.batch * tiles_per_batch, (p.n + TN - 1) / TN);
+  M2S_TRY(profile_before(stream));
   conv_simt_kernel<<<grid, 256, 0, stream>>>(p, w_plain, tiles_per_batch);
   M2S_CUDA_OK(cudaGetLastError());
-  return M2S_OK;
+  return profile_after(stream, 2.0 * p.batch * static_cast<double>(p.l_out) * p.n * p.c_in * p.taps);
 }
 
 int conv_post_tanh(const float* a, const float* w, float bias, float* out, int batch, int rows, int c, int k,
                    long long a_batch_rows, long long out_batch_stride, cudaStream_t stream) {
   if (batch <= 0 || rows <= 0) return M2S_OK;
+  profile_set_tag(PROF_VOC_SIMT);
+  M2S_TRY(profile_before(stream));
   if (c == 32 && k == 7) {
     dim3 grid((rows + 255) / 256, batch);
     conv_post_kernel<32, 7><<<grid, 256, 0, stream>>>(a, w, bias, out, rows, a_batch_rows, out_batch_stride);
@@ -187,27 +190,31 @@ int conv_post_tanh(const float* a, const float* w, float bias, float* out, int b
     conv_post_generic_kernel<<<grid, 256, 0, stream>>>(a, w, bias, out, rows, c, k, a_batch_rows, out_batch_stride);
   }
   M2S_CUDA_OK(cudaGetLastError());
-  return M2S_OK;
+  return profile_after(stream, 2.0 * batch * static_cast<double>(rows) * c * k);
 }
 
 int bct_to_btc(const float* in, float* out, int batch, int c, int t, const int32_t* lens, bool round,
                cudaStream_t stream) {
   if (batch <= 0 || t <= 0) return M2S_OK;
   dim3 grid((t + 31) / 32, (c + 31) / 32, batch);
+  profile_set_tag(PROF_VOC_SIMT);
+  M2S_TRY(profile_before(stream));
   bct_to_btc_kernel<<<grid, dim3(32, 8), 0, stream>>>(in, out, c, t, lens, round ? 1 : 0);
   M2S_CUDA_OK(cudaGetLastError());
-  return M2S_OK;
+  return profile_after(stream, 0.0);
 }
 
 int mel_glue(const float* pred, const float* mean, const float* stdv, int batch, int frames, int n_mels,
              const int32_t* lens, float* mel_db, float* mel_log, float* voc_in, cudaStream_t stream) {
   const size_t total = static_cast<size_t>(batch) * frames * n_mels;
   if (!total) return M2S_OK;
+  profile_set_tag(PROF_VOC_SIMT);
+  M2S_TRY(profile_before(stream));
   mel_glue_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(pred, mean, stdv, batch, frames,
                                                                                  n_mels, lens, mel_db, mel_log,
                                                                                  voc_in);
   M2S_CUDA_OK(cudaGetLastError());
-  return M2S_OK;
+  return profile_after(stream, 0.0);
 }
 
 }  // namespace m2s

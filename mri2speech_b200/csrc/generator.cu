@@ -206,6 +206,7 @@ void free_layer(Layer* L) {
 }
 
 int run_conv(const m2s_generator* g, const ConvProblem& p, const Layer& L, cudaStream_t st) {
+  profile_set_tag(PROF_VOC_GEMM);
   return g->tf32 ? conv_tcgen05(p, L.w, st) : conv_simt(p, L.w.plain, st);
 }
 
@@ -497,6 +498,7 @@ int generator_forward_impl(m2s_generator* g, const float* mel, bool mel_btc, int
         }
         // fp16 build, C <= 128: conv1 -> leaky-ReLU -> conv2 in ONE kernel, the intermediate stays in SMEM
         if (hs && g->fuse_pairs && resblock_pair_supported(p1, l1.w, p2, l2.w)) {
+          profile_set_tag(PROF_VOC_GEMM);
           M2S_TRY(resblock_pair_fused(p1, l1.w, p2, l2.w, st));
         } else {
           M2S_TRY(run_conv(g, p1, l1, st));

@@ -176,8 +176,15 @@ bool resblock_pair_supported(const ConvProblem& p1, const PackedWeights& w1, con
                              const PackedWeights& w2);
 int resblock_pair_fused(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& p2, const PackedWeights& w2,
                         cudaStream_t stream);
+// Launch accounting (bench.py): every launch site brackets its kernel(s) with profile_before / profile_after.  The pair
+// always counts the launch (m2s_debug_launch_count) and, when the probe is on, records two CUDA events on the launching
+// stream plus the executed flops and the current tag (which part of the path the launch belongs to).
+enum { PROF_OTHER = 0, PROF_ENC_GEMM = 1, PROF_ENC_SIMT = 2, PROF_RNN = 3, PROF_VOC_GEMM = 4, PROF_VOC_SIMT = 5 };
 int profile_before(cudaStream_t stream);
-int profile_after(cudaStream_t stream, double flops);
+int profile_after(cudaStream_t stream, double flops, int kernels = 1);
+void profile_set_tag(int tag);
+int profile_read_tags(int32_t* tags, int cap);
+long long launch_count(bool reset);
 int conv_simt(const ConvProblem& p, const float* w_plain, cudaStream_t stream);
 
 // debug / probe knobs for the tcgen05 engine (environment-driven, read once)

@@ -250,3 +250,33 @@ def gather_waveforms(local: Sequence[torch.Tensor], local_ids: Sequence[int], ds
             cid, n = table[k]
             out[cid] = bufs[r][k, :n]
     return out
+
+
+def gather_planned(local_flat: torch.Tensor, samples_per_rank: Sequence[int], dst: int = 0, cache: Optional[dict] = None):
+    """Final gather when the plan is known to every rank (the batch runner shards a clip list whose lengths all ranks
+    hold): rank r contributes ``samples_per_rank[r]`` samples, its clips' waveforms concatenated in shard order.  ONE
+    gather of max-padded flat buffers -- no metadata exchange, no host round trip, nothing blocks the stream (LPT keeps
+    the per-rank totals within one clip of each other, so the padding is negligible).  ``cache``: dict reused across
+    calls for the send / receive buffers.  Returns the per-rank flat waveforms (views) on ``dst``, None elsewhere."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if len(samples_per_rank) != world:
+        raise ValueError(f"plan has {len(samples_per_rank)} ranks, world size is {world}")
+    if int(local_flat.numel()) != int(samples_per_rank[rank]):
+        raise ValueError(f"rank {rank} holds {local_flat.numel()} samples, the plan says {samples_per_rank[rank]}")
+    max_n = max(max(int(n) for n in samples_per_rank), 1)
+    cache = cache if cache is not None else {}
+    dev = local_flat.device
+    send = cache.get(("send", max_n, dev))
+    if send is None:
+        send = cache[("send", max_n, dev)] = torch.zeros(max_n, dtype=torch.float32, device=dev)
+    send[: local_flat.numel()].copy_(local_flat.reshape(-1))
+    recv = None
+    if rank == dst:
+        recv = cache.get(("recv", max_n, dev))
+        if recv is None:
+            recv = cache[("recv", max_n, dev)] = [torch.empty(max_n, dtype=torch.float32, device=dev) for _ in range(world)]
+    dist.gather(send, recv, dst=dst)
+    if rank != dst:
+        return None
+    return [recv[r][: int(samples_per_rank[r])] for r in range(world)]

@@ -70,3 +70,66 @@ def test_gather_waveforms_world2_gloo():
         p.join(timeout=30)
         assert p.exitcode == 0
     assert ok
+
+
+def _worker_planned(rank, world, port, lengths, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mri2speech_b200.pipeline import gather_planned, shard_utterances
+    hop = 4
+    shards = shard_utterances(lengths, world)
+    per_rank = [sum(lengths[i] for i in s) * hop for s in shards]
+    cache = {}
+    ok = True
+    for rep in range(2):                                   # second call reuses the cached buffers
+        local = [torch.arange(lengths[i] * hop, dtype=torch.float32) + 1000.0 * i + rep for i in shards[rank]]
+        flat = torch.cat(local) if local else torch.empty(0)
+        got = gather_planned(flat, per_rank, dst=0, cache=cache)
+        if rank == 0:
+            for r in range(world):
+                off = 0
+                for i in shards[r]:
+                    n = lengths[i] * hop
+                    ok = ok and torch.equal(got[r][off:off + n], torch.arange(n, dtype=torch.float32) + 1000.0 * i + rep)
+                    off += n
+                ok = ok and off == got[r].numel()
+        else:
+            assert got is None
+    if rank == 0:
+        bad = False
+        try:
+            gather_planned(torch.zeros(3), [1, 1], dst=0)      # local size disagrees with the plan
+        except ValueError:
+            bad = True
+        out_q.put(ok and bad)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_gather_planned_world2_gloo():
+    """bench.py's N>1 step: every rank knows the plan, one padded gather, no metadata exchange."""
+    lengths = [7, 3, 11, 5, 2, 9]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_planned, args=(r, 2, port, lengths, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=90)
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    assert ok
+
+
+def test_micro_batch_plan_covers_every_clip_once():
+    from mri2speech_b200.pipeline import MriToSpeech
+    from mri2speech_b200.synth import synthetic_lengths
+    lengths = synthetic_lengths(64)
+    plan = MriToSpeech.plan_micro_batches(lengths, 4096)
+    assert sorted(i for mb in plan for i in mb) == list(range(64))
+    for mb in plan:
+        assert len(mb) * max(lengths[i] for i in mb) <= 4096 or len(mb) == 1
+    assert MriToSpeech.plan_micro_batches([700], 512) == [[0]]        # a clip longer than the budget still runs
