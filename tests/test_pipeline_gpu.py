@@ -154,7 +154,9 @@ def test_alternate_vocoder_clis(tmp_path):
     sr, wa = wavfile.read(tmp_path / "syn" / "a_from_mel.wav")
     _, wb = wavfile.read(tmp_path / "syn" / "b_from_mel.wav")
     assert sr == 11413 and wa.shape == (9 * 420,) and wb.shape == (5 * 420,)
-    assert np.abs(wa - ref_a).max() < 2e-4 and np.abs(wb - ref_b).max() < 2e-4      # ragged batch == own B=1 run
+    # PCM_16 like the reference's sf.write default (io_formats.write_wav_pcm16): one LSB = 1/32767
+    assert wa.dtype == np.int16 and wb.dtype == np.int16
+    assert np.abs(wa / 32767.0 - ref_a).max() < 2e-4 and np.abs(wb / 32767.0 - ref_b).max() < 2e-4   # ragged batch == own B=1 run
     assert (tmp_path / "syn" / "overall_synthesis_stats.json").exists()
     outs = inference_e2e.main(["--input_mels_dir", str(mels), "--output_dir", str(tmp_path / "e2e"),
                                "--checkpoint_file", str(tmp_path / "g_00000002")])
