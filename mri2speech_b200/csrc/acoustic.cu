@@ -10,6 +10,7 @@
 // stride-1 conv is 9 row-shifted taps on the conv engine; stages 3-5 are plain (frame, pixel) rows.
 #include "m2s_common.cuh"
 #include <cmath>
+#include <cuda_fp16.h>
 #include <cstring>
 #include <map>
 #include <string>
@@ -29,6 +30,14 @@ int enc_se_apply(void* x, int half, float* sums, const float* w1, const float* b
                  int n, int C, int rd, int hw, cudaStream_t st);
 int enc_gap(const float* x, const int32_t* fmap, float* feats, int n, int hw, int C, int feat_ld, cudaStream_t st);
 int enc_build_fmap(const int32_t* lens, int batch, int frames, int32_t* fmap, cudaStream_t st);
+bool mb_expand_dw_supported(int H, int W, int c_in, int c_mid);
+int mb_expand_dw(const void* x, const void* w_exp, const float* bias1, const void* dw_w16, const float* dw_w32, const float* dw_b,
+                 void* out, float* sums, int n, int H, int W, int c_in, int c_mid, cudaStream_t st);
+bool mb_project_supported(int hw, int c_mid, int c_out);
+int mb_project(const void* a, const void* w, const float* scales, const float* bias, const float* res, float* d32, void* d16,
+               int n_frames, int hw, int c_mid, int c_out, cudaStream_t st);
+int enc_se_mlp(float* sums, const float* w1, const float* b1, const float* w2, const float* b2, int n, int C, int rd, int hw,
+               cudaStream_t st);
 int lstm_recurrence(const float* gin, const float* w_hh_fwd, const float* w_hh_bwd, const int32_t* lens, float* hcat,
                     unsigned int* counters, int batch, int frames, int max_len, int hidden,
                     cudaStream_t stream);
@@ -77,6 +86,18 @@ int bn_fold(const TMap& m, const std::string& p, int ch, std::vector<float>* s, 
   return M2S_OK;
 }
 
+// fp32 host values -> fp16 (round to nearest even) device array
+int upload_half(const std::vector<float>& h, void** dev) {
+  std::vector<uint16_t> v(h.size());
+  for (size_t i = 0; i < h.size(); ++i) {
+    const __half x = __float2half_rn(h[i]);
+    std::memcpy(&v[i], &x, 2);
+  }
+  M2S_CUDA_OK(cudaMalloc(dev, v.size() * 2));
+  M2S_CUDA_OK(cudaMemcpy(*dev, v.data(), v.size() * 2, cudaMemcpyHostToDevice));
+  return M2S_OK;
+}
+
 int upload(const std::vector<float>& h, float** dev) {
   M2S_CUDA_OK(cudaMalloc(dev, h.size() * sizeof(float)));
   M2S_CUDA_OK(cudaMemcpy(*dev, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -86,6 +107,7 @@ int upload(const std::vector<float>& h, float** dev) {
 struct GemmLayer {
   PackedWeights w;
   float* bias = nullptr;
+  void* w16 = nullptr;   // 1x1 layers of the fp16 build: plain [n][c_in] fp16, K-major (TMA operand of the fused MBConv kernels)
   int taps = 1;
   int shift[M2S_MAX_TAPS] = {};
 };
@@ -93,7 +115,9 @@ struct GemmLayer {
 void free_gemm(GemmLayer* L) {
   free_weights(&L->w);
   if (L->bias) cudaFree(L->bias);
+  if (L->w16) cudaFree(L->w16);
   L->bias = nullptr;
+  L->w16 = nullptr;
 }
 
 // conv weight (cout, cin, k, k) + BN -> engine layer.  mode 0: k*k shifted taps (pitch given); mode 1: single tap
@@ -117,6 +141,7 @@ int make_conv_layer(const TMap& m, const std::string& conv, const std::string& b
     L->taps = kk;
     for (int tap = 0; tap < kk; ++tap) L->shift[tap] = (tap / k) * pitch + (tap % k);
     M2S_TRY(pack_weights(e.data(), kk, cout, cin, pack, &L->w));
+    if (kk == 1 && pack == PACK_FP16) M2S_TRY(upload_half(e, &L->w16));
   } else {
     L->taps = 1;
     L->shift[0] = 0;
@@ -142,6 +167,7 @@ struct Block {
   GemmLayer conv;    // CN conv / ER conv_exp / IR conv_pw
   GemmLayer pwl;     // ER / IR projection
   float *dw_w = nullptr, *dw_b = nullptr;                                   // IR depthwise [9][mid], [mid]
+  void* dw_w16 = nullptr;                                                   // ... and its fp16 copy (fp16 build)
   float *se_w1 = nullptr, *se_b1 = nullptr, *se_w2 = nullptr, *se_b2 = nullptr;
 };
 
@@ -155,6 +181,9 @@ struct m2s_acoustic {
   std::vector<Block> blocks;
   GemmLayer inproj, head;
   float* w_hh[2] = {nullptr, nullptr};
+  // fused MBConv kernels (csrc/mbconv_sm100.cu; fp16 build): bit0 = expand + depthwise + squeeze in one kernel, bit1 = SE
+  // scale inside the project GEMM.  M2S_MBCONV=0 keeps the five-launch path (the A/B reference of tests/).
+  int mbconv = 3;
   int chunk = 1024;  // frames per encoder pass (M2S_ENCODER_CHUNK): 1024 frames = ~7 GB of work buffers; measured
                      // 26.4 / 22.2 / 20.6 / 19.7 us per frame at 128 / 256 / 512 / 1024 (fp16 build)
   // per-frame buffer sizes (floats)
@@ -172,6 +201,8 @@ void free_block(Block* b) {
     if (*p) cudaFree(*p);
     *p = nullptr;
   }
+  if (b->dw_w16) cudaFree(b->dw_w16);
+  b->dw_w16 = nullptr;
 }
 
 size_t padded_rows(int h, int w) { return static_cast<size_t>(h + 2) * (w + 2); }
@@ -320,17 +351,35 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
       // The 1x1 convs have no halo, so all frames of the chunk are flattened into ONE batch item: tiles then
       // span frame boundaries (a per-frame batch would waste 3/4 of every 256-row tile at 8x8 = 64 rows/frame).
       const int rows_in = b.in_padded ? static_cast<int>(padded_rows(hin, win)) : hin * win;
-      {
-        const int rows = n * rows_in;
-        ConvProblem p = gemm_problem(op(x), rows, rows, b.cin, 1, rows, B.e, rows, b.mid, 0, b.conv);
-        set_operand_out(&p, B.e);
-        p.epi.act = M2S_ACT_SILU;
-        M2S_TRY(run_gemm(m, p, b.conv, st));
-      }
-      const int pitch_in = b.in_padded ? win + 2 : win;
-      const int o = b.in_padded ? 1 : 0;
-      M2S_TRY(simt(0, [&] { return enc_dwconv(B.e, B.e2, h, B.sums, b.dw_w, b.dw_b, n, b.mid, hin, win, pitch_in, o, o, rows_in, b.stride, st); }, 1));
       const int hw = hout * wout;
+      const bool fuse_e = (m->mbconv & 1) && b.stride == 1 && !b.in_padded && b.conv.w16 && b.dw_w16 &&
+                          mb_expand_dw_supported(hin, win, b.cin, b.mid);
+      const bool fuse_p = (m->mbconv & 2) && b.pwl.w16 && mb_project_supported(hw, b.mid, b.cout);
+      if (fuse_e) {
+        // expand GEMM with the depthwise conv as its epilogue: the expanded tensor stays in SMEM / TMEM
+        profile_set_tag(PROF_ENC_GEMM);
+        M2S_TRY(mb_expand_dw(x.f16, b.conv.w16, b.conv.bias, b.dw_w16, b.dw_w, b.dw_b, B.e2, B.sums, n, hin, win, b.cin, b.mid, st));
+      } else {
+        {
+          const int rows = n * rows_in;
+          ConvProblem p = gemm_problem(op(x), rows, rows, b.cin, 1, rows, B.e, rows, b.mid, 0, b.conv);
+          set_operand_out(&p, B.e);
+          p.epi.act = M2S_ACT_SILU;
+          M2S_TRY(run_gemm(m, p, b.conv, st));
+        }
+        const int pitch_in = b.in_padded ? win + 2 : win;
+        const int o = b.in_padded ? 1 : 0;
+        M2S_TRY(simt(0, [&] { return enc_dwconv(B.e, B.e2, h, B.sums, b.dw_w, b.dw_b, n, b.mid, hin, win, pitch_in, o, o, rows_in, b.stride, st); }, 1));
+      }
+      if (fuse_p) {
+        // SE MLP (sums -> scales, in place), then the project GEMM scales its A operand in SMEM
+        M2S_TRY(simt(0, [&] { return enc_se_mlp(B.sums, b.se_w1, b.se_b1, b.se_w2, b.se_b2, n, b.mid, b.rd, hw, st); }, 1));
+        profile_set_tag(PROF_ENC_GEMM);
+        M2S_TRY(mb_project(B.e2, b.pwl.w16, B.sums, b.pwl.bias, b.skip ? x.f32 : nullptr, out32 ? y.f32 : nullptr,
+                           out16 ? y.f16 : nullptr, n, hw, b.mid, b.cout, st));
+        std::swap(x, y);
+        continue;
+      }
       M2S_TRY(simt(0, [&] { return enc_se_apply(B.e2, h, B.sums, b.se_w1, b.se_b1, b.se_w2, b.se_b2, n, b.mid, b.rd, hw, st); }, 2));
       const int rows_out = n * hw;
       ConvProblem p = gemm_problem(B.e2, rows_out, rows_out, b.mid, 1, rows_out, y.f32, rows_out, b.cout, 0, b.pwl);
@@ -429,6 +478,8 @@ extern "C" int m2s_acoustic_create(const m2s_acoustic_config* cfg, const m2s_ten
   // projection and the head stay on tf32 (fp32 features / hidden states, 0.2 % of the FLOPs)
   const int enc_pack = !m->tf32 ? PACK_FP32 : (m->fp16 ? PACK_FP16 : PACK_TF32);
   if (const char* c = std::getenv("M2S_ENCODER_CHUNK")) m->chunk = std::max(1, std::atoi(c));
+  if (const char* c = std::getenv("M2S_MBCONV")) m->mbconv = std::atoi(c);
+  if (!m->fp16) m->mbconv = 0;
   int st = M2S_OK;
   auto bail = [&](int s) { m2s_acoustic_destroy(m); return s; };
   const std::string bb = "cnn.backbone.";
@@ -495,6 +546,7 @@ extern "C" int m2s_acoustic_create(const m2s_acoustic_config* cfg, const m2s_ten
           for (int c = 0; c < b.mid; ++c)
             for (int tap = 0; tap < 9; ++tap) e[static_cast<size_t>(tap) * b.mid + c] = dw->data[c * 9 + tap] * s2[c];
           if ((st = upload(e, &b.dw_w)) != M2S_OK || (st = upload(t2, &b.dw_b)) != M2S_OK) return bail(st);
+          if (m->fp16 && (st = upload_half(e, &b.dw_w16)) != M2S_OK) return bail(st);
         }
         {
           const HT *w1, *b1, *w2, *b2;
@@ -516,7 +568,10 @@ extern "C" int m2s_acoustic_create(const m2s_acoustic_config* cfg, const m2s_ten
         m->e2_floats = std::max(m->e2_floats, static_cast<size_t>(ho) * wo * b.mid);
         m->x_floats = std::max(m->x_floats, static_cast<size_t>(ho) * wo * b.cout);
         m->max_mid = std::max(m->max_mid, b.mid);
-        launches += 5;  // expand, depthwise, SE MLP, SE scale, project
+        // expand, depthwise, SE MLP, SE scale, project; the fused kernels fold depthwise into expand and scale into project
+        const bool fe = (m->mbconv & 1) && b.stride == 1 && !padded && mb_expand_dw_supported(h, w, cin, b.mid);
+        const bool fp = (m->mbconv & 2) && mb_project_supported(ho * wo, b.mid, b.cout);
+        launches += 5 - (fe ? 1 : 0) - (fp ? 1 : 0);
       }
       m->blocks.push_back(b);
       padded = b.out_padded;

@@ -568,8 +568,9 @@ int enc_dwconv(const void* in, void* out, int half, float* sums, const float* w,
 }
 
 // Squeeze-excite: batched MLP (scales written over the squeeze sums), then the streaming in-place multiply.
-int enc_se_apply(void* x, int half, float* sums, const float* w1, const float* b1, const float* w2, const float* b2,
-                 int n, int C, int rd, int hw, cudaStream_t st) {
+// SE MLP alone: sums[n][C] (squeeze sums over hw pixels) -> excite scales, in place
+int enc_se_mlp(float* sums, const float* w1, const float* b1, const float* w2, const float* b2, int n, int C, int rd, int hw,
+               cudaStream_t st) {
   constexpr int kF = 8;  // frames per MLP block
   const size_t sm_mlp = (static_cast<size_t>(kF) * C + static_cast<size_t>(kF) * rd) * sizeof(float);
   static PerDeviceOnce attr_once;
@@ -580,6 +581,12 @@ int enc_se_apply(void* x, int half, float* sums, const float* w1, const float* b
   if (sm_mlp > 100 * 1024) return fail(M2S_ERR_UNSUPPORTED, "squeeze-excite: %d channels exceed the MLP kernel's SMEM", C);
   se_mlp_kernel<kF><<<(n + kF - 1) / kF, 1024, sm_mlp, st>>>(sums, w1, b1, w2, b2, C, rd, 1.f / hw, n);
   M2S_CUDA_OK(cudaGetLastError());
+  return M2S_OK;
+}
+
+int enc_se_apply(void* x, int half, float* sums, const float* w1, const float* b1, const float* w2, const float* b2,
+                 int n, int C, int rd, int hw, cudaStream_t st) {
+  M2S_TRY(enc_se_mlp(sums, w1, b1, w2, b2, n, C, rd, hw, st));
   const size_t bytes = static_cast<size_t>(hw) * C * (half ? 2 : 4);
   int splits = static_cast<int>((bytes + 192 * 1024 - 1) / (192 * 1024));  // ~<= 192 KB of the tensor per block
   if (splits < 1) splits = 1;

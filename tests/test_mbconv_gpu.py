@@ -1,0 +1,73 @@
+"""Fused MBConv kernels (csrc/mbconv_sm100.cu) against the five-launch path they replace.
+
+The reference block is timm's InvertedResidual + SqueezeExcite as called by EffNetV2B2Backbone.forward
+(mri2speech_code/mri_acoustic_model.py:28-48).  M2S_MBCONV selects the path when the handle is created: 0 = expand GEMM,
+depthwise kernel, SE MLP, SE scale pass, project GEMM; bit0 = expand GEMM with the depthwise conv + squeeze as its
+epilogue; bit1 = SE scale applied to the project GEMM's A operand in SMEM.  Both kernels keep the arithmetic of the
+launches they replace (fp32 depthwise accumulation in tap order, fp32 scale * fp16 activation rounded once), so the
+encoder features must agree far below the fp16 operand noise (2^-11); the oracle comparison of the fused default runs
+in tests/test_acoustic_gpu.py / test_bench_paths_gpu.py / test_scaled_init_gpu.py."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _encode(mode, frames, randomize_bn=True, dw32=None):
+    from mri2speech_b200 import synth
+    from mri2speech_b200.acoustic import build_acoustic_model
+    torch.manual_seed(1234)
+    m = build_acoustic_model(precision="fp16")
+    if randomize_bn:
+        synth.randomize_batchnorm(m)
+    m = m.cuda().eval()
+    old = os.environ.get("M2S_MBCONV")
+    os.environ["M2S_MBCONV"] = str(mode)
+    try:
+        m.refresh()                       # the knob is read when the handle is created
+        out = m.encode_frames(frames)
+        torch.cuda.synchronize()
+    finally:
+        if old is None:
+            os.environ.pop("M2S_MBCONV", None)
+        else:
+            os.environ["M2S_MBCONV"] = old
+    return out.cpu(), m.launches_per_forward()
+
+
+def _frames(n, seed=0):
+    from mri2speech_b200 import synth
+    return synth.synthetic_clip(seed, n).cuda()
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("n", [5, 301])
+def test_fused_equals_unfused(mode, n):
+    """5 frames: partial tiles (two 8x8 frames per tile, odd count); 301 frames: several tiles per CTA (ring phases wrap)."""
+    frames = _frames(n)
+    ref, l0 = _encode(0, frames)
+    got, l1 = _encode(mode, frames)
+    assert torch.isfinite(got).all()
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-4 * scale, (mode, n, err, scale)
+    assert l1 < l0                                   # fewer launches per forward
+    if mode == 3:
+        assert l0 - l1 == 18 + 20                    # 18 stride-1 blocks lose the depthwise launch, all 20 the scale pass
+
+
+def test_fused_default_is_on():
+    from mri2speech_b200.acoustic import build_acoustic_model
+    torch.manual_seed(1234)
+    m = build_acoustic_model(precision="fp16").cuda().eval()
+    m.refresh()
+    fused = m.launches_per_forward()
+    os.environ["M2S_MBCONV"] = "0"
+    try:
+        m.refresh()
+        plain = m.launches_per_forward()
+    finally:
+        os.environ.pop("M2S_MBCONV", None)
+    assert plain - fused == 38
