@@ -36,6 +36,9 @@ int mb_expand_dw(const void* x, const void* w_exp, const float* bias1, const voi
 bool mb_project_supported(int hw, int c_mid, int c_out);
 int mb_project(const void* a, const void* w, const float* scales, const float* bias, const float* res, float* d32, void* d16,
                int n_frames, int hw, int c_mid, int c_out, cudaStream_t st);
+bool fused_er_supported(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& p2, const PackedWeights& w2);
+int fused_er(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& p2, const PackedWeights& w2,
+             cudaStream_t stream);
 int enc_se_mlp(float* sums, const float* w1, const float* b1, const float* w2, const float* b2, int n, int C, int rd, int hw,
                cudaStream_t st);
 int lstm_recurrence(const float* gin, const float* w_hh_fwd, const float* w_hh_bwd, const int32_t* lens, float* hcat,
@@ -181,9 +184,10 @@ struct m2s_acoustic {
   std::vector<Block> blocks;
   GemmLayer inproj, head;
   float* w_hh[2] = {nullptr, nullptr};
-  // fused MBConv kernels (csrc/mbconv_sm100.cu; fp16 build): bit0 = expand + depthwise + squeeze in one kernel, bit1 = SE
-  // scale inside the project GEMM.  M2S_MBCONV=0 keeps the five-launch path (the A/B reference of tests/).
-  int mbconv = 3;
+  // fused block kernels (fp16 build): bit0 = InvertedResidual expand + depthwise + squeeze in one kernel, bit1 = SE scale
+  // inside the project GEMM (csrc/mbconv_sm100.cu); bit2 = EdgeResidual 3x3 expand + 1x1 project in one kernel
+  // (csrc/fused_er_sm100.cu).  M2S_MBCONV=0 keeps the unfused launches (the A/B reference of tests/).
+  int mbconv = 7;
   int chunk = 1024;  // frames per encoder pass (M2S_ENCODER_CHUNK): 1024 frames = ~7 GB of work buffers; measured
                      // 26.4 / 22.2 / 20.6 / 19.7 us per frame at 128 / 256 / 512 / 1024 (fp16 build)
   // per-frame buffer sizes (floats)
@@ -333,17 +337,26 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
         set_operand_out(&p, B.e);
         p.epi.act = M2S_ACT_SILU;
         M2S_TRY(run_gemm(m, p, b.conv, st));
-      } else {
-        ConvProblem p = gemm_problem(op(x), rows_in, rows_in, b.cin, n, lq, B.e, lq, b.mid, 0, b.conv);
-        set_operand_out(&p, B.e);
-        p.epi.act = M2S_ACT_SILU;
-        M2S_TRY(run_gemm(m, p, b.conv, st));
       }
       ConvProblem p = gemm_problem(B.e, lq, lq, b.mid, n, lq, y.f32, rows_out, b.cout, wout + 3, b.pwl);
       set_block_out(&p);
       set_pitch_mask(&p, hout, wout);
       if (b.skip) { p.epi.res = x.f32; p.epi.res_ld = b.cin; }
-      M2S_TRY(run_gemm(m, p, b.pwl, st));
+      bool fused = false;
+      if (b.stride == 1) {
+        ConvProblem p1 = gemm_problem(op(x), rows_in, rows_in, b.cin, n, lq, B.e, lq, b.mid, 0, b.conv);
+        set_operand_out(&p1, B.e);
+        p1.epi.act = M2S_ACT_SILU;
+        if ((m->mbconv & 4) && fused_er_supported(p1, b.conv.w, p, b.pwl.w)) {
+          // 3x3 expand -> SiLU -> 1x1 project in one kernel: the expanded tile stays in SMEM
+          profile_set_tag(PROF_ENC_GEMM);
+          M2S_TRY(fused_er(p1, b.conv.w, p, b.pwl.w, st));
+          fused = true;
+        } else {
+          M2S_TRY(run_gemm(m, p1, b.conv, st));
+        }
+      }
+      if (!fused) M2S_TRY(run_gemm(m, p, b.pwl, st));
       M2S_TRY(zero_border(rows_out, b.cout, wout + 3, hout * (wout + 2) + wout + 3));
       std::swap(x, y);
     } else {
@@ -530,7 +543,7 @@ extern "C" int m2s_acoustic_create(const m2s_acoustic_config* cfg, const m2s_ten
         m->e_floats = std::max(m->e_floats, lq * b.mid);
         if (b.stride == 2) m->col_floats = std::max(m->col_floats, lq * 9 * cin);
         m->x_floats = std::max(m->x_floats, padded_rows(ho, wo) * b.cout);
-        launches += b.stride == 2 ? 4 : 3;
+        launches += b.stride == 2 ? 4 : ((m->mbconv & 4) ? 2 : 3);   // (im2col,) expand, project (one fused kernel), border rows
       } else {
         b.out_padded = false;
         if ((st = make_conv_layer(tm, p + ".conv_pw", p + ".bn1", b.mid, cin, 1, 0, 0, enc_pack, &b.conv)) != M2S_OK)

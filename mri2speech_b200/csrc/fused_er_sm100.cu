@@ -1,0 +1,436 @@
+// Fused EdgeResidual (FusedMBConv) block of the frame-CNN encoder for sm_100a (fp16 build):
+//     y = bn2(conv_pwl( silu( bn1(conv_exp_3x3(x)) ) )) [+ x]                       in ONE kernel.
+//
+// Reference: timm EdgeResidual (conv_exp 3x3 -> bn1 -> SiLU -> conv_pwl 1x1 -> bn2, shortcut when in == out and stride
+// 1) as called through EffNetV2B2Backbone.forward (mri2speech_code/mri_acoustic_model.py:28-48); SURVEY.md 8a-1 stages
+// 1-2.  The two-launch path writes the 4x-expanded tensor (1.1 GB per 1024 frames at stage 1) to HBM and reads it back;
+// here the expanded tile T never leaves the SM:
+//
+//   TMA (x tile with its 3x3 halo, weights)  ->  tcgen05.mma kind::f16, 9 row-shifted taps  ->  acc1 (TMEM, N1 = 4 C)
+//   epilogue warps: acc1 -> + bias -> SiLU -> fp16 -> T tile in SMEM, written directly in the K-major SWIZZLE_128B
+//                   operand layout
+//   tcgen05.mma (A = T tile, K = N1)  ->  acc2 (TMEM, N2 = C_out)  ->  the engine's fused epilogue (bias, fp32 shortcut,
+//   image-border mask) -> fp32 and / or fp16 stores.
+//
+// Same structure as resblock_pair_kernel (csrc/resblock_pair_sm100.cu), generalised where the block needs it: the two
+// convs have different widths (N1 = 128 / 224 in one or two N tiles, N2 = 32 / 64) and different operand formats (x has
+// 32 or 56 channels: 64-byte SWIZZLE_64B rows or one 128-byte block; T always 128-byte rows), conv2 has one tap (no halo,
+// no recompute), shifts of conv1 are the non-negative dy * pitch + dx of the zero-bordered image.
+#include "engine_device.cuh"
+#include <mutex>
+
+namespace m2s {
+
+using namespace engine;
+
+namespace {
+
+struct ErParams {
+  ConvProblem p2;          // epilogue / outputs / bias2 of the project conv; p2.l_out, p2.batch, p2.n
+  const float* bias1;      // [n1]
+  const void* w1;          // packed weights (single-CTA layout): expand [nt1][cb1][9][n_tile1 rows], project [cb2][n_tile2 rows]
+  const void* w2;
+  int taps1;
+  int rel_shift1[M2S_MAX_TAPS];
+  int c_in, n1;                  // channels of x / of T
+  int n_tile1, n_tiles1;         // N tiling of the expand conv (n_tile1 * n_tiles1 >= n1)
+  int n_tile2;                   // N of the project MMA (>= p2.n, multiple of 16)
+  int cblocks1, cblocks2;
+  int kblock1, row_bytes1;       // operand format of x / the expand weights
+  uint64_t desc_hi1, desc_hi2;
+  uint32_t idesc1, idesc2;
+  int x_row0;                    // first x row of a tile relative to q0 (min shift)
+  int tiles_per_batch, total_tiles;
+  int a_box_rows, a_nbox;
+  uint32_t a_stage_bytes, b_stage_bytes, b_tap_bytes1, b_tap_bytes2, t_buf_bytes;
+  int na, nb, tg1;
+  int nbuf;                      // 1 or 2 buffers of acc1 / acc2 / T; lookahead = nbuf - 1
+};
+
+constexpr uint32_t kTkbBytes = 128 * 128;   // one K block (64 channels) of the T tile: 128 rows x 128 bytes
+
+template <int kEpi>
+__global__ void __launch_bounds__(kThreads, 1)
+fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ ErParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t t_base = a_base + prm.na * prm.a_stage_bytes;
+  const uint32_t b_base = t_base + prm.nbuf * prm.t_buf_bytes;
+  const uint32_t bar_base = b_base + prm.nb * prm.b_stage_bytes;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (kMaxStagesA + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * kMaxStagesA + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * kMaxStagesA + kMaxStagesB + s); };
+  const uint32_t x_base = bar_base + 8u * (2 * kMaxStagesA + 2 * kMaxStagesB);
+  auto acc1_full = [&](int s) { return x_base + 8u * s; };
+  auto acc1_empty = [&](int s) { return x_base + 8u * (2 + s); };
+  auto acc2_full = [&](int s) { return x_base + 8u * (4 + s); };
+  auto acc2_empty = [&](int s) { return x_base + 8u * (6 + s); };
+  auto t_full = [&](int s) { return x_base + 8u * (8 + s); };
+  auto t_empty = [&](int s) { return x_base + 8u * (10 + s); };
+  const uint32_t tmem_slot = x_base + 8u * 12;
+  const uint32_t bias1_smem = bar_base + 1024u;             // n1 floats (<= 256)
+  const uint32_t stage_base = bar_base + 2048u;             // 16 epilogue warps x 2 KB transpose staging (+ staged bias2)
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const ConvProblem& p = prm.p2;
+  const int nbuf = prm.nbuf;
+  const int la = nbuf - 1;  // the expand conv of tile i+la is issued before the project conv of tile i
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < prm.na; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < prm.nb; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    for (int s = 0; s < nbuf; ++s) {
+      mbar_init(acc1_full(s), 1); mbar_init(acc1_empty(s), kEpiWarps);
+      mbar_init(acc2_full(s), 1); mbar_init(acc2_empty(s), kEpiWarps);
+      mbar_init(t_full(s), kEpiWarps); mbar_init(t_empty(s), 1);
+    }
+    fence_barrier_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+  }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias1_smem + 4u * i), "f"(i < prm.n1 ? __ldg(prm.bias1 + i) : 0.f) : "memory");
+  const uint32_t bias_smem = stage_bias(p, stage_base);
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int n1p = prm.n_tile1 * prm.n_tiles1;   // columns of one acc1 buffer
+  const int my_tiles = (prm.total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                       static_cast<int>(gridDim.x);
+  auto acc1_addr = [&](int buf) { return tmem_base + static_cast<uint32_t>(buf * n1p); };
+  auto acc2_addr = [&](int buf) { return tmem_base + static_cast<uint32_t>(nbuf * n1p + buf * prm.n_tile2); };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    const uint32_t a_bytes = prm.a_nbox * prm.a_box_rows * prm.row_bytes1;
+    auto load_b = [&](const uint8_t* src, uint32_t bytes) {
+      mbar_wait(b_empty(sb), pb ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(b_full(sb), bytes);
+        bulk_load(b_base + sb * prm.b_stage_bytes, src, bytes, b_full(sb));
+      }
+      __syncwarp();
+      if (++sb == prm.nb) { sb = 0; pb ^= 1; }
+    };
+    for (int s = 0; s < my_tiles + la; ++s) {
+      if (s < my_tiles) {
+        const int tile = blockIdx.x + s * gridDim.x;
+        const int b = tile / prm.tiles_per_batch;
+        const int q0 = (tile - b * prm.tiles_per_batch) * 128;
+        for (int cb = 0; cb < prm.cblocks1; ++cb) {
+          mbar_wait(a_empty(sa), pa ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(a_full(sa), a_bytes);
+            for (int bx = 0; bx < prm.a_nbox; ++bx)
+              tma_load_3d(a_base + sa * prm.a_stage_bytes + bx * prm.a_box_rows * prm.row_bytes1, &tmap_x, a_full(sa),
+                          cb * prm.kblock1, q0 + prm.x_row0 + bx * prm.a_box_rows, b);
+          }
+          __syncwarp();
+          if (++sa == prm.na) { sa = 0; pa ^= 1; }
+          for (int nt = 0; nt < prm.n_tiles1; ++nt)
+            for (int tap0 = 0; tap0 < prm.taps1; tap0 += prm.tg1) {
+              const int cnt = min(prm.tg1, prm.taps1 - tap0);
+              load_b(static_cast<const uint8_t*>(prm.w1) +
+                         static_cast<size_t>((nt * prm.cblocks1 + cb) * prm.taps1 + tap0) * prm.b_tap_bytes1,
+                     cnt * prm.b_tap_bytes1);
+            }
+        }
+      }
+      if (s >= la)
+        for (int cb = 0; cb < prm.cblocks2; ++cb)
+          load_b(static_cast<const uint8_t*>(prm.w2) + static_cast<size_t>(cb) * prm.b_tap_bytes2, prm.b_tap_bytes2);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    const int ksteps_full1 = prm.row_bytes1 >> 5;
+    for (int s = 0; s < my_tiles + la; ++s) {
+      if (s < my_tiles) {
+        // ---- expand: 9 row-shifted taps over the x tile ----
+        const int buf = s % nbuf;
+        mbar_wait(acc1_empty(buf), ((s / nbuf) & 1) ^ 1);
+        tc_fence_after();
+        for (int cb = 0; cb < prm.cblocks1; ++cb) {
+          const int rem = prm.c_in - cb * prm.kblock1;
+          const int ksteps = rem >= prm.kblock1 ? ksteps_full1 : (rem + 15) >> 4;
+          mbar_wait(a_full(sa), pa);
+          const uint32_t a_tile = a_base + sa * prm.a_stage_bytes;
+          for (int nt = 0; nt < prm.n_tiles1; ++nt)
+            for (int tap0 = 0; tap0 < prm.taps1; tap0 += prm.tg1) {
+              const int cnt = min(prm.tg1, prm.taps1 - tap0);
+              mbar_wait(b_full(sb), pb);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t b_tile = b_base + sb * prm.b_stage_bytes;
+                for (int t = 0; t < cnt; ++t) {
+                  const uint64_t db = prm.desc_hi1 | (((b_tile + t * prm.b_tap_bytes1) & 0x3FFFF) >> 4);
+                  const uint64_t da = prm.desc_hi1 | (((a_tile + prm.rel_shift1[tap0 + t] * prm.row_bytes1) & 0x3FFFF) >> 4);
+                  mma_f16_k4(acc1_addr(buf) + nt * prm.n_tile1, da, db, prm.idesc1, (cb | tap0 | t) ? 1u : 0u, ksteps);
+                }
+                tc_commit(b_empty(sb));
+                const bool last = nt == prm.n_tiles1 - 1 && tap0 + cnt >= prm.taps1;
+                if (last) tc_commit(a_empty(sa));
+                if (last && cb == prm.cblocks1 - 1) tc_commit(acc1_full(buf));
+              }
+              __syncwarp();
+              if (++sb == prm.nb) { sb = 0; pb ^= 1; }
+            }
+          if (++sa == prm.na) { sa = 0; pa ^= 1; }
+        }
+      }
+      if (s >= la) {
+        // ---- project: A = the T tile, K = n1 ----
+        const int i = s - la;
+        const int buf = i % nbuf;
+        mbar_wait(t_full(buf), (i / nbuf) & 1);
+        mbar_wait(acc2_empty(buf), ((i / nbuf) & 1) ^ 1);
+        tc_fence_after();
+        for (int cb = 0; cb < prm.cblocks2; ++cb) {
+          const int rem = prm.n1 - cb * 64;
+          const int ksteps = rem >= 64 ? 4 : (rem + 15) >> 4;
+          mbar_wait(b_full(sb), pb);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t db = prm.desc_hi2 | (((b_base + sb * prm.b_stage_bytes) & 0x3FFFF) >> 4);
+            const uint64_t da = prm.desc_hi2 | (((t_base + buf * prm.t_buf_bytes + cb * kTkbBytes) & 0x3FFFF) >> 4);
+            mma_f16_k4(acc2_addr(buf), da, db, prm.idesc2, cb ? 1u : 0u, ksteps);
+            tc_commit(b_empty(sb));
+            if (cb == prm.cblocks2 - 1) {
+              tc_commit(acc2_full(buf));
+              tc_commit(t_empty(buf));
+            }
+          }
+          __syncwarp();
+          if (++sb == prm.nb) { sb = 0; pb ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int ew = warp - 2;
+    const EpiWarp epw = make_epi_warp(p.epi, stage_base, ew, warp, lane, 0, bias_smem);
+    const int quad = epw.quad, grp = epw.grp;
+    const int nchunks = (prm.n1 + kEpiUnitCols - 1) / kEpiUnitCols;
+    for (int s = 0; s < my_tiles + la; ++s) {
+      if (s < my_tiles) {
+        // ---- epilogue 1: acc1 -> + bias -> SiLU -> T tile (fp16, SWIZZLE_128B K-major operand layout) ----
+        const int buf = s % nbuf;
+        mbar_wait(acc1_full(buf), (s / nbuf) & 1);
+        mbar_wait(t_empty(buf), ((s / nbuf) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = acc1_addr(buf) + (static_cast<uint32_t>(quad * 32) << 16);
+        const uint32_t tt = t_base + buf * prm.t_buf_bytes;
+        const int row = quad * 32 + lane;
+        const uint32_t swz = row & 7;
+        for (int ci = grp; ci < nchunks; ci += kEpiGroups) {
+          const int c0 = ci * kEpiUnitCols;
+          uint32_t r[16];
+          tmem_ld16(tacc + c0, r);
+          tmem_ld_wait();
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4 b4;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w)
+                         : "r"(bias1_smem + 4u * (c0 + 4 * j)));
+            const float v0 = fast_silu(__uint_as_float(r[4 * j]) + b4.x), v1 = fast_silu(__uint_as_float(r[4 * j + 1]) + b4.y);
+            const float v2 = fast_silu(__uint_as_float(r[4 * j + 2]) + b4.z), v3 = fast_silu(__uint_as_float(r[4 * j + 3]) + b4.w);
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk[2 * j]) : "f"(v1), "f"(v0));
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk[2 * j + 1]) : "f"(v3), "f"(v2));
+          }
+          // 16 halves = 32 bytes = two 16-byte chunks of this row inside K block kb
+          const int kb = c0 >> 6;
+          const int chunk0 = (c0 & 63) >> 3;
+          const uint32_t rbase = tt + kb * kTkbBytes + row * 128;
+#pragma unroll
+          for (int m = 0; m < 2; ++m)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rbase + (((chunk0 + m) ^ swz) << 4)),
+                         "r"(pk[4 * m]), "r"(pk[4 * m + 1]), "r"(pk[4 * m + 2]), "r"(pk[4 * m + 3])
+                         : "memory");
+        }
+        fence_proxy_async();   // generic-proxy writes of T -> visible to the tensor core's async-proxy reads
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(t_full(buf));
+          mbar_arrive(acc1_empty(buf));
+        }
+      }
+      if (s >= la) {
+        // ---- epilogue 2: acc2 -> fused epilogue (bias, shortcut, border mask) -> global ----
+        const int i = s - la;
+        const int tile = blockIdx.x + i * gridDim.x;
+        const int b = tile / prm.tiles_per_batch;
+        const int q0 = (tile - b * prm.tiles_per_batch) * 128;
+        const int buf = i % nbuf;
+        mbar_wait(acc2_full(buf), (i / nbuf) & 1);
+        tc_fence_after();
+        const uint32_t tacc = acc2_addr(buf) + (static_cast<uint32_t>(quad * 32) << 16);
+        epilogue_tile<kEpi>(p, epw, tacc, b, q0, 0, 1, prm.n_tile2);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc2_empty(buf));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn_er() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+}  // namespace
+
+// p1: the expand conv as the engine would run it (a = x fp16, taps / shifts, bias = folded bn1, act = SiLU; its outputs are
+//     ignored: T stays on chip).  p2: the project conv's bias, epilogue and outputs (its `a` is ignored; c_in == p1.n).
+bool fused_er_supported(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& p2, const PackedWeights& w2) {
+  if (!p1.a_half || !w1.half || w2.half != 1) return false;                      // T is written with 128-byte rows
+  if (p1.epi.act != M2S_ACT_SILU || p2.taps != 1 || p2.shift[0] != 0 || p2.c_in != p1.n) return false;
+  if (p1.n > 256 || p1.n % 16 || w2.n_tiles != 1 || w2.n_tile > 64) return false;
+  if (p1.batch != p2.batch || p1.l_out != p2.l_out) return false;
+  const int epi = choose_epilogue(p2.epi);
+  if (epi < 0 || p2.epi.res_hi || p2.d16_lo) return false;
+  if (w1.n_tile * w1.n_tiles + w2.n_tile > kTmemCols) return false;
+  for (int j = 0; j < p1.taps; ++j)
+    if (p1.shift[j] < 0) return false;
+  return true;
+}
+
+int fused_er(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& p2, const PackedWeights& w2,
+             cudaStream_t stream) {
+  if (!fused_er_supported(p1, w1, p2, w2)) return fail(M2S_ERR_UNSUPPORTED, "block not supported by the fused EdgeResidual kernel");
+  if (p2.batch <= 0 || p2.l_out <= 0) return M2S_OK;
+  EncodeTiledFn enc = encode_fn_er();
+  if (!enc) return fail(M2S_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  ErParams prm{};
+  prm.p2 = p2;
+  finalize_epilogue(&prm.p2.epi, static_cast<long long>(p2.l_out) + p2.d_row_offset);
+  prm.bias1 = p1.epi.bias;
+  prm.w1 = w1.dev;
+  prm.w2 = w2.dev;
+  prm.taps1 = p1.taps;
+  prm.c_in = p1.c_in;
+  prm.n1 = p1.n;
+  prm.n_tile1 = w1.n_tile; prm.n_tiles1 = w1.n_tiles;
+  prm.n_tile2 = w2.n_tile;
+  prm.cblocks1 = w1.cblocks;
+  prm.cblocks2 = w2.cblocks;
+  prm.kblock1 = w1.kblock; prm.row_bytes1 = w1.row_bytes;
+  prm.desc_hi1 = make_desc_hi(w1.row_bytes);
+  prm.desc_hi2 = make_desc_hi(128);
+  prm.idesc1 = (1u << 4) | (static_cast<uint32_t>(prm.n_tile1 >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+  prm.idesc2 = (1u << 4) | (static_cast<uint32_t>(prm.n_tile2 >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+  int smin = p1.shift[0], smax = p1.shift[0];
+  for (int j = 1; j < p1.taps; ++j) { smin = p1.shift[j] < smin ? p1.shift[j] : smin; smax = p1.shift[j] > smax ? p1.shift[j] : smax; }
+  for (int j = 0; j < p1.taps; ++j) prm.rel_shift1[j] = p1.shift[j] - smin;
+  prm.x_row0 = smin;
+  prm.tiles_per_batch = (p2.l_out + 127) / 128;
+  prm.total_tiles = p2.batch * prm.tiles_per_batch;
+  const int n1p = prm.n_tile1 * prm.n_tiles1;
+  prm.nbuf = (2 * (n1p + prm.n_tile2) <= kTmemCols) ? 2 : 1;
+
+  const int a_rows_needed = 128 + smax - smin;
+  prm.a_nbox = (a_rows_needed + 255) / 256;
+  prm.a_box_rows = (((a_rows_needed + prm.a_nbox - 1) / prm.a_nbox) + 7) / 8 * 8;
+  prm.a_stage_bytes = (static_cast<uint32_t>(prm.a_nbox * prm.a_box_rows * prm.row_bytes1) + 1023u) & ~1023u;
+  prm.t_buf_bytes = prm.cblocks2 * kTkbBytes;
+  prm.b_tap_bytes1 = static_cast<uint32_t>(prm.n_tile1 * prm.row_bytes1);
+  prm.b_tap_bytes2 = static_cast<uint32_t>(prm.n_tile2 * 128);
+  if ((prm.b_tap_bytes1 & 1023u) || (prm.b_tap_bytes2 & 1023u))
+    return fail(M2S_ERR_UNSUPPORTED, "fused EdgeResidual: weight blocks not 1 KB aligned (n_tile %d / %d)", prm.n_tile1, prm.n_tile2);
+  // SMEM plan: A stages, T buffers, weight stages (tap groups), epilogue staging
+  const uint32_t fixed = 2048u + kEpiSmemBytes + 1024u;
+  const uint32_t budget = 225u * 1024u;
+  int na = 2;
+  uint32_t used = fixed + na * prm.a_stage_bytes + prm.nbuf * prm.t_buf_bytes;
+  if (used + 2 * prm.b_tap_bytes1 > budget && prm.nbuf == 2) {
+    prm.nbuf = 1;
+    used = fixed + na * prm.a_stage_bytes + prm.t_buf_bytes;
+  }
+  if (used + 2 * prm.b_tap_bytes1 > budget) return fail(M2S_ERR_UNSUPPORTED, "fused EdgeResidual: tile does not fit SMEM");
+  int tg = static_cast<int>(32768u / prm.b_tap_bytes1);
+  if (tg < 1) tg = 1;
+  if (tg > p1.taps) tg = p1.taps;
+  while (tg > 1 && used + 2u * tg * prm.b_tap_bytes1 > budget) --tg;
+  prm.tg1 = tg;
+  prm.b_stage_bytes = static_cast<uint32_t>(tg) * prm.b_tap_bytes1;
+  if (prm.b_stage_bytes < prm.b_tap_bytes2) prm.b_stage_bytes = prm.b_tap_bytes2;
+  int nb = 2;
+  while (nb < 4 && used + (nb + 1) * prm.b_stage_bytes <= budget) ++nb;
+  used += nb * prm.b_stage_bytes;
+  while (na < 3 && used + prm.a_stage_bytes <= budget) { ++na; used += prm.a_stage_bytes; }
+  while (nb < kMaxStagesB && used + prm.b_stage_bytes <= budget) { ++nb; used += prm.b_stage_bytes; }
+  prm.na = na;
+  prm.nb = nb;
+  uint32_t smem_bytes = used + 1024u;  // alignment slack
+  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // one CTA per SM (whole-TMEM allocation)
+
+  CUtensorMap tmap;
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(p1.c_in), static_cast<cuuint64_t>(p1.a_rows),
+                        static_cast<cuuint64_t>(p1.batch)};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(p1.a_ld) * 2ull,
+                           static_cast<cuuint64_t>(p1.a_batch_rows) * static_cast<cuuint64_t>(p1.a_ld) * 2ull};
+  if (p1.batch == 1) gstride[1] = gstride[0] * static_cast<cuuint64_t>(p1.a_rows > 0 ? p1.a_rows : 1);
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(prm.kblock1), static_cast<cuuint32_t>(prm.a_box_rows), 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<float*>(p1.a), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    prm.row_bytes1 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(M2S_ERR_CUDA, "fused EdgeResidual: x tensor map failed (%d)", static_cast<int>(cr));
+
+  using KernelFn = void (*)(const CUtensorMap, const ErParams);
+  // the project conv has no activation: bias, or bias + fp32 shortcut (other programs fall back to the two-launch path)
+  const int epi = choose_epilogue(p2.epi);
+  KernelFn k = epi == EPI_BIAS ? fused_er_kernel<EPI_BIAS> : epi == EPI_RES ? fused_er_kernel<EPI_RES> : nullptr;
+  if (!k) return fail(M2S_ERR_UNSUPPORTED, "fused EdgeResidual: epilogue program %d not instantiated", epi);
+  static PerDeviceOnce attr_once;
+  M2S_TRY(attr_once.run([&]() -> int {
+    M2S_CUDA_OK(cudaFuncSetAttribute(fused_er_kernel<EPI_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    M2S_CUDA_OK(cudaFuncSetAttribute(fused_er_kernel<EPI_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    return M2S_OK;
+  }));
+  int grid = sm_count();
+  if (grid > prm.total_tiles) grid = prm.total_tiles;
+  M2S_TRY(profile_before(stream));
+  k<<<grid, kThreads, smem_bytes, stream>>>(tmap, prm);
+  M2S_CUDA_OK(cudaGetLastError());
+  const double rows = static_cast<double>(p2.batch) * p2.l_out;
+  return profile_after(stream, 2.0 * rows * p1.n * (static_cast<double>(p1.c_in) * p1.taps + p2.n));
+}
+
+bool fused_er_epilogue_ok(const ConvProblem& p2) {
+  const int epi = choose_epilogue(p2.epi);
+  return epi == EPI_BIAS || epi == EPI_RES;
+}
+
+}  // namespace m2s
