@@ -37,6 +37,7 @@ bool mb_project_supported(int hw, int c_mid, int c_out);
 int mb_project(const void* a, const void* w, const float* scales, const float* bias, const float* res, float* d32, void* d16,
                int n_frames, int hw, int c_mid, int c_out, cudaStream_t st);
 bool fused_er_supported(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& p2, const PackedWeights& w2);
+bool fused_er_resident(const PackedWeights& w1, const PackedWeights& w2);
 int fused_er(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& p2, const PackedWeights& w2,
              cudaStream_t stream);
 int enc_se_mlp(float* sums, const float* w1, const float* b1, const float* w2, const float* b2, int n, int C, int rd, int hw,
@@ -347,7 +348,8 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
         ConvProblem p1 = gemm_problem(op(x), rows_in, rows_in, b.cin, n, lq, B.e, lq, b.mid, 0, b.conv);
         set_operand_out(&p1, B.e);
         p1.epi.act = M2S_ACT_SILU;
-        if ((m->mbconv & 4) && fused_er_supported(p1, b.conv.w, p, b.pwl.w)) {
+        if ((m->mbconv & 4) && fused_er_supported(p1, b.conv.w, p, b.pwl.w) &&
+            ((m->mbconv & 8) || fused_er_resident(b.conv.w, b.pwl.w))) {
           // 3x3 expand -> SiLU -> 1x1 project in one kernel: the expanded tile stays in SMEM
           profile_set_tag(PROF_ENC_GEMM);
           M2S_TRY(fused_er(p1, b.conv.w, p, b.pwl.w, st));
@@ -543,7 +545,7 @@ extern "C" int m2s_acoustic_create(const m2s_acoustic_config* cfg, const m2s_ten
         m->e_floats = std::max(m->e_floats, lq * b.mid);
         if (b.stride == 2) m->col_floats = std::max(m->col_floats, lq * 9 * cin);
         m->x_floats = std::max(m->x_floats, padded_rows(ho, wo) * b.cout);
-        launches += b.stride == 2 ? 4 : ((m->mbconv & 4) ? 2 : 3);   // (im2col,) expand, project (one fused kernel), border rows
+        launches += b.stride == 2 ? 4 : (((m->mbconv & 4) && ((m->mbconv & 8) || b.mid * 9 * cin * 2 <= 90 * 1024)) ? 2 : 3);   // (im2col,) expand, project (one fused kernel), border rows
       } else {
         b.out_padded = false;
         if ((st = make_conv_layer(tm, p + ".conv_pw", p + ".bn1", b.mid, cin, 1, 0, 0, enc_pack, &b.conv)) != M2S_OK)

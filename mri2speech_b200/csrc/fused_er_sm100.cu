@@ -45,19 +45,27 @@ struct ErParams {
   uint32_t a_stage_bytes, b_stage_bytes, b_tap_bytes1, b_tap_bytes2, t_buf_bytes;
   int na, nb, tg1;
   int nbuf;                      // 1 or 2 buffers of acc1 / acc2 / T; lookahead = nbuf - 1
+  int resident;                  // all weights of the block are loaded into SMEM once (no weight ring)
+  uint32_t w1_bytes, w2_bytes;   // packed sizes of the two weight tensors
 };
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 
 constexpr uint32_t kTkbBytes = 128 * 128;   // one K block (64 channels) of the T tile: 128 rows x 128 bytes
 
-template <int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ ErParams prm) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t t_base = a_base + prm.na * prm.a_stage_bytes;
-  const uint32_t b_base = t_base + prm.nbuf * prm.t_buf_bytes;
-  const uint32_t bar_base = b_base + prm.nb * prm.b_stage_bytes;
+  const uint32_t b_base = t_base + prm.nbuf * prm.t_buf_bytes;   // weight ring, or the resident weights (w1 then w2)
+  const uint32_t bar_base = b_base + (prm.resident ? prm.w1_bytes + prm.w2_bytes : prm.nb * prm.b_stage_bytes);
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (kMaxStagesA + s); };
   auto b_full = [&](int s) { return bar_base + 8u * (2 * kMaxStagesA + s); };
@@ -70,6 +78,7 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   auto t_full = [&](int s) { return x_base + 8u * (8 + s); };
   auto t_empty = [&](int s) { return x_base + 8u * (10 + s); };
   const uint32_t tmem_slot = x_base + 8u * 12;
+  const uint32_t w_full = x_base + 8u * 13;
   const uint32_t bias1_smem = bar_base + 1024u;             // n1 floats (<= 256)
   const uint32_t stage_base = bar_base + 2048u;             // 16 epilogue warps x 2 KB transpose staging (+ staged bias2)
 
@@ -87,6 +96,7 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       mbar_init(acc2_full(s), 1); mbar_init(acc2_empty(s), kEpiWarps);
       mbar_init(t_full(s), kEpiWarps); mbar_init(t_empty(s), 1);
     }
+    mbar_init(w_full, 1);
     fence_barrier_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
   }
@@ -120,6 +130,16 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       __syncwarp();
       if (++sb == prm.nb) { sb = 0; pb ^= 1; }
     };
+    if (prm.resident) {   // the block's weights: once per CTA
+      if (elect_one()) {
+        mbar_expect_tx(w_full, prm.w1_bytes + prm.w2_bytes);
+        for (uint32_t off = 0; off < prm.w1_bytes; off += 16384u)
+          bulk_load(b_base + off, static_cast<const uint8_t*>(prm.w1) + off, min(16384u, prm.w1_bytes - off), w_full);
+        for (uint32_t off = 0; off < prm.w2_bytes; off += 16384u)
+          bulk_load(b_base + prm.w1_bytes + off, static_cast<const uint8_t*>(prm.w2) + off, min(16384u, prm.w2_bytes - off), w_full);
+      }
+      __syncwarp();
+    }
     for (int s = 0; s < my_tiles + la; ++s) {
       if (s < my_tiles) {
         const int tile = blockIdx.x + s * gridDim.x;
@@ -135,6 +155,7 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           }
           __syncwarp();
           if (++sa == prm.na) { sa = 0; pa ^= 1; }
+          if (prm.resident) continue;
           for (int nt = 0; nt < prm.n_tiles1; ++nt)
             for (int tap0 = 0; tap0 < prm.taps1; tap0 += prm.tg1) {
               const int cnt = min(prm.tg1, prm.taps1 - tap0);
@@ -144,7 +165,7 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             }
         }
       }
-      if (s >= la)
+      if (s >= la && !prm.resident)
         for (int cb = 0; cb < prm.cblocks2; ++cb)
           load_b(static_cast<const uint8_t*>(prm.w2) + static_cast<size_t>(cb) * prm.b_tap_bytes2, prm.b_tap_bytes2);
     }
@@ -153,6 +174,7 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
     const int ksteps_full1 = prm.row_bytes1 >> 5;
+    if (prm.resident) mbar_wait(w_full, 0);
     for (int s = 0; s < my_tiles + la; ++s) {
       if (s < my_tiles) {
         // ---- expand: 9 row-shifted taps over the x tile ----
@@ -164,6 +186,21 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           const int ksteps = rem >= prm.kblock1 ? ksteps_full1 : (rem + 15) >> 4;
           mbar_wait(a_full(sa), pa);
           const uint32_t a_tile = a_base + sa * prm.a_stage_bytes;
+          if (prm.resident) {
+            tc_fence_after();
+            if (elect_one()) {
+              for (int nt = 0; nt < prm.n_tiles1; ++nt)
+                for (int t = 0; t < prm.taps1; ++t) {
+                  const uint32_t wt = b_base + static_cast<uint32_t>((nt * prm.cblocks1 + cb) * prm.taps1 + t) * prm.b_tap_bytes1;
+                  const uint64_t db = prm.desc_hi1 | ((wt & 0x3FFFF) >> 4);
+                  const uint64_t da = prm.desc_hi1 | (((a_tile + prm.rel_shift1[t] * prm.row_bytes1) & 0x3FFFF) >> 4);
+                  mma_f16_k4(acc1_addr(buf) + nt * prm.n_tile1, da, db, prm.idesc1, (cb | t) ? 1u : 0u, ksteps);
+                }
+              tc_commit(a_empty(sa));
+              if (cb == prm.cblocks1 - 1) tc_commit(acc1_full(buf));
+            }
+            __syncwarp();
+          } else
           for (int nt = 0; nt < prm.n_tiles1; ++nt)
             for (int tap0 = 0; tap0 < prm.taps1; tap0 += prm.tg1) {
               const int cnt = min(prm.tg1, prm.taps1 - tap0);
@@ -194,6 +231,20 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         mbar_wait(t_full(buf), (i / nbuf) & 1);
         mbar_wait(acc2_empty(buf), ((i / nbuf) & 1) ^ 1);
         tc_fence_after();
+        if (prm.resident) {
+          if (elect_one()) {
+            for (int cb = 0; cb < prm.cblocks2; ++cb) {
+              const int rem = prm.n1 - cb * 64;
+              const int ksteps = rem >= 64 ? 4 : (rem + 15) >> 4;
+              const uint64_t db = prm.desc_hi2 | (((b_base + prm.w1_bytes + cb * prm.b_tap_bytes2) & 0x3FFFF) >> 4);
+              const uint64_t da = prm.desc_hi2 | (((t_base + buf * prm.t_buf_bytes + cb * kTkbBytes) & 0x3FFFF) >> 4);
+              mma_f16_k4(acc2_addr(buf), da, db, prm.idesc2, cb ? 1u : 0u, ksteps);
+            }
+            tc_commit(acc2_full(buf));
+            tc_commit(t_empty(buf));
+          }
+          __syncwarp();
+        } else
         for (int cb = 0; cb < prm.cblocks2; ++cb) {
           const int rem = prm.n1 - cb * 64;
           const int ksteps = rem >= 64 ? 4 : (rem + 15) >> 4;
@@ -267,16 +318,61 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         }
       }
       if (s >= la) {
-        // ---- epilogue 2: acc2 -> fused epilogue (bias, shortcut, border mask) -> global ----
+        // ---- epilogue 2: acc2 -> + bias (+ fp32 shortcut) -> image-border mask -> global, a row per thread ----
+        // Every warp takes 32 rows x n_tile2 / 4 columns.  The shortcut rows are requested BEFORE the wait for the project
+        // MMAs: with the engine's unit epilogue (8 of the 16 warps busy, loads issued after the accumulators arrive) this
+        // phase was a 3.5 k-cycle latency chain per tile and bounded the kernel (profiles/README.md round 2).
         const int i = s - la;
         const int tile = blockIdx.x + i * gridDim.x;
         const int b = tile / prm.tiles_per_batch;
-        const int q0 = (tile - b * prm.tiles_per_batch) * 128;
+        const int q = (tile - b * prm.tiles_per_batch) * 128 + quad * 32 + lane;
         const int buf = i % nbuf;
+        const Epilogue& e = p.epi;
+        const int cw = prm.n_tile2 >> 2;                 // 8 or 16 columns per warp
+        const int col0 = grp * cw;
+        const bool row_ok = q < p.l_out;
+        const size_t grow = static_cast<size_t>(b) * p.d_batch_rows + p.d_row_offset + q;
+        bool keep = row_ok;
+        if (e.mask_mode == M2S_MASK_PITCH) {
+          const int drow = q + p.d_row_offset;
+          const int mi = drow / e.pitch, mj = drow - mi * e.pitch;
+          keep = keep && mi >= e.i_lo && mi < e.i_hi && mj >= e.j_lo && mj < e.j_hi;
+        }
+        float4 rv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = col0 + 4 * j;
+          rv[j] = (4 * j < cw && row_ok && c < p.n && e.res)
+                      ? *reinterpret_cast<const float4*>(e.res + grow * e.res_ld + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         mbar_wait(acc2_full(buf), (i / nbuf) & 1);
         tc_fence_after();
-        const uint32_t tacc = acc2_addr(buf) + (static_cast<uint32_t>(quad * 32) << 16);
-        epilogue_tile<kEpi>(p, epw, tacc, b, q0, 0, 1, prm.n_tile2);
+        const uint32_t tacc = acc2_addr(buf) + (static_cast<uint32_t>(quad * 32) << 16) + col0;
+        uint32_t r[16];
+        if (cw == 16) tmem_ld16(tacc, r);
+        else tmem_ld8(tacc, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = col0 + 4 * j;
+          if (4 * j < cw && row_ok && c < p.n) {
+            float4 b4;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w)
+                         : "r"(bias_smem + 4u * c));
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (keep)
+              o = make_float4(__uint_as_float(r[4 * j]) + b4.x + rv[j].x, __uint_as_float(r[4 * j + 1]) + b4.y + rv[j].y,
+                              __uint_as_float(r[4 * j + 2]) + b4.z + rv[j].z, __uint_as_float(r[4 * j + 3]) + b4.w + rv[j].w);
+            if (p.d) *reinterpret_cast<float4*>(p.d + grow * p.d_ld + c) = o;
+            if (p.d16) {
+              uint2 h;
+              asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h.x) : "f"(o.y), "f"(o.x));
+              asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h.y) : "f"(o.w), "f"(o.z));
+              *reinterpret_cast<uint2*>(static_cast<__half*>(p.d16) + grow * p.d_ld + c) = h;
+            }
+          }
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc2_empty(buf));
@@ -310,12 +406,50 @@ EncodeTiledFn encode_fn_er() {
 
 }  // namespace
 
+namespace {
+int launch_er(const ErParams& prm_in, const ConvProblem& p1, const ConvProblem& p2, uint32_t smem_bytes, cudaStream_t stream) {
+  ErParams prm = prm_in;
+  EncodeTiledFn enc = encode_fn_er();
+  if (!enc) return fail(M2S_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // one CTA per SM (whole-TMEM allocation)
+
+  CUtensorMap tmap;
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(p1.c_in), static_cast<cuuint64_t>(p1.a_rows),
+                        static_cast<cuuint64_t>(p1.batch)};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(p1.a_ld) * 2ull,
+                           static_cast<cuuint64_t>(p1.a_batch_rows) * static_cast<cuuint64_t>(p1.a_ld) * 2ull};
+  if (p1.batch == 1) gstride[1] = gstride[0] * static_cast<cuuint64_t>(p1.a_rows > 0 ? p1.a_rows : 1);
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(prm.kblock1), static_cast<cuuint32_t>(prm.a_box_rows), 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<float*>(p1.a), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    prm.row_bytes1 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(M2S_ERR_CUDA, "fused EdgeResidual: x tensor map failed (%d)", static_cast<int>(cr));
+  static PerDeviceOnce attr_once;
+  M2S_TRY(attr_once.run([&]() -> int {
+    M2S_CUDA_OK(cudaFuncSetAttribute(fused_er_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    return M2S_OK;
+  }));
+  int grid = sm_count();
+  if (grid > prm.total_tiles) grid = prm.total_tiles;
+  M2S_TRY(profile_before(stream));
+  fused_er_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap, prm);
+  M2S_CUDA_OK(cudaGetLastError());
+  const double rows = static_cast<double>(p2.batch) * p2.l_out;
+  return profile_after(stream, 2.0 * rows * p1.n * (static_cast<double>(p1.c_in) * p1.taps + p2.n));
+}
+}  // namespace
+
 // p1: the expand conv as the engine would run it (a = x fp16, taps / shifts, bias = folded bn1, act = SiLU; its outputs are
 //     ignored: T stays on chip).  p2: the project conv's bias, epilogue and outputs (its `a` is ignored; c_in == p1.n).
 bool fused_er_supported(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& p2, const PackedWeights& w2) {
   if (!p1.a_half || !w1.half || w2.half != 1) return false;                      // T is written with 128-byte rows
   if (p1.epi.act != M2S_ACT_SILU || p2.taps != 1 || p2.shift[0] != 0 || p2.c_in != p1.n) return false;
-  if (p1.n > 256 || p1.n % 16 || w2.n_tiles != 1 || w2.n_tile > 64) return false;
+  if (p1.n > 256 || p1.n % 16 || w2.n_tiles != 1 || (w2.n_tile != 32 && w2.n_tile != 64)) return false;
+  if (p2.epi.act != M2S_ACT_NONE || p2.epi.accum || p2.epi.out_scale != 1.f || p2.epi.res_after_act ||
+      (p2.epi.res && p2.epi.res_inv_slope != 1.f) || p2.epi.mask_mode == M2S_MASK_LEN || p2.n % 4 || p2.d_ld % 4)
+    return false;
   if (p1.batch != p2.batch || p1.l_out != p2.l_out) return false;
   const int epi = choose_epilogue(p2.epi);
   if (epi < 0 || p2.epi.res_hi || p2.d16_lo) return false;
@@ -329,8 +463,6 @@ int fused_er(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& 
              cudaStream_t stream) {
   if (!fused_er_supported(p1, w1, p2, w2)) return fail(M2S_ERR_UNSUPPORTED, "block not supported by the fused EdgeResidual kernel");
   if (p2.batch <= 0 || p2.l_out <= 0) return M2S_OK;
-  EncodeTiledFn enc = encode_fn_er();
-  if (!enc) return fail(M2S_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   ErParams prm{};
   prm.p2 = p2;
   finalize_epilogue(&prm.p2.epi, static_cast<long long>(p2.l_out) + p2.d_row_offset);
@@ -367,9 +499,23 @@ int fused_er(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& 
   prm.b_tap_bytes2 = static_cast<uint32_t>(prm.n_tile2 * 128);
   if ((prm.b_tap_bytes1 & 1023u) || (prm.b_tap_bytes2 & 1023u))
     return fail(M2S_ERR_UNSUPPORTED, "fused EdgeResidual: weight blocks not 1 KB aligned (n_tile %d / %d)", prm.n_tile1, prm.n_tile2);
-  // SMEM plan: A stages, T buffers, weight stages (tap groups), epilogue staging
+  // SMEM plan: A stages, T buffers, weights (resident when the whole block's fit next to two T buffers, else a ring of
+  // tap groups re-streamed per tile), epilogue staging
   const uint32_t fixed = 2048u + kEpiSmemBytes + 1024u;
   const uint32_t budget = 225u * 1024u;
+  prm.w1_bytes = static_cast<uint32_t>(w1.n_tiles * w1.cblocks * p1.taps) * prm.b_tap_bytes1;
+  prm.w2_bytes = static_cast<uint32_t>(w2.cblocks) * prm.b_tap_bytes2;
+  if (fixed + 2 * prm.a_stage_bytes + prm.nbuf * prm.t_buf_bytes + prm.w1_bytes + prm.w2_bytes <= budget) {
+    prm.resident = 1;
+    uint32_t used = fixed + 2 * prm.a_stage_bytes + prm.nbuf * prm.t_buf_bytes + prm.w1_bytes + prm.w2_bytes;
+    int na_r = 2;
+    while (na_r < kMaxStagesA && used + prm.a_stage_bytes <= budget) { ++na_r; used += prm.a_stage_bytes; }
+    prm.na = na_r;
+    prm.nb = 0;
+    prm.tg1 = 1;
+    prm.b_stage_bytes = 0;
+    return launch_er(prm, p1, p2, used + 1024u, stream);
+  }
   int na = 2;
   uint32_t used = fixed + na * prm.a_stage_bytes + prm.nbuf * prm.t_buf_bytes;
   if (used + 2 * prm.b_tap_bytes1 > budget && prm.nbuf == 2) {
@@ -391,46 +537,15 @@ int fused_er(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& 
   while (nb < kMaxStagesB && used + prm.b_stage_bytes <= budget) { ++nb; used += prm.b_stage_bytes; }
   prm.na = na;
   prm.nb = nb;
-  uint32_t smem_bytes = used + 1024u;  // alignment slack
-  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // one CTA per SM (whole-TMEM allocation)
-
-  CUtensorMap tmap;
-  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(p1.c_in), static_cast<cuuint64_t>(p1.a_rows),
-                        static_cast<cuuint64_t>(p1.batch)};
-  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(p1.a_ld) * 2ull,
-                           static_cast<cuuint64_t>(p1.a_batch_rows) * static_cast<cuuint64_t>(p1.a_ld) * 2ull};
-  if (p1.batch == 1) gstride[1] = gstride[0] * static_cast<cuuint64_t>(p1.a_rows > 0 ? p1.a_rows : 1);
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(prm.kblock1), static_cast<cuuint32_t>(prm.a_box_rows), 1u};
-  cuuint32_t estr[3] = {1u, 1u, 1u};
-  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<float*>(p1.a), gdim, gstride, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    prm.row_bytes1 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (cr != CUDA_SUCCESS) return fail(M2S_ERR_CUDA, "fused EdgeResidual: x tensor map failed (%d)", static_cast<int>(cr));
-
-  using KernelFn = void (*)(const CUtensorMap, const ErParams);
-  // the project conv has no activation: bias, or bias + fp32 shortcut (other programs fall back to the two-launch path)
-  const int epi = choose_epilogue(p2.epi);
-  KernelFn k = epi == EPI_BIAS ? fused_er_kernel<EPI_BIAS> : epi == EPI_RES ? fused_er_kernel<EPI_RES> : nullptr;
-  if (!k) return fail(M2S_ERR_UNSUPPORTED, "fused EdgeResidual: epilogue program %d not instantiated", epi);
-  static PerDeviceOnce attr_once;
-  M2S_TRY(attr_once.run([&]() -> int {
-    M2S_CUDA_OK(cudaFuncSetAttribute(fused_er_kernel<EPI_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    M2S_CUDA_OK(cudaFuncSetAttribute(fused_er_kernel<EPI_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    return M2S_OK;
-  }));
-  int grid = sm_count();
-  if (grid > prm.total_tiles) grid = prm.total_tiles;
-  M2S_TRY(profile_before(stream));
-  k<<<grid, kThreads, smem_bytes, stream>>>(tmap, prm);
-  M2S_CUDA_OK(cudaGetLastError());
-  const double rows = static_cast<double>(p2.batch) * p2.l_out;
-  return profile_after(stream, 2.0 * rows * p1.n * (static_cast<double>(p1.c_in) * p1.taps + p2.n));
+  return launch_er(prm, p1, p2, used + 1024u, stream);
 }
 
-bool fused_er_epilogue_ok(const ConvProblem& p2) {
-  const int epi = choose_epilogue(p2.epi);
-  return epi == EPI_BIAS || epi == EPI_RES;
+// Do the block's weights stay in SMEM for the whole launch?  (Otherwise they are re-streamed for every 128-row tile:
+// 290 KB per tile at stage 2, which makes the fused kernel no faster than two launches -- profiles/README.md round 2.)
+bool fused_er_resident(const PackedWeights& w1, const PackedWeights& w2) {
+  const size_t w = static_cast<size_t>(w1.n_tiles) * w1.cblocks * w1.taps * w1.n_tile * w1.row_bytes +
+                   static_cast<size_t>(w2.cblocks) * w2.n_tile * 128;
+  return w <= 96 * 1024;
 }
 
 }  // namespace m2s

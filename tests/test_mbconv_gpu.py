@@ -43,7 +43,7 @@ def _frames(n, seed=0):
     return synth.synthetic_clip(seed, n).cuda()
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3, 4, 7])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 12, 7])
 @pytest.mark.parametrize("n", [5, 301])
 def test_fused_equals_unfused(mode, n):
     """5 frames: partial tiles (two 8x8 frames per tile, odd count); 301 frames: several tiles per CTA (ring phases wrap)."""
@@ -58,7 +58,9 @@ def test_fused_equals_unfused(mode, n):
     if mode == 3:
         assert l0 - l1 == 18 + 20                    # 18 stride-1 blocks lose the depthwise launch, all 20 the scale pass
     if mode == 4:
-        assert l0 - l1 == 4                          # the four stride-1 EdgeResidual blocks: expand + project in one launch
+        assert l0 - l1 == 2                          # stage 1's two stride-1 EdgeResidual blocks (weights resident in SMEM)
+    if mode == 12:
+        assert l0 - l1 == 4                          # ... and stage 2's (weights streamed per tile; slower, opt-in)
 
 
 def test_fused_default_is_on():
@@ -73,4 +75,4 @@ def test_fused_default_is_on():
         plain = m.launches_per_forward()
     finally:
         os.environ.pop("M2S_MBCONV", None)
-    assert plain - fused == 42
+    assert plain - fused == 40
