@@ -209,6 +209,183 @@ __global__ void __launch_bounds__(256) dwconv_tma_kernel(const __grid_constant__
   }
 }
 
+// ---- stride 2 (the first block of stages 3 and 5), fp16 activations -------------------------------------------------
+// TF "same" padding of a stride-2 3x3 conv on an even-sized input pads only the right / bottom edge: output (y, x) reads
+// input rows 2y .. 2y+2, columns 2x .. 2x+2.  One TMA box brings (2 R + 1) input rows x (W + 1) columns x a 64-channel
+// slab (column W / row H come from the tensor's zero border or from the TMA unit's out-of-bounds fill); two SMEM stages.
+// A WARP owns a 4 x 4 block of outputs and its 32 lanes own the slab's 32 channel pairs: an LDS.32 of the warp reads one
+// pixel's 128 bytes (one wavefront), the 9 tap weights of a lane's two channels live in registers, a pixel's 64 outputs
+// leave as one 128-byte line.  fp32 arithmetic, bias first, taps in (dy, dx) order (= dwconv_kernel<2, 1, __half>).
+struct DwS2Params {
+  int C, Ho, Wo;           // channels, output height / width
+  int n_frames, kf;        // frames, frames per load (small images)
+  int r_out;               // output rows per load
+  int n_sub;               // loads per (frame group, slab) item: Ho / r_out
+  int n_cslabs, n_items;
+  int ox, oy;              // input pixel (0, 0) inside the tensor map's (x, y) space
+  uint32_t stage_bytes;
+};
+
+__device__ __forceinline__ unsigned long long pk2f(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned long long ffma2u(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+// grid = persistent CTAs, block = 256 (8 warps = 8 blocks of 4 x 4 outputs per load)
+__global__ void __launch_bounds__(256) dwconv_s2_tma_kernel(const __grid_constant__ CUtensorMap tmap, __half* __restrict__ out,
+                                                            float* __restrict__ sums, const float* __restrict__ w /*[9][C]*/,
+                                                            const float* __restrict__ bias, const DwS2Params prm) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) unsigned long long bars[2];
+  __shared__ float2 red[8][32];
+  const uint32_t base = (smem_addr(smem) + 127u) & ~127u;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Wo = prm.Wo, Wi1 = 2 * prm.Wo + 1;                   // box width in pixels
+  const int rows_box = 2 * prm.r_out + 1;
+  const int hw = prm.Ho * Wo;
+  const uint32_t bar0 = smem_addr(&bars[0]);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+  }
+  __syncthreads();
+  // load l = (item, sub): item = (frame group, slab)
+  const int my_items = (prm.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int my_loads = my_items * prm.n_sub;
+  auto issue = [&](int l) {
+    const int item = blockIdx.x + (l / prm.n_sub) * gridDim.x, sub = l % prm.n_sub;
+    const int cs = item % prm.n_cslabs, fg = item / prm.n_cslabs;
+    const uint32_t bar = bar0 + 8u * (l & 1);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(prm.stage_bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(base + (l & 1) * prm.stage_bytes), "l"(&tmap), "r"(bar), "r"(cs * 64), "r"(prm.ox),
+        "r"(prm.oy + 2 * sub * prm.r_out), "r"(fg * prm.kf)
+        : "memory");
+  };
+  // this warp's 4 x 4 block inside a load: blocks are laid out (frame of the group, block row, block column)
+  const int bpr = Wo >> 2;                            // blocks per output row
+  const int bpf = (prm.r_out >> 2) * bpr;             // blocks per frame per load
+  const int bf = warp / bpf, bb = warp % bpf;
+  const int by = (bb / bpr) * 4, bx = (bb % bpr) * 4; // first output row (inside the load) / column of the block
+  const bool warp_on = bf < prm.kf;
+  uint32_t ph[2] = {0u, 0u};
+  if (tid == 0 && my_loads > 0) issue(0);
+  unsigned long long fsum = pk2f(0.f, 0.f);
+  unsigned long long wv[9], b2 = pk2f(0.f, 0.f);
+  int c = 0;
+  bool c_ok = false;
+  for (int l = 0; l < my_loads; ++l) {
+    if (tid == 0 && l + 1 < my_loads) issue(l + 1);   // the other stage was released by the barrier at the end of l - 1
+    const int item = blockIdx.x + (l / prm.n_sub) * gridDim.x, sub = l % prm.n_sub;
+    const int cs = item % prm.n_cslabs, f0 = (item / prm.n_cslabs) * prm.kf;
+    if (sub == 0) {
+      c = cs * 64 + 2 * lane;
+      c_ok = c < prm.C;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float2 v = make_float2(0.f, 0.f);
+        if (c_ok) v = __ldg(reinterpret_cast<const float2*>(w + static_cast<size_t>(t) * prm.C + c));
+        wv[t] = pk2f(v.x, v.y);
+      }
+      float2 v = make_float2(0.f, 0.f);
+      if (c_ok) v = __ldg(reinterpret_cast<const float2*>(bias + c));
+      b2 = pk2f(v.x, v.y);
+      fsum = pk2f(0.f, 0.f);
+    }
+    {
+      const uint32_t bar = bar0 + 8u * (l & 1);
+      uint32_t ok = 0;
+      while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(ph[l & 1])
+            : "memory");
+      }
+      ph[l & 1] ^= 1u;
+    }
+    if (warp_on) {
+      // window of the block: input rows 2 by .. 2 by + 8, columns 2 bx .. 2 bx + 8 of frame bf of the box
+      const uint32_t win = base + (l & 1) * prm.stage_bytes +
+                           ((bf * rows_box + 2 * by) * Wi1 + 2 * bx) * 128 + lane * 4;
+      unsigned long long res[4][4];
+#pragma unroll
+      for (int y = 0; y < 4; ++y)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) res[y][k] = b2;
+#pragma unroll
+      for (int r = 0; r < 9; ++r) {
+        unsigned long long a[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          uint32_t v;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(win + (r * Wi1 + j) * 128));
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
+          a[j] = pk2f(f.x, f.y);
+        }
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+          const int dy = r - 2 * y;
+          if (dy < 0 || dy > 2) continue;
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) res[y][k] = ffma2u(a[2 * k + dx], wv[dy * 3 + dx], res[y][k]);
+        }
+      }
+      const bool st_ok = c_ok && f0 + bf < prm.n_frames;
+      __half* op = out + (static_cast<size_t>(f0 + bf) * hw + (sub * prm.r_out + by) * Wo + bx) * prm.C + c;
+#pragma unroll
+      for (int y = 0; y < 4; ++y)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float lo, hi;
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(res[y][k]));
+          lo = fsilu2<__half>(lo);
+          hi = fsilu2<__half>(hi);
+          float slo, shi;
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(slo), "=f"(shi) : "l"(fsum));
+          fsum = pk2f(slo + lo, shi + hi);
+          if (st_ok) {
+            uint32_t h2;
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(hi), "f"(lo));
+            *reinterpret_cast<uint32_t*>(op + static_cast<size_t>(y * Wo + k) * prm.C) = h2;
+          }
+        }
+    }
+    if (sub == prm.n_sub - 1) {
+      // squeeze sums of the item: per frame of the group, over the warps that hold its blocks
+      float slo, shi;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(slo), "=f"(shi) : "l"(fsum));
+      red[warp][lane] = make_float2(slo, shi);
+      __syncthreads();
+      if (tid < 32 * prm.kf) {
+        const int fr = tid >> 5, ln = tid & 31;
+        float2 sacc = make_float2(0.f, 0.f);
+        for (int k = 0; k < bpf; ++k) {
+          const float2 v = red[fr * bpf + k][ln];
+          sacc.x += v.x; sacc.y += v.y;
+        }
+        const int cc = cs * 64 + 2 * ln;
+        if (cc < prm.C && f0 + fr < prm.n_frames)
+          *reinterpret_cast<float2*>(sums + static_cast<size_t>(f0 + fr) * prm.C + cc) = sacc;
+      }
+    }
+    __syncthreads();   // the stage may now be refilled (and `red` reused)
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -290,6 +467,57 @@ int dwconv_tma(const void* in, void* out, int half, float* sums, const float* w,
                   oy, ox, st);
   return launch(static_cast<const float*>(in), static_cast<float*>(out), sums, w, bias, n, C, H, W, pitch_in, rows_in, oy,
                 ox, st);
+}
+
+// stride 2, fp16: blocks of 4 x 4 outputs, 8 per load
+bool dwconv_s2_tma_supported(int C, int Hin, int Win) {
+  const int Ho = Hin / 2, Wo = Win / 2;
+  if (Hin != Win || C % 8 || Wo % 4) return false;
+  return Ho == 16 || Ho == 8;
+}
+
+int dwconv_s2_tma(const void* in, void* out, float* sums, const float* w, const float* bias, int n, int C, int Hin, int Win,
+                  int pitch_in, int rows_in, int oy, int ox, cudaStream_t st) {
+  if (!dwconv_s2_tma_supported(C, Hin, Win)) return fail(M2S_ERR_UNSUPPORTED, "stride-2 depthwise %dx%d not supported", Hin, Win);
+  EncodeTiledFn enc = encode_fn4();
+  if (!enc) return fail(M2S_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  DwS2Params prm{};
+  prm.C = C; prm.Ho = Hin / 2; prm.Wo = Win / 2; prm.n_frames = n; prm.ox = ox; prm.oy = oy;
+  // 8 blocks of 4 x 4 outputs per load: 16 x 16 outputs -> 8 rows of one frame; 8 x 8 outputs -> two whole frames
+  if (prm.Ho == 16) { prm.kf = 1; prm.r_out = 8; } else { prm.kf = 2; prm.r_out = 8; }
+  prm.n_sub = prm.Ho / prm.r_out;
+  prm.n_cslabs = (C + 63) / 64;
+  prm.n_items = prm.n_cslabs * ((n + prm.kf - 1) / prm.kf);
+  const int rows_box = 2 * prm.r_out + 1, cols_box = Win + 1;
+  prm.stage_bytes = static_cast<uint32_t>(prm.kf) * rows_box * cols_box * 128;
+  // The map covers the INTERIOR Hin x Win pixels only (base moved to pixel (oy, ox)): column Win and row Hin are then the
+  // TMA unit's out-of-bounds zero fill.  (The physical border of a zero-bordered input is NOT zero here: the expand
+  // GEMM ran over every row of the padded layout and left silu(bias) in it.)
+  const __half* base_in = static_cast<const __half*>(in) + (static_cast<size_t>(oy) * pitch_in + ox) * C;
+  prm.ox = 0; prm.oy = 0;
+  CUtensorMap tmap;
+  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(Win), static_cast<cuuint64_t>(Hin),
+                        static_cast<cuuint64_t>(n)};
+  cuuint64_t gstride[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(pitch_in) * C * 2,
+                           static_cast<cuuint64_t>(rows_in) * C * 2};
+  cuuint32_t box[4] = {64u, static_cast<cuuint32_t>(cols_box), static_cast<cuuint32_t>(rows_box), static_cast<cuuint32_t>(prm.kf)};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base_in), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(M2S_ERR_CUDA, "stride-2 depthwise tensor map failed (%d)", static_cast<int>(cr));
+  const size_t smem = 2 * static_cast<size_t>(prm.stage_bytes) + 256;
+  static PerDeviceOnce attr_once;
+  M2S_TRY(attr_once.run([&]() -> int {
+    M2S_CUDA_OK(cudaFuncSetAttribute(dwconv_s2_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    return M2S_OK;
+  }));
+  if (smem > 200 * 1024) return fail(M2S_ERR_UNSUPPORTED, "stride-2 depthwise: tile does not fit SMEM");
+  int grid = sm_count();
+  if (grid > prm.n_items) grid = prm.n_items;
+  dwconv_s2_tma_kernel<<<grid, 256, smem, st>>>(tmap, static_cast<__half*>(out), sums, w, bias, prm);
+  M2S_CUDA_OK(cudaGetLastError());
+  return M2S_OK;
 }
 
 }  // namespace m2s

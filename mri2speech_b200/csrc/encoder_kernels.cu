@@ -555,11 +555,18 @@ bool dwconv_tma_supported(int half, int C, int H, int W);
 int dwconv_tma(const void* in, void* out, int half, float* sums, const float* w, const float* bias, int n, int C, int H,
                int W, int pitch_in, int rows_in, int oy, int ox, cudaStream_t st);
 
+bool dwconv_s2_tma_supported(int C, int Hin, int Win);
+int dwconv_s2_tma(const void* in, void* out, float* sums, const float* w, const float* bias, int n, int C, int Hin, int Win,
+                  int pitch_in, int rows_in, int oy, int ox, cudaStream_t st);
+
 int enc_dwconv(const void* in, void* out, int half, float* sums, const float* w, const float* bias, int n, int C, int Hin,
                int Win, int pitch_in, int oy, int ox, int rows_in, int stride, cudaStream_t st) {
   static const bool use_tma = !(std::getenv("M2S_DWCONV_TMA") && std::atoi(std::getenv("M2S_DWCONV_TMA")) == 0);
   if (stride == 1 && use_tma && dwconv_tma_supported(half, C, Hin, Win))
     return dwconv_tma(in, out, half, sums, w, bias, n, C, Hin, Win, pitch_in, rows_in, oy, ox, st);
+  const char* s2 = std::getenv("M2S_DWCONV_S2_TMA");   // (read per call: the A/B switch of tests/test_mbconv_gpu.py)
+  if (stride == 2 && half && use_tma && !(s2 && std::atoi(s2) == 0) && dwconv_s2_tma_supported(C, Hin, Win))
+    return dwconv_s2_tma(in, out, sums, w, bias, n, C, Hin, Win, pitch_in, rows_in, oy, ox, st);
   if (half)
     return dwconv_launch(static_cast<const __half*>(in), static_cast<__half*>(out), sums, w, bias, n, C, Hin, Win,
                          pitch_in, oy, ox, rows_in, stride, st);

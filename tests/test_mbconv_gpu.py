@@ -76,3 +76,18 @@ def test_fused_default_is_on():
     finally:
         os.environ.pop("M2S_MBCONV", None)
     assert plain - fused == 40
+
+
+def test_stride2_depthwise_tma_equals_slab_kernel():
+    """dwconv_s2_tma_kernel (TMA tiles, channel-pair lanes) against dwconv_kernel<2>: same fp32 arithmetic in the same
+    order, so the two stride-2 blocks (stage 3 / stage 5, the second on an unpadded 16 x 16 input with an odd frame
+    count in its two-frame loads) must reproduce the features to fp32 summation-order noise."""
+    frames = _frames(7, seed=3)
+    os.environ["M2S_DWCONV_S2_TMA"] = "0"
+    try:
+        ref, _ = _encode(0, frames)
+    finally:
+        os.environ.pop("M2S_DWCONV_S2_TMA", None)
+    got, _ = _encode(0, frames)
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() <= 2e-4 * scale
