@@ -18,6 +18,11 @@ M2S_MAX_TAPS = 16
 M2S_MAX_UPS = 8
 M2S_MAX_RBK = 8
 PREC_TF32, PREC_FP32, PREC_FP16 = 0, 1, 2
+# The build the drop-in modules and CLIs run when no precision is given: fp16 operands (tcgen05 kind::f16; the same
+# 10-bit mantissa as tf32, fp32 accumulation and fp32 residual streams) -- what bench.py measures.  Parity evidence:
+# tests/test_scaled_init_gpu.py, tests/test_bench_paths_gpu.py.  M2S_PRECISION=tf32|fp32 selects the other builds.
+DEFAULT_PRECISION = os.environ.get("M2S_PRECISION", "fp16")
+
 PRECISIONS = {"tf32": PREC_TF32, "fp32": PREC_FP32, "fp16": PREC_FP16}
 ACT_NONE, ACT_LRELU, ACT_SILU = 0, 1, 2
 MASK_NONE, MASK_LEN, MASK_PITCH = 0, 1, 2

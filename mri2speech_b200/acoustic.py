@@ -153,7 +153,7 @@ class OTNLikeCNNBiLSTM(nn.Module):
 
     def __init__(self, n_mels: int = 64, cnn_pretrained: bool = False, rnn_hidden: int = 640, dropout: float = 0.5,
                  use_checkpoint: bool = False, ckpt_segments: int = 2, use_reentrant: bool = False,
-                 precision: str = "tf32"):
+                 precision: Optional[str] = None):
         super().__init__()
         if rnn_hidden != 640:
             # the persistent recurrence kernel (csrc/lstm_sm100.cu) partitions exactly 640 hidden units over its CTAs
@@ -168,7 +168,7 @@ class OTNLikeCNNBiLSTM(nn.Module):
         self.rnn = BiLSTMSumMerge(in_dim=self.cnn.out_channels, hidden_size=rnn_hidden, dropout=dropout)
         self.head = nn.Linear(rnn_hidden, n_mels)
         self.rnn_hidden = rnn_hidden
-        self.precision = precision
+        self.precision = precision or _lib.DEFAULT_PRECISION
         self._handle: Optional[int] = None
         self._handle_key = None
         self._workspace: Optional[torch.Tensor] = None
@@ -342,7 +342,7 @@ MRIAcousticModel = OTNLikeCNNBiLSTM
 
 def build_acoustic_model(n_mels: int = 64, cnn_pretrained: bool = False, rnn_hidden: int = 640,
                          dropout: float = 0.5, use_checkpoint: bool = False, ckpt_segments: int = 2,
-                         use_reentrant: bool = False, precision: str = "tf32") -> nn.Module:
+                         use_reentrant: bool = False, precision: Optional[str] = None) -> nn.Module:
     return OTNLikeCNNBiLSTM(n_mels=n_mels, cnn_pretrained=cnn_pretrained, rnn_hidden=rnn_hidden, dropout=dropout,
                             use_checkpoint=use_checkpoint, ckpt_segments=ckpt_segments,
                             use_reentrant=use_reentrant, precision=precision)

@@ -332,31 +332,29 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
       const int rows_in = static_cast<int>(padded_rows(hin, win));
       const int rows_out = static_cast<int>(padded_rows(hout, wout));
       const int lq = hout * (wout + 2);  // rows in the (W+2)-pitch output space
+      // expand: 9 row-shifted taps over the zero-bordered input (stride 1), or one tap over the im2col'd input (stride 2)
+      ConvProblem p1;
       if (b.stride == 2) {
         M2S_TRY(simt(0, [&] { return enc_im2col_s2(op(x), B.col, esz, n, hin, win, b.cin, st); }, 1));
-        ConvProblem p = gemm_problem(B.col, lq, lq, 9 * b.cin, n, lq, B.e, lq, b.mid, 0, b.conv);
-        set_operand_out(&p, B.e);
-        p.epi.act = M2S_ACT_SILU;
-        M2S_TRY(run_gemm(m, p, b.conv, st));
+        p1 = gemm_problem(B.col, lq, lq, 9 * b.cin, n, lq, B.e, lq, b.mid, 0, b.conv);
+      } else {
+        p1 = gemm_problem(op(x), rows_in, rows_in, b.cin, n, lq, B.e, lq, b.mid, 0, b.conv);
       }
+      set_operand_out(&p1, B.e);
+      p1.epi.act = M2S_ACT_SILU;
       ConvProblem p = gemm_problem(B.e, lq, lq, b.mid, n, lq, y.f32, rows_out, b.cout, wout + 3, b.pwl);
       set_block_out(&p);
       set_pitch_mask(&p, hout, wout);
       if (b.skip) { p.epi.res = x.f32; p.epi.res_ld = b.cin; }
       bool fused = false;
-      if (b.stride == 1) {
-        ConvProblem p1 = gemm_problem(op(x), rows_in, rows_in, b.cin, n, lq, B.e, lq, b.mid, 0, b.conv);
-        set_operand_out(&p1, B.e);
-        p1.epi.act = M2S_ACT_SILU;
-        if ((m->mbconv & 4) && fused_er_supported(p1, b.conv.w, p, b.pwl.w) &&
-            ((m->mbconv & 8) || fused_er_resident(b.conv.w, b.pwl.w))) {
-          // 3x3 expand -> SiLU -> 1x1 project in one kernel: the expanded tile stays in SMEM
-          profile_set_tag(PROF_ENC_GEMM);
-          M2S_TRY(fused_er(p1, b.conv.w, p, b.pwl.w, st));
-          fused = true;
-        } else {
-          M2S_TRY(run_gemm(m, p1, b.conv, st));
-        }
+      if ((m->mbconv & 4) && fused_er_supported(p1, b.conv.w, p, b.pwl.w) &&
+          ((m->mbconv & 8) || fused_er_resident(b.conv.w, b.pwl.w))) {
+        // expand -> SiLU -> 1x1 project in one kernel: the expanded tile stays in SMEM
+        profile_set_tag(PROF_ENC_GEMM);
+        M2S_TRY(fused_er(p1, b.conv.w, p, b.pwl.w, st));
+        fused = true;
+      } else {
+        M2S_TRY(run_gemm(m, p1, b.conv, st));
       }
       if (!fused) M2S_TRY(run_gemm(m, p, b.pwl, st));
       M2S_TRY(zero_border(rows_out, b.cout, wout + 3, hout * (wout + 2) + wout + 3));
@@ -545,7 +543,7 @@ extern "C" int m2s_acoustic_create(const m2s_acoustic_config* cfg, const m2s_ten
         m->e_floats = std::max(m->e_floats, lq * b.mid);
         if (b.stride == 2) m->col_floats = std::max(m->col_floats, lq * 9 * cin);
         m->x_floats = std::max(m->x_floats, padded_rows(ho, wo) * b.cout);
-        launches += b.stride == 2 ? 4 : (((m->mbconv & 4) && ((m->mbconv & 8) || b.mid * 9 * cin * 2 <= 90 * 1024)) ? 2 : 3);   // (im2col,) expand, project (one fused kernel), border rows
+        launches += (b.stride == 2 ? 4 : 3) - (((m->mbconv & 4) && ((m->mbconv & 8) || b.mid * 9 * cin * 2 <= 90 * 1024)) ? 1 : 0);   // (im2col,) expand, project (one fused kernel), border rows
       } else {
         b.out_padded = false;
         if ((st = make_conv_layer(tm, p + ".conv_pw", p + ".bn1", b.mid, cin, 1, 0, 0, enc_pack, &b.conv)) != M2S_OK)

@@ -80,7 +80,7 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   const uint32_t tmem_slot = x_base + 8u * 12;
   const uint32_t w_full = x_base + 8u * 13;
   const uint32_t bias1_smem = bar_base + 1024u;             // n1 floats (<= 256)
-  const uint32_t stage_base = bar_base + 2048u;             // 16 epilogue warps x 2 KB transpose staging (+ staged bias2)
+  const uint32_t bias2_smem = bar_base + 2048u;             // p2.n floats (<= 64)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -102,7 +102,9 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   }
   for (int i = threadIdx.x; i < 256; i += blockDim.x)
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias1_smem + 4u * i), "f"(i < prm.n1 ? __ldg(prm.bias1 + i) : 0.f) : "memory");
-  const uint32_t bias_smem = stage_bias(p, stage_base);
+  for (int i = threadIdx.x; i < 64; i += blockDim.x)
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias2_smem + 4u * i), "f"((i < p.n && p.epi.bias) ? __ldg(p.epi.bias + i) : 0.f) : "memory");
+  const uint32_t bias_smem = bias2_smem;
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
@@ -268,8 +270,7 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   } else {
     // ===================== epilogue warps =====================
     const int ew = warp - 2;
-    const EpiWarp epw = make_epi_warp(p.epi, stage_base, ew, warp, lane, 0, bias_smem);
-    const int quad = epw.quad, grp = epw.grp;
+    const int quad = warp & 3, grp = ew >> 2;   // TMEM lane quadrant / column group of this warp
     const int nchunks = (prm.n1 + kEpiUnitCols - 1) / kEpiUnitCols;
     for (int s = 0; s < my_tiles + la; ++s) {
       if (s < my_tiles) {
@@ -501,7 +502,7 @@ int fused_er(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& 
     return fail(M2S_ERR_UNSUPPORTED, "fused EdgeResidual: weight blocks not 1 KB aligned (n_tile %d / %d)", prm.n_tile1, prm.n_tile2);
   // SMEM plan: A stages, T buffers, weights (resident when the whole block's fit next to two T buffers, else a ring of
   // tap groups re-streamed per tile), epilogue staging
-  const uint32_t fixed = 2048u + kEpiSmemBytes + 1024u;
+  const uint32_t fixed = 2048u + 1024u + 1024u;   // barriers + bias1, bias2, alignment slack
   const uint32_t budget = 225u * 1024u;
   prm.w1_bytes = static_cast<uint32_t>(w1.n_tiles * w1.cblocks * p1.taps) * prm.b_tap_bytes1;
   prm.w2_bytes = static_cast<uint32_t>(w2.cblocks) * prm.b_tap_bytes2;

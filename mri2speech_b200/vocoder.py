@@ -91,7 +91,7 @@ class ResBlock2(nn.Module):
 
 
 class Generator(nn.Module):
-    def __init__(self, h, precision: str = "tf32"):
+    def __init__(self, h, precision: Optional[str] = None):
         super().__init__()
         self.h = h
         self.resblock_type = 1 if str(_cfg(h, "resblock")) == "1" else 2   # models.py:95
@@ -115,7 +115,7 @@ class Generator(nn.Module):
         self.conv_post = _wn(Conv1d(ch, 1, 7, 1, padding=0))
         self.ups.apply(init_weights)
         self.conv_post.apply(init_weights)
-        self.precision = precision
+        self.precision = precision or _lib.DEFAULT_PRECISION
         self._handle: Optional[int] = None
         self._handle_key = None
         self._workspace: Optional[torch.Tensor] = None
