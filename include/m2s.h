@@ -222,6 +222,13 @@ int m2s_acoustic_forward_u8(m2s_acoustic* m, const uint8_t* frames_dev, const fl
 int m2s_acoustic_forward_packed(m2s_acoustic* m, const void* frames_dev, int32_t frames_are_u8, const float* mask,
                                 int32_t batch, int32_t max_frames, const int32_t* lengths, const int32_t* lengths_host,
                                 float* mel_norm, void* workspace, size_t workspace_bytes, m2s_stream_t stream);
+/* Encoder only, ragged batch fed packed (as m2s_acoustic_forward_packed): feats (batch, max_frames, 208) float32, rows
+ * past lengths[b] zero.  With m2s_acoustic_rnn_head it splits the forward in two, so that a batch runner can encode
+ * micro-batch after micro-batch (bounded work buffers) and run the recurrence ONCE over many clips: the BiLSTM is a
+ * chain of dependent steps whose cost per step barely depends on how many utterances ride along. */
+int m2s_acoustic_encode_packed(m2s_acoustic* m, const void* frames_dev, int32_t frames_are_u8, const float* mask,
+                               int32_t batch, int32_t max_frames, const int32_t* lengths, const int32_t* lengths_host,
+                               float* feats, void* workspace, size_t workspace_bytes, m2s_stream_t stream);
 /* Encoder only: (n_frames, height, width) -> (n_frames, 208) features. */
 int m2s_acoustic_encode(m2s_acoustic* m, const float* frames_dev, int32_t n_frames, float* feats,
                         void* workspace, size_t workspace_bytes, m2s_stream_t stream);

@@ -76,7 +76,7 @@ EXPORTS = (
     "m2s_generator_forward_btc",
     "m2s_generator_launches",
     "m2s_acoustic_create", "m2s_acoustic_destroy", "m2s_acoustic_workspace_bytes", "m2s_acoustic_forward",
-    "m2s_acoustic_forward_u8", "m2s_acoustic_forward_packed", "m2s_acoustic_encode", "m2s_acoustic_rnn_head", "m2s_acoustic_launches", "m2s_mel_glue",
+    "m2s_acoustic_forward_u8", "m2s_acoustic_forward_packed", "m2s_acoustic_encode_packed", "m2s_acoustic_encode", "m2s_acoustic_rnn_head", "m2s_acoustic_launches", "m2s_mel_glue",
 )
 
 
@@ -138,6 +138,9 @@ def _bind_acoustic(L) -> None:
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.m2s_acoustic_forward_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.m2s_acoustic_encode_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.m2s_acoustic_encode_packed.restype = C.c_int
     L.m2s_acoustic_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t,
                                       C.c_void_p]
     L.m2s_acoustic_rnn_head.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,

@@ -305,6 +305,37 @@ class OTNLikeCNNBiLSTM(nn.Module):
                 _lib.current_stream()))
         return out
 
+    def encode_packed(self, frames: torch.Tensor, lengths: torch.Tensor, max_frames: int, out: torch.Tensor,
+                      mask: Optional[torch.Tensor] = None, lengths_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Encoder half of ``forward_packed``: packed frames (sum(lengths), H, W) -> ``out`` (B, max_frames, 208) float32
+        cuda, contiguous (rows past lengths[b] zero).  ``rnn_head`` is the other half: a batch runner encodes micro-batch
+        after micro-batch into slices of one feature tensor and runs the recurrence once over all of its clips."""
+        _lib.require_device(frames)
+        raw = frames.dtype == torch.uint8
+        if mask is not None and not raw:
+            raise ValueError("mask applies to raw uint8 frames (it is applied before normalisation)")
+        frames = frames.contiguous() if raw else frames.contiguous().float()
+        lens_host = lengths.detach().to("cpu", torch.int32).contiguous()
+        B = int(lens_host.numel())
+        total, H, W = frames.shape
+        if int(lens_host.sum()) != total:
+            raise ValueError(f"sum(lengths)={int(lens_host.sum())} != packed frames {total}")
+        if tuple(out.shape) != (B, int(max_frames), self.cnn.out_channels) or not out.is_contiguous() or \
+                out.dtype != torch.float32 or out.device != frames.device:
+            raise ValueError(f"out must be a contiguous float32 ({B}, {max_frames}, {self.cnn.out_channels}) tensor on {frames.device}")
+        with torch.cuda.device(frames.device):
+            self._prepare(frames, B, int(max_frames), (H, W))
+            lens_dev = lengths_dev if lengths_dev is not None else lens_host.to(frames.device, non_blocking=True)
+            if mask is not None:
+                if tuple(mask.shape) != (H, W):
+                    raise ValueError(f"Mask shape {tuple(mask.shape)} != frame shape {(H, W)}")
+                mask = mask.to(frames.device, torch.float32).contiguous()
+            _lib.check(_lib.lib().m2s_acoustic_encode_packed(
+                self._handle, frames.data_ptr(), int(raw), _lib.ptr(mask), B, int(max_frames), lens_dev.data_ptr(),
+                lens_host.data_ptr(), out.data_ptr(), self._workspace.data_ptr(), self._workspace.numel(),
+                _lib.current_stream()))
+        return out
+
     def encode_frames(self, frames: torch.Tensor) -> torch.Tensor:
         """(N,H,W) float32 cuda -> (N,208): the time-distributed CNN of _cnn_time_distributed."""
         _lib.require_device(frames)

@@ -733,6 +733,31 @@ int acoustic_forward_impl(m2s_acoustic* m, const void* frames_dev, bool u8, bool
 }
 }  // namespace
 
+extern "C" int m2s_acoustic_encode_packed(m2s_acoustic* m, const void* frames_dev, int32_t frames_are_u8, const float* mask,
+                                          int32_t batch, int32_t max_frames, const int32_t* lengths,
+                                          const int32_t* lengths_host, float* feats, void* workspace,
+                                          size_t workspace_bytes, m2s_stream_t stream) {
+  if (!m || !frames_dev || !feats || !lengths || !lengths_host) return fail(M2S_ERR_BAD_ARG, "null argument");
+  if (mask && !frames_are_u8) return fail(M2S_ERR_BAD_ARG, "the articulator mask applies to raw uint8 frames");
+  if (batch <= 0 || max_frames <= 0) return M2S_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  WsPtrs w;
+  M2S_TRY(carve(m, batch, max_frames, workspace, workspace_bytes, &w));
+  long long valid = 0;
+  for (int b = 0; b < batch; ++b) {
+    if (lengths_host[b] < 0 || lengths_host[b] > max_frames)
+      return fail(M2S_ERR_BAD_ARG, "lengths[%d]=%d out of range", b, lengths_host[b]);
+    valid += lengths_host[b];
+  }
+  M2S_CUDA_OK(cudaMemsetAsync(feats, 0, static_cast<size_t>(batch) * max_frames * kFeat * sizeof(float), st));
+  if (valid == 0) return M2S_OK;
+  profile_set_tag(PROF_ENC_SIMT);
+  M2S_TRY(profile_before(st));
+  M2S_TRY(enc_build_fmap(lengths, batch, max_frames, w.fmap, st));
+  M2S_TRY(profile_after(st, 0.0));
+  return encode_all(m, frames_dev, frames_are_u8 != 0, mask, nullptr, w.fmap, static_cast<int>(valid), feats, w.enc, st);
+}
+
 extern "C" int m2s_acoustic_forward(m2s_acoustic* m, const float* frames_dev, int32_t batch, int32_t frames,
                                     const int32_t* lengths, const int32_t* lengths_host, float* mel_norm,
                                     void* workspace, size_t workspace_bytes, m2s_stream_t stream) {

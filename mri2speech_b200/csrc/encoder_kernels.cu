@@ -31,6 +31,20 @@ __device__ __forceinline__ float silu_t(float v) {
   return fmaf(h, t, h);
 }
 __device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); }
+// packed fp32 pairs (Blackwell FFMA2: two IEEE fp32 FMAs per issued instruction)
+__device__ __forceinline__ unsigned long long pack2f(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2f(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2f(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 
 // 4 consecutive channels <-> float4
 __device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -203,6 +217,40 @@ __global__ void __launch_bounds__(256) stem_rows_kernel(const void* __restrict__
 #pragma unroll
   for (int c = 0; c < 8; ++c) br[c] = sw[288 + cg + c];
   const int per_row = Wo * 4;
+  if (sizeof(T) == 2) {
+    // fp16 build: the same fp32 FMAs, issued two channels at a time (FFMA2 / FMUL2: the loop is bound by the FMA pipe)
+    unsigned long long wp[9][4], bp[4];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) wp[t][c] = pack2f(wr[t][2 * c], wr[t][2 * c + 1]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) bp[c] = pack2f(br[2 * c], br[2 * c + 1]);
+    for (int k = tid; k < R * per_row; k += 256) {
+      const int r = k / per_row, x = (k - r * per_row) >> 2;
+      unsigned long long v[4] = {bp[0], bp[1], bp[2], bp[3]};
+      const float* px0 = srow + (2 * r) * Wp + 2 * x;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float px = px0[dy * Wp + dx];
+          const unsigned long long pp = pack2f(px, px);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) v[c] = fma2f(pp, wp[dy * 3 + dx][c], v[c]);
+        }
+      float o[8];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        unpack2f(v[c], o[2 * c], o[2 * c + 1]);
+        o[2 * c] = silu_t<T>(o[2 * c]);
+        o[2 * c + 1] = silu_t<T>(o[2 * c + 1]);
+      }
+      T* op = obase + (static_cast<size_t>(y0 + r + 1) * pitch + x + 1) * 32 + cg;
+      store4(op, make_float4(o[0], o[1], o[2], o[3]));
+      store4(op + 4, make_float4(o[4], o[5], o[6], o[7]));
+    }
+  } else {
   for (int k = tid; k < R * per_row; k += 256) {
     const int r = k / per_row, x = (k - r * per_row) >> 2;
     float v[8];
@@ -222,6 +270,7 @@ __global__ void __launch_bounds__(256) stem_rows_kernel(const void* __restrict__
     T* o = obase + (static_cast<size_t>(y0 + r + 1) * pitch + x + 1) * 32 + cg;
     store4(o, make_float4(v[0], v[1], v[2], v[3]));
     store4(o + 4, make_float4(v[4], v[5], v[6], v[7]));
+  }
   }
   // the zero border: columns 0 and Wo + 1 of these rows, plus padded row 0 / Ho + 1 from the first / last block
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -39,6 +39,19 @@ struct LstmParams {
 };
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2_pk(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 
 __global__ void __launch_bounds__(kThreads, 1) lstm_recurrence_kernel(LstmParams prm) {
   __shared__ float4 sh_h[kChunk][kHidden / 4];
@@ -64,6 +77,9 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_recurrence_kernel(LstmParams
       w[i * 4 + 0] = v.x; w[i * 4 + 1] = v.y; w[i * 4 + 2] = v.z; w[i * 4 + 3] = v.w;
     }
   }
+  unsigned long long w2[kWPerThread / 2];   // the same weights as (k, k + 1) pairs
+#pragma unroll
+  for (int i = 0; i < kWPerThread / 2; ++i) w2[i] = pack2(w[2 * i], w[2 * i + 1]);
   for (int i = tid; i < prm.batch * kUnits; i += kThreads) sh_c[i] = 0.f;
   __syncthreads();
 
@@ -111,17 +127,21 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_recurrence_kernel(LstmParams
         const int t = dir == 0 ? s : len - 1 - s;
         float gin = 0.f;
         if (ks == 0) gin = __ldg(prm.gin + (static_cast<size_t>(b) * prm.frames + t) * G + dir * 4 * kHidden + grow);
-        float acc0 = 0.f, acc1 = 0.f;
+        // packed fp32 FMAs (FFMA2: two IEEE FMAs per issued instruction -- the step is bound by the FMA pipe's issue
+        // rate once more than a few utterances ride along); four independent pair accumulators
+        unsigned long long a0 = 0ull, a1 = 0ull, a2 = 0ull, a3 = 0ull;
 #pragma unroll
         for (int i = 0; i < kWPerThread / 4; i += 2) {
           const float4 h0 = sh_h[bb][i * kKSplit + ks];
           const float4 h1 = sh_h[bb][(i + 1) * kKSplit + ks];
-          acc0 = fmaf(w[i * 4 + 0], h0.x, acc0); acc0 = fmaf(w[i * 4 + 1], h0.y, acc0);
-          acc0 = fmaf(w[i * 4 + 2], h0.z, acc0); acc0 = fmaf(w[i * 4 + 3], h0.w, acc0);
-          acc1 = fmaf(w[i * 4 + 4], h1.x, acc1); acc1 = fmaf(w[i * 4 + 5], h1.y, acc1);
-          acc1 = fmaf(w[i * 4 + 6], h1.z, acc1); acc1 = fmaf(w[i * 4 + 7], h1.w, acc1);
+          a0 = ffma2_pk(w2[i * 2 + 0], pack2(h0.x, h0.y), a0);
+          a1 = ffma2_pk(w2[i * 2 + 1], pack2(h0.z, h0.w), a1);
+          a2 = ffma2_pk(w2[i * 2 + 2], pack2(h1.x, h1.y), a2);
+          a3 = ffma2_pk(w2[i * 2 + 3], pack2(h1.z, h1.w), a3);
         }
-        float acc = acc0 + acc1;
+        float s0, s1, s2, s3, s4, s5, s6, s7;
+        unpack2(a0, s0, s1); unpack2(a1, s2, s3); unpack2(a2, s4, s5); unpack2(a3, s6, s7);
+        float acc = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
