@@ -17,6 +17,7 @@
 // 32 or 56 channels: 64-byte SWIZZLE_64B rows or one 128-byte block; T always 128-byte rows), conv2 has one tap (no halo,
 // no recompute), shifts of conv1 are the non-negative dy * pitch + dx of the zero-bordered image.
 #include "engine_device.cuh"
+#include <cstdlib>
 #include <mutex>
 
 namespace m2s {
@@ -47,7 +48,11 @@ struct ErParams {
   int nbuf;                      // 1 or 2 buffers of acc1 / acc2 / T; lookahead = nbuf - 1
   int resident;                  // all weights of the block are loaded into SMEM once (no weight ring)
   uint32_t w1_bytes, w2_bytes;   // packed sizes of the two weight tensors
+  int tma_epi;                   // epilogue 2 through SMEM tiles: shortcut rows by TMA load, outputs by TMA store (C_out = 32)
 };
+
+constexpr uint32_t kRsBytes = 128 * 128;   // fp32 tile of 128 rows x 32 channels (shortcut in, fp32 output out -- in place)
+constexpr uint32_t kH16Bytes = 128 * 64;   // fp16 output tile
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -56,16 +61,30 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[16]) {
                : "memory");
 }
 
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_er(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 constexpr uint32_t kTkbBytes = 128 * 128;   // one K block (64 channels) of the T tile: 128 rows x 128 bytes
 
 __global__ void __launch_bounds__(kThreads, 1)
-fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ ErParams prm) {
+fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tm_r,
+                const __grid_constant__ CUtensorMap tm_d32, const __grid_constant__ CUtensorMap tm_d16,
+                const __grid_constant__ ErParams prm) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t t_base = a_base + prm.na * prm.a_stage_bytes;
   const uint32_t b_base = t_base + prm.nbuf * prm.t_buf_bytes;   // weight ring, or the resident weights (w1 then w2)
-  const uint32_t bar_base = b_base + (prm.resident ? prm.w1_bytes + prm.w2_bytes : prm.nb * prm.b_stage_bytes);
+  const uint32_t rs_base = b_base + (prm.resident ? prm.w1_bytes + prm.w2_bytes : prm.nb * prm.b_stage_bytes);
+  const uint32_t h16_base = rs_base + 2 * kRsBytes;     // (both only when prm.tma_epi)
+  const uint32_t bar_base = rs_base + (prm.tma_epi ? 2 * kRsBytes + kH16Bytes : 0u);
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (kMaxStagesA + s); };
   auto b_full = [&](int s) { return bar_base + 8u * (2 * kMaxStagesA + s); };
@@ -79,6 +98,8 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   auto t_empty = [&](int s) { return x_base + 8u * (10 + s); };
   const uint32_t tmem_slot = x_base + 8u * 12;
   const uint32_t w_full = x_base + 8u * 13;
+  auto r_full = [&](int s) { return x_base + 8u * (14 + s); };
+  auto r_empty = [&](int s) { return x_base + 8u * (16 + s); };
   const uint32_t bias1_smem = bar_base + 1024u;             // n1 floats (<= 256)
   const uint32_t bias2_smem = bar_base + 2048u;             // p2.n floats (<= 64)
 
@@ -97,6 +118,7 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       mbar_init(t_full(s), kEpiWarps); mbar_init(t_empty(s), 1);
     }
     mbar_init(w_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(r_full(s), 1); mbar_init(r_empty(s), 4); }
     fence_barrier_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
   }
@@ -165,6 +187,15 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
                          static_cast<size_t>((nt * prm.cblocks1 + cb) * prm.taps1 + tap0) * prm.b_tap_bytes1,
                      cnt * prm.b_tap_bytes1);
             }
+        }
+        // the tile's shortcut rows, consumed by epilogue 2 (the buffer is released at the end of epilogue 2 of tile s-2)
+        if (prm.tma_epi && p.epi.res) {
+          mbar_wait(r_empty(s & 1), ((s >> 1) & 1) ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(r_full(s & 1), kRsBytes);
+            tma_load_3d(rs_base + (s & 1) * kRsBytes, &tm_r, r_full(s & 1), 0, q0, b);
+          }
+          __syncwarp();
         }
       }
       if (s >= la && !prm.resident)
@@ -329,6 +360,73 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const int q = (tile - b * prm.tiles_per_batch) * 128 + quad * 32 + lane;
         const int buf = i % nbuf;
         const Epilogue& e = p.epi;
+        if (prm.tma_epi) {
+          // ---- C_out = 32: whole 128-byte rows through SMEM tiles.  The shortcut tile arrived by TMA (requested with the x
+          // tile), every thread updates its row's 32 bytes in place (fp32) and writes the fp16 copy, and ONE thread per
+          // TMEM lane quadrant hands 32 rows x 128 / 64 bytes to the TMA unit.  (A row per thread straight to global
+          // memory touches 32 different lines per warp instruction: the LSU, not the MMAs, bounded the kernel.) ----
+          const bool issuer = grp == 0 && lane == 0;
+          const int rbuf = i & 1;
+          named_bar_er(1 + quad, 128);   // (the issuer comes here after its stores of tile i-1 have read their SMEM tiles)
+          if (e.res) mbar_wait(r_full(rbuf), (i >> 1) & 1);
+          mbar_wait(acc2_full(buf), (i / nbuf) & 1);
+          tc_fence_after();
+          uint32_t r[16];
+          tmem_ld8(acc2_addr(buf) + (static_cast<uint32_t>(quad * 32) << 16) + grp * 8, r);
+          const int row = quad * 32 + lane;
+          bool keep = q < p.l_out;
+          if (e.mask_mode == M2S_MASK_PITCH) {
+            const int drow = q + p.d_row_offset;
+            const int mi = drow / e.pitch, mj = drow - mi * e.pitch;
+            keep = keep && mi >= e.i_lo && mi < e.i_hi && mj >= e.j_lo && mj < e.j_hi;
+          }
+          const uint32_t a32 = rs_base + rbuf * kRsBytes + row * 128;
+          float4 rv[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+          if (e.res) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(rv[m].x), "=f"(rv[m].y), "=f"(rv[m].z), "=f"(rv[m].w)
+                           : "r"(a32 + (((2 * grp + m) ^ (row & 7)) << 4)));
+          }
+          tmem_ld_wait();
+          uint32_t hp[4];
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            float4 b4;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w)
+                         : "r"(bias_smem + 4u * (grp * 8 + 4 * m)));
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (keep)
+              o = make_float4(__uint_as_float(r[4 * m]) + b4.x + rv[m].x, __uint_as_float(r[4 * m + 1]) + b4.y + rv[m].y,
+                              __uint_as_float(r[4 * m + 2]) + b4.z + rv[m].z, __uint_as_float(r[4 * m + 3]) + b4.w + rv[m].w);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a32 + (((2 * grp + m) ^ (row & 7)) << 4)),
+                         "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
+                         : "memory");
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hp[2 * m]) : "f"(o.y), "f"(o.x));
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hp[2 * m + 1]) : "f"(o.w), "f"(o.z));
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h16_base + row * 64 + ((grp ^ ((row >> 1) & 3)) << 4)),
+                       "r"(hp[0]), "r"(hp[1]), "r"(hp[2]), "r"(hp[3])
+                       : "memory");
+          fence_proxy_async();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc2_empty(buf));
+          named_bar_er(1 + quad, 128);
+          if (issuer) {
+            const int q0 = (tile - b * prm.tiles_per_batch) * 128 + quad * 32;
+            if (p.d) tma_store_3d(&tm_d32, rs_base + rbuf * kRsBytes + quad * 4096, 0, q0, b);
+            if (p.d16) tma_store_3d(&tm_d16, h16_base + quad * 2048, 0, q0, b);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // wait until the TMA unit has read the tiles (a few hundred cycles; the other warps move on): the fp16 tile is
+            // single-buffered, and the shortcut buffer can be refilled a whole tile period before it is needed again
+            tma_store_wait_read();
+            if (e.res) mbar_arrive(r_empty(rbuf));
+          }
+          continue;
+        }
         const int cw = prm.n_tile2 >> 2;                 // 8 or 16 columns per warp
         const int col0 = grp * cw;
         const bool row_ok = q < p.l_out;
@@ -379,6 +477,7 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         if (lane == 0) mbar_arrive(acc2_empty(buf));
       }
     }
+    if (prm.tma_epi && grp == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -427,6 +526,30 @@ int launch_er(const ErParams& prm_in, const ConvProblem& p1, const ConvProblem& 
                     prm.row_bytes1 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(M2S_ERR_CUDA, "fused EdgeResidual: x tensor map failed (%d)", static_cast<int>(cr));
+  // epilogue-2 tiles (tma_epi): shortcut / fp32 output / fp16 output as (32 channels, l_out rows, batch) tensors whose row 0
+  // is output row q = 0 of a frame (base moved by d_row_offset rows); rows >= l_out are clipped / zero-filled by the TMA unit
+  CUtensorMap tm_r = tmap, tm_d32 = tmap, tm_d16 = tmap;
+  if (prm.tma_epi) {
+    auto map3 = [&](CUtensorMap* tm, const void* base, int esize, long long batch_rows, int ld, int box_rows,
+                    CUtensorMapSwizzle sw, const char* what) -> int {
+      cuuint64_t gd[3] = {32ull, static_cast<cuuint64_t>(p2.l_out), static_cast<cuuint64_t>(p2.batch)};
+      cuuint64_t gs[2] = {static_cast<cuuint64_t>(ld) * esize, static_cast<cuuint64_t>(batch_rows) * ld * esize};
+      if (p2.batch == 1) gs[1] = gs[0] * static_cast<cuuint64_t>(p2.l_out);
+      cuuint32_t bx[3] = {32u, static_cast<cuuint32_t>(box_rows), 1u};
+      cuuint32_t es[3] = {1u, 1u, 1u};
+      CUresult r = enc(tm, esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                       const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(M2S_ERR_CUDA, "fused EdgeResidual: %s tensor map failed (%d)", what, static_cast<int>(r));
+      return M2S_OK;
+    };
+    const size_t off = static_cast<size_t>(p2.d_row_offset);
+    if (p2.epi.res)
+      M2S_TRY(map3(&tm_r, p2.epi.res + off * p2.epi.res_ld, 4, p2.d_batch_rows, p2.epi.res_ld, 128, CU_TENSOR_MAP_SWIZZLE_128B, "shortcut"));
+    if (p2.d) M2S_TRY(map3(&tm_d32, p2.d + off * p2.d_ld, 4, p2.d_batch_rows, p2.d_ld, 32, CU_TENSOR_MAP_SWIZZLE_128B, "fp32 output"));
+    if (p2.d16)
+      M2S_TRY(map3(&tm_d16, static_cast<const __half*>(p2.d16) + off * p2.d_ld, 2, p2.d_batch_rows, p2.d_ld, 32, CU_TENSOR_MAP_SWIZZLE_64B, "fp16 output"));
+  }
   static PerDeviceOnce attr_once;
   M2S_TRY(attr_once.run([&]() -> int {
     M2S_CUDA_OK(cudaFuncSetAttribute(fused_er_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -435,7 +558,7 @@ int launch_er(const ErParams& prm_in, const ConvProblem& p1, const ConvProblem& 
   int grid = sm_count();
   if (grid > prm.total_tiles) grid = prm.total_tiles;
   M2S_TRY(profile_before(stream));
-  fused_er_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap, prm);
+  fused_er_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap, tm_r, tm_d32, tm_d16, prm);
   M2S_CUDA_OK(cudaGetLastError());
   const double rows = static_cast<double>(p2.batch) * p2.l_out;
   return profile_after(stream, 2.0 * rows * p1.n * (static_cast<double>(p1.c_in) * p1.taps + p2.n));
@@ -509,6 +632,12 @@ int fused_er(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& 
   if (fixed + 2 * prm.a_stage_bytes + prm.nbuf * prm.t_buf_bytes + prm.w1_bytes + prm.w2_bytes <= budget) {
     prm.resident = 1;
     uint32_t used = fixed + 2 * prm.a_stage_bytes + prm.nbuf * prm.t_buf_bytes + prm.w1_bytes + prm.w2_bytes;
+    static const bool tma_epi_on = !(std::getenv("M2S_ER_TMA_EPI") && std::atoi(std::getenv("M2S_ER_TMA_EPI")) == 0);
+    if (tma_epi_on && p2.n == 32 && prm.n_tile2 == 32 && p2.d_ld == 32 && (!p2.epi.res || p2.epi.res_ld == 32) &&
+        used + 2 * kRsBytes + kH16Bytes <= budget) {
+      prm.tma_epi = 1;
+      used += 2 * kRsBytes + kH16Bytes;
+    }
     int na_r = 2;
     while (na_r < kMaxStagesA && used + prm.a_stage_bytes <= budget) { ++na_r; used += prm.a_stage_bytes; }
     prm.na = na_r;
