@@ -328,7 +328,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "e2e", "sharded", "vocoder"])
     ap.add_argument("--precision", default=os.environ.get("M2S_BENCH_PRECISION", DEFAULT_PRECISION), choices=["tf32", "fp16"])
-    ap.add_argument("--max-batch-frames", type=int, default=int(os.environ.get("M2S_BENCH_MBF", "4096")))
+    ap.add_argument("--max-batch-frames", type=int, default=int(os.environ.get("M2S_BENCH_MBF", "8192")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (other build, vocoder-only)")
     args = ap.parse_args()
