@@ -189,8 +189,8 @@ struct m2s_acoustic {
   // inside the project GEMM (csrc/mbconv_sm100.cu); bit2 = EdgeResidual 3x3 expand + 1x1 project in one kernel
   // (csrc/fused_er_sm100.cu).  M2S_MBCONV=0 keeps the unfused launches (the A/B reference of tests/).
   int mbconv = 7;
-  int chunk = 1024;  // frames per encoder pass (M2S_ENCODER_CHUNK): 1024 frames = ~7 GB of work buffers; measured
-                     // 26.4 / 22.2 / 20.6 / 19.7 us per frame at 128 / 256 / 512 / 1024 (fp16 build)
+  int chunk = 2048;  // frames per encoder pass (M2S_ENCODER_CHUNK): 2048 frames = ~14 GB of work buffers.  Measured with the
+                     // round-2 kernels: 14.1 / 12.6 / 12.1 / 12.2 us per frame at 512 / 1024 / 2048 / 4096 (fp16 build)
   // per-frame buffer sizes (floats)
   size_t x_floats = 0, e_floats = 0, e2_floats = 0, col_floats = 0;
   int max_mid = 0;

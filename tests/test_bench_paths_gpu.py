@@ -2,7 +2,7 @@
 
 The small-clip tests elsewhere encode <= 9 frames: the engine then picks msub <= 2 tiles, the encoder's chunk loop
 runs once and a ragged batch's frame map never spans a chunk.  Here:
-  * >= 1100 frames through the encoder with M2S_ENCODER_CHUNK in {64, default 1024}: the 512 / 1024-row tiles, the
+  * >= 1100 frames through the encoder with M2S_ENCODER_CHUNK in {64, 1024, default 2048}: the 512 / 1024-row tiles, the
     CTA-pair dispatch and multi-chunk passes, 32 sampled frames against the CPU oracle;
   * a ragged batch whose compact frame list spans a chunk boundary, every valid frame against the oracle;
   * BASELINE.json configs[0]: one 150-frame clip end to end (run_mri_video_inference's chain) against the oracle at
@@ -43,7 +43,7 @@ def _restore_chunk_env():
 
 
 @pytest.mark.parametrize("precision,rel_tol", [("tf32", 5e-3), ("fp16", 5e-3)])
-@pytest.mark.parametrize("chunk", [64, None])
+@pytest.mark.parametrize("chunk", [64, 1024, None])
 def test_encoder_1100_frames_sampled_vs_oracle(precision, rel_tol, chunk):
     from mri2speech_b200 import synth
     from oracle.acoustic import encoder_forward
@@ -55,11 +55,11 @@ def test_encoder_1100_frames_sampled_vs_oracle(precision, rel_tol, chunk):
     assert got.shape == (n, 208) and torch.isfinite(got).all()
     pick = torch.randperm(n, generator=torch.Generator().manual_seed(6))[:32].sort().values
     pick[0], pick[-1] = 0, n - 1                                 # first / last frame, a chunk's first / last rows
-    pick[1], pick[2] = 1023, 1024                                # either side of the default chunk boundary
+    pick[1], pick[2] = 1023, 1024                                # either side of a 1024-frame chunk boundary
     with torch.no_grad():
         ref = encoder_forward(_cpu_sd(m), frames[pick].unsqueeze(1))
     rel = (got[pick] - ref).abs().max().item() / ref.abs().max().item()
-    print(f"[{precision} chunk={chunk or 1024}] 1100 frames, 32 sampled: feature rel err {rel:.2e}")
+    print(f"[{precision} chunk={chunk or 2048}] 1100 frames, 32 sampled: feature rel err {rel:.2e}")
     assert rel < rel_tol
     # frame independence at size: the same frames encoded on their own (small tiles, one chunk) agree closely
     solo = m.encode_frames(frames[pick].cuda()).cpu()
