@@ -8,8 +8,8 @@
 //
 // Design: one cooperative launch, 2 directions x 64 CTAs.  CTA p of a direction owns 10 hidden units
 // (40 gate rows of W_hh); the 40 x 640 weight slice lives in REGISTERS for the whole sequence
-// (320 threads x 80 weights; thread = (row, 1/8 of k)), so a step costs 80 FMAs per (thread, utterance)
-// plus a 3-step shuffle reduction.  h_t is exchanged through the output buffer itself (it is both the
+// (320 threads x 80 weights; a warp = 4 rows, a lane = 1/32 of k), so a step costs 40 packed FMAs per (thread,
+// utterance), 5 coalesced LDS.128 of h and a halving butterfly over the lanes.  h_t is exchanged through the output buffer itself (it is both the
 // layer output and the next step's operand, read back through L2 with ld.cg) and a per-direction
 // monotonic arrive counter acts as the grid barrier between steps.  Utterances of a ragged batch are
 // skipped once s >= len_b; the reverse direction starts at each utterance's own last frame.
@@ -24,10 +24,11 @@ constexpr int kHidden = 640;
 constexpr int kUnits = 10;                 // hidden units per CTA
 constexpr int kParts = kHidden / kUnits;   // 64 CTAs per direction
 constexpr int kRows = 4 * kUnits;          // 40 gate rows per CTA
-constexpr int kKSplit = 8;
-constexpr int kThreads = kRows * kKSplit;  // 320
-constexpr int kWPerThread = kHidden / kKSplit;  // 80
-constexpr int kChunk = 8;                  // utterances per SMEM pass
+constexpr int kWarps = 10;                 // a warp owns 4 gate rows, its 32 lanes split K 32 ways
+constexpr int kRowsPerWarp = kRows / kWarps;            // 4
+constexpr int kThreads = 32 * kWarps;      // 320
+constexpr int kK4 = kHidden / 4 / 32;      // 5 float4 of h (20 k values) per lane
+constexpr int kChunk = 16;                 // utterances per SMEM pass
 
 struct LstmParams {
   const float* gin;      // (B, T, 2*4*H): [dir][gate][unit] pre-activations incl. both biases
@@ -53,6 +54,11 @@ __device__ __forceinline__ unsigned long long ffma2_pk(unsigned long long a, uns
   return r;
 }
 
+// Thread mapping (round 2).  The first version gave a thread one gate row and an eighth of K: all 40 rows of a CTA then
+// read the same h values, 20 broadcast LDS.128 per utterance per thread, and the step was bound by SMEM wavefronts
+// (3.3 us per 8 utterances, whatever the FMA count).  Now a WARP owns 4 gate rows and its 32 lanes split K 32 ways: a
+// lane reads its 5 float4 of h once per utterance (the warp's LDS.128 covers 512 contiguous bytes) and uses them for
+// all 4 rows; the 4 row sums are reduced over the lanes with a halving butterfly (6 shuffles).
 __global__ void __launch_bounds__(kThreads, 1) lstm_recurrence_kernel(LstmParams prm) {
   __shared__ float4 sh_h[kChunk][kHidden / 4];
   __shared__ float sh_z[kChunk][kRows];
@@ -61,25 +67,29 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_recurrence_kernel(LstmParams
   const int dir = blockIdx.x / kParts;
   const int part = blockIdx.x % kParts;
   const int tid = threadIdx.x;
-  const int ks = tid & (kKSplit - 1);
-  const int r = tid >> 3;                 // 0..39 : gate*10 + unit
-  const int gate = r / kUnits, ul = r % kUnits;
-  const int grow = gate * kHidden + part * kUnits + ul;  // row in W_hh / gate vector
+  const int warp = tid >> 5, lane = tid & 31;
   const int H2 = 2 * kHidden, G = 8 * kHidden;
 
-  // weights -> registers: w[i*4+j] = W[grow][(i*8+ks)*4 + j]
-  float w[kWPerThread];
-  {
-    const float4* wrow = reinterpret_cast<const float4*>(prm.w_hh[dir] + static_cast<size_t>(grow) * kHidden);
+  // weights -> registers: row q of this warp is CTA row r = 4 warp + q = gate * 10 + unit
+  unsigned long long w2[kRowsPerWarp][kK4 * 2];   // (k, k+1) pairs of W[grow][(j * 32 + lane) * 4 ..]
+  int grow[kRowsPerWarp];
 #pragma unroll
-    for (int i = 0; i < kWPerThread / 4; ++i) {
-      const float4 v = __ldg(wrow + i * kKSplit + ks);
-      w[i * 4 + 0] = v.x; w[i * 4 + 1] = v.y; w[i * 4 + 2] = v.z; w[i * 4 + 3] = v.w;
+  for (int q = 0; q < kRowsPerWarp; ++q) {
+    const int r = warp * kRowsPerWarp + q;
+    grow[q] = (r / kUnits) * kHidden + part * kUnits + (r % kUnits);
+    const float4* wrow = reinterpret_cast<const float4*>(prm.w_hh[dir] + static_cast<size_t>(grow[q]) * kHidden);
+#pragma unroll
+    for (int j = 0; j < kK4; ++j) {
+      const float4 v = __ldg(wrow + j * 32 + lane);
+      w2[q][2 * j] = pack2(v.x, v.y);
+      w2[q][2 * j + 1] = pack2(v.z, v.w);
     }
   }
-  unsigned long long w2[kWPerThread / 2];   // the same weights as (k, k + 1) pairs
-#pragma unroll
-  for (int i = 0; i < kWPerThread / 2; ++i) w2[i] = pack2(w[2 * i], w[2 * i + 1]);
+  // after the butterfly, lane l holds the sum of row q_of(l) = ((l >> 4) & 1) * 2 + ((l >> 3) & 1); lanes with (l & 7) == 0
+  // publish it
+  const int my_q = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+  const int my_r = warp * kRowsPerWarp + my_q;
+  const int my_grow = (my_r / kUnits) * kHidden + part * kUnits + (my_r % kUnits);
   for (int i = tid; i < prm.batch * kUnits; i += kThreads) sh_c[i] = 0.f;
   __syncthreads();
 
@@ -126,26 +136,42 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_recurrence_kernel(LstmParams
         if (s >= len) continue;  // block-uniform
         const int t = dir == 0 ? s : len - 1 - s;
         float gin = 0.f;
-        if (ks == 0) gin = __ldg(prm.gin + (static_cast<size_t>(b) * prm.frames + t) * G + dir * 4 * kHidden + grow);
-        // packed fp32 FMAs (FFMA2: two IEEE FMAs per issued instruction -- the step is bound by the FMA pipe's issue
-        // rate once more than a few utterances ride along); four independent pair accumulators
-        unsigned long long a0 = 0ull, a1 = 0ull, a2 = 0ull, a3 = 0ull;
+        if ((lane & 7) == 0) gin = __ldg(prm.gin + (static_cast<size_t>(b) * prm.frames + t) * G + dir * 4 * kHidden + my_grow);
+        unsigned long long acc[kRowsPerWarp][2];
 #pragma unroll
-        for (int i = 0; i < kWPerThread / 4; i += 2) {
-          const float4 h0 = sh_h[bb][i * kKSplit + ks];
-          const float4 h1 = sh_h[bb][(i + 1) * kKSplit + ks];
-          a0 = ffma2_pk(w2[i * 2 + 0], pack2(h0.x, h0.y), a0);
-          a1 = ffma2_pk(w2[i * 2 + 1], pack2(h0.z, h0.w), a1);
-          a2 = ffma2_pk(w2[i * 2 + 2], pack2(h1.x, h1.y), a2);
-          a3 = ffma2_pk(w2[i * 2 + 3], pack2(h1.z, h1.w), a3);
+        for (int q = 0; q < kRowsPerWarp; ++q) acc[q][0] = acc[q][1] = 0ull;
+#pragma unroll
+        for (int j = 0; j < kK4; ++j) {
+          const float4 h = sh_h[bb][j * 32 + lane];
+          const unsigned long long h01 = pack2(h.x, h.y), h23 = pack2(h.z, h.w);
+#pragma unroll
+          for (int q = 0; q < kRowsPerWarp; ++q) {
+            acc[q][0] = ffma2_pk(w2[q][2 * j], h01, acc[q][0]);
+            acc[q][1] = ffma2_pk(w2[q][2 * j + 1], h23, acc[q][1]);
+          }
         }
-        float s0, s1, s2, s3, s4, s5, s6, s7;
-        unpack2(a0, s0, s1); unpack2(a1, s2, s3); unpack2(a2, s4, s5); unpack2(a3, s6, s7);
-        float acc = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-        if (ks == 0) sh_z[bb][r] = acc + gin;
+        float sum[kRowsPerWarp];
+#pragma unroll
+        for (int q = 0; q < kRowsPerWarp; ++q) {
+          float a, b2, c, d;
+          unpack2(acc[q][0], a, b2);
+          unpack2(acc[q][1], c, d);
+          sum[q] = (a + b2) + (c + d);
+        }
+        // halving butterfly: after xor 16 a lane keeps rows {0,1} (lanes 0-15) or {2,3} (16-31); after xor 8 one row
+        {
+          const bool up = (lane & 16) != 0;
+          const float s0 = up ? sum[0] : sum[2], s1 = up ? sum[1] : sum[3];   // what the partner keeps
+          const float k0 = up ? sum[2] : sum[0], k1 = up ? sum[3] : sum[1];   // what this lane keeps
+          const float r0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+          const float r1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+          const bool up8 = (lane & 8) != 0;
+          float v = (up8 ? r1 : r0) + __shfl_xor_sync(0xffffffffu, up8 ? r0 : r1, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          if ((lane & 7) == 0) sh_z[bb][my_r] = v + gin;
+        }
       }
       __syncthreads();
       // ---- gate math for (utterance, unit) ----
