@@ -23,6 +23,7 @@ int enc_stem_u8(const uint8_t* frames, const int32_t* fmap, const float* mask, f
                 const float* w, const float* bias, int n, int H, int W, cudaStream_t st);
 int enc_zero_rows(void* buf, int esize, int n, int rows_per_frame, int ld, int head_rows, int tail_start,
                   cudaStream_t st);
+int enc_zero_cols(void* buf, int esize, int n, int rows_per_frame, int ld, int pitch, int H, cudaStream_t st);
 int enc_im2col_s2(const void* in, void* col, int esize, int n, int Hin, int Win, int C, cudaStream_t st);
 int enc_dwconv(const void* in, void* out, int half, float* sums, const float* w, const float* bias, int n, int C, int Hin,
                int Win, int pitch_in, int oy, int ox, int rows_in, int stride, cudaStream_t st);
@@ -34,8 +35,8 @@ bool mb_expand_dw_supported(int H, int W, int c_in, int c_mid);
 int mb_expand_dw(const void* x, const void* w_exp, const float* bias1, const void* dw_w16, const float* dw_w32, const float* dw_b,
                  void* out, float* sums, int n, int H, int W, int c_in, int c_mid, cudaStream_t st);
 bool mb_project_supported(int hw, int c_mid, int c_out);
-int mb_project(const void* a, const void* w, const float* scales, const float* bias, const float* res, float* d32, void* d16,
-               int n_frames, int hw, int c_mid, int c_out, cudaStream_t st);
+int mb_project(const void* a, const void* w, const float* scales, const float* bias, const float* res, const void* res16,
+               float* d32, void* d16, int n_frames, int hw, int c_mid, int c_out, cudaStream_t st);
 bool fused_er_supported(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& p2, const PackedWeights& w2);
 bool fused_er_resident(const PackedWeights& w1, const PackedWeights& w2);
 int fused_er(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& p2, const PackedWeights& w2,
@@ -114,6 +115,8 @@ struct GemmLayer {
   void* w16 = nullptr;   // 1x1 layers of the fp16 build: plain [n][c_in] fp16, K-major (TMA operand of the fused MBConv kernels)
   int taps = 1;
   int shift[M2S_MAX_TAPS] = {};
+  int planes = 1;                    // interleaved A planes (pixel-pair layers of stage 0), see ConvProblem::a_planes
+  int plane[M2S_MAX_TAPS] = {};
 };
 
 void free_gemm(GemmLayer* L) {
@@ -154,6 +157,43 @@ int make_conv_layer(const TMap& m, const std::string& conv, const std::string& b
   return upload(t, &L->bias);
 }
 
+// 3x3 stride-1 conv over the zero-bordered layout with TWO consecutive pixels per GEMM row (N = 2 * cout): the convs of
+// stage 0 have 16 output channels, and an M128 x N16 MMA fetches 4 KB of A for 32 K MACs -- the tensor core spends its time
+// on operand fetches (SURVEY.md 8a-1 "stage 0/1 are large-M/small-N").  Output pixel o = 2 Q + p (p = 0, 1) reads input
+// pixels o + (dy - 1) * pitch + (dx - 1) = 2 Q + t with t = (dy - 1) * pitch + s - 1, s = p + dx in 0..3: tap (dy, s) is
+// plane t mod 2, pair-row shift floor(t / 2) of the input seen as (pair rows, 2, cin), and its weight block holds
+// W[dy][s - p] for the p whose dx = s - p is a real tap (zeros otherwise: 12 taps for 9, a quarter of the MACs are padding).
+int make_pair_conv_layer(const TMap& m, const std::string& conv, const std::string& bn, int cout, int cin, int pitch,
+                         int pack, GemmLayer* L) {
+  const HT* w;
+  M2S_TRY(need(m, conv + ".weight", static_cast<size_t>(cout) * cin * 9, &w));
+  std::vector<float> s, t;
+  M2S_TRY(bn_fold(m, bn, cout, &s, &t));
+  const int taps = 12, n = 2 * cout;
+  std::vector<float> e(static_cast<size_t>(taps) * n * cin, 0.f);
+  for (int dy = 0; dy < 3; ++dy)
+    for (int sx = 0; sx < 4; ++sx) {
+      const int tap = dy * 4 + sx;
+      for (int p = 0; p < 2; ++p) {
+        const int dx = sx - p;
+        if (dx < 0 || dx > 2) continue;
+        for (int o = 0; o < cout; ++o)
+          for (int c = 0; c < cin; ++c)
+            e[(static_cast<size_t>(tap) * n + p * cout + o) * cin + c] =
+                w->data[(static_cast<size_t>(o) * cin + c) * 9 + dy * 3 + dx] * s[o];
+      }
+      const int tt = (dy - 1) * pitch + sx - 1;
+      L->plane[tap] = ((tt % 2) + 2) % 2;
+      L->shift[tap] = (tt - L->plane[tap]) / 2;   // floor(tt / 2)
+    }
+  L->taps = taps;
+  L->planes = 2;
+  M2S_TRY(pack_weights(e.data(), taps, n, cin, pack, &L->w));
+  std::vector<float> t2(n);
+  for (int i = 0; i < n; ++i) t2[i] = t[i % cout];
+  return upload(t2, &L->bias);
+}
+
 enum BlockKind { CN, ER, IR };
 struct StageDef { BlockKind kind; int reps, stride, expand, cout, se; };
 const StageDef kStages[6] = {{CN, 2, 1, 1, 16, 0},  {ER, 3, 2, 4, 32, 0},   {ER, 3, 2, 4, 56, 0},
@@ -169,6 +209,7 @@ struct Block {
   bool out_padded;   // output activation carries a zero border
   bool skip;
   GemmLayer conv;    // CN conv / ER conv_exp / IR conv_pw
+  GemmLayer pair;    // CN conv with two pixels per GEMM row (fp16 build; empty otherwise)
   GemmLayer pwl;     // ER / IR projection
   float *dw_w = nullptr, *dw_b = nullptr;                                   // IR depthwise [9][mid], [mid]
   void* dw_w16 = nullptr;                                                   // ... and its fp16 copy (fp16 build)
@@ -187,8 +228,11 @@ struct m2s_acoustic {
   float* w_hh[2] = {nullptr, nullptr};
   // fused block kernels (fp16 build): bit0 = InvertedResidual expand + depthwise + squeeze in one kernel, bit1 = SE scale
   // inside the project GEMM (csrc/mbconv_sm100.cu); bit2 = EdgeResidual 3x3 expand + 1x1 project in one kernel
-  // (csrc/fused_er_sm100.cu).  M2S_MBCONV=0 keeps the unfused launches (the A/B reference of tests/).
-  int mbconv = 7;
+  // (csrc/fused_er_sm100.cu); bit3 = that kernel also where the weights must be streamed per tile (slower); bit4 = stage 0's
+  // 3x3 convs with two pixels per GEMM row (N = 32 instead of 16; measured: no faster, off by default); bit5 = fp16
+  // residual stream (no fp32 copies of the block outputs).  M2S_MBCONV=0 keeps the unfused launches and the fp32 stream
+  // (the A/B reference of tests/).
+  int mbconv = 39;
   int chunk = 2048;  // frames per encoder pass (M2S_ENCODER_CHUNK): 2048 frames = ~14 GB of work buffers.  Measured with the
                      // round-2 kernels: 14.1 / 12.6 / 12.1 / 12.2 us per frame at 512 / 1024 / 2048 / 4096 (fp16 build)
   // per-frame buffer sizes (floats)
@@ -201,6 +245,7 @@ namespace {
 
 void free_block(Block* b) {
   free_gemm(&b->conv);
+  free_gemm(&b->pair);
   free_gemm(&b->pwl);
   for (float** p : {&b->dw_w, &b->dw_b, &b->se_w1, &b->se_b1, &b->se_w2, &b->se_b2}) {
     if (*p) cudaFree(*p);
@@ -304,8 +349,17 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
     const bool last = bi + 1 == m->blocks.size();
     // block output copies: fp32 when the next block adds it as a shortcut (or the GAP reads it), fp16 when the next
     // consumer is a GEMM of the fp16 build
-    const bool out32 = !h || last || m->blocks[bi + 1].skip;
+    // fp16 residual stream (mbconv bit 5, fp16 build): a shortcut is read from the fp16 copy the next GEMM reads anyway,
+    // and no fp32 copy is written (26 % of the encoder's HBM traffic; the rounding it adds is below the operand rounding
+    // already there: tools/emulate_residual_rounding.py)
+    const bool res16 = h && (m->mbconv & 32);
+    const bool out32 = !h || last || (m->blocks[bi + 1].skip && !res16);
     const bool out16 = h && !last;
+    auto set_skip = [&](ConvProblem* p, int ld) {
+      p->epi.res = res16 ? reinterpret_cast<const float*>(x.f16) : x.f32;
+      p->epi.res_half = res16 ? 1 : 0;
+      p->epi.res_ld = ld;
+    };
     auto set_block_out = [&](ConvProblem* p) {
       p->d = out32 ? y.f32 : nullptr;
       p->d16 = out16 ? y.f16 : nullptr;
@@ -320,11 +374,28 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
     if (b.kind == CN) {
       // 3x3 s1 conv on the padded layout -> padded layout, SiLU, (+ skip after the activation)
       const int rows = static_cast<int>(padded_rows(hin, win));
+      if (b.pair.w.dev) {
+        // two pixels per GEMM row over EVERY pair-row of the padded frame (no offset, no mask: the border pixels come
+        // out as garbage and are zeroed below)
+        const int prow = rows / 2;
+        ConvProblem p = gemm_problem(op(x), prow, prow, b.cin, n, prow, y.f32, prow, 2 * b.cout, 0, b.pair);
+        p.a_planes = 2;
+        for (int j = 0; j < b.pair.taps; ++j) p.plane[j] = b.pair.plane[j];
+        set_block_out(&p);
+        p.epi.act = M2S_ACT_SILU;
+        if (b.skip) { set_skip(&p, 2 * b.cin); p.epi.res_after_act = 1; }
+        M2S_TRY(run_gemm(m, p, b.pair, st));
+        M2S_TRY(zero_border(rows, b.cout, win + 3, hin * (win + 2) + win + 3));
+        if (out32) M2S_TRY(simt(0, [&] { return enc_zero_cols(y.f32, 4, n, rows, b.cout, win + 2, hin, st); }, 1));
+        if (out16) M2S_TRY(simt(0, [&] { return enc_zero_cols(y.f16, 2, n, rows, b.cout, win + 2, hin, st); }, 1));
+        std::swap(x, y);
+        continue;
+      }
       ConvProblem p = gemm_problem(op(x), rows, rows, b.cin, n, hin * (win + 2), y.f32, rows, b.cout, win + 3, b.conv);
       set_block_out(&p);
       p.epi.act = M2S_ACT_SILU;
       set_pitch_mask(&p, hin, win);
-      if (b.skip) { p.epi.res = x.f32; p.epi.res_ld = b.cin; p.epi.res_after_act = 1; }
+      if (b.skip) { set_skip(&p, b.cin); p.epi.res_after_act = 1; }
       M2S_TRY(run_gemm(m, p, b.conv, st));
       M2S_TRY(zero_border(rows, b.cout, win + 3, hin * (win + 2) + win + 3));
       std::swap(x, y);
@@ -345,7 +416,7 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
       ConvProblem p = gemm_problem(B.e, lq, lq, b.mid, n, lq, y.f32, rows_out, b.cout, wout + 3, b.pwl);
       set_block_out(&p);
       set_pitch_mask(&p, hout, wout);
-      if (b.skip) { p.epi.res = x.f32; p.epi.res_ld = b.cin; }
+      if (b.skip) set_skip(&p, b.cin);
       bool fused = false;
       if ((m->mbconv & 4) && fused_er_supported(p1, b.conv.w, p, b.pwl.w) &&
           ((m->mbconv & 8) || fused_er_resident(b.conv.w, b.pwl.w))) {
@@ -388,8 +459,9 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
         // SE MLP (sums -> scales, in place), then the project GEMM scales its A operand in SMEM
         M2S_TRY(simt(0, [&] { return enc_se_mlp(B.sums, b.se_w1, b.se_b1, b.se_w2, b.se_b2, n, b.mid, b.rd, hw, st); }, 1));
         profile_set_tag(PROF_ENC_GEMM);
-        M2S_TRY(mb_project(B.e2, b.pwl.w16, B.sums, b.pwl.bias, b.skip ? x.f32 : nullptr, out32 ? y.f32 : nullptr,
-                           out16 ? y.f16 : nullptr, n, hw, b.mid, b.cout, st));
+        M2S_TRY(mb_project(B.e2, b.pwl.w16, B.sums, b.pwl.bias, (b.skip && !res16) ? x.f32 : nullptr,
+                           (b.skip && res16) ? x.f16 : nullptr, out32 ? y.f32 : nullptr, out16 ? y.f16 : nullptr, n, hw, b.mid,
+                           b.cout, st));
         std::swap(x, y);
         continue;
       }
@@ -397,7 +469,7 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
       const int rows_out = n * hw;
       ConvProblem p = gemm_problem(B.e2, rows_out, rows_out, b.mid, 1, rows_out, y.f32, rows_out, b.cout, 0, b.pwl);
       set_block_out(&p);
-      if (b.skip) { p.epi.res = x.f32; p.epi.res_ld = b.cin; }
+      if (b.skip) set_skip(&p, b.cin);
       M2S_TRY(run_gemm(m, p, b.pwl, st));
       std::swap(x, y);
     }
@@ -530,8 +602,11 @@ extern "C" int m2s_acoustic_create(const m2s_acoustic_config* cfg, const m2s_ten
         b.out_padded = true;
         if ((st = make_conv_layer(tm, p + ".conv", p + ".bn1", b.cout, cin, 3, w + 2, 0, enc_pack, &b.conv)) != M2S_OK)
           return bail(st);
+        if ((m->mbconv & 16) && (w + 2) % 2 == 0 && ((h + 2) * (w + 2)) % 2 == 0 && b.cout % 8 == 0 &&
+            (st = make_pair_conv_layer(tm, p + ".conv", p + ".bn1", b.cout, cin, w + 2, enc_pack, &b.pair)) != M2S_OK)
+          return bail(st);
         m->x_floats = std::max(m->x_floats, padded_rows(ho, wo) * b.cout);
-        launches += 2;
+        launches += b.pair.w.dev ? 3 : 2;
       } else if (sd.kind == ER) {
         b.out_padded = true;
         if ((st = make_conv_layer(tm, p + ".conv_exp", p + ".bn1", b.mid, cin, 3, w + 2, b.stride == 2 ? 1 : 0,

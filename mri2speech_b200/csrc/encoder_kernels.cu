@@ -301,6 +301,18 @@ __global__ void zero_rows_kernel(float* __restrict__ buf, int rows_per_frame, in
   }
 }
 
+// Zero the left / right border pixels of a padded layout's interior rows: pixels (y, pitch - 1) and (y + 1, 0) for
+// y = 1 .. H are adjacent in memory.  (The two-pixels-per-row convs of stage 0 run without the engine's border mask.)
+__global__ void zero_cols_kernel(float* __restrict__ buf, int rows_per_frame, int ld4, int pitch, int H) {
+  const int n = blockIdx.y;
+  float4* base = reinterpret_cast<float4*>(buf) + static_cast<size_t>(n) * rows_per_frame * ld4;
+  const int per_row = 2 * ld4;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < H * per_row; k += gridDim.x * blockDim.x) {
+    const int y = k / per_row + 1, c = k % per_row;
+    base[(static_cast<size_t>(y) * pitch + pitch - 1) * ld4 + c] = make_float4(0, 0, 0, 0);
+  }
+}
+
 // im2col for a 3x3 stride-2 TF-"same" conv.  Input: padded layout (pitch_in = W_in + 2, origin (1,1));
 // output rows q = y*(Wo+2) + x (x >= Wo rows are zero), columns (dy*3+dx)*C + c.
 // (Type-agnostic copy: `c4n` = 16-byte vectors per pixel = C * sizeof(element) / 16.)
@@ -558,6 +570,14 @@ int enc_zero_rows(void* buf, int esize, int n, int rows_per_frame, int ld, int h
   const int nz = (head_rows + rows_per_frame - tail_start) * ld4;
   dim3 grid((nz + 255) / 256, n);
   zero_rows_kernel<<<grid, 256, 0, st>>>(static_cast<float*>(buf), rows_per_frame, ld4, head_rows, tail_start);
+  M2S_CUDA_OK(cudaGetLastError());
+  return M2S_OK;
+}
+
+int enc_zero_cols(void* buf, int esize, int n, int rows_per_frame, int ld, int pitch, int H, cudaStream_t st) {
+  const int ld4 = ld * esize / 16;
+  dim3 grid((H * 2 * ld4 + 255) / 256, n);
+  zero_cols_kernel<<<grid, 256, 0, st>>>(static_cast<float*>(buf), rows_per_frame, ld4, pitch, H);
   M2S_CUDA_OK(cudaGetLastError());
   return M2S_OK;
 }

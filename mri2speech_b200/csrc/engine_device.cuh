@@ -49,6 +49,7 @@ struct EngineParams {
   uint32_t idesc;
   int base_offset_mode;
   int a_per_tap;
+  int a_planes;         // interleaved A planes per stage (1 = plain); plane p of a stage starts p * a_nbox * a_box_rows rows in
   int rel_shift[M2S_MAX_TAPS];
   int tg;               // taps per weight stage
   uint32_t b_tap_bytes; // bytes of one tap's weight block (n_tile x 128)
@@ -108,6 +109,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -464,9 +472,20 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
               res4[i] = make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
             }
           } else if (!kSplit && has_res && lane_ok) {
-            const float4* rp = reinterpret_cast<const float4*>(e.res + row0 * e.res_ld + n);
+            if (e.res_half) {   // fp16 residual stream: 8 bytes per lane
+              const uint2* rp = reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(e.res) + row0 * e.res_ld + n);
 #pragma unroll
-            for (int i = 0; i < kR; ++i) res4[i] = rp[static_cast<size_t>(i) * 2 * e.res_ld];
+              for (int i = 0; i < kR; ++i) {
+                const uint2 u = rp[static_cast<size_t>(i) * 2 * e.res_ld];
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+                res4[i] = make_float4(a.x, a.y, b.x, b.y);
+              }
+            } else {
+              const float4* rp = reinterpret_cast<const float4*>(e.res + row0 * e.res_ld + n);
+#pragma unroll
+              for (int i = 0; i < kR; ++i) res4[i] = rp[static_cast<size_t>(i) * 2 * e.res_ld];
+            }
           } else {
 #pragma unroll
             for (int i = 0; i < kR; ++i) res4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -612,11 +631,23 @@ __device__ __forceinline__ void epilogue_tile(const ConvProblem& p, const EpiWar
       for (int i = 0; i < kR; ++i) res4[i] = split_decode(res4[i]);   // zero bits decode to zero
     } else if (kHasRes) {
       if (has_res) {
-        const float* rptr = e.res + row0 * e.res_ld + n;
         const size_t r_step = static_cast<size_t>(8) * e.res_ld;
+        if (e.res_half) {
+          const __half* rptr = reinterpret_cast<const __half*>(e.res) + row0 * e.res_ld + n;
 #pragma unroll
-        for (int i = 0; i < kR; ++i)
-          if (i * 8 + rr0 < rows_ok) res4[i] = *reinterpret_cast<const float4*>(rptr + i * r_step);
+          for (int i = 0; i < kR; ++i)
+            if (i * 8 + rr0 < rows_ok) {
+              const uint2 u = *reinterpret_cast<const uint2*>(rptr + i * r_step);
+              const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+              const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+              res4[i] = make_float4(a.x, a.y, b.x, b.y);
+            }
+        } else {
+          const float* rptr = e.res + row0 * e.res_ld + n;
+#pragma unroll
+          for (int i = 0; i < kR; ++i)
+            if (i * 8 + rr0 < rows_ok) res4[i] = *reinterpret_cast<const float4*>(rptr + i * r_step);
+        }
       }
     }
     if (kHasAcc) {

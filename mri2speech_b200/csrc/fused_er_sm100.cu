@@ -192,7 +192,7 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         if (prm.tma_epi && p.epi.res) {
           mbar_wait(r_empty(s & 1), ((s >> 1) & 1) ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(r_full(s & 1), kRsBytes);
+            mbar_expect_tx(r_full(s & 1), p.epi.res_half ? kH16Bytes : kRsBytes);
             tma_load_3d(rs_base + (s & 1) * kRsBytes, &tm_r, r_full(s & 1), 0, q0, b);
           }
           __syncwarp();
@@ -382,7 +382,19 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           }
           const uint32_t a32 = rs_base + rbuf * kRsBytes + row * 128;
           float4 rv[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
-          if (e.res) {
+          if (e.res && e.res_half) {
+            // fp16 residual stream: the tile is 128 rows x 64 bytes (SWIZZLE_64B) at the start of the buffer
+            uint32_t u0, u1, u2, u3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3)
+                         : "r"(rs_base + rbuf * kRsBytes + row * 64 + ((grp ^ ((row >> 1) & 3)) << 4)));
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u0));
+            const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&u1));
+            const float2 c2 = __half22float2(*reinterpret_cast<const __half2*>(&u2));
+            const float2 d2 = __half22float2(*reinterpret_cast<const __half2*>(&u3));
+            rv[0] = make_float4(a.x, a.y, b2.x, b2.y);
+            rv[1] = make_float4(c2.x, c2.y, d2.x, d2.y);
+          } else if (e.res) {
 #pragma unroll
             for (int m = 0; m < 2; ++m)
               asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -401,9 +413,10 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             if (keep)
               o = make_float4(__uint_as_float(r[4 * m]) + b4.x + rv[m].x, __uint_as_float(r[4 * m + 1]) + b4.y + rv[m].y,
                               __uint_as_float(r[4 * m + 2]) + b4.z + rv[m].z, __uint_as_float(r[4 * m + 3]) + b4.w + rv[m].w);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a32 + (((2 * grp + m) ^ (row & 7)) << 4)),
-                         "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
-                         : "memory");
+            if (p.d)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a32 + (((2 * grp + m) ^ (row & 7)) << 4)),
+                           "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
+                           : "memory");
             asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hp[2 * m]) : "f"(o.y), "f"(o.x));
             asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hp[2 * m + 1]) : "f"(o.w), "f"(o.z));
           }
@@ -441,8 +454,17 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int c = col0 + 4 * j;
-          rv[j] = (4 * j < cw && row_ok && c < p.n && e.res)
-                      ? *reinterpret_cast<const float4*>(e.res + grow * e.res_ld + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (4 * j < cw && row_ok && c < p.n && e.res) {
+            if (e.res_half) {
+              const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(e.res) + grow * e.res_ld + c);
+              const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+              const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+              rv[j] = make_float4(a.x, a.y, b2.x, b2.y);
+            } else {
+              rv[j] = *reinterpret_cast<const float4*>(e.res + grow * e.res_ld + c);
+            }
+          }
         }
         mbar_wait(acc2_full(buf), (i / nbuf) & 1);
         tc_fence_after();
@@ -544,7 +566,10 @@ int launch_er(const ErParams& prm_in, const ConvProblem& p1, const ConvProblem& 
       return M2S_OK;
     };
     const size_t off = static_cast<size_t>(p2.d_row_offset);
-    if (p2.epi.res)
+    if (p2.epi.res && p2.epi.res_half)
+      M2S_TRY(map3(&tm_r, reinterpret_cast<const __half*>(p2.epi.res) + off * p2.epi.res_ld, 2, p2.d_batch_rows, p2.epi.res_ld, 128,
+                   CU_TENSOR_MAP_SWIZZLE_64B, "shortcut (fp16)"));
+    else if (p2.epi.res)
       M2S_TRY(map3(&tm_r, p2.epi.res + off * p2.epi.res_ld, 4, p2.d_batch_rows, p2.epi.res_ld, 128, CU_TENSOR_MAP_SWIZZLE_128B, "shortcut"));
     if (p2.d) M2S_TRY(map3(&tm_d32, p2.d + off * p2.d_ld, 4, p2.d_batch_rows, p2.d_ld, 32, CU_TENSOR_MAP_SWIZZLE_128B, "fp32 output"));
     if (p2.d16)
@@ -634,6 +659,7 @@ int fused_er(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& 
     uint32_t used = fixed + 2 * prm.a_stage_bytes + prm.nbuf * prm.t_buf_bytes + prm.w1_bytes + prm.w2_bytes;
     static const bool tma_epi_on = !(std::getenv("M2S_ER_TMA_EPI") && std::atoi(std::getenv("M2S_ER_TMA_EPI")) == 0);
     if (tma_epi_on && p2.n == 32 && prm.n_tile2 == 32 && p2.d_ld == 32 && (!p2.epi.res || p2.epi.res_ld == 32) &&
+        !(p2.d && p2.epi.res && p2.epi.res_half) &&   // (an fp16 shortcut tile and an fp32 output tile would share a buffer)
         used + 2 * kRsBytes + kH16Bytes <= budget) {
       prm.tma_epi = 1;
       used += 2 * kRsBytes + kH16Bytes;

@@ -66,6 +66,7 @@ struct Epilogue {
   int mask_mode;
   int len_scale;
   int pitch, i_lo, i_hi, j_lo, j_hi;
+  int res_half;          // `res` points at __half data (res_ld in elements): the encoder's fp16 residual stream (internal)
   unsigned pitch_magic;  // floor(2^32 / pitch) + 1: row / pitch == __umulhi(row, pitch_magic) for row * pitch < 2^32
                          // (filled in by the launchers: finalize_epilogue)
 };
@@ -85,6 +86,11 @@ struct ConvProblem {
   int a_half;          // A operand is fp16 (tcgen05 kind::f16); 0 = fp32 rounded to tf32 by TMA
   void* d16;           // optional second output, fp16, indexed like d (same d_ld in elements); null = none
   void* d16_lo;        // optional lo plane of the split-fp16 pair (d16 = hi): fp16(v - float(fp16(v))); needs d16
+  // Interleaved A planes (internal; 0 / 1 = off).  With a_planes = P the A tensor is read as (batch, a_rows, P, c_in): GEMM
+  // row q of tap j is A[b, q + shift[j], plane[j], :].  This is how a conv over P consecutive pixels per GEMM row (N =
+  // P * C_out: the narrow first stage of the encoder) addresses pixel 2 q + t as plane t mod P, row q + floor(t / P).
+  int a_planes;
+  int plane[M2S_MAX_TAPS];
 };
 
 inline ConvProblem problem_from_args(const m2s_conv_args& a) {

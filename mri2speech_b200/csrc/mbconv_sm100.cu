@@ -435,6 +435,7 @@ struct ProjectParams {
   const float* scales;   // [n_frames][c_mid] fp32 excite scales (null: plain GEMM)
   const float* bias;     // [c_out]
   const float* res;      // [rows][c_out] fp32 shortcut or null
+  const __half* res16;   // ... or the fp16 residual stream (res == null)
   int store32, store16;
   uint32_t idesc;
   uint64_t desc_hi;
@@ -599,11 +600,21 @@ mb_project_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           float4 bv[8], rv[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const bool c_ok = col0 + 4 * j < prm.c_out;   // c_out % 4 == 0
+            const bool c_ok = col0 + 4 * j < prm.c_out;   // c_out % 8 == 0
             bv[j] = c_ok ? __ldg(reinterpret_cast<const float4*>(prm.bias + col0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
             rv[j] = (c_ok && row_ok && prm.res)
                         ? *(reinterpret_cast<const float4*>(prm.res + static_cast<size_t>(row) * prm.c_out + col0) + j)
                         : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (prm.res16 && row_ok) {   // fp16 residual stream: 16 bytes = 8 channels per load
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (col0 + 8 * j < prm.c_out) {
+                const uint4 u = *(reinterpret_cast<const uint4*>(prm.res16 + static_cast<size_t>(row) * prm.c_out + col0) + j);
+                const float2 a = unpack_h2(u.x), b = unpack_h2(u.y), c = unpack_h2(u.z), d = unpack_h2(u.w);
+                rv[2 * j] = make_float4(a.x, a.y, b.x, b.y);
+                rv[2 * j + 1] = make_float4(c.x, c.y, d.x, d.y);
+              }
           }
           if (pending) {   // the staging buffers are free once the previous unit's stores have read them
             if (lane == 0) tma_store_wait_read();
@@ -750,9 +761,10 @@ bool mb_project_supported(int hw, int c_mid, int c_out) {
 }
 
 // a: [rows][c_mid] fp16 (depthwise output); w: [c_out][c_mid] fp16; scales: [n_frames][c_mid] fp32 or null;
-// res: [rows][c_out] fp32 or null; d32 / d16: [rows][c_out] outputs (either may be null)
-int mb_project(const void* a, const void* w, const float* scales, const float* bias, const float* res, float* d32, void* d16,
-               int n_frames, int hw, int c_mid, int c_out, cudaStream_t st) {
+// res / res16: [rows][c_out] shortcut, fp32 or fp16 (at most one; both may be null); d32 / d16: [rows][c_out] outputs
+// (either may be null)
+int mb_project(const void* a, const void* w, const float* scales, const float* bias, const float* res, const void* res16,
+               float* d32, void* d16, int n_frames, int hw, int c_mid, int c_out, cudaStream_t st) {
   if (!mb_project_supported(hw, c_mid, c_out))
     return fail(M2S_ERR_UNSUPPORTED, "fused SE project: hw=%d c_mid=%d c_out=%d not supported", hw, c_mid, c_out);
   if (!d32 && !d16) return fail(M2S_ERR_BAD_ARG, "no output pointer");
@@ -766,7 +778,7 @@ int mb_project(const void* a, const void* w, const float* scales, const float* b
   prm.n_tiles = (prm.rows + M - 1) / M;
   prm.a_bytes = static_cast<uint32_t>(M) * 128;
   prm.stage_bytes = (prm.a_bytes + static_cast<uint32_t>(prm.n_pad) * 128 + 1023u) & ~1023u;
-  prm.scales = scales; prm.bias = bias; prm.res = res;
+  prm.scales = scales; prm.bias = bias; prm.res = res; prm.res16 = res ? nullptr : static_cast<const __half*>(res16);
   prm.store32 = d32 != nullptr; prm.store16 = d16 != nullptr;
   prm.idesc = idesc_f16(prm.n_pad);
   prm.desc_hi = make_desc_hi(128);

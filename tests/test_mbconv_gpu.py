@@ -4,7 +4,9 @@ The reference block is timm's InvertedResidual + SqueezeExcite as called by EffN
 (mri2speech_code/mri_acoustic_model.py:28-48).  M2S_MBCONV selects the path when the handle is created: 0 = expand GEMM,
 depthwise kernel, SE MLP, SE scale pass, project GEMM; bit0 = expand GEMM with the depthwise conv + squeeze as its
 epilogue; bit1 = SE scale applied to the project GEMM's A operand in SMEM; bit2 = the stride-1 EdgeResidual blocks of
-stages 1-2 (3x3 expand -> SiLU -> 1x1 project) in one kernel with the expanded tile in SMEM (csrc/fused_er_sm100.cu).  Both kernels keep the arithmetic of the
+stages 1-2 (3x3 expand -> SiLU -> 1x1 project) in one kernel with the expanded tile in SMEM (csrc/fused_er_sm100.cu);
+bit4 = stage 0's 3x3 convs with two pixels per GEMM row (N = 32 instead of 16: interleaved A planes of the conv engine);
+bit5 = the residual stream in fp16 (shortcuts read from the fp16 operand copies, no fp32 copies of the block outputs).  Both kernels keep the arithmetic of the
 launches they replace (fp32 depthwise accumulation in tap order, fp32 scale * fp16 activation rounded once), so the
 encoder features must agree far below the fp16 operand noise (2^-11); the oracle comparison of the fused default runs
 in tests/test_acoustic_gpu.py / test_bench_paths_gpu.py / test_scaled_init_gpu.py."""
@@ -43,7 +45,7 @@ def _frames(n, seed=0):
     return synth.synthetic_clip(seed, n).cuda()
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3, 4, 12, 7])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 12, 16, 23, 32, 39])
 @pytest.mark.parametrize("n", [5, 301])
 def test_fused_equals_unfused(mode, n):
     """5 frames: partial tiles (two 8x8 frames per tile, odd count); 301 frames: several tiles per CTA (ring phases wrap)."""
@@ -53,8 +55,11 @@ def test_fused_equals_unfused(mode, n):
     assert torch.isfinite(got).all()
     scale = ref.abs().max().item()
     err = (got - ref).abs().max().item()
-    assert err <= 2e-4 * scale, (mode, n, err, scale)
-    assert l1 < l0                                   # fewer launches per forward
+    # bit 5 (32) = the residual stream in fp16: one more fp16 rounding per block with a shortcut (tools/
+    # emulate_residual_rounding.py: ~3e-4 of the features' abs-max on these weights); everything else keeps the arithmetic
+    tol = 2e-3 if mode & 32 else 2e-4
+    assert err <= tol * scale, (mode, n, err, scale)
+    assert l1 < l0 or mode in (16, 32)               # fewer launches per forward (16 adds two border passes, 32 none)
     if mode == 3:
         assert l0 - l1 == 18 + 20                    # 18 stride-1 blocks lose the depthwise launch, all 20 the scale pass
     if mode == 4:
