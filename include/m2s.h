@@ -45,12 +45,13 @@ typedef enum {
 
 /* arithmetic of the GEMM-shaped layers */
 enum {
-  M2S_PREC_TF32 = 0, /* tcgen05 kind::tf32, fp32 accumulate in TMEM (default build) */
+  M2S_PREC_TF32 = 0, /* tcgen05 kind::tf32, fp32 accumulate in TMEM                  */
   M2S_PREC_FP32 = 1, /* CUDA-core fp32 FMA kernels (exact-fp32 build, slow)          */
   M2S_PREC_FP16 = 2  /* tcgen05 kind::f16: fp16 operands (10-bit mantissa, the same as tf32), fp32 accumulate,
                         fp32 residual / MRF streams.  A layer runs kind::f16 iff its c_in is a multiple of 8
                         (16-byte rows of halves); conv_pre (fp32 mel operand), the BiLSTM input projection
-                        and the mel head stay on tf32 */
+                        and the mel head stay on tf32.  The Python modules' default since round 2; the encoder
+                        then also keeps its residual stream in fp16 */
 };
 
 const char* m2s_version(void);
