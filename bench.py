@@ -162,7 +162,7 @@ def workload_config(args, world):
               "(variable length, seed 4321), raw uint8 256x256 frames, 1 x B200")
     return {
         "workload": wl, "precision": prec, "max_batch_frames": args.max_batch_frames,
-        "l2": "one step streams 1.5 GB (N=1) of frames and multi-GB activations: far beyond the 126 MB L2, no explicit flush",
+        "l2": "one step streams 1.66 GB (N=1) of frames and multi-GB activations: far beyond the 126 MB L2, no explicit flush",
         "clips": f"{N_BASE} unique synthetic uint8 clips of {BASE_FRAMES} frames behind the clip list (clip i = "
                  "base[i % 16][:len_i]); kernels are data-independent",
         "sharding": "utterances per rank (LPT on frames), no collective on the hot path, one gather per step" if world > 1
@@ -501,8 +501,9 @@ def main():
             tj = json.load(f)
         traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
     roofline = {
-        "kernel": f"conv_engine_kernel / conv_engine_pair_kernel, encoder launches (tcgen05 kind::"
-                  f"{'f16' if args.precision == 'fp16' else 'tf32'} implicit-GEMM convs of the frame-CNN: "
+        "kernel": f"the encoder's tcgen05 launches: mb_expand_dw_kernel / mb_project_kernel / fused_er_kernel / conv_engine_kernel / "
+                  f"conv_engine_pair_kernel (kind::{'f16' if args.precision == 'fp16' else 'tf32'} implicit-GEMM convs of the "
+                  f"frame-CNN; the fused kernels also carry the depthwise / squeeze-excite work of their blocks: "
                   f"{100 * enc['ms_per_step'] / max(kernel_ms, 1e-9):.0f} % of the step's kernel time)",
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "traffic": traffic, "traffic_source": traffic_src,
