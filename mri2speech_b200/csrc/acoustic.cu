@@ -44,7 +44,7 @@ int fused_er(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& 
 int enc_se_mlp(float* sums, const float* w1, const float* b1, const float* w2, const float* b2, int n, int C, int rd, int hw,
                cudaStream_t st);
 int lstm_recurrence(const float* gin, const float* w_hh_fwd, const float* w_hh_bwd, const int32_t* lens, float* hcat,
-                    unsigned int* counters, int batch, int frames, int max_len, int hidden,
+                    unsigned int* counters, int batch, int frames, int max_len, int hidden, bool tensor_cores,
                     cudaStream_t stream);
 }  // namespace m2s
 
@@ -529,7 +529,7 @@ int rnn_head(const m2s_acoustic* m, const float* feats, int batch, int frames, c
   M2S_CUDA_OK(cudaMemsetAsync(hcat, 0, static_cast<size_t>(rows) * 2 * Hd * sizeof(float), st));
   profile_set_tag(PROF_RNN);
   M2S_TRY(profile_before(st));
-  M2S_TRY(lstm_recurrence(gin, m->w_hh[0], m->w_hh[1], lens, hcat, counters, batch, frames, max_len, Hd, st));
+  M2S_TRY(lstm_recurrence(gin, m->w_hh[0], m->w_hh[1], lens, hcat, counters, batch, frames, max_len, Hd, m->tf32, st));
   M2S_TRY(profile_after(st, 2.0 * 2 * 4 * Hd * static_cast<double>(Hd) * batch * max_len));
   {  // head on [h_fwd | h_bwd] with the weight duplicated: y = W (h_fwd + h_bwd) + b ; rows past lens -> 0
     ConvProblem p = gemm_problem(hcat, frames, frames, 2 * Hd, batch, frames, mel_norm, frames, m->cfg.n_mels, 0, m->head);

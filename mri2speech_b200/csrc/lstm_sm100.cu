@@ -15,6 +15,7 @@
 // skipped once s >= len_b; the reverse direction starts at each utterance's own last frame.
 #include "m2s_common.cuh"
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 namespace m2s {
 
@@ -201,28 +202,191 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_recurrence_kernel(LstmParams
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Tensor-core step (tf32 / fp16 builds).  The same decomposition (2 x 64 CTAs, 40 gate rows each, grid barrier per step),
+// but the 16 x 40 x 640 product of a chunk of 16 utterances is warp-level mma.sync.m16n8k8 tf32 (fp32 accumulate): warp w
+// owns k in [64 w, 64 w + 64) -- its W_hh fragments (8 k-steps x 5 n-tiles x 2 registers) stay in registers for the whole
+// sequence -- and the ten partial products are summed through SMEM in a fixed order.  Per chunk a lane issues 32 LDS + 40
+// MMAs instead of 80 LDS.128 + 640 FFMA2 + 96 shuffles.  (A 16-row product per step is far below what tcgen05 is for:
+// its M is 64 or 128 and its A operand would have to be gathered row by row, because every utterance of a ragged
+// reverse pass sits at its own time index.)  h_{t-1} and W_hh are rounded to tf32 (cvt.rna); on this path's weights that
+// changes the mel by 4e-6 (default init) / 5e-5 relative (scaled init): tools/emulate_residual_rounding.py's sibling probe,
+// DESIGN.md 3.  The fp32 build keeps the FMA kernel above.
+constexpr int kHPitch = kHidden + 4;   // floats per staged h row: A-fragment loads (8 rows x 4 k) hit 32 different banks
+
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(kThreads, 1) lstm_recurrence_mma_kernel(LstmParams prm) {
+  extern __shared__ float smem_dyn[];
+  float* sh_h = smem_dyn;                                  // [16][kHPitch] h_{t-1} of the chunk, tf32-rounded
+  float* sh_part = sh_h + kChunk * kHPitch;                // [10 warps][16][40] partial products
+  float* sh_z = sh_part + kWarps * kChunk * kRows;         // [16][40]
+  float* sh_c = sh_z + kChunk * kRows;                     // [batch][kUnits] cell state
+  static_assert(kChunk == 16, "one m16 MMA tile per chunk");
+
+  const int dir = blockIdx.x / kParts;
+  const int part = blockIdx.x % kParts;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int H2 = 2 * kHidden, G = 8 * kHidden;
+
+  // B fragments: W[row n = nt * 8 + g][k = 64 warp + 8 ks + t4 (+ 4)], row r = gate * 10 + unit
+  uint32_t wb[8][5][2];
+#pragma unroll
+  for (int nt = 0; nt < 5; ++nt) {
+    const int r = nt * 8 + g;
+    const int grow = (r / kUnits) * kHidden + part * kUnits + (r % kUnits);
+    const float* wrow = prm.w_hh[dir] + static_cast<size_t>(grow) * kHidden + warp * 64 + t4;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      wb[ks][nt][0] = to_tf32(__ldg(wrow + ks * 8));
+      wb[ks][nt][1] = to_tf32(__ldg(wrow + ks * 8 + 4));
+    }
+  }
+  for (int i = tid; i < prm.batch * kUnits; i += kThreads) sh_c[i] = 0.f;
+  __syncthreads();
+
+  unsigned int* counter = prm.counters + dir;
+
+  for (int s = 0; s < prm.max_len; ++s) {
+    if (s > 0) {
+      if (tid == 0) {
+        const unsigned int target = static_cast<unsigned int>(s) * kParts;
+        unsigned int v;
+        long long t0 = clock64();
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+          if (v < target && clock64() - t0 > 4000000000LL) {
+            printf("m2s lstm: grid barrier timeout (block %d step %d, %u < %u)\n", blockIdx.x, s, v, target);
+            __trap();
+          }
+        } while (v < target);
+      }
+      __syncthreads();
+    }
+    for (int b0 = 0; b0 < prm.batch; b0 += kChunk) {
+      const int nb = min(kChunk, prm.batch - b0);
+      // ---- stage h_{t-1} of the chunk (tf32-rounded; zeros at the first step, for finished / absent utterances) ----
+      for (int i = tid; i < kChunk * (kHidden / 4); i += kThreads) {
+        const int bb = i / (kHidden / 4), k4 = i % (kHidden / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bb < nb && s > 0) {
+          const int b = b0 + bb;
+          const int len = prm.lens ? prm.lens[b] : prm.frames;
+          if (s < len) {
+            const int tprev = dir == 0 ? s - 1 : len - s;
+            v = __ldcg(reinterpret_cast<const float4*>(prm.hcat + (static_cast<size_t>(b) * prm.frames + tprev) * H2 +
+                                                       dir * kHidden) + k4);
+          }
+        }
+        float* dst = sh_h + bb * kHPitch + 4 * k4;
+        dst[0] = __uint_as_float(to_tf32(v.x)); dst[1] = __uint_as_float(to_tf32(v.y));
+        dst[2] = __uint_as_float(to_tf32(v.z)); dst[3] = __uint_as_float(to_tf32(v.w));
+      }
+      __syncthreads();
+      // ---- partial product of this warp's K slice: (16 utterances) x (40 rows) ----
+      {
+        float acc[5][4];
+#pragma unroll
+        for (int nt = 0; nt < 5; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+        const float* hp = sh_h + g * kHPitch + warp * 64 + t4;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          uint32_t a[4];
+          a[0] = __float_as_uint(hp[ks * 8]);
+          a[1] = __float_as_uint(hp[8 * kHPitch + ks * 8]);
+          a[2] = __float_as_uint(hp[ks * 8 + 4]);
+          a[3] = __float_as_uint(hp[8 * kHPitch + ks * 8 + 4]);
+#pragma unroll
+          for (int nt = 0; nt < 5; ++nt) mma_tf32_16x8x8(acc[nt], a, wb[ks][nt][0], wb[ks][nt][1]);
+        }
+        // C fragment: (utt g, row nt*8 + 2 t4 + {0,1}), (utt g + 8, ...)
+        float* pp = sh_part + warp * (kChunk * kRows);
+#pragma unroll
+        for (int nt = 0; nt < 5; ++nt) {
+          *reinterpret_cast<float2*>(pp + g * kRows + nt * 8 + 2 * t4) = make_float2(acc[nt][0], acc[nt][1]);
+          *reinterpret_cast<float2*>(pp + (g + 8) * kRows + nt * 8 + 2 * t4) = make_float2(acc[nt][2], acc[nt][3]);
+        }
+      }
+      __syncthreads();
+      // ---- sum the ten K slices (fixed order) + the input projection ----
+      for (int i = tid; i < nb * kRows; i += kThreads) {
+        const int bb = i / kRows, r = i % kRows;
+        const int b = b0 + bb;
+        const int len = prm.lens ? prm.lens[b] : prm.frames;
+        if (s >= len) continue;
+        const int t = dir == 0 ? s : len - 1 - s;
+        const int grow = (r / kUnits) * kHidden + part * kUnits + (r % kUnits);
+        float z = __ldg(prm.gin + (static_cast<size_t>(b) * prm.frames + t) * G + dir * 4 * kHidden + grow);
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) z += sh_part[w * (kChunk * kRows) + i];
+        sh_z[i] = z;
+      }
+      __syncthreads();
+      // ---- gate math for (utterance, unit) ----
+      if (tid < nb * kUnits) {
+        const int bb = tid / kUnits, u = tid % kUnits;
+        const int b = b0 + bb;
+        const int len = prm.lens ? prm.lens[b] : prm.frames;
+        if (s < len) {
+          const int t = dir == 0 ? s : len - 1 - s;
+          const float* zr = sh_z + bb * kRows;
+          const float zi = zr[u], zf = zr[kUnits + u], zg = zr[2 * kUnits + u], zo = zr[3 * kUnits + u];
+          float c = sh_c[b * kUnits + u];
+          c = sigmoidf_acc(zf) * c + sigmoidf_acc(zi) * tanhf(zg);
+          const float h = sigmoidf_acc(zo) * tanhf(c);
+          sh_c[b * kUnits + u] = c;
+          __stcg(prm.hcat + (static_cast<size_t>(b) * prm.frames + t) * H2 + dir * kHidden + part * kUnits + u, h);
+        }
+      }
+      // (no barrier needed here: the next chunk's staging writes sh_h, which nobody reads any more, and the barrier after
+      // it orders sh_part / sh_z)
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+  }
+}
+
 }  // namespace
 
 // hcat must be zero-initialised by the caller where rows past lens[b] are expected to read as zero.
 int lstm_recurrence(const float* gin, const float* w_hh_fwd, const float* w_hh_bwd, const int32_t* lens, float* hcat,
-                    unsigned int* counters, int batch, int frames, int max_len, int hidden,
+                    unsigned int* counters, int batch, int frames, int max_len, int hidden, bool tensor_cores,
                     cudaStream_t stream) {
   if (hidden != kHidden) return fail(M2S_ERR_UNSUPPORTED, "LSTM recurrence is specialised for hidden=640 (got %d)", hidden);
   if (batch <= 0 || max_len <= 0) return M2S_OK;
-  const size_t dyn = static_cast<size_t>(batch) * kUnits * sizeof(float);
-  if (dyn > 64 * 1024) return fail(M2S_ERR_UNSUPPORTED, "LSTM batch %d too large for one launch (max 1638)", batch);
+  static const bool mma_on = !(std::getenv("M2S_LSTM_MMA") && std::atoi(std::getenv("M2S_LSTM_MMA")) == 0);
+  const bool mma = tensor_cores && mma_on;
+  const size_t cells = static_cast<size_t>(batch) * kUnits * sizeof(float);
+  const size_t dyn = mma ? (static_cast<size_t>(kChunk) * kHPitch + static_cast<size_t>(kWarps + 1) * kChunk * kRows) * sizeof(float) + cells
+                         : cells;
+  if (dyn > 160 * 1024) return fail(M2S_ERR_UNSUPPORTED, "LSTM batch %d too large for one launch", batch);
   LstmParams prm{};
   prm.gin = gin; prm.w_hh[0] = w_hh_fwd; prm.w_hh[1] = w_hh_bwd; prm.lens = lens; prm.hcat = hcat;
   prm.counters = counters; prm.batch = batch; prm.frames = frames; prm.max_len = max_len;
   static PerDeviceOnce attr_once;
   M2S_TRY(attr_once.run([&]() -> int {
-    M2S_CUDA_OK(cudaFuncSetAttribute(lstm_recurrence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    M2S_CUDA_OK(cudaFuncSetAttribute(lstm_recurrence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    M2S_CUDA_OK(cudaFuncSetAttribute(lstm_recurrence_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     return M2S_OK;
   }));
   M2S_CUDA_OK(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), stream));
   void* args[] = {&prm};
-  M2S_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_recurrence_kernel), dim3(2 * kParts),
-                                          dim3(kThreads), args, dyn, stream));
+  M2S_CUDA_OK(cudaLaunchCooperativeKernel(mma ? reinterpret_cast<void*>(lstm_recurrence_mma_kernel)
+                                              : reinterpret_cast<void*>(lstm_recurrence_kernel),
+                                          dim3(2 * kParts), dim3(kThreads), args, dyn, stream));
   return M2S_OK;
 }
 
