@@ -115,8 +115,8 @@ struct GemmLayer {
   void* w16 = nullptr;   // 1x1 layers of the fp16 build: plain [n][c_in] fp16, K-major (TMA operand of the fused MBConv kernels)
   int taps = 1;
   int shift[M2S_MAX_TAPS] = {};
-  int planes = 1;                    // interleaved A planes (pixel-pair layers of stage 0), see ConvProblem::a_planes
-  int plane[M2S_MAX_TAPS] = {};
+  int tap_ksteps = 0;                // per-tap K windows (pixel-pair layers of stage 0), see ConvProblem::tap_ksteps
+  int kofs[M2S_MAX_TAPS] = {};
 };
 
 void free_gemm(GemmLayer* L) {
@@ -159,36 +159,38 @@ int make_conv_layer(const TMap& m, const std::string& conv, const std::string& b
 
 // 3x3 stride-1 conv over the zero-bordered layout with TWO consecutive pixels per GEMM row (N = 2 * cout): the convs of
 // stage 0 have 16 output channels, and an M128 x N16 MMA fetches 4 KB of A for 32 K MACs -- the tensor core spends its time
-// on operand fetches (SURVEY.md 8a-1 "stage 0/1 are large-M/small-N").  Output pixel o = 2 Q + p (p = 0, 1) reads input
-// pixels o + (dy - 1) * pitch + (dx - 1) = 2 Q + t with t = (dy - 1) * pitch + s - 1, s = p + dx in 0..3: tap (dy, s) is
-// plane t mod 2, pair-row shift floor(t / 2) of the input seen as (pair rows, 2, cin), and its weight block holds
-// W[dy][s - p] for the p whose dx = s - p is a real tap (zeros otherwise: 12 taps for 9, a quarter of the MACs are padding).
+// on operand fetches (SURVEY.md 8a-1 "stage 0/1 are large-M/small-N").  The GEMM row Q is pixels 2 Q, 2 Q + 1 side by side
+// (2 * cin channels: one 128- or 64-byte row).  Output pixel o = 2 Q + p (p = 0, 1) reads input pixels
+// o + (dy - 1) * pitch + (dx - 1) = 2 Q + t with t = (dy - 1) * pitch + s - 1, s = p + dx in 0..3: tap (dy, s) is row shift
+// floor(t / 2) and the K window of pixel t mod 2, and its weight block holds W[dy][s - p] for the p whose dx = s - p is a
+// real tap (zeros otherwise, and zeros outside the K window: 12 taps for 9, a quarter of the MACs are padding).
 int make_pair_conv_layer(const TMap& m, const std::string& conv, const std::string& bn, int cout, int cin, int pitch,
                          int pack, GemmLayer* L) {
   const HT* w;
   M2S_TRY(need(m, conv + ".weight", static_cast<size_t>(cout) * cin * 9, &w));
   std::vector<float> s, t;
   M2S_TRY(bn_fold(m, bn, cout, &s, &t));
-  const int taps = 12, n = 2 * cout;
-  std::vector<float> e(static_cast<size_t>(taps) * n * cin, 0.f);
+  const int taps = 12, n = 2 * cout, k2 = 2 * cin;
+  std::vector<float> e(static_cast<size_t>(taps) * n * k2, 0.f);
   for (int dy = 0; dy < 3; ++dy)
     for (int sx = 0; sx < 4; ++sx) {
       const int tap = dy * 4 + sx;
+      const int tt = (dy - 1) * pitch + sx - 1;
+      const int plane = ((tt % 2) + 2) % 2;
+      L->shift[tap] = (tt - plane) / 2;            // floor(tt / 2)
+      L->kofs[tap] = plane * (cin / 16);           // K-steps of 16 channels
       for (int p = 0; p < 2; ++p) {
         const int dx = sx - p;
         if (dx < 0 || dx > 2) continue;
         for (int o = 0; o < cout; ++o)
           for (int c = 0; c < cin; ++c)
-            e[(static_cast<size_t>(tap) * n + p * cout + o) * cin + c] =
+            e[(static_cast<size_t>(tap) * n + p * cout + o) * k2 + plane * cin + c] =
                 w->data[(static_cast<size_t>(o) * cin + c) * 9 + dy * 3 + dx] * s[o];
       }
-      const int tt = (dy - 1) * pitch + sx - 1;
-      L->plane[tap] = ((tt % 2) + 2) % 2;
-      L->shift[tap] = (tt - L->plane[tap]) / 2;   // floor(tt / 2)
     }
   L->taps = taps;
-  L->planes = 2;
-  M2S_TRY(pack_weights(e.data(), taps, n, cin, pack, &L->w));
+  L->tap_ksteps = cin / 16;
+  M2S_TRY(pack_weights(e.data(), taps, n, k2, pack, &L->w));
   std::vector<float> t2(n);
   for (int i = 0; i < n; ++i) t2[i] = t[i % cout];
   return upload(t2, &L->bias);
@@ -229,10 +231,10 @@ struct m2s_acoustic {
   // fused block kernels (fp16 build): bit0 = InvertedResidual expand + depthwise + squeeze in one kernel, bit1 = SE scale
   // inside the project GEMM (csrc/mbconv_sm100.cu); bit2 = EdgeResidual 3x3 expand + 1x1 project in one kernel
   // (csrc/fused_er_sm100.cu); bit3 = that kernel also where the weights must be streamed per tile (slower); bit4 = stage 0's
-  // 3x3 convs with two pixels per GEMM row (N = 32 instead of 16; measured: no faster, off by default); bit5 = fp16
+  // 3x3 convs with two pixels per GEMM row (N = 32 instead of 16: per-tap K windows of the conv engine); bit5 = fp16
   // residual stream (no fp32 copies of the block outputs).  M2S_MBCONV=0 keeps the unfused launches and the fp32 stream
   // (the A/B reference of tests/).
-  int mbconv = 39;
+  int mbconv = 55;
   int chunk = 2048;  // frames per encoder pass (M2S_ENCODER_CHUNK): 2048 frames = ~14 GB of work buffers.  Measured with the
                      // round-2 kernels: 14.1 / 12.6 / 12.1 / 12.2 us per frame at 512 / 1024 / 2048 / 4096 (fp16 build)
   // per-frame buffer sizes (floats)
@@ -378,9 +380,9 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
         // two pixels per GEMM row over EVERY pair-row of the padded frame (no offset, no mask: the border pixels come
         // out as garbage and are zeroed below)
         const int prow = rows / 2;
-        ConvProblem p = gemm_problem(op(x), prow, prow, b.cin, n, prow, y.f32, prow, 2 * b.cout, 0, b.pair);
-        p.a_planes = 2;
-        for (int j = 0; j < b.pair.taps; ++j) p.plane[j] = b.pair.plane[j];
+        ConvProblem p = gemm_problem(op(x), prow, prow, 2 * b.cin, n, prow, y.f32, prow, 2 * b.cout, 0, b.pair);
+        p.tap_ksteps = b.pair.tap_ksteps;
+        for (int j = 0; j < b.pair.taps; ++j) p.kofs[j] = b.pair.kofs[j];
         set_block_out(&p);
         p.epi.act = M2S_ACT_SILU;
         if (b.skip) { set_skip(&p, 2 * b.cin); p.epi.res_after_act = 1; }
@@ -602,7 +604,7 @@ extern "C" int m2s_acoustic_create(const m2s_acoustic_config* cfg, const m2s_ten
         b.out_padded = true;
         if ((st = make_conv_layer(tm, p + ".conv", p + ".bn1", b.cout, cin, 3, w + 2, 0, enc_pack, &b.conv)) != M2S_OK)
           return bail(st);
-        if ((m->mbconv & 16) && (w + 2) % 2 == 0 && ((h + 2) * (w + 2)) % 2 == 0 && b.cout % 8 == 0 &&
+        if ((m->mbconv & 16) && (w + 2) % 2 == 0 && ((h + 2) * (w + 2)) % 2 == 0 && b.cout % 8 == 0 && cin % 16 == 0 &&
             (st = make_pair_conv_layer(tm, p + ".conv", p + ".bn1", b.cout, cin, w + 2, enc_pack, &b.pair)) != M2S_OK)
           return bail(st);
         m->x_floats = std::max(m->x_floats, padded_rows(ho, wo) * b.cout);

@@ -24,6 +24,7 @@
 //   warps 2-17: epilogue (four per TMEM lane quadrant, 32 x 16 units): tcgen05.ld -> SMEM transpose -> bias / residual /
 //              MRF accumulate / scale / activation / mask -> coalesced global stores
 #include "engine_device.cuh"
+#include <algorithm>
 #include <cstdlib>
 #include <atomic>
 #include <cstring>
@@ -98,17 +99,10 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           mbar_wait(a_empty(sa), pa ^ 1);
           if (cb == 0 && lane == 0) trace_stamp(prm, it, 1);
           if (elect_one()) {
-            mbar_expect_tx(a_full(sa), a_bytes * prm.a_planes);
-            if (prm.a_planes == 1) {
-              for (int bx = 0; bx < prm.a_nbox; ++bx)
-                tma_load_3d(a_base + sa * prm.a_stage_bytes + bx * prm.a_box_rows * row_bytes, &tmap_a, a_full(sa),
-                            cb * prm.kblock, q0 + prm.shift_min + bx * prm.a_box_rows, b);
-            } else {
-              for (int pl = 0; pl < prm.a_planes; ++pl)
-                for (int bx = 0; bx < prm.a_nbox; ++bx)
-                  tma_load_4d(a_base + sa * prm.a_stage_bytes + (pl * prm.a_nbox + bx) * prm.a_box_rows * row_bytes, &tmap_a,
-                              a_full(sa), cb * prm.kblock, pl, q0 + prm.shift_min + bx * prm.a_box_rows, b);
-            }
+            mbar_expect_tx(a_full(sa), a_bytes);
+            for (int bx = 0; bx < prm.a_nbox; ++bx)
+              tma_load_3d(a_base + sa * prm.a_stage_bytes + bx * prm.a_box_rows * row_bytes, &tmap_a, a_full(sa),
+                          cb * prm.kblock, q0 + prm.shift_min + bx * prm.a_box_rows, b);
           }
           __syncwarp();
           if (++sa == prm.na) { sa = 0; pa ^= 1; }
@@ -175,7 +169,11 @@ conv_engine_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 const uint32_t first = (cb | tap0 | t) ? 1u : 0u;
                 const uint64_t da0 = desc_hi | (((a_tile + row_shift * row_bytes) & 0x3FFFF) >> 4);
                 const uint32_t sub_step = (128 * row_bytes) >> 4;   // next 128-row sub-tile of the A stage
-                if (prm.half) {
+                if (prm.tap_ksteps) {   // per-tap K window (fp16 only): both descriptors advance 32 bytes per K-step
+                  const uint32_t ko = 2u * prm.tap_kofs[tap0 + t];
+                  for (int sub = 0; sub < msub; ++sub)
+                    mma_f16_k4(tmem_acc + sub * n_tile, da0 + ko + sub * sub_step, db + ko, prm.idesc, first, prm.tap_ksteps);
+                } else if (prm.half) {
                   for (int sub = 0; sub < msub; ++sub)
                     mma_f16_k4(tmem_acc + sub * n_tile, da0 + sub * sub_step, db, prm.idesc, first, ksteps);
                 } else {
@@ -504,9 +502,9 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
   if (w.n != p.n || w.c_in != p.c_in || w.taps != p.taps)
     return fail(M2S_ERR_BAD_ARG, "packed weights do not match the problem");
   if (p.batch <= 0 || p.l_out <= 0) return M2S_OK;
-  const int planes = p.a_planes > 1 ? p.a_planes : 1;
-  if (planes > 1 && engine_knobs().a_per_tap) return fail(M2S_ERR_UNSUPPORTED, "interleaved A planes with the per-tap A fallback");
-  if (w.dev_pair && planes == 1 && engine_knobs().pair && !engine_knobs().a_per_tap && !engine_knobs().trace) {
+  if (p.tap_ksteps && (!w.half || w.cblocks != 1 || engine_knobs().a_per_tap))
+    return fail(M2S_ERR_UNSUPPORTED, "per-tap K windows need fp16 operands in a single K block");
+  if (w.dev_pair && !p.tap_ksteps && engine_knobs().pair && !engine_knobs().a_per_tap && !engine_knobs().trace) {
     // CTA-pair (cta_group::2) kernel when the layer is wide, or narrow but bound by the MMA's SMEM operand fetch
     // rather than by HBM (measured model: ~75 B/clk/SM of operand fetch, ~23 B/clk/SM of HBM).
     const long long pair_tiles = static_cast<long long>(p.batch) * ((p.l_out + 255) / 256) * w.n_tiles_pair;
@@ -547,7 +545,8 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
   for (int j = 1; j < p.taps; ++j) { smin = p.shift[j] < smin ? p.shift[j] : smin; smax = p.shift[j] > smax ? p.shift[j] : smax; }
   prm.shift_min = smin;
   const int halo = prm.a_per_tap ? 0 : smax - smin;
-  prm.a_planes = planes;
+  prm.tap_ksteps = p.tap_ksteps;
+  for (int j = 0; j < p.taps; ++j) prm.tap_kofs[j] = p.tap_ksteps ? p.kofs[j] : 0;
 
   // M sub-tiles per CTA: 2 halves the weight traffic per output row; use it when there is enough work.
   int msub = knobs.msub;
@@ -560,8 +559,11 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
     msub = 1;
     for (int cand = 2; cand <= 8; cand *= 2) {
       const long long tiles = static_cast<long long>(p.batch) * ((p.l_out + 128 * cand - 1) / (128 * cand)) * w.n_tiles;
-      const size_t a_stage = static_cast<size_t>(128 * cand + halo + 16) * w.row_bytes * planes;
+      const size_t a_stage = static_cast<size_t>(128 * cand + halo + 16) * w.row_bytes;
+      const size_t tap_b = static_cast<size_t>(w.n_tile) * w.row_bytes;
+      const size_t b_stage = std::min<size_t>(static_cast<size_t>(p.taps), std::max<size_t>(1, 32768 / tap_b)) * tap_b;
       if (2 * cand * w.n_tile <= kTmemCols && tiles >= 2LL * sm_count() && 2 * a_stage <= 150 * 1024 &&
+          2 * a_stage + 2 * b_stage <= 186 * 1024 &&
           (cand <= 2 || (halo >= 64 && w.n_tile <= 64)))
         msub = cand;
     }
@@ -577,10 +579,9 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
   const int a_rows_needed = prm.m_tile + halo;
   prm.a_nbox = (a_rows_needed + 255) / 256;
   prm.a_box_rows = (((a_rows_needed + prm.a_nbox - 1) / prm.a_nbox) + 7) / 8 * 8;
-  prm.a_stage_bytes = static_cast<uint32_t>(planes * prm.a_nbox * prm.a_box_rows * w.row_bytes);
+  prm.a_stage_bytes = static_cast<uint32_t>(prm.a_nbox * prm.a_box_rows * w.row_bytes);
   prm.a_stage_bytes = (prm.a_stage_bytes + 1023u) & ~1023u;
-  for (int j = 0; j < p.taps; ++j)
-    prm.rel_shift[j] = (planes > 1 ? p.plane[j] * prm.a_nbox * prm.a_box_rows : 0) + p.shift[j] - smin;
+  for (int j = 0; j < p.taps; ++j) prm.rel_shift[j] = p.shift[j] - smin;
   prm.b_tap_bytes = static_cast<uint32_t>(w.n_tile * w.row_bytes);
   // several taps share one weight stage when the per-tap block is small (amortises barrier round trips)
   int tg = static_cast<int>(32768u / prm.b_tap_bytes);
@@ -625,23 +626,9 @@ int conv_tcgen05(const ConvProblem& p, const PackedWeights& w, cudaStream_t stre
   cuuint32_t estr[3] = {1u, 1u, 1u};
   const CUtensorMapDataType dt = w.half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
                                         : (knobs.tmap_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
-  CUresult cr;
-  if (planes == 1) {
-    cr = enc(&tmap, dt, 3, const_cast<float*>(p.a), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             w.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  } else {
-    // (c_in, plane, a_rows, batch): a GEMM row is `planes` consecutive a_ld-element rows of the tensor
-    cuuint64_t gdim4[4] = {static_cast<cuuint64_t>(p.c_in), static_cast<cuuint64_t>(planes), static_cast<cuuint64_t>(p.a_rows),
-                           static_cast<cuuint64_t>(p.batch)};
-    cuuint64_t gstride4[3] = {static_cast<cuuint64_t>(p.a_ld) * esize, static_cast<cuuint64_t>(p.a_ld) * esize * planes,
-                              static_cast<cuuint64_t>(p.a_batch_rows) * static_cast<cuuint64_t>(p.a_ld) * esize * planes};
-    cuuint32_t box4[4] = {static_cast<cuuint32_t>(w.kblock), 1u, static_cast<cuuint32_t>(prm.a_box_rows), 1u};
-    cuuint32_t estr4[4] = {1u, 1u, 1u, 1u};
-    cr = enc(&tmap, dt, 4, const_cast<float*>(p.a), gdim4, gstride4, box4, estr4, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             w.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  }
+  CUresult cr = enc(&tmap, dt, 3, const_cast<float*>(p.a), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    w.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS)
     return fail(M2S_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): c_in=%d rows=%d batch=%d ld=%d box_rows=%d",
                 static_cast<int>(cr), p.c_in, p.a_rows, p.batch, p.a_ld, prm.a_box_rows);

@@ -49,7 +49,8 @@ struct EngineParams {
   uint32_t idesc;
   int base_offset_mode;
   int a_per_tap;
-  int a_planes;         // interleaved A planes per stage (1 = plain); plane p of a stage starts p * a_nbox * a_box_rows rows in
+  int tap_ksteps;       // per-tap K windows (0 = off): tap j contracts K-steps tap_kofs[j] .. + tap_ksteps - 1 of its K block
+  int tap_kofs[M2S_MAX_TAPS];
   int rel_shift[M2S_MAX_TAPS];
   int tg;               // taps per weight stage
   uint32_t b_tap_bytes; // bytes of one tap's weight block (n_tile x 128)

@@ -86,11 +86,13 @@ struct ConvProblem {
   int a_half;          // A operand is fp16 (tcgen05 kind::f16); 0 = fp32 rounded to tf32 by TMA
   void* d16;           // optional second output, fp16, indexed like d (same d_ld in elements); null = none
   void* d16_lo;        // optional lo plane of the split-fp16 pair (d16 = hi): fp16(v - float(fp16(v))); needs d16
-  // Interleaved A planes (internal; 0 / 1 = off).  With a_planes = P the A tensor is read as (batch, a_rows, P, c_in): GEMM
-  // row q of tap j is A[b, q + shift[j], plane[j], :].  This is how a conv over P consecutive pixels per GEMM row (N =
-  // P * C_out: the narrow first stage of the encoder) addresses pixel 2 q + t as plane t mod P, row q + floor(t / P).
-  int a_planes;
-  int plane[M2S_MAX_TAPS];
+  // Per-tap K windows (internal; tap_ksteps = 0: off).  When set, tap j contracts only K-steps kofs[j] .. kofs[j] +
+  // tap_ksteps - 1 (16 fp16 elements each) of the single K block -- of the A row AND of its weight block.  This is how a
+  // conv over P consecutive pixels per GEMM row (N = P * C_out: the narrow first stage of the encoder) reads pixel
+  // P q + t: the GEMM row is the P pixels' channels side by side (one 64 / 128-byte row), tap (.., t) is row shift
+  // floor(t / P) and the K window of pixel t mod P; the weight blocks carry zeros outside their window.
+  int tap_ksteps;
+  int kofs[M2S_MAX_TAPS];
 };
 
 inline ConvProblem problem_from_args(const m2s_conv_args& a) {

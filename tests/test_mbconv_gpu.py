@@ -45,7 +45,7 @@ def _frames(n, seed=0):
     return synth.synthetic_clip(seed, n).cuda()
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3, 4, 12, 16, 23, 32, 39])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 12, 16, 23, 32, 39, 55])
 @pytest.mark.parametrize("n", [5, 301])
 def test_fused_equals_unfused(mode, n):
     """5 frames: partial tiles (two 8x8 frames per tile, odd count); 301 frames: several tiles per CTA (ring phases wrap)."""
@@ -80,7 +80,7 @@ def test_fused_default_is_on():
         plain = m.launches_per_forward()
     finally:
         os.environ.pop("M2S_MBCONV", None)
-    assert plain - fused == 42
+    assert plain - fused == 40                       # 42 launches fewer, 2 border-column passes more
 
 
 def test_stride2_depthwise_tma_equals_slab_kernel():
