@@ -647,15 +647,23 @@ int enc_dwconv(const void* in, void* out, int half, float* sums, const float* w,
 // SE MLP alone: sums[n][C] (squeeze sums over hw pixels) -> excite scales, in place
 int enc_se_mlp(float* sums, const float* w1, const float* b1, const float* w2, const float* b2, int n, int C, int rd, int hw,
                cudaStream_t st) {
-  constexpr int kF = 8;  // frames per MLP block
-  const size_t sm_mlp = (static_cast<size_t>(kF) * C + static_cast<size_t>(kF) * rd) * sizeof(float);
+  // Frames per MLP block: every block reads the whole weight set (2 * rd * C floats: 520 KB at C = 1248) from L2, so with 8
+  // frames per block a 2048-frame chunk pulled 133 MB through L2 per launch (50 us: L2-bound).  16 frames per block when
+  // the chunk still fills the machine, 8 otherwise.  (M2S_SE_MLP_KF overrides: 8 or 16.)
+  static const int kf_env = std::getenv("M2S_SE_MLP_KF") ? std::atoi(std::getenv("M2S_SE_MLP_KF")) : 0;
+  const int kf = kf_env == 8 || kf_env == 16 ? kf_env : (n >= 16 * 128 ? 16 : 8);
+  const size_t sm_mlp = (static_cast<size_t>(kf) * C + static_cast<size_t>(kf) * rd) * sizeof(float);
   static PerDeviceOnce attr_once;
   M2S_TRY(attr_once.run([&]() -> int {
-    M2S_CUDA_OK(cudaFuncSetAttribute(se_mlp_kernel<kF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    M2S_CUDA_OK(cudaFuncSetAttribute(se_mlp_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    M2S_CUDA_OK(cudaFuncSetAttribute(se_mlp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     return M2S_OK;
   }));
   if (sm_mlp > 100 * 1024) return fail(M2S_ERR_UNSUPPORTED, "squeeze-excite: %d channels exceed the MLP kernel's SMEM", C);
-  se_mlp_kernel<kF><<<(n + kF - 1) / kF, 1024, sm_mlp, st>>>(sums, w1, b1, w2, b2, C, rd, 1.f / hw, n);
+  if (kf == 16)
+    se_mlp_kernel<16><<<(n + 15) / 16, 1024, sm_mlp, st>>>(sums, w1, b1, w2, b2, C, rd, 1.f / hw, n);
+  else
+    se_mlp_kernel<8><<<(n + 7) / 8, 1024, sm_mlp, st>>>(sums, w1, b1, w2, b2, C, rd, 1.f / hw, n);
   M2S_CUDA_OK(cudaGetLastError());
   return M2S_OK;
 }
