@@ -110,14 +110,19 @@ class MriToSpeech:
         return {"mel_norm": pred, "mel_db": mel_db, "mel_log": mel_log, "audio": wav}
 
     @staticmethod
-    def plan_micro_batches(lengths: Sequence[int], max_batch_frames: int) -> List[List[int]]:
+    def plan_micro_batches(lengths: Sequence[int], max_batch_frames: int, ramp: bool = False) -> List[List[int]]:
         """Clip indices sorted by length (longest first) and cut into micro-batches of at most ``max_batch_frames``
-        PADDED frames (batch x longest clip: what the recurrence and the vocoder run on)."""
+        PADDED frames (batch x longest clip: what the recurrence and the vocoder run on).  ``ramp``: the first two
+        micro-batches get a quarter / half of the budget -- for clips that still have to cross PCIe, so that the GPU
+        starts after a quarter of a micro-batch's copy instead of a whole one (nothing hides the first copy)."""
         order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
         plan, i = [], 0
         while i < len(order):
             tmax = int(lengths[order[i]])
-            nb = max(1, min(len(order) - i, max_batch_frames // max(tmax, 1)))
+            budget = max_batch_frames
+            if ramp and len(plan) < 2:
+                budget = max(max_batch_frames // (4 >> len(plan)), tmax)
+            nb = max(1, min(len(order) - i, budget // max(tmax, 1)))
             plan.append(order[i:i + nb])
             i += nb
         return plan
@@ -138,7 +143,7 @@ class MriToSpeech:
         if not len(clips):
             return []
         lens_all = [int(c.shape[0]) for c in clips]
-        plan = self.plan_micro_batches(lens_all, max_batch_frames)
+        plan = self.plan_micro_batches(lens_all, max_batch_frames, ramp=not clips[0].is_cuda)
         H, W = clips[0].shape[-2:]
         dtype = torch.uint8 if clips[0].dtype == torch.uint8 else torch.float32
         dev = self.device
