@@ -226,13 +226,16 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// MT: m16 tiles (16 utterances each) per pass over the chunk: 2 halves the barriers / staging round trips per step for
+// batches above 16 utterances.
+template <int MT>
 __global__ void __launch_bounds__(kThreads, 1) lstm_recurrence_mma_kernel(LstmParams prm) {
+  constexpr int kCh = 16 * MT;                             // utterances per pass
   extern __shared__ float smem_dyn[];
-  float* sh_h = smem_dyn;                                  // [16][kHPitch] h_{t-1} of the chunk, tf32-rounded
-  float* sh_part = sh_h + kChunk * kHPitch;                // [10 warps][16][40] partial products
-  float* sh_z = sh_part + kWarps * kChunk * kRows;         // [16][40]
-  float* sh_c = sh_z + kChunk * kRows;                     // [batch][kUnits] cell state
-  static_assert(kChunk == 16, "one m16 MMA tile per chunk");
+  float* sh_h = smem_dyn;                                  // [kCh][kHPitch] h_{t-1} of the chunk, tf32-rounded
+  float* sh_part = sh_h + kCh * kHPitch;                   // [10 warps][kCh][40] partial products
+  float* sh_z = sh_part + kWarps * kCh * kRows;            // [kCh][40]
+  float* sh_c = sh_z + kCh * kRows;                        // [batch][kUnits] cell state
 
   const int dir = blockIdx.x / kParts;
   const int part = blockIdx.x % kParts;
@@ -258,6 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_recurrence_mma_kernel(LstmPa
   __syncthreads();
 
   unsigned int* counter = prm.counters + dir;
+  constexpr int kZPerThread = (kCh * kRows + kThreads - 1) / kThreads;   // (utterance, row) sums per thread: 2 or 4
 
   for (int s = 0; s < prm.max_len; ++s) {
     if (s > 0) {
@@ -275,10 +279,27 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_recurrence_mma_kernel(LstmPa
       }
       __syncthreads();
     }
-    for (int b0 = 0; b0 < prm.batch; b0 += kChunk) {
-      const int nb = min(kChunk, prm.batch - b0);
+    for (int b0 = 0; b0 < prm.batch; b0 += kCh) {
+      const int nb = min(kCh, prm.batch - b0);
+      // the input projections this thread will add below: requested now, used after the MMAs
+      float zin[kZPerThread];
+#pragma unroll
+      for (int j = 0; j < kZPerThread; ++j) {
+        const int i = tid + j * kThreads;
+        zin[j] = 0.f;
+        if (i < nb * kRows) {
+          const int bb = i / kRows, r = i % kRows;
+          const int b = b0 + bb;
+          const int len = prm.lens ? prm.lens[b] : prm.frames;
+          if (s < len) {
+            const int t = dir == 0 ? s : len - 1 - s;
+            const int grow = (r / kUnits) * kHidden + part * kUnits + (r % kUnits);
+            zin[j] = __ldg(prm.gin + (static_cast<size_t>(b) * prm.frames + t) * G + dir * 4 * kHidden + grow);
+          }
+        }
+      }
       // ---- stage h_{t-1} of the chunk (tf32-rounded; zeros at the first step, for finished / absent utterances) ----
-      for (int i = tid; i < kChunk * (kHidden / 4); i += kThreads) {
+      for (int i = tid; i < kCh * (kHidden / 4); i += kThreads) {
         const int bb = i / (kHidden / 4), k4 = i % (kHidden / 4);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bb < nb && s > 0) {
@@ -295,12 +316,14 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_recurrence_mma_kernel(LstmPa
         dst[2] = __uint_as_float(to_tf32(v.z)); dst[3] = __uint_as_float(to_tf32(v.w));
       }
       __syncthreads();
-      // ---- partial product of this warp's K slice: (16 utterances) x (40 rows) ----
-      {
+      // ---- partial product of this warp's K slice: (16 MT utterances) x (40 rows) ----
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        if (mt * 16 >= nb) break;   // (block-uniform)
         float acc[5][4];
 #pragma unroll
         for (int nt = 0; nt < 5; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-        const float* hp = sh_h + g * kHPitch + warp * 64 + t4;
+        const float* hp = sh_h + (mt * 16 + g) * kHPitch + warp * 64 + t4;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
           uint32_t a[4];
@@ -312,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_recurrence_mma_kernel(LstmPa
           for (int nt = 0; nt < 5; ++nt) mma_tf32_16x8x8(acc[nt], a, wb[ks][nt][0], wb[ks][nt][1]);
         }
         // C fragment: (utt g, row nt*8 + 2 t4 + {0,1}), (utt g + 8, ...)
-        float* pp = sh_part + warp * (kChunk * kRows);
+        float* pp = sh_part + warp * (kCh * kRows) + mt * 16 * kRows;
 #pragma unroll
         for (int nt = 0; nt < 5; ++nt) {
           *reinterpret_cast<float2*>(pp + g * kRows + nt * 8 + 2 * t4) = make_float2(acc[nt][0], acc[nt][1]);
@@ -321,22 +344,20 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_recurrence_mma_kernel(LstmPa
       }
       __syncthreads();
       // ---- sum the ten K slices (fixed order) + the input projection ----
-      for (int i = tid; i < nb * kRows; i += kThreads) {
-        const int bb = i / kRows, r = i % kRows;
-        const int b = b0 + bb;
-        const int len = prm.lens ? prm.lens[b] : prm.frames;
-        if (s >= len) continue;
-        const int t = dir == 0 ? s : len - 1 - s;
-        const int grow = (r / kUnits) * kHidden + part * kUnits + (r % kUnits);
-        float z = __ldg(prm.gin + (static_cast<size_t>(b) * prm.frames + t) * G + dir * 4 * kHidden + grow);
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) z += sh_part[w * (kChunk * kRows) + i];
-        sh_z[i] = z;
+      for (int j = 0; j < kZPerThread; ++j) {
+        const int i = tid + j * kThreads;
+        if (i < nb * kRows) {
+          float z = zin[j];
+#pragma unroll
+          for (int w = 0; w < kWarps; ++w) z += sh_part[w * (kCh * kRows) + i];
+          sh_z[i] = z;
+        }
       }
       __syncthreads();
       // ---- gate math for (utterance, unit) ----
-      if (tid < nb * kUnits) {
-        const int bb = tid / kUnits, u = tid % kUnits;
+      for (int i = tid; i < nb * kUnits; i += kThreads) {
+        const int bb = i / kUnits, u = i % kUnits;
         const int b = b0 + bb;
         const int len = prm.lens ? prm.lens[b] : prm.frames;
         if (s < len) {
@@ -370,22 +391,25 @@ int lstm_recurrence(const float* gin, const float* w_hh_fwd, const float* w_hh_b
   static const bool mma_on = !(std::getenv("M2S_LSTM_MMA") && std::atoi(std::getenv("M2S_LSTM_MMA")) == 0);
   const bool mma = tensor_cores && mma_on;
   const size_t cells = static_cast<size_t>(batch) * kUnits * sizeof(float);
-  const size_t dyn = mma ? (static_cast<size_t>(kChunk) * kHPitch + static_cast<size_t>(kWarps + 1) * kChunk * kRows) * sizeof(float) + cells
+  const int mt = batch > 16 ? 2 : 1;   // m16 tiles per pass
+  const size_t dyn = mma ? (static_cast<size_t>(16 * mt) * kHPitch + static_cast<size_t>(kWarps + 1) * 16 * mt * kRows) * sizeof(float) + cells
                          : cells;
-  if (dyn > 160 * 1024) return fail(M2S_ERR_UNSUPPORTED, "LSTM batch %d too large for one launch", batch);
+  if (dyn > (mma ? 200 : 160) * 1024) return fail(M2S_ERR_UNSUPPORTED, "LSTM batch %d too large for one launch", batch);
   LstmParams prm{};
   prm.gin = gin; prm.w_hh[0] = w_hh_fwd; prm.w_hh[1] = w_hh_bwd; prm.lens = lens; prm.hcat = hcat;
   prm.counters = counters; prm.batch = batch; prm.frames = frames; prm.max_len = max_len;
   static PerDeviceOnce attr_once;
   M2S_TRY(attr_once.run([&]() -> int {
     M2S_CUDA_OK(cudaFuncSetAttribute(lstm_recurrence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    M2S_CUDA_OK(cudaFuncSetAttribute(lstm_recurrence_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    M2S_CUDA_OK(cudaFuncSetAttribute(lstm_recurrence_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    M2S_CUDA_OK(cudaFuncSetAttribute(lstm_recurrence_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     return M2S_OK;
   }));
   M2S_CUDA_OK(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), stream));
   void* args[] = {&prm};
-  M2S_CUDA_OK(cudaLaunchCooperativeKernel(mma ? reinterpret_cast<void*>(lstm_recurrence_mma_kernel)
-                                              : reinterpret_cast<void*>(lstm_recurrence_kernel),
+  void* fn = !mma ? reinterpret_cast<void*>(lstm_recurrence_kernel)
+                  : (mt == 2 ? reinterpret_cast<void*>(lstm_recurrence_mma_kernel<2>) : reinterpret_cast<void*>(lstm_recurrence_mma_kernel<1>));
+  M2S_CUDA_OK(cudaLaunchCooperativeKernel(fn,
                                           dim3(2 * kParts), dim3(kThreads), args, dyn, stream));
   return M2S_OK;
 }
