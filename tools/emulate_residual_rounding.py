@@ -3,7 +3,7 @@
 Reproduces the errors measured on the B200 (scaled init: features 6.8e-3 relative, mel 5.2e-2) and shows what the fp16
 residual stream adds (default init: nothing measurable; scaled init: +18 % / +7 %): python tools/emulate_residual_rounding.py"""
 import sys, math, torch, torch.nn.functional as F
-sys.path.insert(0,'/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from oracle import acoustic as A
 from oracle.acoustic import STAGES, STEM_CH, BN_EPS, _conv_same
 from mri2speech_b200 import synth
