@@ -34,7 +34,7 @@ def main():
     for a in per.values():
         a["tensor_pipe_pct_time_weighted"] /= max(a["us"], 1e-9)
         a["dram_GBps"] = a["dram_MB"] / max(a["us"], 1e-9) * 1e3
-    out = {"source": f"{os.path.basename(path)}: {how}", "frames": 1024, "tc_launches": n, "tc_us": tot_t,
+    out = {"source": f"{os.path.basename(path)}: {how}", "frames": int(sys.argv[3]) if len(sys.argv) > 3 else 2048, "tc_launches": n, "tc_us": tot_t,
            "dram_bytes_per_pass": tot_b, "dram_bytes_per_launch": tot_b / max(n, 1),
            "tensor_pipe_active_pct_time_weighted": tp / max(tot_t, 1e-9), "per_kernel": per}
     dst = os.path.join(os.path.dirname(path), "traffic_encoder_engine.json")
