@@ -58,11 +58,6 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   return r;
 }
 __device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
-__device__ __forceinline__ uint32_t hfma2_u(uint32_t a, uint32_t b, uint32_t c) {
-  const __half2 r = __hfma2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b),
-                            *reinterpret_cast<const __half2*>(&c));
-  return *reinterpret_cast<const uint32_t*>(&r);
-}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
