@@ -382,7 +382,14 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_recurrence_mma_kernel(LstmPa
 
 }  // namespace
 
+// lstm_cluster_sm100.cu: the recurrence on 16-CTA clusters (W_hh resident in SMEM, h exchanged through DSMEM)
+int lstm_cluster_max_active();
+int lstm_recurrence_cluster(const float* gin, const float* w_hh_fwd, const float* w_hh_bwd, const int32_t* lens,
+                            float* hcat, int batch, int frames, int hidden, cudaStream_t stream);
+
 // hcat must be zero-initialised by the caller where rows past lens[b] are expected to read as zero.
+// Dispatch: fp32 build -> FMA kernel (grid barrier); tf32 / fp16 builds -> cluster kernel when the device can launch
+// 16-CTA clusters (M2S_LSTM_CLUSTER=0 forces the grid-barrier tensor-core kernel, M2S_LSTM_MMA=0 the FMA kernel).
 int lstm_recurrence(const float* gin, const float* w_hh_fwd, const float* w_hh_bwd, const int32_t* lens, float* hcat,
                     unsigned int* counters, int batch, int frames, int max_len, int hidden, bool tensor_cores,
                     cudaStream_t stream) {
@@ -390,6 +397,9 @@ int lstm_recurrence(const float* gin, const float* w_hh_fwd, const float* w_hh_b
   if (batch <= 0 || max_len <= 0) return M2S_OK;
   static const bool mma_on = !(std::getenv("M2S_LSTM_MMA") && std::atoi(std::getenv("M2S_LSTM_MMA")) == 0);
   const bool mma = tensor_cores && mma_on;
+  static const bool cluster_on = !(std::getenv("M2S_LSTM_CLUSTER") && std::atoi(std::getenv("M2S_LSTM_CLUSTER")) == 0);
+  if (mma && cluster_on && lstm_cluster_max_active() >= 1)
+    return lstm_recurrence_cluster(gin, w_hh_fwd, w_hh_bwd, lens, hcat, batch, frames, hidden, stream);
   const size_t cells = static_cast<size_t>(batch) * kUnits * sizeof(float);
   const int mt = batch > 16 ? 2 : 1;   // m16 tiles per pass
   const size_t dyn = mma ? (static_cast<size_t>(16 * mt) * kHPitch + static_cast<size_t>(kWarps + 1) * 16 * mt * kRows) * sizeof(float) + cells

@@ -56,6 +56,31 @@ def test_bilstm_long_sequence_t600():
     assert (got - ref).abs().max().item() < 1e-3
 
 
+@pytest.mark.parametrize("precision", ["tf32", "fp16"])
+@pytest.mark.parametrize("B,T", [(1, 37), (9, 30), (20, 48), (33, 21), (64, 16), (100, 9)])
+def test_bilstm_cluster_groups(precision, B, T):
+    """The cluster recurrence (lstm_cluster_sm100.cu): one 16-CTA cluster per (direction, group of up to 8 / 16 / 24
+    utterances).  The batch sizes walk through the one-, two- and three-tile kernels, partly filled groups, and more groups
+    than the device holds at once (100 clips); lengths include 1 and T."""
+    from oracle.acoustic import bilstm_head_forward
+    m = _model(precision)
+    g = torch.Generator().manual_seed(100 + B)
+    feats = torch.randn(B, T, 208, generator=g) * 0.5
+    lens = torch.randint(1, T + 1, (B,), generator=g, dtype=torch.int32)
+    lens[0] = T
+    if B > 2:
+        lens[B - 1] = 1
+    got = m.rnn_head(feats.cuda(), lens).cpu()
+    sd = _cpu_sd(m)
+    for b in range(B):
+        ln = int(lens[b])
+        ref = bilstm_head_forward(sd, feats[b:b + 1, :ln])[0]
+        err = (got[b, :ln] - ref).abs().max().item()
+        assert err < 1e-3, (b, ln, err)
+        if ln < T:
+            assert got[b, ln:].abs().max().item() == 0.0
+
+
 @pytest.mark.parametrize("precision,rel_tol", [("fp32", 2e-4), ("tf32", 5e-3), ("fp16", 5e-3)])
 @pytest.mark.parametrize("randomize_bn", [False, True])
 def test_encoder_features(precision, rel_tol, randomize_bn):
