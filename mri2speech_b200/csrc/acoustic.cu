@@ -25,6 +25,7 @@ int enc_zero_rows(void* buf, int esize, int n, int rows_per_frame, int ld, int h
                   cudaStream_t st);
 int enc_zero_cols(void* buf, int esize, int n, int rows_per_frame, int ld, int pitch, int H, cudaStream_t st);
 int enc_im2col_s2(const void* in, void* col, int esize, int n, int Hin, int Win, int C, cudaStream_t st);
+int enc_s2d(const void* in, void* out, int esize, int n, int Hin, int Win, int C, cudaStream_t st);
 int enc_dwconv(const void* in, void* out, int half, float* sums, const float* w, const float* bias, int n, int C, int Hin,
                int Win, int pitch_in, int oy, int ox, int rows_in, int stride, cudaStream_t st);
 int enc_se_apply(void* x, int half, float* sums, const float* w1, const float* b1, const float* w2, const float* b2,
@@ -212,6 +213,7 @@ struct Block {
   bool skip;
   GemmLayer conv;    // CN conv / ER conv_exp / IR conv_pw
   GemmLayer pair;    // CN conv with two pixels per GEMM row (fp16 build; empty otherwise)
+  GemmLayer s2d;     // stride-2 ER conv_exp over the space-to-depth input: 9 taps = K windows of the 4 parity planes (fp16 build)
   GemmLayer pwl;     // ER / IR projection
   float *dw_w = nullptr, *dw_b = nullptr;                                   // IR depthwise [9][mid], [mid]
   void* dw_w16 = nullptr;                                                   // ... and its fp16 copy (fp16 build)
@@ -232,9 +234,10 @@ struct m2s_acoustic {
   // inside the project GEMM (csrc/mbconv_sm100.cu); bit2 = EdgeResidual 3x3 expand + 1x1 project in one kernel
   // (csrc/fused_er_sm100.cu); bit3 = that kernel also where the weights must be streamed per tile (slower); bit4 = stage 0's
   // 3x3 convs with two pixels per GEMM row (N = 32 instead of 16: per-tap K windows of the conv engine); bit5 = fp16
-  // residual stream (no fp32 copies of the block outputs).  M2S_MBCONV=0 keeps the unfused launches and the fp32 stream
-  // (the A/B reference of tests/).
-  int mbconv = 55;
+  // residual stream (no fp32 copies of the block outputs); bit6 = the stride-2 EdgeResidual blocks read a space-to-depth
+  // copy of their input (K windows over the 4 parity planes) instead of an im2col matrix.  M2S_MBCONV=0 keeps the
+  // unfused launches and the fp32 stream (the A/B reference of tests/).
+  int mbconv = 119;
   int chunk = 2048;  // frames per encoder pass (M2S_ENCODER_CHUNK): 2048 frames = ~14 GB of work buffers.  Measured with the
                      // round-2 kernels: 14.1 / 12.6 / 12.1 / 12.2 us per frame at 512 / 1024 / 2048 / 4096 (fp16 build)
   // per-frame buffer sizes (floats)
@@ -248,6 +251,7 @@ namespace {
 void free_block(Block* b) {
   free_gemm(&b->conv);
   free_gemm(&b->pair);
+  free_gemm(&b->s2d);
   free_gemm(&b->pwl);
   for (float** p : {&b->dw_w, &b->dw_b, &b->se_w1, &b->se_b1, &b->se_w2, &b->se_b2}) {
     if (*p) cudaFree(*p);
@@ -407,7 +411,16 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
       const int lq = hout * (wout + 2);  // rows in the (W+2)-pitch output space
       // expand: 9 row-shifted taps over the zero-bordered input (stride 1), or one tap over the im2col'd input (stride 2)
       ConvProblem p1;
-      if (b.stride == 2) {
+      const GemmLayer* exp_layer = &b.conv;
+      if (b.stride == 2 && b.s2d.w.dev) {
+        // space-to-depth copy of the input ((hout + 1) x (wout + 2) rows of 4 cin channels), then 9 K-window taps
+        const int rows_s2d = (hout + 1) * (wout + 2);
+        M2S_TRY(simt(0, [&] { return enc_s2d(op(x), B.col, esz, n, hin, win, b.cin, st); }, 1));
+        p1 = gemm_problem(B.col, rows_s2d, rows_s2d, 4 * b.cin, n, lq, B.e, lq, b.mid, 0, b.s2d);
+        p1.tap_ksteps = b.s2d.tap_ksteps;
+        for (int j = 0; j < b.s2d.taps; ++j) p1.kofs[j] = b.s2d.kofs[j];
+        exp_layer = &b.s2d;
+      } else if (b.stride == 2) {
         M2S_TRY(simt(0, [&] { return enc_im2col_s2(op(x), B.col, esz, n, hin, win, b.cin, st); }, 1));
         p1 = gemm_problem(B.col, lq, lq, 9 * b.cin, n, lq, B.e, lq, b.mid, 0, b.conv);
       } else {
@@ -420,12 +433,14 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
       set_pitch_mask(&p, hout, wout);
       if (b.skip) set_skip(&p, b.cin);
       bool fused = false;
-      if ((m->mbconv & 4) && fused_er_supported(p1, b.conv.w, p, b.pwl.w) &&
-          ((m->mbconv & 8) || fused_er_resident(b.conv.w, b.pwl.w))) {
+      if ((m->mbconv & 4) && fused_er_supported(p1, exp_layer->w, p, b.pwl.w) &&
+          ((m->mbconv & 8) || fused_er_resident(exp_layer->w, b.pwl.w))) {
         // expand -> SiLU -> 1x1 project in one kernel: the expanded tile stays in SMEM
         profile_set_tag(PROF_ENC_GEMM);
-        M2S_TRY(fused_er(p1, b.conv.w, p, b.pwl.w, st));
+        M2S_TRY(fused_er(p1, exp_layer->w, p, b.pwl.w, st));
         fused = true;
+      } else if (exp_layer != &b.conv) {
+        return fail(M2S_ERR_UNSUPPORTED, "space-to-depth EdgeResidual block needs the fused kernel");
       } else {
         M2S_TRY(run_gemm(m, p1, b.conv, st));
       }
@@ -616,6 +631,18 @@ extern "C" int m2s_acoustic_create(const m2s_acoustic_config* cfg, const m2s_ten
           return bail(st);
         if ((st = make_conv_layer(tm, p + ".conv_pwl", p + ".bn2", b.cout, b.mid, 1, 0, 0, enc_pack, &b.pwl)) != M2S_OK)
           return bail(st);
+        if (b.stride == 2 && enc_pack == PACK_FP16 && (m->mbconv & 64) && (m->mbconv & 4) && cin % 16 == 0 && cin <= 32) {
+          // the same conv over the space-to-depth input (enc_s2d): tap (dy, dx) = plane (dy & 1, dx & 1) as a K window of
+          // the 4 cin-channel row, at row shift (dy >> 1) * (wo + 2) + (dx >> 1)
+          if ((st = make_conv_layer(tm, p + ".conv_exp", p + ".bn1", b.mid, cin, 3, wo + 2, 0, enc_pack, &b.s2d)) != M2S_OK)
+            return bail(st);
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap % 3;
+            b.s2d.shift[tap] = (dy >> 1) * (wo + 2) + (dx >> 1);
+            b.s2d.kofs[tap] = (2 * (dy & 1) + (dx & 1)) * (cin / 16);
+          }
+          b.s2d.tap_ksteps = cin / 16;
+        }
         const size_t lq = static_cast<size_t>(ho) * (wo + 2);
         m->e_floats = std::max(m->e_floats, lq * b.mid);
         if (b.stride == 2) m->col_floats = std::max(m->col_floats, lq * 9 * cin);

@@ -338,6 +338,32 @@ __global__ void im2col_s2_kernel(const float* __restrict__ in, float* __restrict
   }
 }
 
+// Space-to-depth for a 3x3 stride-2 TF-"same" conv (fp16 build, fused EdgeResidual kernel).  Input: padded layout (pitch
+// Win + 2, origin (1, 1)).  Output row q' = y' * (Wo + 2) + x', y' in [0, Ho], x' in [0, Wo + 1]; its 4 C channels are the
+// four parity planes (py, px) of the 2x2 pixel block: column (2 py + px) * C + c = in(2 y' + py, 2 x' + px)[c], zero beyond
+// the image (the extra row / columns are the conv's bottom / right padding).  The stride-2 conv then reads tap (dy, dx) as
+// the K window of plane (dy & 1, dx & 1) at the CONSTANT row shift (dy >> 1) * (Wo + 2) + (dx >> 1): the input crosses
+// HBM once more instead of 2.25 times (im2col).  `c16` = 16-byte vectors per pixel.
+__global__ void s2d_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int Hin, int Win, int c16) {
+  const int Ho = Hin / 2, Wo = Win / 2, pitch_in = Win + 2, pitch_o = Wo + 2;
+  const int n = blockIdx.y;
+  const int per_row = 4 * c16;
+  const size_t total = static_cast<size_t>(Ho + 1) * pitch_o * per_row;
+  const uint4* src = in + static_cast<size_t>(n) * (Hin + 2) * pitch_in * c16;
+  uint4* dst = out + static_cast<size_t>(n) * total;
+  for (size_t k = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < total;
+       k += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(k % per_row);
+    const int q = static_cast<int>(k / per_row);
+    const int plane = v / c16, part = v - plane * c16;
+    const int y = q / pitch_o, x = q - y * pitch_o;
+    const int iy = 2 * y + (plane >> 1), ix = 2 * x + (plane & 1);
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (iy < Hin && ix < Win) val = src[(static_cast<size_t>(iy + 1) * pitch_in + (ix + 1)) * c16 + part];
+    dst[k] = val;
+  }
+}
+
 // Depthwise 3x3 + bias (folded BN) + SiLU, with the SE squeeze (per-frame channel sums) fused.
 // Input pixel (y, x) is row (y + oy) * pitch_in + (x + ox) of the frame.  TF "same" padding: stride 1 pads 1/1,
 // stride 2 pads 0/1 -- both are served by ONE zero-bordered SMEM slab ((Hin+2) x (Win+2) pixels x 32 channels),
@@ -587,6 +613,17 @@ int enc_im2col_s2(const void* in, void* col, int esize, int n, int Hin, int Win,
   const size_t total = static_cast<size_t>(Hin / 2) * (Win / 2 + 2) * 9 * c4n;
   dim3 grid(static_cast<unsigned>((total + 255) / 256), n);
   im2col_s2_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(in), static_cast<float*>(col), Hin, Win, c4n);
+  M2S_CUDA_OK(cudaGetLastError());
+  return M2S_OK;
+}
+
+// rows per frame of the space-to-depth tensor: (Hin / 2 + 1) * (Win / 2 + 2)
+int enc_s2d(const void* in, void* out, int esize, int n, int Hin, int Win, int C, cudaStream_t st) {
+  if ((C * esize) % 16) return fail(M2S_ERR_UNSUPPORTED, "space-to-depth: %d channels x %d bytes not a multiple of 16", C, esize);
+  const int c16 = C * esize / 16;
+  const size_t total = static_cast<size_t>(Hin / 2 + 1) * (Win / 2 + 2) * 4 * c16;
+  dim3 grid(static_cast<unsigned>((total + 255) / 256), n);
+  s2d_kernel<<<grid, 256, 0, st>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), Hin, Win, c16);
   M2S_CUDA_OK(cudaGetLastError());
   return M2S_OK;
 }

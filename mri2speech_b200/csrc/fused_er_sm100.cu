@@ -37,7 +37,14 @@ struct ErParams {
   int n_tile1, n_tiles1;         // N tiling of the expand conv (n_tile1 * n_tiles1 >= n1)
   int n_tile2;                   // N of the project MMA (>= p2.n, multiple of 16)
   int cblocks1, cblocks2;
-  int kblock1, row_bytes1;       // operand format of x / the expand weights
+  int kblock1, row_bytes1;       // operand format of the expand weights (and of x unless K windows are on)
+  // operand format of x.  Normally the weights' format; with per-tap K windows (stride-2 blocks over the space-to-depth
+  // input, ConvProblem::tap_ksteps) x has 4 c_in channels per row (128-byte rows, cblocks_a K blocks) and tap t contracts
+  // K-steps tap_kofs[t] .. + win_ksteps - 1 of K block tap_cb[t] against the whole (c_in-wide) weight block of the tap
+  int cblocks_a, kblock_a, row_bytes_a;
+  uint64_t desc_hi_a;
+  int win_ksteps;                // 0 = off
+  int tap_cb[M2S_MAX_TAPS], tap_kofs[M2S_MAX_TAPS];
   uint64_t desc_hi1, desc_hi2;
   uint32_t idesc1, idesc2;
   int x_row0;                    // first x row of a tile relative to q0 (min shift)
@@ -144,7 +151,7 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     // ===================== TMA producer =====================
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
-    const uint32_t a_bytes = prm.a_nbox * prm.a_box_rows * prm.row_bytes1;
+    const uint32_t a_bytes = prm.a_nbox * prm.a_box_rows * prm.row_bytes_a;
     auto load_b = [&](const uint8_t* src, uint32_t bytes) {
       mbar_wait(b_empty(sb), pb ^ 1);
       if (elect_one()) {
@@ -169,13 +176,13 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const int tile = blockIdx.x + s * gridDim.x;
         const int b = tile / prm.tiles_per_batch;
         const int q0 = (tile - b * prm.tiles_per_batch) * 128;
-        for (int cb = 0; cb < prm.cblocks1; ++cb) {
+        for (int cb = 0; cb < prm.cblocks_a; ++cb) {
           mbar_wait(a_empty(sa), pa ^ 1);
           if (elect_one()) {
             mbar_expect_tx(a_full(sa), a_bytes);
             for (int bx = 0; bx < prm.a_nbox; ++bx)
-              tma_load_3d(a_base + sa * prm.a_stage_bytes + bx * prm.a_box_rows * prm.row_bytes1, &tmap_x, a_full(sa),
-                          cb * prm.kblock1, q0 + prm.x_row0 + bx * prm.a_box_rows, b);
+              tma_load_3d(a_base + sa * prm.a_stage_bytes + bx * prm.a_box_rows * prm.row_bytes_a, &tmap_x, a_full(sa),
+                          cb * prm.kblock_a, q0 + prm.x_row0 + bx * prm.a_box_rows, b);
           }
           __syncwarp();
           if (++sa == prm.na) { sa = 0; pa ^= 1; }
@@ -214,12 +221,29 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const int buf = s % nbuf;
         mbar_wait(acc1_empty(buf), ((s / nbuf) & 1) ^ 1);
         tc_fence_after();
-        for (int cb = 0; cb < prm.cblocks1; ++cb) {
+        for (int cb = 0; cb < prm.cblocks_a; ++cb) {
           const int rem = prm.c_in - cb * prm.kblock1;
           const int ksteps = rem >= prm.kblock1 ? ksteps_full1 : (rem + 15) >> 4;
           mbar_wait(a_full(sa), pa);
           const uint32_t a_tile = a_base + sa * prm.a_stage_bytes;
-          if (prm.resident) {
+          if (prm.win_ksteps) {
+            // K windows (resident weights only): the taps whose parity plane lies in K block cb of the x tile
+            tc_fence_after();
+            if (elect_one()) {
+              for (int nt = 0; nt < prm.n_tiles1; ++nt)
+                for (int t = 0; t < prm.taps1; ++t) {
+                  if (prm.tap_cb[t] != cb) continue;
+                  const uint32_t wt = b_base + static_cast<uint32_t>(nt * prm.taps1 + t) * prm.b_tap_bytes1;
+                  const uint64_t db = prm.desc_hi1 | ((wt & 0x3FFFF) >> 4);
+                  const uint64_t da = prm.desc_hi_a |
+                                      (((a_tile + prm.rel_shift1[t] * prm.row_bytes_a + prm.tap_kofs[t] * 32) & 0x3FFFF) >> 4);
+                  mma_f16_k4(acc1_addr(buf) + nt * prm.n_tile1, da, db, prm.idesc1, (cb | t) ? 1u : 0u, prm.win_ksteps);
+                }
+              tc_commit(a_empty(sa));
+              if (cb == prm.cblocks_a - 1) tc_commit(acc1_full(buf));
+            }
+            __syncwarp();
+          } else if (prm.resident) {
             tc_fence_after();
             if (elect_one()) {
               for (int nt = 0; nt < prm.n_tiles1; ++nt)
@@ -541,11 +565,11 @@ int launch_er(const ErParams& prm_in, const ConvProblem& p1, const ConvProblem& 
   cuuint64_t gstride[2] = {static_cast<cuuint64_t>(p1.a_ld) * 2ull,
                            static_cast<cuuint64_t>(p1.a_batch_rows) * static_cast<cuuint64_t>(p1.a_ld) * 2ull};
   if (p1.batch == 1) gstride[1] = gstride[0] * static_cast<cuuint64_t>(p1.a_rows > 0 ? p1.a_rows : 1);
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(prm.kblock1), static_cast<cuuint32_t>(prm.a_box_rows), 1u};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(prm.kblock_a), static_cast<cuuint32_t>(prm.a_box_rows), 1u};
   cuuint32_t estr[3] = {1u, 1u, 1u};
   CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<float*>(p1.a), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    prm.row_bytes1 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    prm.row_bytes_a == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(M2S_ERR_CUDA, "fused EdgeResidual: x tensor map failed (%d)", static_cast<int>(cr));
   // epilogue-2 tiles (tma_epi): shortcut / fp32 output / fp16 output as (32 channels, l_out rows, batch) tensors whose row 0
@@ -586,7 +610,8 @@ int launch_er(const ErParams& prm_in, const ConvProblem& p1, const ConvProblem& 
   fused_er_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmap, tm_r, tm_d32, tm_d16, prm);
   M2S_CUDA_OK(cudaGetLastError());
   const double rows = static_cast<double>(p2.batch) * p2.l_out;
-  return profile_after(stream, 2.0 * rows * p1.n * (static_cast<double>(p1.c_in) * p1.taps + p2.n));
+  const double k1 = prm.win_ksteps ? 16.0 * prm.win_ksteps * p1.taps : static_cast<double>(p1.c_in) * p1.taps;
+  return profile_after(stream, 2.0 * rows * p1.n * (k1 + p2.n));
 }
 }  // namespace
 
@@ -605,6 +630,12 @@ bool fused_er_supported(const ConvProblem& p1, const PackedWeights& w1, const Co
   if (w1.n_tile * w1.n_tiles + w2.n_tile > kTmemCols) return false;
   for (int j = 0; j < p1.taps; ++j)
     if (p1.shift[j] < 0) return false;
+  if (p1.tap_ksteps) {
+    // K windows: x rows of 4 c_in' channels in 64-channel K blocks, weights c_in' = 16 tap_ksteps wide in one K block
+    if (w1.cblocks != 1 || w1.c_in != 16 * p1.tap_ksteps || p1.c_in != 4 * w1.c_in || p1.a_ld != p1.c_in || p1.kofs[0] != 0) return false;
+    for (int j = 0; j < p1.taps; ++j)
+      if (p1.kofs[j] < 0 || (p1.kofs[j] & 3) + p1.tap_ksteps > 4 || 16 * (p1.kofs[j] + p1.tap_ksteps) > p1.c_in) return false;
+  }
   return true;
 }
 
@@ -627,6 +658,13 @@ int fused_er(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& 
   prm.cblocks2 = w2.cblocks;
   prm.kblock1 = w1.kblock; prm.row_bytes1 = w1.row_bytes;
   prm.desc_hi1 = make_desc_hi(w1.row_bytes);
+  prm.cblocks_a = w1.cblocks; prm.kblock_a = w1.kblock; prm.row_bytes_a = w1.row_bytes; prm.desc_hi_a = prm.desc_hi1;
+  if (p1.tap_ksteps) {
+    prm.win_ksteps = p1.tap_ksteps;
+    prm.kblock_a = 64; prm.row_bytes_a = 128; prm.desc_hi_a = make_desc_hi(128);
+    prm.cblocks_a = (p1.c_in + 63) / 64;
+    for (int j = 0; j < p1.taps; ++j) { prm.tap_cb[j] = p1.kofs[j] >> 2; prm.tap_kofs[j] = p1.kofs[j] & 3; }
+  }
   prm.desc_hi2 = make_desc_hi(128);
   prm.idesc1 = (1u << 4) | (static_cast<uint32_t>(prm.n_tile1 >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
   prm.idesc2 = (1u << 4) | (static_cast<uint32_t>(prm.n_tile2 >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
@@ -642,7 +680,7 @@ int fused_er(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& 
   const int a_rows_needed = 128 + smax - smin;
   prm.a_nbox = (a_rows_needed + 255) / 256;
   prm.a_box_rows = (((a_rows_needed + prm.a_nbox - 1) / prm.a_nbox) + 7) / 8 * 8;
-  prm.a_stage_bytes = (static_cast<uint32_t>(prm.a_nbox * prm.a_box_rows * prm.row_bytes1) + 1023u) & ~1023u;
+  prm.a_stage_bytes = (static_cast<uint32_t>(prm.a_nbox * prm.a_box_rows * prm.row_bytes_a) + 1023u) & ~1023u;
   prm.t_buf_bytes = prm.cblocks2 * kTkbBytes;
   prm.b_tap_bytes1 = static_cast<uint32_t>(prm.n_tile1 * prm.row_bytes1);
   prm.b_tap_bytes2 = static_cast<uint32_t>(prm.n_tile2 * 128);
@@ -666,12 +704,14 @@ int fused_er(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& 
     }
     int na_r = 2;
     while (na_r < kMaxStagesA && used + prm.a_stage_bytes <= budget) { ++na_r; used += prm.a_stage_bytes; }
+    if (prm.win_ksteps && na_r < prm.cblocks_a) return fail(M2S_ERR_UNSUPPORTED, "fused EdgeResidual: x tile of the K-window mode does not fit SMEM");
     prm.na = na_r;
     prm.nb = 0;
     prm.tg1 = 1;
     prm.b_stage_bytes = 0;
     return launch_er(prm, p1, p2, used + 1024u, stream);
   }
+  if (prm.win_ksteps) return fail(M2S_ERR_UNSUPPORTED, "fused EdgeResidual: the K-window mode needs resident weights");
   int na = 2;
   uint32_t used = fixed + na * prm.a_stage_bytes + prm.nbuf * prm.t_buf_bytes;
   if (used + 2 * prm.b_tap_bytes1 > budget && prm.nbuf == 2) {
