@@ -41,7 +41,7 @@ int mb_project(const void* a, const void* w, const float* scales, const float* b
 bool fused_er_supported(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& p2, const PackedWeights& w2);
 bool fused_er_resident(const PackedWeights& w1, const PackedWeights& w2);
 int fused_er(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& p2, const PackedWeights& w2,
-             cudaStream_t stream);
+             cudaStream_t stream, const ErS2d* s2d = nullptr);
 int enc_se_mlp(float* sums, const float* w1, const float* b1, const float* w2, const float* b2, int n, int C, int rd, int hw,
                cudaStream_t st);
 int lstm_recurrence(const float* gin, const float* w_hh_fwd, const float* w_hh_bwd, const int32_t* lens, float* hcat,
@@ -236,8 +236,9 @@ struct m2s_acoustic {
   // 3x3 convs with two pixels per GEMM row (N = 32 instead of 16: per-tap K windows of the conv engine); bit5 = fp16
   // residual stream (no fp32 copies of the block outputs); bit6 = the stride-2 EdgeResidual blocks read a space-to-depth
   // copy of their input (K windows over the 4 parity planes) instead of an im2col matrix.  M2S_MBCONV=0 keeps the
-  // unfused launches and the fp32 stream (the A/B reference of tests/).
-  int mbconv = 119;
+  // unfused launches and the fp32 stream (the A/B reference of tests/).  bit7 = no copy at all: the fused kernel's TMA
+  // loads gather the space-to-depth tile from the NHWC input (5-D box).
+  int mbconv = 247;
   int chunk = 2048;  // frames per encoder pass (M2S_ENCODER_CHUNK): 2048 frames = ~14 GB of work buffers.  Measured with the
                      // round-2 kernels: 14.1 / 12.6 / 12.1 / 12.2 us per frame at 512 / 1024 / 2048 / 4096 (fp16 build)
   // per-frame buffer sizes (floats)
@@ -412,11 +413,13 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
       // expand: 9 row-shifted taps over the zero-bordered input (stride 1), or one tap over the im2col'd input (stride 2)
       ConvProblem p1;
       const GemmLayer* exp_layer = &b.conv;
+      ErS2d s2d_geo{hin, win, b.cin, static_cast<long long>(rows_in)};
+      const bool s2d_tma = (m->mbconv & 128) != 0;   // the fused kernel's TMA loads gather the space-to-depth tile themselves
       if (b.stride == 2 && b.s2d.w.dev) {
-        // space-to-depth copy of the input ((hout + 1) x (wout + 2) rows of 4 cin channels), then 9 K-window taps
+        // space-to-depth view of the input ((hout + 1) x (wout + 2) rows of 4 cin channels), then 9 K-window taps
         const int rows_s2d = (hout + 1) * (wout + 2);
-        M2S_TRY(simt(0, [&] { return enc_s2d(op(x), B.col, esz, n, hin, win, b.cin, st); }, 1));
-        p1 = gemm_problem(B.col, rows_s2d, rows_s2d, 4 * b.cin, n, lq, B.e, lq, b.mid, 0, b.s2d);
+        if (!s2d_tma) M2S_TRY(simt(0, [&] { return enc_s2d(op(x), B.col, esz, n, hin, win, b.cin, st); }, 1));
+        p1 = gemm_problem(s2d_tma ? op(x) : static_cast<const void*>(B.col), rows_s2d, rows_s2d, 4 * b.cin, n, lq, B.e, lq, b.mid, 0, b.s2d);
         p1.tap_ksteps = b.s2d.tap_ksteps;
         for (int j = 0; j < b.s2d.taps; ++j) p1.kofs[j] = b.s2d.kofs[j];
         exp_layer = &b.s2d;
@@ -437,7 +440,7 @@ int encode_chunk(const m2s_acoustic* m, const void* frames, bool u8, const float
           ((m->mbconv & 8) || fused_er_resident(exp_layer->w, b.pwl.w))) {
         // expand -> SiLU -> 1x1 project in one kernel: the expanded tile stays in SMEM
         profile_set_tag(PROF_ENC_GEMM);
-        M2S_TRY(fused_er(p1, exp_layer->w, p, b.pwl.w, st));
+        M2S_TRY(fused_er(p1, exp_layer->w, p, b.pwl.w, st, (exp_layer == &b.s2d && s2d_tma) ? &s2d_geo : nullptr));
         fused = true;
       } else if (exp_layer != &b.conv) {
         return fail(M2S_ERR_UNSUPPORTED, "space-to-depth EdgeResidual block needs the fused kernel");
@@ -647,7 +650,8 @@ extern "C" int m2s_acoustic_create(const m2s_acoustic_config* cfg, const m2s_ten
         m->e_floats = std::max(m->e_floats, lq * b.mid);
         if (b.stride == 2) m->col_floats = std::max(m->col_floats, lq * 9 * cin);
         m->x_floats = std::max(m->x_floats, padded_rows(ho, wo) * b.cout);
-        launches += (b.stride == 2 ? 4 : 3) - (((m->mbconv & 4) && ((m->mbconv & 8) || b.mid * 9 * cin * 2 <= 90 * 1024)) ? 1 : 0);   // (im2col,) expand, project (one fused kernel), border rows
+        launches += (b.stride == 2 ? 4 : 3) - (((m->mbconv & 4) && ((m->mbconv & 8) || b.mid * 9 * cin * 2 <= 90 * 1024)) ? 1 : 0)   // (im2col,) expand, project (one fused kernel), border rows
+                    - ((b.s2d.w.dev && (m->mbconv & 128)) ? 1 : 0);   // no im2col / space-to-depth pass
       } else {
         b.out_padded = false;
         if ((st = make_conv_layer(tm, p + ".conv_pw", p + ".bn1", b.mid, cin, 1, 0, 0, enc_pack, &b.conv)) != M2S_OK)

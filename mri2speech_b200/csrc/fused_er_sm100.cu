@@ -45,6 +45,9 @@ struct ErParams {
   uint64_t desc_hi_a;
   int win_ksteps;                // 0 = off
   int tap_cb[M2S_MAX_TAPS], tap_kofs[M2S_MAX_TAPS];
+  // space-to-depth by TMA (s2d_pitch > 0, with K windows): the x tile is `s2d_ny` whole rows of the space-to-depth image
+  // (pitch s2d_pitch = W_out + 2), gathered straight from the zero-bordered NHWC input by a 5-D box (ErS2d below)
+  int s2d_pitch, s2d_ny;
   uint64_t desc_hi1, desc_hi2;
   uint32_t idesc1, idesc2;
   int x_row0;                    // first x row of a tile relative to q0 (min shift)
@@ -68,6 +71,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[16]) {
                : "memory");
 }
 
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
                "r"(c0), "r"(c1), "r"(c2)
@@ -151,7 +161,8 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     // ===================== TMA producer =====================
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
-    const uint32_t a_bytes = prm.a_nbox * prm.a_box_rows * prm.row_bytes_a;
+    const uint32_t a_bytes = prm.s2d_pitch ? static_cast<uint32_t>(prm.s2d_ny * prm.s2d_pitch * prm.row_bytes_a)
+                                           : prm.a_nbox * prm.a_box_rows * prm.row_bytes_a;
     auto load_b = [&](const uint8_t* src, uint32_t bytes) {
       mbar_wait(b_empty(sb), pb ^ 1);
       if (elect_one()) {
@@ -180,6 +191,9 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           mbar_wait(a_empty(sa), pa ^ 1);
           if (elect_one()) {
             mbar_expect_tx(a_full(sa), a_bytes);
+            if (prm.s2d_pitch)   // (pixel pair x channel, row parity, x', y', frame): K block cb = row parity when there are two
+              tma_load_5d(a_base + sa * prm.a_stage_bytes, &tmap_x, a_full(sa), 0, cb, 0, q0 / prm.s2d_pitch, b);
+            else
             for (int bx = 0; bx < prm.a_nbox; ++bx)
               tma_load_3d(a_base + sa * prm.a_stage_bytes + bx * prm.a_box_rows * prm.row_bytes_a, &tmap_x, a_full(sa),
                           cb * prm.kblock_a, q0 + prm.x_row0 + bx * prm.a_box_rows, b);
@@ -229,6 +243,12 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           if (prm.win_ksteps) {
             // K windows (resident weights only): the taps whose parity plane lies in K block cb of the x tile
             tc_fence_after();
+            int row_off = 0;   // s2d by TMA: the tile starts at the first pixel of an image row, q0 somewhere inside it
+            if (prm.s2d_pitch) {
+              const int tile = blockIdx.x + s * gridDim.x;
+              const int q0 = (tile - (tile / prm.tiles_per_batch) * prm.tiles_per_batch) * 128;
+              row_off = q0 - (q0 / prm.s2d_pitch) * prm.s2d_pitch;
+            }
             if (elect_one()) {
               for (int nt = 0; nt < prm.n_tiles1; ++nt)
                 for (int t = 0; t < prm.taps1; ++t) {
@@ -236,7 +256,7 @@ fused_er_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
                   const uint32_t wt = b_base + static_cast<uint32_t>(nt * prm.taps1 + t) * prm.b_tap_bytes1;
                   const uint64_t db = prm.desc_hi1 | ((wt & 0x3FFFF) >> 4);
                   const uint64_t da = prm.desc_hi_a |
-                                      (((a_tile + prm.rel_shift1[t] * prm.row_bytes_a + prm.tap_kofs[t] * 32) & 0x3FFFF) >> 4);
+                                      (((a_tile + (row_off + prm.rel_shift1[t]) * prm.row_bytes_a + prm.tap_kofs[t] * 32) & 0x3FFFF) >> 4);
                   mma_f16_k4(acc1_addr(buf) + nt * prm.n_tile1, da, db, prm.idesc1, (cb | t) ? 1u : 0u, prm.win_ksteps);
                 }
               tc_commit(a_empty(sa));
@@ -553,25 +573,52 @@ EncodeTiledFn encode_fn_er() {
 }  // namespace
 
 namespace {
-int launch_er(const ErParams& prm_in, const ConvProblem& p1, const ConvProblem& p2, uint32_t smem_bytes, cudaStream_t stream) {
+int launch_er(const ErParams& prm_in, const ConvProblem& p1, const ConvProblem& p2, uint32_t smem_bytes, cudaStream_t stream,
+              const ErS2d* s2d) {
   ErParams prm = prm_in;
   EncodeTiledFn enc = encode_fn_er();
   if (!enc) return fail(M2S_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;   // one CTA per SM (whole-TMEM allocation)
 
   CUtensorMap tmap;
-  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(p1.c_in), static_cast<cuuint64_t>(p1.a_rows),
-                        static_cast<cuuint64_t>(p1.batch)};
-  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(p1.a_ld) * 2ull,
-                           static_cast<cuuint64_t>(p1.a_batch_rows) * static_cast<cuuint64_t>(p1.a_ld) * 2ull};
-  if (p1.batch == 1) gstride[1] = gstride[0] * static_cast<cuuint64_t>(p1.a_rows > 0 ? p1.a_rows : 1);
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(prm.kblock_a), static_cast<cuuint32_t>(prm.a_box_rows), 1u};
-  cuuint32_t estr[3] = {1u, 1u, 1u};
-  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<float*>(p1.a), gdim, gstride, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    prm.row_bytes_a == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (cr != CUDA_SUCCESS) return fail(M2S_ERR_CUDA, "fused EdgeResidual: x tensor map failed (%d)", static_cast<int>(cr));
+  CUresult cr = CUDA_SUCCESS;
+  if (!s2d) {
+    cuuint64_t gdim[3] = {static_cast<cuuint64_t>(p1.c_in), static_cast<cuuint64_t>(p1.a_rows),
+                          static_cast<cuuint64_t>(p1.batch)};
+    cuuint64_t gstride[2] = {static_cast<cuuint64_t>(p1.a_ld) * 2ull,
+                             static_cast<cuuint64_t>(p1.a_batch_rows) * static_cast<cuuint64_t>(p1.a_ld) * 2ull};
+    if (p1.batch == 1) gstride[1] = gstride[0] * static_cast<cuuint64_t>(p1.a_rows > 0 ? p1.a_rows : 1);
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(prm.kblock_a), static_cast<cuuint32_t>(prm.a_box_rows), 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<float*>(p1.a), gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE,
+             prm.row_bytes_a == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(M2S_ERR_CUDA, "fused EdgeResidual: x tensor map failed (%d)", static_cast<int>(cr));
+  }
+  if (s2d) {
+    // The zero-bordered NHWC input (pitch W + 2, origin (1, 1)) seen as (pixel pair x channel, row parity, x', y', frame):
+    // element (2 x' + px, 2 y' + py).  The dimensions are not in stride order on purpose: a box lands in SMEM as
+    // [y'][x'][py][px][c], i.e. one row per space-to-depth pixel with its parity planes side by side in K.  x' = W / 2 and
+    // y' = H / 2 (the conv's right / bottom padding) and the pitch's extra column are out of bounds: the TMA unit writes zeros.
+    const int C = s2d->c, Wp = s2d->w + 2;
+    const cuuint64_t esz = 2;
+    cuuint64_t gd5[5] = {static_cast<cuuint64_t>(2 * C), 2ull, static_cast<cuuint64_t>(s2d->w / 2),
+                         static_cast<cuuint64_t>(s2d->h / 2), static_cast<cuuint64_t>(p1.batch)};
+    cuuint64_t gs5[4] = {static_cast<cuuint64_t>(Wp) * C * esz, 2ull * C * esz, 2ull * Wp * C * esz,
+                         static_cast<cuuint64_t>(s2d->frame_rows) * C * esz};
+    // one row parity per K block: the box's inner extent (a pixel pair, 4 C bytes) is then exactly the swizzle span.  (A
+    // 64-byte inner extent under SWIZZLE_128B -- both parities of C = 16 in one 128-byte row -- does NOT land in the
+    // operand layout: measured, tests/test_mbconv_gpu.py mode 196.)
+    cuuint32_t bx5[5] = {static_cast<cuuint32_t>(2 * C), 1u, static_cast<cuuint32_t>(prm.s2d_pitch),
+                         static_cast<cuuint32_t>(prm.s2d_ny), 1u};
+    cuuint32_t es5[5] = {1u, 1u, 1u, 1u, 1u};
+    const __half* base = reinterpret_cast<const __half*>(p1.a) + static_cast<size_t>(Wp + 1) * C;
+    cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), gd5, gs5, bx5, es5,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, prm.row_bytes_a == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(M2S_ERR_CUDA, "fused EdgeResidual: space-to-depth tensor map failed (%d)", static_cast<int>(cr));
+  }
   // epilogue-2 tiles (tma_epi): shortcut / fp32 output / fp16 output as (32 channels, l_out rows, batch) tensors whose row 0
   // is output row q = 0 of a frame (base moved by d_row_offset rows); rows >= l_out are clipped / zero-filled by the TMA unit
   CUtensorMap tm_r = tmap, tm_d32 = tmap, tm_d16 = tmap;
@@ -640,8 +687,11 @@ bool fused_er_supported(const ConvProblem& p1, const PackedWeights& w1, const Co
 }
 
 int fused_er(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& p2, const PackedWeights& w2,
-             cudaStream_t stream) {
+             cudaStream_t stream, const ErS2d* s2d) {
   if (!fused_er_supported(p1, w1, p2, w2)) return fail(M2S_ERR_UNSUPPORTED, "block not supported by the fused EdgeResidual kernel");
+  if (s2d && (!p1.tap_ksteps || s2d->c != w1.c_in || (s2d->c != 16 && s2d->c != 32) || s2d->h % 2 || s2d->w % 2 ||
+              s2d->w / 2 + 2 > 256))
+    return fail(M2S_ERR_UNSUPPORTED, "fused EdgeResidual: space-to-depth geometry not supported");
   if (p2.batch <= 0 || p2.l_out <= 0) return M2S_OK;
   ErParams prm{};
   prm.p2 = p2;
@@ -664,6 +714,13 @@ int fused_er(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& 
     prm.kblock_a = 64; prm.row_bytes_a = 128; prm.desc_hi_a = make_desc_hi(128);
     prm.cblocks_a = (p1.c_in + 63) / 64;
     for (int j = 0; j < p1.taps; ++j) { prm.tap_cb[j] = p1.kofs[j] >> 2; prm.tap_kofs[j] = p1.kofs[j] & 3; }
+    if (s2d) {
+      // TMA gather: a K block is one row parity = a pixel pair of 2 C channels (64- or 128-byte rows)
+      const int kpb = w1.c_in / 8;   // K-steps per block
+      prm.kblock_a = 2 * w1.c_in; prm.row_bytes_a = 4 * w1.c_in; prm.desc_hi_a = make_desc_hi(prm.row_bytes_a);
+      prm.cblocks_a = 2;
+      for (int j = 0; j < p1.taps; ++j) { prm.tap_cb[j] = p1.kofs[j] / kpb; prm.tap_kofs[j] = p1.kofs[j] % kpb; }
+    }
   }
   prm.desc_hi2 = make_desc_hi(128);
   prm.idesc1 = (1u << 4) | (static_cast<uint32_t>(prm.n_tile1 >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
@@ -681,6 +738,13 @@ int fused_er(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& 
   prm.a_nbox = (a_rows_needed + 255) / 256;
   prm.a_box_rows = (((a_rows_needed + prm.a_nbox - 1) / prm.a_nbox) + 7) / 8 * 8;
   prm.a_stage_bytes = (static_cast<uint32_t>(prm.a_nbox * prm.a_box_rows * prm.row_bytes_a) + 1023u) & ~1023u;
+  if (s2d) {
+    // whole image rows: the tile's first row may sit anywhere inside the first one
+    prm.s2d_pitch = s2d->w / 2 + 2;
+    prm.s2d_ny = (a_rows_needed + prm.s2d_pitch - 1 + prm.s2d_pitch - 1) / prm.s2d_pitch;
+    if (prm.s2d_ny > 256) return fail(M2S_ERR_UNSUPPORTED, "fused EdgeResidual: space-to-depth tile too tall");
+    prm.a_stage_bytes = (static_cast<uint32_t>(prm.s2d_ny * prm.s2d_pitch * prm.row_bytes_a) + 1023u) & ~1023u;
+  }
   prm.t_buf_bytes = prm.cblocks2 * kTkbBytes;
   prm.b_tap_bytes1 = static_cast<uint32_t>(prm.n_tile1 * prm.row_bytes1);
   prm.b_tap_bytes2 = static_cast<uint32_t>(prm.n_tile2 * 128);
@@ -709,7 +773,7 @@ int fused_er(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& 
     prm.nb = 0;
     prm.tg1 = 1;
     prm.b_stage_bytes = 0;
-    return launch_er(prm, p1, p2, used + 1024u, stream);
+    return launch_er(prm, p1, p2, used + 1024u, stream, s2d);
   }
   if (prm.win_ksteps) return fail(M2S_ERR_UNSUPPORTED, "fused EdgeResidual: the K-window mode needs resident weights");
   int na = 2;
@@ -733,7 +797,7 @@ int fused_er(const ConvProblem& p1, const PackedWeights& w1, const ConvProblem& 
   while (nb < kMaxStagesB && used + prm.b_stage_bytes <= budget) { ++nb; used += prm.b_stage_bytes; }
   prm.na = na;
   prm.nb = nb;
-  return launch_er(prm, p1, p2, used + 1024u, stream);
+  return launch_er(prm, p1, p2, used + 1024u, stream, nullptr);
 }
 
 // Do the block's weights stay in SMEM for the whole launch?  (Otherwise they are re-streamed for every 128-row tile:

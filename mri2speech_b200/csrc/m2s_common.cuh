@@ -169,6 +169,13 @@ struct PackedWeights {
 
 // Choose N tiling for the tcgen05 engine (n_tile multiple of 16, <= 256).
 void choose_n_tiling(int n, int* n_tile, int* n_tiles);
+// Geometry of a stride-2 3x3 conv input for the fused EdgeResidual kernel's space-to-depth loads (fused_er_sm100.cu):
+// the zero-bordered NHWC frame has h x w pixels of c channels, frame_rows = (h + 2) * (w + 2) rows per frame.
+struct ErS2d {
+  int h, w, c;
+  long long frame_rows;
+};
+
 // Pack host weights [taps][n][c_in] (already folded) into both device layouts.  mode = PACK_FP32 (values kept),
 // PACK_TF32 (RNE-rounded to tf32) or PACK_FP16 (fp16 operands for tcgen05 kind::f16; `plain` keeps the rounded fp32).
 int pack_weights(const float* host_w, int taps, int n, int c_in, int mode, PackedWeights* out);

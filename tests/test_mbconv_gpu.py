@@ -8,7 +8,8 @@ stages 1-2 (3x3 expand -> SiLU -> 1x1 project) in one kernel with the expanded t
 bit4 = stage 0's 3x3 convs with two pixels per GEMM row (N = 32 instead of 16: interleaved A planes of the conv engine);
 bit5 = the residual stream in fp16 (shortcuts read from the fp16 operand copies, no fp32 copies of the block outputs);
 bit6 = the stride-2 EdgeResidual blocks read a space-to-depth copy of their input (9 K-window taps over the 4 parity
-planes, with bit2) instead of an im2col matrix.  Both kernels keep the arithmetic of the
+planes, with bit2) instead of an im2col matrix; bit7 = no copy either: the fused kernel's TMA loads gather the
+space-to-depth tile from the NHWC input (5-D box, out-of-bounds zero fill as the conv's padding).  Both kernels keep the arithmetic of the
 launches they replace (fp32 depthwise accumulation in tap order, fp32 scale * fp16 activation rounded once), so the
 encoder features must agree far below the fp16 operand noise (2^-11); the oracle comparison of the fused default runs
 in tests/test_acoustic_gpu.py / test_bench_paths_gpu.py / test_scaled_init_gpu.py."""
@@ -47,7 +48,7 @@ def _frames(n, seed=0):
     return synth.synthetic_clip(seed, n).cuda()
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3, 4, 12, 16, 23, 32, 39, 55, 68, 119])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 12, 16, 23, 32, 39, 55, 68, 119, 196, 247])
 @pytest.mark.parametrize("n", [5, 301])
 def test_fused_equals_unfused(mode, n):
     """5 frames: partial tiles (two 8x8 frames per tile, odd count); 301 frames: several tiles per CTA (ring phases wrap)."""
