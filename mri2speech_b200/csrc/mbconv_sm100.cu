@@ -440,24 +440,26 @@ constexpr int kPScalerWarps = 8;
 constexpr int kPThreads = 64 + 32 * kPScalerWarps + 128;   // TMA, MMA, 8 scaler warps, 4 epilogue warps
 constexpr int kPMaxStages = 6;
 constexpr uint32_t kPStage32 = 32 * 128, kPStage16 = 32 * 64;   // per-warp output staging (fp32 / fp16 unit of 32 x 32)
+constexpr uint32_t kPEpiWarpBytes = kPStage32 + 3 * kPStage16;  // ... + two fp16 shortcut tiles
 
 template <int HALVES>
 __global__ void __launch_bounds__(kPThreads, 1)
 mb_project_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                   const __grid_constant__ CUtensorMap tm_d32, const __grid_constant__ CUtensorMap tm_d16,
-                  const __grid_constant__ ProjectParams prm) {
+                  const __grid_constant__ CUtensorMap tm_r16, const __grid_constant__ ProjectParams prm) {
   constexpr int M = 128 * HALVES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t ring_base = smem_base;
-  const uint32_t st_base = ring_base + prm.stages * prm.stage_bytes;   // 4 warps x (4 KB + 2 KB) output staging
-  const uint32_t bar_base = st_base + 4 * (kPStage32 + kPStage16);
+  const uint32_t st_base = ring_base + prm.stages * prm.stage_bytes;   // 4 warps x (4 KB + 2 KB output staging + 2 x 2 KB shortcut tiles)
+  const uint32_t bar_base = st_base + 4 * kPEpiWarpBytes;
   auto full = [&](int s) { return bar_base + 8u * s; };
   auto scaled = [&](int s) { return bar_base + 8u * (kPMaxStages + s); };
   auto empty = [&](int s) { return bar_base + 8u * (2 * kPMaxStages + s); };
   auto acc_full = [&](int s) { return bar_base + 8u * (3 * kPMaxStages + s); };
   auto acc_empty = [&](int s) { return bar_base + 8u * (3 * kPMaxStages + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (3 * kPMaxStages + 4);
+  auto r_full = [&](int w, int b) { return bar_base + 8u * (3 * kPMaxStages + 5 + 2 * w + b); };   // shortcut tile b of epilogue warp w
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -466,7 +468,9 @@ mb_project_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < prm.stages; ++s) { mbar_init(full(s), 1); mbar_init(scaled(s), kPScalerWarps); mbar_init(empty(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 4); }
+    for (int w = 0; w < 4; ++w) { mbar_init(r_full(w, 0), 1); mbar_init(r_full(w, 1), 1); }
     fence_barrier_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_r16) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_d32) : "memory");
@@ -527,23 +531,30 @@ mb_project_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       if (++acc == 2) { acc = 0; pacc ^= 1; }
     }
   } else if (warp < 2 + kPScalerWarps) {
-    // ===================== scaler warps: A[row][k] *= scale[frame(row)][k], in place in the stage =====================
+    // ===================== scaler warps: the excite scale, in place in the stage =====================
+    // HALVES == 2 (16 x 16 frames: a tile IS a frame): W[n][k] *= scale[frame][k] -- the weight block has at most half the
+    // rows of the A tile and one scale row serves the whole block.  HALVES == 1 (8 x 8 frames: two frames per tile):
+    // A[row][k] *= scale[frame(row)][k].  Either way one fp16 rounding per product term.  (The first version scaled A
+    // everywhere and re-read the scale row for each of its 8 row passes: with the epilogue's row-per-lane shortcut loads
+    // that put the LSU data pipe at 72 % of its wavefront rate -- profiles/README.md, round 2 late.)
     if (has_scale) {
       const int t = threadIdx.x - 64;   // 0..255
       const int c8 = t & 7, r0 = t >> 3;  // 16-byte chunk, first row (32 rows per pass)
       int s = 0;
       uint32_t ph = 0;
+      constexpr int kSets = HALVES == 2 ? 1 : 4;   // distinct frames a tile can touch (M / hw, hw >= 32)
       for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
         const int row0 = tile * M;
+        const int f0 = row0 / prm.hw;
+        const int ppf = prm.hw >> 5;                 // 32-row passes per frame
         for (int kb = 0; kb < kblocks; ++kb) {
           const int c = kb * 64 + c8 * 8;
           const bool c_ok = c < prm.c_mid;
-          // the scale rows this thread needs (one per pass; a pass of 32 rows lies inside one frame: hw % 32 == 0)
-          float4 sa[M / 32], sb2[M / 32];
+          float4 sa[kSets], sb2[kSets];
 #pragma unroll
-          for (int i = 0; i < M / 32; ++i) {
-            const int f = (row0 + i * 32) / prm.hw;
-            if (c_ok && f < prm.n_frames) {
+          for (int i = 0; i < kSets; ++i) {
+            const int f = f0 + i;
+            if (c_ok && f < prm.n_frames && (HALVES == 2 || i * ppf < M / 32)) {
               const float4* sp = reinterpret_cast<const float4*>(prm.scales + static_cast<size_t>(f) * prm.c_mid + c);
               sa[i] = __ldg(sp);
               sb2[i] = __ldg(sp + 1);
@@ -553,14 +564,32 @@ mb_project_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           }
           mbar_wait(full(s), ph);
           const uint32_t st = ring_base + s * prm.stage_bytes;
+          if (HALVES == 2) {
+            const uint32_t wb = st + prm.a_bytes;
 #pragma unroll
-          for (int i = 0; i < M / 32; ++i) {
-            const int r = r0 + i * 32;
-            const uint32_t addr = st + r * 128 + ((c8 ^ (r & 7)) << 4);
-            const uint4 v = lds128(addr);
-            const float2 v0 = unpack_h2(v.x), v1 = unpack_h2(v.y), v2 = unpack_h2(v.z), v3 = unpack_h2(v.w);
-            sts128(addr, pack_h2(v0.x * sa[i].x, v0.y * sa[i].y), pack_h2(v1.x * sa[i].z, v1.y * sa[i].w),
-                   pack_h2(v2.x * sb2[i].x, v2.y * sb2[i].y), pack_h2(v3.x * sb2[i].z, v3.y * sb2[i].w));
+            for (int i = 0; i < 4; ++i) {
+              const int r = r0 + i * 32;
+              if (r < prm.n_pad) {
+                const uint32_t addr = wb + r * 128 + ((c8 ^ (r & 7)) << 4);
+                const uint4 v = lds128(addr);
+                const float2 v0 = unpack_h2(v.x), v1 = unpack_h2(v.y), v2 = unpack_h2(v.z), v3 = unpack_h2(v.w);
+                sts128(addr, pack_h2(v0.x * sa[0].x, v0.y * sa[0].y), pack_h2(v1.x * sa[0].z, v1.y * sa[0].w),
+                       pack_h2(v2.x * sb2[0].x, v2.y * sb2[0].y), pack_h2(v3.x * sb2[0].z, v3.y * sb2[0].w));
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < M / 32; ++i) {
+              const int r = r0 + i * 32;
+              const int fi = i / ppf;              // (ppf is 2 for the 8 x 8 frames this instantiation serves)
+              const float4 a4 = fi == 0 ? sa[0] : (fi == 1 ? sa[1 % kSets] : (fi == 2 ? sa[2 % kSets] : sa[3 % kSets]));
+              const float4 b4 = fi == 0 ? sb2[0] : (fi == 1 ? sb2[1 % kSets] : (fi == 2 ? sb2[2 % kSets] : sb2[3 % kSets]));
+              const uint32_t addr = st + r * 128 + ((c8 ^ (r & 7)) << 4);
+              const uint4 v = lds128(addr);
+              const float2 v0 = unpack_h2(v.x), v1 = unpack_h2(v.y), v2 = unpack_h2(v.z), v3 = unpack_h2(v.w);
+              sts128(addr, pack_h2(v0.x * a4.x, v0.y * a4.y), pack_h2(v1.x * a4.z, v1.y * a4.w),
+                     pack_h2(v2.x * b4.x, v2.y * b4.y), pack_h2(v3.x * b4.z, v3.y * b4.w));
+            }
           }
           fence_proxy_async();   // the MMA reads the stage through the async proxy
           __syncwarp();
@@ -571,14 +600,28 @@ mb_project_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     }
   } else {
     // ===================== epilogue: TMEM -> bias (+ shortcut) -> SMEM staging -> TMA store =====================
+    // A warp walks its 32-row x 32-column units of every tile in a fixed order (tile, half, unit).  The fp16 shortcut
+    // tile of unit k + 1 is requested by TMA into one of two 2 KB buffers before unit k is processed, and a lane reads its
+    // row from SMEM (4 LDS.128): a row per lane straight from global memory touched 32 lines per load instruction and,
+    // with the scaler's traffic, saturated the LSU data pipe (profiles/README.md, round 2 late).
     const int ew = warp - (2 + kPScalerWarps);   // 0..3
     const int quad = warp & 3;
-    const uint32_t st32 = st_base + ew * (kPStage32 + kPStage16);
+    const uint32_t st32 = st_base + ew * kPEpiWarpBytes;
     const uint32_t st16 = st32 + kPStage32;
+    const uint32_t rbuf = st16 + kPStage16;          // 2 x kPStage16
     const int units = (prm.c_out + 31) >> 5;
+    const bool tma_res = prm.res16 != nullptr;
     int acc = 0;
     uint32_t pacc = 0;
     bool pending = false;
+    int k = 0;                                       // running unit index of this warp
+    auto request = [&](int tile, int h, int u, int kk) {   // shortcut tile of unit (tile, h, u) -> buffer kk & 1
+      if (lane == 0) {
+        mbar_expect_tx(r_full(ew, kk & 1), kPStage16);
+        tma_load_2d(rbuf + (kk & 1) * kPStage16, &tm_r16, r_full(ew, kk & 1), u * 32, tile * M + h * 128 + quad * 32);
+      }
+    };
+    if (tma_res && static_cast<int>(blockIdx.x) < prm.n_tiles) request(blockIdx.x, 0, 0, 0);
     for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
       mbar_wait(acc_full(acc), pacc);
       tc_fence_after();
@@ -588,8 +631,13 @@ mb_project_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         const int row = row_base + lane;
         const bool row_ok = row < prm.rows;
 #pragma unroll 1
-        for (int u = 0; u < units; ++u) {
+        for (int u = 0; u < units; ++u, ++k) {
           const int col0 = u * 32;
+          if (tma_res) {   // next unit's shortcut tile (its buffer was read two units ago)
+            int nu = u + 1, nh = h, nt = tile;
+            if (nu == units) { nu = 0; if (++nh == HALVES) { nh = 0; nt += gridDim.x; } }
+            if (nt < prm.n_tiles) request(nt, nh, nu, k + 1);
+          }
           uint32_t r[32];
           tmem_ld32(tmem_base + acc * 256 + h * 128 + col0 + (static_cast<uint32_t>(quad * 32) << 16), r);
           float4 bv[8], rv[8];
@@ -601,15 +649,16 @@ mb_project_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                         ? *(reinterpret_cast<const float4*>(prm.res + static_cast<size_t>(row) * prm.c_out + col0) + j)
                         : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          if (prm.res16 && row_ok) {   // fp16 residual stream: 16 bytes = 8 channels per load
+          if (tma_res) {   // fp16 residual stream: this lane's 64 bytes of the TMA-loaded tile (out of bounds = zeros)
+            mbar_wait(r_full(ew, k & 1), (k >> 1) & 1);
+            const uint32_t rb = rbuf + (k & 1) * kPStage16 + lane * 64;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (col0 + 8 * j < prm.c_out) {
-                const uint4 u = *(reinterpret_cast<const uint4*>(prm.res16 + static_cast<size_t>(row) * prm.c_out + col0) + j);
-                const float2 a = unpack_h2(u.x), b = unpack_h2(u.y), c = unpack_h2(u.z), d = unpack_h2(u.w);
-                rv[2 * j] = make_float4(a.x, a.y, b.x, b.y);
-                rv[2 * j + 1] = make_float4(c.x, c.y, d.x, d.y);
-              }
+            for (int j = 0; j < 4; ++j) {
+              const uint4 uu = lds128(rb + ((j ^ ((lane >> 1) & 3)) << 4));
+              const float2 a = unpack_h2(uu.x), b = unpack_h2(uu.y), c = unpack_h2(uu.z), d = unpack_h2(uu.w);
+              rv[2 * j] = make_float4(a.x, a.y, b.x, b.y);
+              rv[2 * j + 1] = make_float4(c.x, c.y, d.x, d.y);
+            }
           }
           if (pending) {   // the staging buffers are free once the previous unit's stores have read them
             if (lane == 0) tma_store_wait_read();
@@ -634,7 +683,7 @@ mb_project_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
               sts128(st16 + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), r[8 * j], r[8 * j + 1], r[8 * j + 4], r[8 * j + 5]);
           }
           fence_proxy_async();
-          __syncwarp();
+          __syncwarp();   // (also: every lane has read its shortcut row before lane 0 requests the tile after next into this buffer)
           if (lane == 0) {
             if (prm.store32) tma_store_2d(&tm_d32, st32, col0, row_base);
             if (prm.store16) tma_store_2d(&tm_d16, st16, col0, row_base);
@@ -777,13 +826,13 @@ int mb_project(const void* a, const void* w, const float* scales, const float* b
   prm.store32 = d32 != nullptr; prm.store16 = d16 != nullptr;
   prm.idesc = idesc_f16(prm.n_pad);
   prm.desc_hi = make_desc_hi(128);
-  const uint32_t fixed = 4 * (kPStage32 + kPStage16) + 512 + 1024;
+  const uint32_t fixed = 4 * kPEpiWarpBytes + 512 + 1024;
   int stages = 2;
-  while (stages < kPMaxStages && fixed + (stages + 1) * prm.stage_bytes <= 208 * 1024) ++stages;
+  while (stages < kPMaxStages && fixed + (stages + 1) * prm.stage_bytes <= 224 * 1024) ++stages;
   prm.stages = stages;
   uint32_t smem = fixed + stages * prm.stage_bytes;
   if (smem < 120 * 1024) smem = 120 * 1024;
-  CUtensorMap tm_a, tm_w, tm_d32, tm_d16;
+  CUtensorMap tm_a, tm_w, tm_d32, tm_d16, tm_r16;
   M2S_TRY(make_map_2d(&tm_a, a, 2, prm.rows, c_mid, c_mid, 64, M, CU_TENSOR_MAP_SWIZZLE_128B, "project A"));
   M2S_TRY(make_map_2d(&tm_w, w, 2, c_out, c_mid, c_mid, 64, prm.n_pad, CU_TENSOR_MAP_SWIZZLE_128B, "project W"));
   // (an absent output still gets a valid map -- over the other buffer -- so that the kernel parameters stay well formed)
@@ -791,7 +840,12 @@ int mb_project(const void* a, const void* w, const float* scales, const float* b
                       d32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "project D32"));
   M2S_TRY(make_map_2d(&tm_d16, d16 ? d16 : static_cast<const void*>(d32), d16 ? 2 : 4, prm.rows, c_out, c_out, 32, 32,
                       d16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, "project D16"));
-  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const ProjectParams);
+  // the fp16 shortcut as 32 x 32 tiles (a valid map over the output when there is none)
+  M2S_TRY(make_map_2d(&tm_r16, prm.res16 ? static_cast<const void*>(prm.res16) : (d16 ? d16 : static_cast<const void*>(d32)),
+                      (prm.res16 || d16) ? 2 : 4, prm.rows, c_out, c_out, 32, 32,
+                      (prm.res16 || d16) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, "project shortcut"));
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                            const ProjectParams);
   static const KernelFn kernels[2] = {mb_project_kernel<1>, mb_project_kernel<2>};
   static PerDeviceOnce attr_once;
   M2S_TRY(attr_once.run([&]() -> int {
@@ -801,7 +855,7 @@ int mb_project(const void* a, const void* w, const float* scales, const float* b
   int grid = sm_count();
   if (grid > prm.n_tiles) grid = prm.n_tiles;
   M2S_TRY(profile_before(st));
-  kernels[halves - 1]<<<grid, kPThreads, smem, st>>>(tm_a, tm_w, tm_d32, tm_d16, prm);
+  kernels[halves - 1]<<<grid, kPThreads, smem, st>>>(tm_a, tm_w, tm_d32, tm_d16, tm_r16, prm);
   M2S_CUDA_OK(cudaGetLastError());
   return profile_after(st, 2.0 * static_cast<double>(prm.rows) * c_mid * c_out);
 }

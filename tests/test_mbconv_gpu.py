@@ -60,7 +60,9 @@ def test_fused_equals_unfused(mode, n):
     err = (got - ref).abs().max().item()
     # bit 5 (32) = the residual stream in fp16: one more fp16 rounding per block with a shortcut (tools/
     # emulate_residual_rounding.py: ~3e-4 of the features' abs-max on these weights); everything else keeps the arithmetic
-    tol = 2e-3 if mode & 32 else 2e-4
+    # bit 1 (2): on 16 x 16 frames the excite scale multiplies the project WEIGHTS (one frame per tile) instead of the
+    # activations: one fp16 rounding per product term either way, but not the same one
+    tol = 2e-3 if mode & 32 else (5e-4 if mode & 2 else 2e-4)
     assert err <= tol * scale, (mode, n, err, scale)
     assert l1 < l0 or mode in (16, 32)               # fewer launches per forward (16 adds two border passes, 32 none)
     if mode == 3:
@@ -83,7 +85,7 @@ def test_fused_default_is_on():
         plain = m.launches_per_forward()
     finally:
         os.environ.pop("M2S_MBCONV", None)
-    assert plain - fused == 40                       # 42 launches fewer, 2 border-column passes more
+    assert plain - fused == 42                       # 42 launches fewer, 2 border-column passes more, the 2 im2col passes gone
 
 
 def test_stride2_depthwise_tma_equals_slab_kernel():
