@@ -185,22 +185,47 @@ __global__ void __launch_bounds__(256) stem_rows_kernel(const void* __restrict__
   float2 nm = make_float2(0.f, 1.f);
   if (kU8) nm = norm[n];
   const int w4 = W >> 2;
-  for (int k = tid; k < kRowsIn * w4; k += 256) {
+  // all of a thread's loads are issued before the first conversion / store: with one load per loop iteration the stores
+  // waited out an HBM round trip per iteration (a quarter of the kernel's stall samples, profiles/README.md round 2 late)
+  constexpr int kStageIters = 6;   // >= ceil(kRowsIn * w4 / 256) for W <= 352 (checked by the launcher)
+  uchar4 u8v[kStageIters];
+  float4 fv[kStageIters], mv[kStageIters];
+#pragma unroll
+  for (int it = 0; it < kStageIters; ++it) {
+    const int k = tid + it * 256;
+    const int r = k / w4, x4 = (k - r * w4) << 2;
+    const int yy = 2 * y0 + r;
+    u8v[it] = make_uchar4(0, 0, 0, 0);
+    fv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    mv[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (k < kRowsIn * w4 && yy < H) {
+      const size_t idx = static_cast<size_t>(yy) * W + x4;
+      if (kU8) {
+        u8v[it] = *reinterpret_cast<const uchar4*>(static_cast<const uint8_t*>(frames_v) + foff + idx);
+        if (mask) mv[it] = *reinterpret_cast<const float4*>(mask + idx);
+      } else {
+        fv[it] = *reinterpret_cast<const float4*>(static_cast<const float*>(frames_v) + foff + idx);
+      }
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < kStageIters; ++it) {
+    const int k = tid + it * 256;
+    if (k >= kRowsIn * w4) break;
     const int r = k / w4, x4 = (k - r * w4) << 2;
     const int yy = 2 * y0 + r;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (yy < H) {
-      const size_t idx = static_cast<size_t>(yy) * W + x4;
       if (kU8) {
-        const uchar4 u = *reinterpret_cast<const uchar4*>(static_cast<const uint8_t*>(frames_v) + foff + idx);
+        const uchar4 u = u8v[it];
         float4 f = make_float4(u.x, u.y, u.z, u.w);
         if (mask) {
-          const float4 m = *reinterpret_cast<const float4*>(mask + idx);
+          const float4 m = mv[it];
           f = make_float4(masked_u8(u.x, m.x), masked_u8(u.y, m.y), masked_u8(u.z, m.z), masked_u8(u.w, m.w));
         }
         v = make_float4((f.x - nm.x) * nm.y, (f.y - nm.x) * nm.y, (f.z - nm.x) * nm.y, (f.w - nm.x) * nm.y);
       } else {
-        v = *reinterpret_cast<const float4*>(static_cast<const float*>(frames_v) + foff + idx);
+        v = fv[it];
       }
     }
     float* d = srow + r * Wp + x4;
@@ -444,70 +469,105 @@ __global__ void __launch_bounds__(256, 3) dwconv_kernel(const T* __restrict__ in
 //      fused kernel re-read them in every block of every frame, which cost more L2 traffic than the tensor it scaled.
 //  (2) se_scale_kernel: the streaming multiply, in place; grid = (frames, splits).
 template <int KF>
-__global__ void __launch_bounds__(1024) se_mlp_kernel(float* __restrict__ sums /* in: sums, out: scales */,
+__global__ void __launch_bounds__(512) se_mlp_kernel(float* __restrict__ sums /* in: sums, out: scales */,
                                                      const float* __restrict__ w1 /*[rd][C]*/, const float* __restrict__ b1,
                                                      const float* __restrict__ w2t /*[rd][C]*/, const float* __restrict__ b2,
                                                      int C, int rd, float inv_hw, int n_frames) {
-  extern __shared__ float sm[];  // mean[KF][C] + r[KF][rd]
+  extern __shared__ float sm[];  // mean[KF][C] + r[KF][rdp], rdp = rd rounded up to 4 (zero padded)
   float* mean = sm;
   float* r = sm + KF * C;
+  const int rdp = (rd + 3) & ~3;
   const int n0 = blockIdx.x * KF;
-  for (int i = threadIdx.x; i < KF * C; i += blockDim.x) {
-    const int f = i / C;
-    mean[i] = n0 + f < n_frames ? sums[static_cast<size_t>(n0) * C + i] * inv_hw : 0.f;
+  {
+    // the block's KF rows of sums are contiguous: 16-byte loads, several in flight per thread (one scalar load per
+    // iteration made this staging loop a chain of ~20-40 exposed L2 round trips: 28 % of the kernel's stall samples)
+    const int valid4 = (min(KF, n_frames - n0) * C) >> 2, total4 = (KF * C) >> 2;   // C % 4 == 0
+    const float4* src = reinterpret_cast<const float4*>(sums + static_cast<size_t>(n0) * C);
+    float4* dst = reinterpret_cast<float4*>(mean);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < total4; i += blockDim.x) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < valid4) v = src[i];
+      dst[i] = make_float4(v.x * inv_hw, v.y * inv_hw, v.z * inv_hw, v.w * inv_hw);
+    }
   }
+  for (int i = threadIdx.x; i < KF * rdp; i += blockDim.x) r[i] = 0.f;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int c4n = C >> 2;
-  for (int j = warp; j < rd; j += nwarps) {
-    const float4* wr = reinterpret_cast<const float4*>(w1 + static_cast<size_t>(j) * C);
-    float a[KF];
+  // FC1: a warp takes TWO rows of W1 at a time and four k steps per iteration (eight independent 16-byte weight loads in
+  // flight: the loop is L2-latency bound); the KF float4 of means a lane reads from SMEM per k serve both rows.
+  for (int j0 = 2 * warp; j0 < rd; j0 += 2 * nwarps) {
+    const float4* wr[2];
 #pragma unroll
-    for (int f = 0; f < KF; ++f) a[f] = 0.f;
-#pragma unroll 2
-    for (int k = lane; k < c4n; k += 32) {
-      const float4 wv = __ldg(wr + k);
+    for (int q = 0; q < 2; ++q) wr[q] = reinterpret_cast<const float4*>(w1 + static_cast<size_t>(min(j0 + q, rd - 1)) * C);
+    float a[2][KF];
 #pragma unroll
-      for (int f = 0; f < KF; ++f) {
-        const float4 mv = reinterpret_cast<const float4*>(mean + f * C)[k];
-        a[f] = fmaf(wv.x, mv.x, a[f]); a[f] = fmaf(wv.y, mv.y, a[f]); a[f] = fmaf(wv.z, mv.z, a[f]); a[f] = fmaf(wv.w, mv.w, a[f]);
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int f = 0; f < KF; ++f) a[q][f] = 0.f;
+    for (int k0 = lane; k0 < c4n; k0 += 128) {
+      float4 wv[4][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+          wv[i][q] = k0 + 32 * i < c4n ? __ldg(wr[q] + k0 + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = k0 + 32 * i < c4n ? k0 + 32 * i : lane;   // (past the end the weights are zero)
+#pragma unroll
+        for (int f = 0; f < KF; ++f) {
+          const float4 mv = reinterpret_cast<const float4*>(mean + f * C)[k];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            a[q][f] = fmaf(wv[i][q].x, mv.x, a[q][f]); a[q][f] = fmaf(wv[i][q].y, mv.y, a[q][f]);
+            a[q][f] = fmaf(wv[i][q].z, mv.z, a[q][f]); a[q][f] = fmaf(wv[i][q].w, mv.w, a[q][f]);
+          }
+        }
       }
     }
 #pragma unroll
-    for (int f = 0; f < KF; ++f) {
+    for (int q = 0; q < 2; ++q)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a[f] += __shfl_xor_sync(0xffffffffu, a[f], o);
-    }
+      for (int f = 0; f < KF; ++f) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a[q][f] += __shfl_xor_sync(0xffffffffu, a[q][f], o);
+      }
     if (lane == 0) {
-      const float bj = b1[j];
 #pragma unroll
-      for (int f = 0; f < KF; ++f) {
-        const float v = a[f] + bj;
-        r[f * rd + j] = v / (1.f + expf(-v));
-      }
+      for (int q = 0; q < 2; ++q)
+        if (j0 + q < rd) {
+          const float bj = b1[j0 + q];
+#pragma unroll
+          for (int f = 0; f < KF; ++f) {
+            const float v = a[q][f] + bj;
+            r[f * rdp + j0 + q] = v / (1.f + expf(-v));
+          }
+        }
     }
   }
   __syncthreads();
+  // FC2: a thread owns channel c; four hidden units per step (one broadcast LDS.128 of r per frame and step)
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float a[KF];
     const float bc = b2[c];
 #pragma unroll
     for (int f = 0; f < KF; ++f) a[f] = bc;
-    int j = 0;
-    for (; j + 8 <= rd; j += 8) {   // eight independent weight loads in flight (the loop is L2-latency bound otherwise)
-      float w[8];
+    for (int j = 0; j < rdp; j += 16) {   // sixteen independent weight loads in flight (the loop is L2-latency bound)
+      float w[16];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) w[u] = __ldg(w2t + static_cast<size_t>(j + u) * C + c);
+      for (int u = 0; u < 16; ++u) w[u] = j + u < rd ? __ldg(w2t + static_cast<size_t>(j + u) * C + c) : 0.f;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int f = 0; f < KF; ++f) {
 #pragma unroll
-        for (int f = 0; f < KF; ++f) a[f] = fmaf(w[u], r[f * rd + j + u], a[f]);
+        for (int u4 = 0; u4 < 4; ++u4)
+          if (j + 4 * u4 < rdp) {
+            const float4 rr = *reinterpret_cast<const float4*>(r + f * rdp + j + 4 * u4);
+            a[f] = fmaf(w[4 * u4], rr.x, a[f]); a[f] = fmaf(w[4 * u4 + 1], rr.y, a[f]);
+            a[f] = fmaf(w[4 * u4 + 2], rr.z, a[f]); a[f] = fmaf(w[4 * u4 + 3], rr.w, a[f]);
+          }
       }
-    }
-    for (; j < rd; ++j) {
-      const float w = __ldg(w2t + static_cast<size_t>(j) * C + c);
-#pragma unroll
-      for (int f = 0; f < KF; ++f) a[f] = fmaf(w, r[f * rd + j], a[f]);
     }
 #pragma unroll
     for (int f = 0; f < KF; ++f)
@@ -551,13 +611,13 @@ __global__ void gap_kernel(const float* __restrict__ x, const int32_t* __restric
 
 // `half` selects the activation element type: 0 = float, 1 = __half (`out` / `in` are then __half buffers).
 namespace {
-constexpr int kStemRows = 4;
+constexpr int kStemRows = 8;
 // the R-rows kernel when the geometry and the frame alignment allow 4-pixel loads, else the one-row kernel
 template <bool kU8, typename T>
 int launch_stem(const void* frames, const int32_t* fmap, const float* mask, const float2* norm, T* out, const float* w,
                 const float* bias, int n, int H, int W, cudaStream_t st) {
   const size_t frame_bytes = static_cast<size_t>(H) * W * (kU8 ? 1 : 4);
-  const bool rows_ok = W % 4 == 0 && (H / 2) % kStemRows == 0 && H % 2 == 0 &&
+  const bool rows_ok = W % 4 == 0 && (H / 2) % kStemRows == 0 && H % 2 == 0 && (2 * kStemRows + 1) * (W / 4) <= 6 * 256 &&
                        (reinterpret_cast<uintptr_t>(frames) % (kU8 ? 4 : 16)) == 0 && frame_bytes % 16 == 0 &&
                        (!mask || reinterpret_cast<uintptr_t>(mask) % 16 == 0);
   if (rows_ok) {
@@ -689,7 +749,7 @@ int enc_se_mlp(float* sums, const float* w1, const float* b1, const float* w2, c
   // the chunk still fills the machine, 8 otherwise.  (M2S_SE_MLP_KF overrides: 8 or 16.)
   static const int kf_env = std::getenv("M2S_SE_MLP_KF") ? std::atoi(std::getenv("M2S_SE_MLP_KF")) : 0;
   const int kf = kf_env == 8 || kf_env == 16 ? kf_env : (n >= 16 * 128 ? 16 : 8);
-  const size_t sm_mlp = (static_cast<size_t>(kf) * C + static_cast<size_t>(kf) * rd) * sizeof(float);
+  const size_t sm_mlp = (static_cast<size_t>(kf) * C + static_cast<size_t>(kf) * ((rd + 3) & ~3)) * sizeof(float);
   static PerDeviceOnce attr_once;
   M2S_TRY(attr_once.run([&]() -> int {
     M2S_CUDA_OK(cudaFuncSetAttribute(se_mlp_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -698,9 +758,9 @@ int enc_se_mlp(float* sums, const float* w1, const float* b1, const float* w2, c
   }));
   if (sm_mlp > 100 * 1024) return fail(M2S_ERR_UNSUPPORTED, "squeeze-excite: %d channels exceed the MLP kernel's SMEM", C);
   if (kf == 16)
-    se_mlp_kernel<16><<<(n + 15) / 16, 1024, sm_mlp, st>>>(sums, w1, b1, w2, b2, C, rd, 1.f / hw, n);
+    se_mlp_kernel<16><<<(n + 15) / 16, 512, sm_mlp, st>>>(sums, w1, b1, w2, b2, C, rd, 1.f / hw, n);
   else
-    se_mlp_kernel<8><<<(n + 7) / 8, 1024, sm_mlp, st>>>(sums, w1, b1, w2, b2, C, rd, 1.f / hw, n);
+    se_mlp_kernel<8><<<(n + 7) / 8, 512, sm_mlp, st>>>(sums, w1, b1, w2, b2, C, rd, 1.f / hw, n);
   M2S_CUDA_OK(cudaGetLastError());
   return M2S_OK;
 }
