@@ -81,6 +81,32 @@ def test_bilstm_cluster_groups(precision, B, T):
             assert got[b, ln:].abs().max().item() == 0.0
 
 
+def test_bilstm_grid_barrier_fallback():
+    """M2S_LSTM_CLUSTER=0 (read once per process, hence the subprocess): the tensor-core grid-barrier recurrence of
+    lstm_sm100.cu, which is what a device without 16-CTA clusters gets, against torch.nn.LSTM on a ragged batch."""
+    import subprocess
+    import sys
+    code = (
+        "import torch\n"
+        "from mri2speech_b200.acoustic import build_acoustic_model\n"
+        "from oracle.acoustic import bilstm_head_forward\n"
+        "torch.manual_seed(1234)\n"
+        "m = build_acoustic_model(precision='fp16').cuda().eval()\n"
+        "g = torch.Generator().manual_seed(77)\n"
+        "feats = torch.randn(20, 40, 208, generator=g) * 0.5\n"
+        "lens = torch.randint(1, 41, (20,), generator=g, dtype=torch.int32); lens[0] = 40\n"
+        "got = m.rnn_head(feats.cuda(), lens).cpu()\n"
+        "sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}\n"
+        "err = max((got[b, :int(lens[b])] - bilstm_head_forward(sd, feats[b:b + 1, :int(lens[b])])[0]).abs().max().item() for b in range(20))\n"
+        "print('ERR', err)\n"
+        "assert err < 1e-3, err\n")
+    env = dict(os.environ, M2S_LSTM_CLUSTER="0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "ERR" in out.stdout
+
+
 @pytest.mark.parametrize("precision,rel_tol", [("fp32", 2e-4), ("tf32", 5e-3), ("fp16", 5e-3)])
 @pytest.mark.parametrize("randomize_bn", [False, True])
 def test_encoder_features(precision, rel_tol, randomize_bn):
