@@ -89,3 +89,26 @@ def test_acoustic_frame_independence_and_shape_errors():
         m(torch.zeros(2, 3, 256, device="cuda"))
     with pytest.raises(ValueError):
         m(torch.zeros(1, 2, 3, 256, 256, device="cuda"))
+
+
+@pytest.mark.parametrize("precision,rel_tol", [("fp16", 5e-3), ("fp32", 2e-4)])
+@pytest.mark.parametrize("hw", [(128, 160), (288, 256)])
+def test_encoder_other_frame_sizes(precision, rel_tol, hw):
+    """The module API takes any frame size that is a multiple of 32 (the reference's CLIs always resize to 256 x 256, its
+    nn.Module does not care).  Non-square / non-256 frames walk the general paths: other pitches for the two-pixel rows of
+    stage 0 and for the space-to-depth TMA boxes of the stride-2 blocks, and the unfused InvertedResidual launches
+    wherever the fused kernels' 16 x 16 / 8 x 8 geometry does not apply."""
+    from mri2speech_b200 import synth
+    from mri2speech_b200.acoustic import build_acoustic_model
+    from oracle.acoustic import encoder_forward
+    torch.manual_seed(1234)
+    m = build_acoustic_model(precision=precision)
+    synth.randomize_batchnorm(m)
+    m = m.cuda().eval()
+    frames = torch.rand(3, hw[0], hw[1], generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        ref = encoder_forward(_cpu(m), frames.unsqueeze(1))
+    got = m.encode_frames(frames.cuda()).cpu()
+    assert got.shape == (3, 208)
+    rel = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert rel < rel_tol, (hw, rel)
