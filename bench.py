@@ -148,7 +148,7 @@ def build_pipeline(device, precision, max_batch_frames):
 
 
 def workload_config(args, world):
-    prec = ("fp16 operands (tcgen05 kind::f16; 10-bit mantissa like tf32), fp32 accumulate, fp32 residual / MRF streams"
+    prec = ("fp16 operands (tcgen05 kind::f16; 10-bit mantissa like tf32), fp32 accumulate, fp16 residual streams, fp32 MRF sums"
             if args.precision == "fp16" else "tf32 (tcgen05 kind::tf32, fp32 accumulate)")
     if args.workload == "vocoder":
         wl = ("BASELINE.json configs[1]: HiFi-GAN Generator only, batch 32 x 64-bin mel, 256 frames, hop 420, 11413 Hz "

@@ -119,6 +119,10 @@ struct m2s_generator {
                            // operand, lo = fp16(v - hi)) instead of fp32 + an fp16 operand copy.  8 instead of 12 bytes
                            // of DRAM traffic per element of a pair, bit-compatible results -- but measured SLOWER
                            // (profiles/README.md): the epilogue is bound by memory requests in flight, not by bytes.
+  bool res16 = false;      // fp16 build (M2S_VOC_RES16): the residual of a ResBlock conv is read from the fp16 operand copy of
+                           // the state the conv reads anyway, and states carry no fp32 copy: 6 instead of 12 bytes of DRAM
+                           // traffic per element of a pair and a third of the epilogue's memory requests gone (one more
+                           // fp16 rounding per pair on the residual chain; the MRF sums stay fp32)
   bool rb2 = false;        // cfg.resblock == 2: ResBlock2 branches (c1 holds their 2 convs each, c2 stays empty)
   int hop = 1;
   Layer pre;
@@ -243,6 +247,8 @@ extern "C" int m2s_generator_create(const m2s_generator_config* cfg, const m2s_t
   if (cfg->resblock < 0 || cfg->resblock > 2) { delete g; return fail(M2S_ERR_BAD_ARG, "resblock must be 1 or 2"); }
   if (const char* f = std::getenv("M2S_FUSE_PAIRS")) g->fuse_pairs = std::atoi(f) != 0;
   if (const char* f = std::getenv("M2S_SPLIT_RES")) g->split_res = g->fp16 && std::atoi(f) != 0;
+  g->res16 = g->fp16 && !g->split_res;
+  if (const char* f = std::getenv("M2S_VOC_RES16")) g->res16 = g->fp16 && !g->split_res && std::atoi(f) != 0;
   // operand format per layer: fp16 needs 16-byte aligned rows of halves (c_in % 8 == 0); conv_pre reads the fp32 mel
   auto mode_for = [&](int c_in) {
     if (!g->tf32) return static_cast<int>(PACK_FP32);
@@ -429,7 +435,7 @@ int generator_forward_impl(m2s_generator* g, const float* mel, bool mel_btc, int
     const bool hs = g->c1[i * cfg.num_kernels * per_block].w.half != 0;  // this stage's ResBlock convs take fp16 operands
     {  // ups: rows = L, N = u*cout; D viewed as (B, L, u*cout) == (B, L*u, cout)
       const bool split = hs && g->split_res;
-      ConvProblem p = base_problem(P, L, ch, batch, L, split ? nullptr : Qs.f32, u * cout, L, L, g->ups[i]);
+      ConvProblem p = base_problem(P, L, ch, batch, L, (split || (hs && g->res16)) ? nullptr : Qs.f32, u * cout, L, L, g->ups[i]);
       if (hs) p.d16 = Qs.hi;
       if (split) p.d16_lo = Qs.lo;
       p.epi.act = M2S_ACT_LRELU; p.epi.act_slope = 0.1f;
@@ -461,8 +467,10 @@ int generator_forward_impl(m2s_generator* g, const float* mel, bool mel_btc, int
           const Stream& out = Rs[d & 1];
           const Layer& l = g->c1[(i * cfg.num_kernels + j) * 2 + d];
           const void* state_op = hs ? static_cast<const void*>(state->hi) : static_cast<const void*>(state->f32);
-          ConvProblem pc = base_problem(state_op, L, ch, batch, L, split ? nullptr : out.f32, ch, L, L, l);
+          const bool r16 = hs && g->res16;
+          ConvProblem pc = base_problem(state_op, L, ch, batch, L, (split || r16) ? nullptr : out.f32, ch, L, L, l);
           if (split) { pc.epi.res_hi = state->hi; pc.epi.res_lo = state->lo; }
+          else if (r16) { pc.epi.res = reinterpret_cast<const float*>(state->hi); pc.epi.res_half = 1; }
           else pc.epi.res = state->f32;
           pc.epi.res_ld = ch; pc.epi.res_inv_slope = 10.f;
           if (d == 0) {
@@ -485,8 +493,10 @@ int generator_forward_impl(m2s_generator* g, const float* mel, bool mel_btc, int
         ConvProblem p1 = base_problem(state_op, L, ch, batch, L, T, ch, L, L, l1);
         if (hs) set_out(&p1, nullptr, T);
         p1.epi.act = M2S_ACT_LRELU; p1.epi.act_slope = 0.1f;
-        ConvProblem p2 = base_problem(T, L, ch, batch, L, split ? nullptr : out.f32, ch, L, L, l2);
+        const bool r16 = hs && g->res16;
+        ConvProblem p2 = base_problem(T, L, ch, batch, L, (split || r16) ? nullptr : out.f32, ch, L, L, l2);
         if (split) { p2.epi.res_hi = state->hi; p2.epi.res_lo = state->lo; }
+        else if (r16) { p2.epi.res = reinterpret_cast<const float*>(state->hi); p2.epi.res_half = 1; }
         else p2.epi.res = state->f32;
         p2.epi.res_ld = ch; p2.epi.res_inv_slope = 10.f;  // 1 / LRELU_SLOPE
         if (d < 2) {
