@@ -155,11 +155,11 @@ class OTNLikeCNNBiLSTM(nn.Module):
                  use_checkpoint: bool = False, ckpt_segments: int = 2, use_reentrant: bool = False,
                  precision: Optional[str] = None):
         super().__init__()
-        if rnn_hidden != 640:
-            # the persistent recurrence kernel (csrc/lstm_sm100.cu) partitions exactly 640 hidden units over its CTAs
-            raise _lib.M2SError(f"rnn_hidden={rnn_hidden}: the sm_100a BiLSTM recurrence is specialised for the "
-                                "reference's hidden size 640 (mri_acoustic_model.py:148); other sizes are refused here "
-                                "rather than at the first forward")
+        if rnn_hidden <= 0 or rnn_hidden % 32:
+            # 640 (the reference's default, mri_acoustic_model.py:148) runs the tuned cluster recurrence; any other multiple
+            # of 32 the generic cooperative kernel of csrc/lstm_sm100.cu
+            raise _lib.M2SError(f"rnn_hidden={rnn_hidden}: the sm_100a BiLSTM recurrence needs a positive multiple of 32 "
+                                "(refused here rather than at the first forward)")
         self.n_mels = n_mels
         self.use_checkpoint = use_checkpoint
         self.ckpt_segments = ckpt_segments

@@ -380,6 +380,112 @@ __global__ void __launch_bounds__(kThreads, 1) lstm_recurrence_mma_kernel(LstmPa
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Any hidden size (H % 32 == 0, H != 640: models trained with another --rnn-hidden).  Not a tuned path: the same
+// cooperative structure as lstm_recurrence_kernel (one arrive counter per direction as the grid barrier, h_t exchanged
+// through the output buffer), but a WARP owns one hidden unit -- its four gate rows, read from L2 every step -- and its
+// lanes split K; an utterance's four row sums are reduced over the lanes with a halving butterfly and lane 0 does the gate
+// math, so the cell state lives in SMEM as [batch][units].  fp32 FMAs in every build.
+constexpr int kGenUnits = 8;                  // hidden units (= warps) per CTA
+constexpr int kGenThreads = 32 * kGenUnits;
+constexpr int kGenChunk = 8;                  // utterances staged per pass
+
+__global__ void __launch_bounds__(kGenThreads) lstm_recurrence_generic_kernel(LstmParams prm, int H) {
+  extern __shared__ float sh_gen[];           // [kGenChunk][H] h_{t-1} of the chunk, then [batch][kGenUnits] cell state
+  float* sh_h = sh_gen;
+  float* sh_c = sh_gen + kGenChunk * H;
+  const int parts = (H + kGenUnits - 1) / kGenUnits;
+  const int dir = blockIdx.x / parts;
+  const int part = blockIdx.x % parts;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int unit = part * kGenUnits + warp;
+  const bool unit_ok = unit < H;
+  const int H2 = 2 * H, G = 8 * H;
+  const int k4n = H >> 2;                     // float4 per row
+  for (int i = tid; i < prm.batch * kGenUnits; i += kGenThreads) sh_c[i] = 0.f;
+  __syncthreads();
+  unsigned int* counter = prm.counters + dir;
+  const float* w = prm.w_hh[dir];
+
+  for (int s = 0; s < prm.max_len; ++s) {
+    if (s > 0) {
+      if (tid == 0) {
+        const unsigned int target = static_cast<unsigned int>(s) * parts;
+        unsigned int v;
+        long long t0 = clock64();
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+          if (v < target && clock64() - t0 > 4000000000LL) {
+            printf("m2s lstm (generic): grid barrier timeout (block %d step %d, %u < %u)\n", blockIdx.x, s, v, target);
+            __trap();
+          }
+        } while (v < target);
+      }
+      __syncthreads();
+    }
+    for (int b0 = 0; b0 < prm.batch; b0 += kGenChunk) {
+      const int nb = min(kGenChunk, prm.batch - b0);
+      for (int i = tid; i < nb * k4n; i += kGenThreads) {
+        const int bb = i / k4n, k4 = i - bb * k4n;
+        const int b = b0 + bb;
+        const int len = prm.lens ? prm.lens[b] : prm.frames;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s > 0 && s < len) {
+          const int tprev = dir == 0 ? s - 1 : len - s;
+          v = __ldcg(reinterpret_cast<const float4*>(prm.hcat + (static_cast<size_t>(b) * prm.frames + tprev) * H2 + dir * H) + k4);
+        }
+        reinterpret_cast<float4*>(sh_h)[bb * k4n + k4] = v;
+      }
+      __syncthreads();
+      if (unit_ok) {
+        float acc[kGenChunk][4];
+#pragma unroll
+        for (int bb = 0; bb < kGenChunk; ++bb) acc[bb][0] = acc[bb][1] = acc[bb][2] = acc[bb][3] = 0.f;
+        for (int k4 = lane; k4 < k4n; k4 += 32) {
+          float4 wv[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) wv[q] = __ldg(reinterpret_cast<const float4*>(w + (static_cast<size_t>(q) * H + unit) * H) + k4);
+#pragma unroll
+          for (int bb = 0; bb < kGenChunk; ++bb) {
+            const float4 h = reinterpret_cast<const float4*>(sh_h)[bb * k4n + k4];   // (rows past nb hold stale data: unused)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              acc[bb][q] = fmaf(wv[q].x, h.x, fmaf(wv[q].y, h.y, fmaf(wv[q].z, h.z, fmaf(wv[q].w, h.w, acc[bb][q]))));
+          }
+        }
+#pragma unroll
+        for (int bb = 0; bb < kGenChunk; ++bb) {
+          if (bb >= nb) break;
+          const int b = b0 + bb;
+          const int len = prm.lens ? prm.lens[b] : prm.frames;
+          float z[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float v = acc[bb][q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            z[q] = v;
+          }
+          if (lane == 0 && s < len) {
+            const int t = dir == 0 ? s : len - 1 - s;
+            const float* gp = prm.gin + (static_cast<size_t>(b) * prm.frames + t) * G + dir * 4 * H + unit;
+            const float zi = z[0] + gp[0], zf = z[1] + gp[H], zg = z[2] + gp[2 * H], zo = z[3] + gp[3 * H];
+            float c = sh_c[b * kGenUnits + warp];
+            c = sigmoidf_acc(zf) * c + sigmoidf_acc(zi) * tanhf(zg);
+            sh_c[b * kGenUnits + warp] = c;
+            __stcg(prm.hcat + (static_cast<size_t>(b) * prm.frames + t) * H2 + dir * H + unit, sigmoidf_acc(zo) * tanhf(c));
+          }
+        }
+      }
+      __syncthreads();
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+  }
+}
+
 }  // namespace
 
 // lstm_cluster_sm100.cu: the recurrence on 16-CTA clusters (W_hh resident in SMEM, h exchanged through DSMEM)
@@ -393,8 +499,32 @@ int lstm_recurrence_cluster(const float* gin, const float* w_hh_fwd, const float
 int lstm_recurrence(const float* gin, const float* w_hh_fwd, const float* w_hh_bwd, const int32_t* lens, float* hcat,
                     unsigned int* counters, int batch, int frames, int max_len, int hidden, bool tensor_cores,
                     cudaStream_t stream) {
-  if (hidden != kHidden) return fail(M2S_ERR_UNSUPPORTED, "LSTM recurrence is specialised for hidden=640 (got %d)", hidden);
   if (batch <= 0 || max_len <= 0) return M2S_OK;
+  if (hidden != kHidden) {
+    // any other hidden size: the generic cooperative kernel (one warp per hidden unit, weights read from L2 every step)
+    if (hidden <= 0 || hidden % 32) return fail(M2S_ERR_UNSUPPORTED, "LSTM hidden size %d: must be a positive multiple of 32", hidden);
+    const int parts = (hidden + kGenUnits - 1) / kGenUnits;
+    const size_t dyn = (static_cast<size_t>(kGenChunk) * hidden + static_cast<size_t>(batch) * kGenUnits) * sizeof(float);
+    if (dyn > 200 * 1024) return fail(M2S_ERR_UNSUPPORTED, "LSTM batch %d / hidden %d too large for one launch", batch, hidden);
+    static PerDeviceOnce gen_once;
+    M2S_TRY(gen_once.run([&]() -> int {
+      M2S_CUDA_OK(cudaFuncSetAttribute(lstm_recurrence_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      return M2S_OK;
+    }));
+    int per_sm = 0;
+    M2S_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_recurrence_generic_kernel, kGenThreads, dyn));
+    if (per_sm * sm_count() < 2 * parts)
+      return fail(M2S_ERR_UNSUPPORTED, "LSTM hidden size %d needs %d co-resident CTAs, the device holds %d", hidden, 2 * parts, per_sm * sm_count());
+    LstmParams gp{};
+    gp.gin = gin; gp.w_hh[0] = w_hh_fwd; gp.w_hh[1] = w_hh_bwd; gp.lens = lens; gp.hcat = hcat;
+    gp.counters = counters; gp.batch = batch; gp.frames = frames; gp.max_len = max_len;
+    M2S_CUDA_OK(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), stream));
+    int h_arg = hidden;
+    void* gargs[] = {&gp, &h_arg};
+    M2S_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_recurrence_generic_kernel), dim3(2 * parts),
+                                            dim3(kGenThreads), gargs, dyn, stream));
+    return M2S_OK;
+  }
   static const bool mma_on = !(std::getenv("M2S_LSTM_MMA") && std::atoi(std::getenv("M2S_LSTM_MMA")) == 0);
   const bool mma = tensor_cores && mma_on;
   static const bool cluster_on = !(std::getenv("M2S_LSTM_CLUSTER") && std::atoi(std::getenv("M2S_LSTM_CLUSTER")) == 0);

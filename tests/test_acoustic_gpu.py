@@ -81,6 +81,30 @@ def test_bilstm_cluster_groups(precision, B, T):
             assert got[b, ln:].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("hidden", [256, 672])
+def test_bilstm_other_hidden_sizes(hidden):
+    """--rnn-hidden other than the reference's 640 (any multiple of 32): the generic cooperative recurrence of
+    csrc/lstm_sm100.cu (a warp per hidden unit, fp32), with the in-projection and the head on the engine as usual."""
+    from mri2speech_b200.acoustic import build_acoustic_model
+    from oracle.acoustic import bilstm_head_forward
+    torch.manual_seed(1234)
+    m = build_acoustic_model(rnn_hidden=hidden, precision="fp16").cuda().eval()
+    g = torch.Generator().manual_seed(hidden)
+    B, T = 11, 29
+    feats = torch.randn(B, T, 208, generator=g) * 0.5
+    lens = torch.randint(1, T + 1, (B,), generator=g, dtype=torch.int32)
+    lens[0] = T
+    got = m.rnn_head(feats.cuda(), lens).cpu()
+    sd = _cpu_sd(m)
+    for b in range(B):
+        ln = int(lens[b])
+        ref = bilstm_head_forward(sd, feats[b:b + 1, :ln])[0]
+        err = (got[b, :ln] - ref).abs().max().item()
+        assert err < 1e-3, (hidden, b, ln, err)
+        if ln < T:
+            assert got[b, ln:].abs().max().item() == 0.0
+
+
 def test_bilstm_grid_barrier_fallback():
     """M2S_LSTM_CLUSTER=0 (read once per process, hence the subprocess): the tensor-core grid-barrier recurrence of
     lstm_sm100.cu, which is what a device without 16-CTA clusters gets, against torch.nn.LSTM on a ragged batch."""
