@@ -239,8 +239,10 @@ struct m2s_acoustic {
   // unfused launches and the fp32 stream (the A/B reference of tests/).  bit7 = no copy at all: the fused kernel's TMA
   // loads gather the space-to-depth tile from the NHWC input (5-D box).
   int mbconv = 247;
-  int chunk = 2048;  // frames per encoder pass (M2S_ENCODER_CHUNK): 2048 frames = ~14 GB of work buffers.  Measured with the
-                     // round-2 kernels: 14.1 / 12.6 / 12.1 / 12.2 us per frame at 512 / 1024 / 2048 / 4096 (fp16 build)
+  int chunk = 4096;  // frames per encoder pass (M2S_ENCODER_CHUNK): ~7 MB of work buffers per frame, 28 GB at 4096 (8192 is
+                     // another 2 % faster, but bench.py's two builds side by side then peak at 156 of 180 GB).  Mid-round kernels: 14.1 / 12.6 / 12.1 / 12.2 us per frame at 512 / 1024 / 2048 / 4096; with the
+                     // late-round kernels the tails weigh more: 11.0 / 10.5 / 10.3 at 1024 / 2048 / 4096 (encoder alone) and
+                     // configs[2] end to end 2 907 / 2 968 / 3 023 audio-s/s at 2048 / 4096 / 8192 (fp16 build)
   // per-frame buffer sizes (floats)
   size_t x_floats = 0, e_floats = 0, e2_floats = 0, col_floats = 0;
   int max_mid = 0;

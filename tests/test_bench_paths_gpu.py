@@ -2,7 +2,7 @@
 
 The small-clip tests elsewhere encode <= 9 frames: the engine then picks msub <= 2 tiles, the encoder's chunk loop
 runs once and a ragged batch's frame map never spans a chunk.  Here:
-  * >= 1100 frames through the encoder with M2S_ENCODER_CHUNK in {64, 1024, default 2048}: the 512 / 1024-row tiles, the
+  * >= 1100 frames through the encoder with M2S_ENCODER_CHUNK in {64, 1024, default}: the 512 / 1024-row tiles, the
     CTA-pair dispatch and multi-chunk passes, 32 sampled frames against the CPU oracle;
   * a ragged batch whose compact frame list spans a chunk boundary, every valid frame against the oracle;
   * BASELINE.json configs[0]: one 150-frame clip end to end (run_mri_video_inference's chain) against the oracle at
