@@ -87,11 +87,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint expires) instead
+// of polling.  The polling loop of the first version (try_wait + clock read + compare + branch per iteration) was a
+// quarter of all issued instructions of resblock_pair_kernel (ncu source page: 5.4 M loop iterations per launch), taken from
+// the schedulers the epilogue warps need.
+__device__ __forceinline__ bool mbar_try_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a pipeline bug must trap, never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_sleep(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
       printf("m2s conv engine: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x,
              threadIdx.x, bar, parity);
